@@ -1,0 +1,54 @@
+"""The C-ABI library builds, loads and exports every symbol that include/*.h declares.  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared(header, macro):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(macro + r"\s+[\w\s\*]+?\b(\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    names = declared("trueno_rag_b200.h", "TRR_API") + declared("trueno_rag_host.h", "TRRH_API")
+    assert len(names) > 50
+    for n in names:
+        assert hasattr(built_lib, n), f"{n} is declared in include/ but not exported"
+
+
+def test_prototype_tables_cover_the_headers(built_lib):
+    from trueno_rag_b200 import _lib
+    assert set(declared("trueno_rag_b200.h", "TRR_API")) == set(_lib.TRR_PROTOS)
+    assert set(declared("trueno_rag_host.h", "TRRH_API")) == set(_lib.TRRH_PROTOS)
+
+
+def test_version_and_error_string(built_lib):
+    assert built_lib.trr_version() >= 100
+    assert isinstance(built_lib.trr_last_error(), bytes)
+    assert built_lib.trr_exchange_bytes(1024, 50) == (4 * 1024 * 50 + 2 * 1024) * 4
+
+
+def test_no_cpu_fallback_without_a_device(built_lib):
+    if built_lib.trr_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    ctx = C.c_void_p()
+    assert built_lib.trr_ctx_create(0, C.byref(ctx)) == 7  # TRR_ERR_NO_DEVICE
+    assert b"no CPU fallback" in built_lib.trr_last_error()
+
+
+def test_product_never_references_the_oracle():
+    bad = []
+    for root, _, files in os.walk(os.path.join(ROOT, "trueno_rag_b200")):
+        if os.path.basename(root) == "build":
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                txt = open(os.path.join(root, f), errors="replace").read()
+                if re.search(r"(from|import)\s+oracle|libtrr_oracle|orc_\w+\s*\(", txt):
+                    bad.append(f)
+    assert not bad, bad

@@ -1,0 +1,136 @@
+"""BM25 parity: CUDA posting-list kernel (through the C ABI) vs the oracle.  Bit-exact ids and scores."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+SEED = 0x5EED0003
+
+
+@pytest.fixture(scope="module")
+def api(ctx):
+    from trueno_rag_b200 import api as a
+    return a
+
+
+def build(api, ctx, oix, n_docs, doc_base=0, k1=1.2, b=0.75):
+    term_off, post_doc, post_tf, doc_len, df = oix.csr()
+    return api.Bm25Device(ctx, n_docs, term_off, post_doc, post_tf, doc_len, oix.avgdl, api.bm25_idf_host(n_docs, df),
+                          k1, b, doc_base)
+
+
+def compare(dev, oix, q_terms, q_off, k, base=0):
+    ords, scores, n = dev.search(q_terms, q_off, k)
+    eo, es, en = oix.search_batch(q_terms, q_off, k)
+    assert np.array_equal(n, en), (n, en)
+    for b in range(len(q_off) - 1):
+        m = int(n[b])
+        assert np.array_equal(ords[b, :m], eo[b, :m] + base), (b, ords[b, :m], eo[b, :m])
+        assert np.array_equal(scores[b, :m], es[b, :m]), (b, scores[b, :m] - es[b, :m])
+
+
+def test_impacts_are_bit_exact(api, ctx):
+    rng = np.random.default_rng(0)
+    docs = [list(rng.integers(0, 50, int(rng.integers(1, 40)))) for _ in range(500)]
+    oix = O.BM25(docs, 50, 1.5, 0.6)
+    dev = build(api, ctx, oix, 500, k1=1.5, b=0.6)
+    term_off, post_doc, post_tf, doc_len, df = oix.csr()
+    exp = np.zeros(oix.n_postings, F32)
+    for t in range(50):
+        for p in range(int(term_off[t]), int(term_off[t + 1])):
+            exp[p] = O.bm25_score_term(int(post_tf[p]), int(df[t]), 500, int(doc_len[post_doc[p]]), oix.avgdl, 1.5, 0.6)
+    assert np.array_equal(dev.impacts(), exp)
+    dev.close()
+
+
+def test_random_small_indexes_vs_literal_oracle(api, ctx):
+    rng = np.random.default_rng(1)
+    for trial in range(12):
+        n_docs, n_terms = int(rng.integers(1, 400)), int(rng.integers(1, 60))
+        docs = [list(rng.integers(0, n_terms, int(rng.integers(0, 30)))) for _ in range(n_docs)]
+        oix = O.BM25(docs, n_terms)
+        dev = build(api, ctx, oix, n_docs)
+        qs = [list(rng.integers(0, n_terms + 3, int(rng.integers(0, 9)))) for _ in range(7)]
+        qs = [[x if x < n_terms else 0xFFFFFFFF for x in q] for q in qs]
+        q_off = np.cumsum([0] + [len(q) for q in qs]).astype(np.uint32)
+        q_terms = np.array([x for q in qs for x in q], np.uint32)
+        for k in (1, 7, 1000):
+            ords, scores, n = dev.search(q_terms, q_off, k)
+            for b, q in enumerate(qs):
+                lo, ls = oix.search(q, k, literal=True)                 # the reference's literal algorithm
+                assert n[b] == len(lo)
+                assert np.array_equal(ords[b, :n[b]], lo) and np.array_equal(scores[b, :n[b]], ls)
+        dev.close()
+
+
+@pytest.mark.parametrize("n_docs,n_terms", [(3000, 500), (40000, 5000), (70000, 20000)])
+def test_zipf_corpus(api, ctx, n_docs, n_terms):
+    cdf = O.zipf_cdf(n_terms)
+    doc_off, toks = O.synth_doc_tokens(SEED, cdf, 0, n_docs)
+    oix = O.BM25(n_terms=n_terms, doc_off=doc_off, tokens=toks)
+    dev = build(api, ctx, oix, n_docs, doc_base=123456)
+    q_off, q_terms = O.synth_query_terms(SEED, cdf, 0, 40)
+    for k in (10, 100):
+        compare(dev, oix, q_terms, q_off, k, base=123456)
+    dev.close()
+
+
+def test_duplicate_terms_and_massive_ties(api, ctx):
+    # every document has the same length and term 0 once -> thousands of exact score ties
+    n_docs = 40000
+    docs = [[0, 1 + (i % 7), 8 + (i % 3)] for i in range(n_docs)]
+    oix = O.BM25(docs, 11)
+    dev = build(api, ctx, oix, n_docs)
+    qs = [[0], [0, 0], [0, 3, 0, 9], [5, 5, 5], [10, 0xFFFFFFFF, 2]]
+    q_off = np.cumsum([0] + [len(q) for q in qs]).astype(np.uint32)
+    q_terms = np.array([x for q in qs for x in q], np.uint32)
+    for k in (1, 50, 1000):
+        compare(dev, oix, q_terms, q_off, k)
+    dev.close()
+
+
+def test_long_posting_lists_exceed_the_stage(api, ctx):
+    # terms 0..3 occur in (almost) every document of every 16K range: segments longer than the 2048-entry stage
+    rng = np.random.default_rng(2)
+    n_docs = 50000
+    docs = []
+    for i in range(n_docs):
+        d = [0, 1, 2] + ([3] if i % 5 else []) + list(rng.integers(4, 200, int(rng.integers(0, 6))))
+        docs.append(d)
+    oix = O.BM25(docs, 200)
+    dev = build(api, ctx, oix, n_docs)
+    qs = [[0, 1, 2, 3], [3, 50, 0], [150, 151, 152, 2, 153, 154], [0] * 12]
+    q_off = np.cumsum([0] + [len(q) for q in qs]).astype(np.uint32)
+    q_terms = np.array([x for q in qs for x in q], np.uint32)
+    compare(dev, oix, q_terms, q_off, 100)
+    dev.close()
+
+
+def test_many_query_terms_and_limits(api, ctx):
+    cdf = O.zipf_cdf(3000)
+    doc_off, toks = O.synth_doc_tokens(SEED + 1, cdf, 0, 20000)
+    oix = O.BM25(n_terms=3000, doc_off=doc_off, tokens=toks)
+    dev = build(api, ctx, oix, 20000)
+    rng = np.random.default_rng(3)
+    q = rng.integers(0, 3000, 512).astype(np.uint32)                    # 512 terms: the per-query limit
+    compare(dev, oix, q, np.array([0, 512], np.uint32), 20)
+    with pytest.raises(api.TrrError):
+        dev.search(np.zeros(513, np.uint32), np.array([0, 513], np.uint32), 5)
+    o, s, n = dev.search(np.zeros(0, np.uint32), np.array([0, 0, 0], np.uint32), 5)   # two empty queries
+    assert list(n) == [0, 0]
+    dev.close()
+
+
+def test_bench_shape_topic_keywords(api, ctx):                          # benches/retrieval.rs:45-69
+    from oracle.tokenizer import TextIndex
+    ti = TextIndex()
+    for i in range(1000):
+        ti.add(f"Document {i} about topic {i % 100} with keywords")
+    oix = ti.build()
+    dev = build(api, ctx, oix, 1000)
+    q = np.array(ti.query_ids("topic keywords"), np.uint32)
+    for k in (10, 100):
+        compare(dev, oix, q, np.array([0, len(q)], np.uint32), k)
+    dev.close()

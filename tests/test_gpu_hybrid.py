@@ -1,0 +1,121 @@
+"""End-to-end hybrid path (dense top-C + BM25 top-C + fusion + take k) and the document-sharded variant.
+The multi-GPU flow is exercised on ONE GPU with G logical shards: each shard has its own dense slab and CSR
+(global BM25 statistics, local doc ids, global ordinals out), the exchange records are concatenated in device memory
+exactly as an all-gather would leave them, and the merge+fusion kernel consumes them.  1/2/4/8 shards must return
+identical ids and scores, equal to the oracle's."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from trueno_rag_b200 import shard
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+SEED = 0x5EED0004
+
+
+@pytest.fixture(scope="module")
+def api(ctx):
+    from trueno_rag_b200 import api as a
+    return a
+
+
+def bf16_round(x):
+    u = np.ascontiguousarray(x, F32).view(np.uint32)
+    return ((u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32).view(F32)
+
+
+@pytest.fixture(scope="module")
+def corpus():
+    N, D, V, B = 40000, 256, 8000, 48
+    f, b = O.synth_corpus(SEED, 0, N, D, bf16=True, dups=True)
+    Q = bf16_round(O.synth_queries(SEED, 0, B, D, N, corpus_bf16=True, dups=True))
+    cdf = O.zipf_cdf(V)
+    doc_off, toks = O.synth_doc_tokens(SEED, cdf, 0, N)
+    q_off, q_terms = O.synth_query_terms(SEED, cdf, 0, B)
+    oix = O.BM25(n_terms=V, doc_off=doc_off, tokens=toks)
+    return dict(N=N, D=D, V=V, B=B, f=f, b=b, Q=Q, doc_off=doc_off, toks=toks, q_off=q_off, q_terms=q_terms, oix=oix)
+
+
+def oracle_hybrid(c, strategy, param, C_, k, use_dense=True, use_sparse=True):
+    out = []
+    for b in range(c["B"]):
+        d = O.dense_search(c["b"], c["Q"][b], C_, literal=False) if use_dense else ([], [])
+        s = c["oix"].search(c["q_terms"][c["q_off"][b]:c["q_off"][b + 1]], C_) if use_sparse else ([], [])
+        out.append(O.hybrid_assemble(strategy, param, d, s, k))
+    return out
+
+
+def assert_hybrid(got, exp):
+    o_ord, o_f, o_d, o_s, o_n = got
+    for b, (i, f, d, s) in enumerate(exp):
+        n = int(o_n[b])
+        assert n == len(i), (b, n, len(i))
+        assert np.array_equal(o_ord[b, :n], i), (b, o_ord[b, :n], i)
+        assert np.array_equal(o_f[b, :n], f), b
+        assert np.array_equal(o_d[b, :n], d, equal_nan=True) and np.array_equal(o_s[b, :n], s, equal_nan=True), b
+
+
+def make_dense(api, ctx, c, lo, hi):
+    ix = api.DenseIndex(ctx, c["D"], api.COSINE, api.BF16, base=lo)
+    ix.append(c["b"][lo:hi])
+    return ix
+
+
+def make_bm25(api, ctx, c, lo, hi):
+    """Shard CSR restricted to docs [lo, hi) with LOCAL doc ids and GLOBAL statistics (N, df, avgdl, idf)."""
+    term_off, post_doc, post_tf, doc_len, df = c["oix"].csr()
+    keep = (post_doc >= lo) & (post_doc < hi)
+    term_of = np.repeat(np.arange(c["V"]), np.diff(term_off).astype(np.int64))
+    cnt = np.bincount(term_of[keep], minlength=c["V"])
+    s_off = np.zeros(c["V"] + 1, np.uint64)
+    np.cumsum(cnt, out=s_off[1:])
+    return api.Bm25Device(ctx, hi - lo, s_off, post_doc[keep] - lo, post_tf[keep], doc_len[lo:hi], c["oix"].avgdl,
+                          api.bm25_idf_host(c["N"], df), doc_base=lo)
+
+
+@pytest.mark.parametrize("strategy,param,C_,k", [(O.RRF, 60.0, 50, 10), (O.LINEAR, 0.7, 50, 10), (O.DBSF, 0.0, 20, 40),
+                                                  (O.UNION, 0.0, 10, 20), (O.INTERSECTION, 0.0, 50, 10),
+                                                  (O.CONVEX, 0.25, 5, 3)])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_hybrid_single_shard(api, ctx, corpus, strategy, param, C_, k, mode):
+    c = corpus
+    dense, bm = make_dense(api, ctx, c, 0, c["N"]), make_bm25(api, ctx, c, 0, c["N"])
+    dense.set_mode(mode)
+    got = api.hybrid_search(dense, bm, c["Q"], c["q_terms"], c["q_off"], C_, strategy, param, k)
+    assert_hybrid(got, oracle_hybrid(c, strategy, np.float32(param), C_, k))
+    dense.close(); bm.close()
+
+
+def test_hybrid_dense_only_and_sparse_only(api, ctx, corpus):
+    c = corpus
+    dense, bm = make_dense(api, ctx, c, 0, c["N"]), make_bm25(api, ctx, c, 0, c["N"])
+    got = api.hybrid_search(dense, bm, c["Q"], c["q_terms"], c["q_off"], 50, O.RRF, 60.0, 10, use_sparse=False)
+    assert_hybrid(got, oracle_hybrid(c, O.RRF, 60.0, 50, 10, use_sparse=False))
+    got = api.hybrid_search(dense, bm, c["Q"], c["q_terms"], c["q_off"], 50, O.RRF, 60.0, 10, use_dense=False)
+    assert_hybrid(got, oracle_hybrid(c, O.RRF, 60.0, 50, 10, use_dense=False))
+    dense.close(); bm.close()
+
+
+@pytest.mark.parametrize("G", [1, 2, 4, 8])
+@pytest.mark.parametrize("strategy,param", [(O.RRF, 60.0), (O.LINEAR, 0.7)])
+def test_sharded_flow_on_logical_shards(api, ctx, corpus, G, strategy, param):
+    c = corpus
+    B, C_, k = c["B"], 50, 10
+    rec_bytes = api.exchange_bytes(B, C_)
+    assert rec_bytes == shard.exchange_words(B, C_) * 4
+    gathered = torch.zeros(G * rec_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()                                         # the library enqueues on its own stream
+    handles = []
+    for g in range(G):
+        lo, hi = shard.shard_range(c["N"], g, G)
+        dense, bm = make_dense(api, ctx, c, lo, hi), make_bm25(api, ctx, c, lo, hi)
+        dense.set_mode(2 if g % 2 == 0 else 1)                      # mix both dense kernels across shards
+        api.hybrid_local(dense, bm, c["Q"], c["q_terms"], c["q_off"], C_, gathered.data_ptr() + g * rec_bytes)
+        handles += [dense, bm]
+    torch.cuda.synchronize()
+    got = api.hybrid_merge(ctx, gathered.data_ptr(), G, B, C_, strategy, param, k)
+    assert_hybrid(got, oracle_hybrid(c, strategy, np.float32(param), C_, k))
+    for h in handles:
+        h.close()

@@ -1,0 +1,127 @@
+"""Host-side logic of the C++ mirror that needs no device: tokenizer, dictionary bookkeeping, validation errors,
+shard planning and the exchange-record layout.  Mirrors the reference's tests where one exists."""
+import numpy as np
+import pytest
+
+from oracle.tokenizer import tokenize as oracle_tokenize
+from trueno_rag_b200 import shard
+
+
+@pytest.fixture(scope="module")
+def api(built_lib):
+    from trueno_rag_b200 import api as a
+    return a
+
+
+def test_bm25_index_new(api):                                   # src/index.rs:481-488
+    ix = api.BM25Index()
+    assert len(ix) == 0 and ix.is_empty()
+    assert abs(ix.k1 - 1.2) < 0.01 and abs(ix.b - 0.75) < 0.01
+
+
+def test_bm25_index_with_params(api):                           # :490-495
+    ix = api.BM25Index.with_params(1.5, 0.5)
+    assert abs(ix.k1 - 1.5) < 0.01 and abs(ix.b - 0.5) < 0.01
+
+
+def test_bm25_tokenize(api):                                    # :497-517
+    ix = api.BM25Index()
+    toks = ix.tokenize("Hello World! This is a test.")
+    assert "hello" in toks and "world" in toks and "test" in toks
+    assert "this" not in toks and "is" not in toks and "a" not in toks
+    toks = ix.tokenize("HELLO World")
+    assert "hello" in toks and "world" in toks
+
+
+@pytest.mark.parametrize("text", [
+    "", "   ", "a I x", "Rust's memory-safety: zero_cost abstractions, 100% (no GC)!",
+    "The quick brown fox jumps over the lazy dog 42 times", "tab\tseparated\nlines\r\nhere",
+    "Ünïcödé Größe ÉCOLE naïve café", "ΑΒΓ δοκιμή Привет МИР", "mixed123abc 7up x9 C3PO", "e-mail@example.com http://a.b/c?d=e",
+])
+def test_tokenizer_matches_oracle_restatement(api, text):
+    assert api.BM25Index().tokenize(text) == oracle_tokenize(text)
+
+
+def test_bm25_add_chunk_and_batch(api):                         # :519-545
+    ix = api.BM25Index()
+    ix.add(api.Chunk("Machine learning is fascinating"))
+    assert len(ix) == 1 and not ix.is_empty()
+    assert ix.contains_term("machine") and ix.contains_term("learning")
+    ix2 = api.BM25Index()
+    ix2.add_batch([api.Chunk("First document about AI"), api.Chunk("Second document about ML"),
+                   api.Chunk("Third document about deep learning")])
+    assert len(ix2) == 3
+
+
+def test_bm25_remove_updates_len(api):                          # :621-634 (search part is a gpu test)
+    ix = api.BM25Index()
+    c = api.Chunk("Test document")
+    ix.add(c)
+    assert len(ix) == 1
+    ix.remove(c.id)
+    assert len(ix) == 0
+
+
+def test_vector_store_new_and_insert_validation(api):           # :688-726
+    store = api.VectorStore.with_dimension(384)
+    assert store.dimension == 384 and store.is_empty()
+    store = api.VectorStore.with_dimension(3)
+    with pytest.raises(api.Error) as e:
+        store.insert(api.Chunk("no embedding"))
+    assert e.value.kind == "InvalidConfig"
+    with pytest.raises(api.Error) as e:
+        store.insert(api.Chunk("test", embedding=[1.0, 0.0]))
+    assert e.value.kind == "DimensionMismatch" and e.value.expected == 3 and e.value.actual == 2
+    store.insert(api.Chunk("ok", embedding=[1.0, 0.0, 0.0]))    # buffered on the host until the first search
+    assert len(store) == 1 and not store.is_empty()
+
+
+def test_vector_store_get_and_remove_nonexistent(api):          # :799-819
+    store = api.VectorStore.with_dimension(3)
+    c = api.Chunk("test", embedding=[1.0, 0.0, 0.0])
+    store.insert(c)
+    assert store.get(c.id) == "test"
+    assert store.get(api.ChunkId()) is None
+    assert store.remove(api.ChunkId()) is False
+
+
+def test_retrieval_result_best_score(api):                      # src/retrieve.rs:69-75
+    r = api.RetrievalResult(api.ChunkId(), "x")
+    assert r.best_score() == 0.0
+    r.sparse_score = 0.1
+    assert r.best_score() == 0.1
+    r.dense_score = 0.2
+    assert r.best_score() == 0.2
+    r.fused_score = 0.3
+    assert r.best_score() == 0.3
+    r.rerank_score = 0.4
+    assert r.best_score() == 0.4
+
+
+def test_hybrid_config_defaults(api):                           # src/retrieve.rs:91-100, src/fusion.rs:33-37
+    c = api.HybridRetrieverConfig()
+    assert c.candidates_per_source == 50 and c.use_dense and c.use_sparse
+    assert c.fusion.kind == api.RRF and abs(c.fusion.param - 60.0) < 0.01
+
+
+def test_shard_ranges_are_contiguous_and_cover():
+    for n in (0, 1, 7, 8, 10_000_000, 20_000_001):
+        for w in (1, 2, 3, 4, 8):
+            rs = [shard.shard_range(n, r, w) for r in range(w)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in rs]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_exchange_record_layout_roundtrip(api):
+    B, C_ = 5, 7
+    rng = np.random.default_rng(0)
+    d = (rng.integers(0, 1000, (B, C_)).astype(np.uint32), rng.random((B, C_)).astype(np.float32),
+         rng.integers(0, C_ + 1, B).astype(np.uint32))
+    s = (rng.integers(0, 1000, (B, C_)).astype(np.uint32), rng.random((B, C_)).astype(np.float32),
+         rng.integers(0, C_ + 1, B).astype(np.uint32))
+    w = shard.pack_exchange(d, s, B, C_)
+    assert w.nbytes == api.exchange_bytes(B, C_)
+    ords, scores, n = shard.unpack_exchange(w, B, C_)
+    assert np.array_equal(ords[0], d[0]) and np.array_equal(scores[1], s[1]) and np.array_equal(n[1], s[2])

@@ -1,0 +1,187 @@
+"""Step-by-step GPU bring-up probe.  Each step runs in its own process (tools/run_probe.sh) so that a faulting
+kernel cannot take the later steps down.  Prints compact diagnostics; used during development only."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+from trueno_rag_b200 import api  # noqa: E402
+
+F32 = np.float32
+SEED = 0x5EED0002
+
+
+def bf16_round(x):
+    u = np.ascontiguousarray(x, F32).view(np.uint32)
+    return ((u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32).view(F32)
+
+
+def cmp_lists(tag, got, exp):
+    (o, s, n), (eo, es, en) = got, exp
+    bad_n = int((n != en).sum())
+    bad_o = bad_s = 0
+    for b in range(len(n)):
+        m = int(min(n[b], en[b]))
+        bad_o += int((o[b, :m] != eo[b, :m]).sum())
+        bad_s += int((s[b, :m] != es[b, :m]).sum())
+    print(f"[{tag}] queries={len(n)} bad_n={bad_n} bad_ids={bad_o} bad_scores={bad_s}", flush=True)
+    if bad_o or bad_s or bad_n:
+        b = 0
+        print("   got ", o[b, :8], s[b, :8], n[b])
+        print("   exp ", eo[b, :8], es[b, :8], en[b])
+    return not (bad_n or bad_o or bad_s)
+
+
+def step_ctx():
+    ctx = api.Context(0)
+    print("sm_count", ctx.sm_count, "stream", hex(ctx.stream))
+
+
+def step_scan_small():
+    ctx = api.Context(0)
+    rng = np.random.default_rng(0)
+    for (n, d) in [(3, 3), (1000, 128), (3000, 6)]:
+        rows = rng.standard_normal((n, d)).astype(F32)
+        Q = rng.standard_normal((3, d)).astype(F32)
+        for metric in (0, 1, 2):
+            ix = api.DenseIndex(ctx, d, metric)
+            ix.append(rows)
+            got = ix.search(Q, 10)
+            cmp_lists(f"scan-generic n={n} d={d} m={metric}", got, O.dense_search_batch(rows, Q, 10, metric=metric))
+            ix.close()
+
+
+def step_scan_bulk():
+    ctx = api.Context(0)
+    for (n, d, dt) in [(20011, 384, 0), (30001, 768, 1), (6000, 4096, 1)]:
+        f, b = O.synth_corpus(SEED, 0, n, d, bf16=bool(dt), dups=True)
+        rows = b if dt else f
+        Q = O.synth_queries(SEED, 0, 3, d, n, corpus_bf16=bool(dt), dups=True)
+        ix = api.DenseIndex(ctx, d, 0, dt)
+        ix.append(rows)
+        ix.set_mode(1)
+        for k in (10, 100):
+            got = ix.search(Q, k)
+            st = ix.stats()
+            cmp_lists(f"scan-bulk n={n} d={d} dt={dt} k={k} ms={st.ms_main_kernel:.3f}", got, O.dense_search_batch(rows, Q, k))
+        ix.close()
+
+
+def step_gemm_debug():
+    ctx = api.Context(0)
+    n, d, B = 1000, 256, 40
+    f, b = O.synth_corpus(SEED, 0, n, d, bf16=True)
+    Q = bf16_round(O.synth_queries(SEED, 0, B, d, n, corpus_bf16=True))
+    ix = api.DenseIndex(ctx, d, api.DOT, api.BF16)
+    ix.append(b)
+    got = ix.debug_gemm_scores(Q, 1024)[:, :n]
+    exp = (Q.astype(np.float64) @ f.astype(np.float64).T)
+    err = np.abs(got - exp)
+    print("gemm-debug max_err", err.max(), "mean_err", err.mean(), "got[0,:4]", got[0, :4], "exp[0,:4]", exp[0, :4])
+    if err.max() > 1e-4:
+        bad = np.argwhere(err > 1e-4)
+        print("  bad count", len(bad), "first", bad[:10].tolist())
+        print("  rows with errors", np.unique(bad[:, 0])[:20], "cols", np.unique(bad[:, 1])[:40])
+        # does got match some permutation / partial K?
+        for kk in (16, 32, 64, 128):
+            part = Q[:, :kk].astype(np.float64) @ f[:, :kk].astype(np.float64).T
+            print(f"  vs partial K={kk}: max_err {np.abs(got - part).max():.4g}")
+    ix.close()
+
+
+def step_gemm_path():
+    ctx = api.Context(0)
+    for (n, d, dt, B, k) in [(20000, 768, 1, 200, 10), (50000, 768, 1, 130, 50), (20000, 384, 0, 64, 10)]:
+        f, b = O.synth_corpus(SEED + 3, 0, n, d, bf16=bool(dt), dups=True)
+        rows = b if dt else f
+        Q = O.synth_queries(SEED + 3, 0, B, d, n, corpus_bf16=bool(dt), dups=True)
+        if dt:
+            Q = bf16_round(Q)
+        ix = api.DenseIndex(ctx, d, 0, dt)
+        ix.append(rows)
+        ix.set_mode(2)
+        got = ix.search(Q, k)
+        st = ix.stats()
+        cmp_lists(f"gemm n={n} d={d} dt={dt} B={B} k={k} fallbacks={st.n_guard_fallbacks} gap={st.max_fast_exact_gap:.2e} "
+                  f"eps={st.eps_bound:.2e} ms={st.ms_main_kernel:.3f}", got, O.dense_search_batch(rows, Q, k))
+        ix.close()
+
+
+def step_bm25():
+    ctx = api.Context(0)
+    for (n_docs, n_terms) in [(3000, 500), (70000, 20000)]:
+        cdf = O.zipf_cdf(n_terms)
+        doc_off, toks = O.synth_doc_tokens(SEED, cdf, 0, n_docs)
+        oix = O.BM25(n_terms=n_terms, doc_off=doc_off, tokens=toks)
+        term_off, post_doc, post_tf, doc_len, df = oix.csr()
+        dev = api.Bm25Device(ctx, n_docs, term_off, post_doc, post_tf, doc_len, oix.avgdl, api.bm25_idf_host(n_docs, df))
+        q_off, q_terms = O.synth_query_terms(SEED, cdf, 0, 40)
+        for k in (10, 100):
+            got = dev.search(q_terms, q_off, k)
+            st = dev.stats()
+            cmp_lists(f"bm25 docs={n_docs} k={k} ms={st.ms_main_kernel:.3f}", got, oix.search_batch(q_terms, q_off, k))
+        dev.close()
+
+
+def step_fusion():
+    ctx = api.Context(0)
+    rng = np.random.default_rng(1)
+    ok = True
+    for strategy, param in ((0, 60.0), (1, 0.7), (3, 0.0), (4, 0.0), (5, 0.0)):
+        dense, sparse = [], []
+        for b in range(32):
+            nd, ns = int(rng.integers(0, 51)), int(rng.integers(0, 51))
+            dense.append((rng.choice(80, nd, replace=False).astype(np.uint32), np.sort(rng.random(nd).astype(F32))[::-1].copy()))
+            sparse.append((rng.choice(80, ns, replace=False).astype(np.uint32), np.sort(rng.random(ns).astype(F32))[::-1].copy()))
+        got = api.fuse(ctx, strategy, param, dense, sparse)
+        bad = 0
+        for b in range(32):
+            ei, ef = O.fuse(strategy, param, dense[b], sparse[b])
+            gi, gf, _, _ = got[b]
+            bad += int(not (np.array_equal(gi, ei) and np.array_equal(gf, ef)))
+        print(f"[fusion strategy={strategy}] bad_queries={bad}")
+        ok = ok and bad == 0
+
+
+def step_perf_scan():
+    ctx = api.Context(0)
+    n, d = 1_000_000, 384
+    ix = api.DenseIndex(ctx, d, 0, 0, capacity=n)
+    ix.append_synth(SEED, 0, n)
+    ix.set_mode(1)
+    Q = O.synth_queries(SEED, 0, 4, d, n)
+    for it in range(3):
+        ix.search(Q[:1], 10)
+        st = ix.stats()
+        print(f"K1 1Mx384 f32 B=1: main {st.ms_main_kernel*1e3:.1f} us total {st.ms_total*1e3:.1f} us  "
+              f"{n*d*4/st.ms_main_kernel/1e6:.0f} GB/s")
+    f, _ = O.synth_corpus(SEED, 0, 200000, d)
+    got = ix.search(Q[:1], 10)
+    print("top1", got[0][0, :5], got[1][0, :5])
+    ix.close()
+
+
+def step_perf_gemm():
+    ctx = api.Context(0)
+    n, d, B = 2_000_000, 768, 1024
+    ix = api.DenseIndex(ctx, d, 0, 1, capacity=n)
+    t0 = time.time()
+    ix.append_synth(SEED, 0, n)
+    print("synth gen s", time.time() - t0)
+    ix.set_mode(2)
+    Q = bf16_round(O.synth_queries(SEED, 0, B, d, n, corpus_bf16=True))
+    for it in range(3):
+        ix.search(Q, 50)
+        st = ix.stats()
+        fl = 2.0 * B * n * d
+        print(f"K2 2Mx768 bf16 B=1024: main {st.ms_main_kernel:.3f} ms total {st.ms_total:.3f} ms "
+              f"{fl/st.ms_main_kernel/1e9:.0f} TFLOP/s fallbacks={st.n_guard_fallbacks} gap={st.max_fast_exact_gap:.2e}")
+    ix.close()
+
+
+if __name__ == "__main__":
+    globals()["step_" + sys.argv[1]]()

@@ -1,0 +1,1051 @@
+// capi.cu — the C ABI of include/trueno_rag_b200.h: handle management and kernel orchestration.
+// No arithmetic of the retrieval path lives here; it sequences the kernels of dense_scan.cu (K1, merge,
+// rescoring), dense_gemm.cu (K2), bm25.cu (K3) and fusion.cu (K4) on the context stream.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "bm25.cuh"
+#include "common.cuh"
+#include "dense.cuh"
+#include "fusion.cuh"
+
+cudaError_t trr_launch_synth_rows(uint64_t seed, uint64_t first_row, uint64_t n, uint32_t dim, int dups, int to_bf16,
+                                  void* out, cudaStream_t st);
+cudaError_t trr_launch_flush(void* p, size_t bytes, cudaStream_t st);
+cudaError_t trr_launch_gemm_topk_dump(const GemmTopkArgs& a, const void* map_q128, const void* map_d128, unsigned grid,
+                                      float* dump, uint32_t dump_ld, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+void trr_set_error(const std::string& msg) { g_last_error = msg; }
+int trr_fail(int status, const std::string& msg) {
+  g_last_error = msg;
+  return status;
+}
+
+extern "C" const char* trr_last_error(void) { return g_last_error.c_str(); }
+extern "C" int trr_version(void) { return 100; }
+extern "C" int trr_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// growable device buffers
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t n) {
+    if (n <= bytes) return TRR_OK;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    n = (n + 4095) & ~size_t(4095);
+    TRR_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+    return TRR_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct CtxExtra {
+  DevBuf scratch;  // kernel-internal scratch of dense / bm25 searches
+  DevBuf io;       // device copies of host inputs / outputs of the host-buffer entry points
+  DevBuf hy;       // hybrid exchange record (single-GPU path)
+  DevBuf flush;
+};
+
+static CtxExtra* extra(trr_ctx* c) { return reinterpret_cast<CtxExtra*>(c->ws); }
+
+int trr_ctx_reserve_ws(trr_ctx* ctx, size_t bytes) { return extra(ctx)->scratch.reserve(bytes); }
+int trr_ctx_reserve_pin(trr_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->pin_bytes) return TRR_OK;
+  if (ctx->pin) cudaFreeHost(ctx->pin);
+  ctx->pin = nullptr; ctx->pin_bytes = 0;
+  TRR_CUDA(cudaMallocHost(&ctx->pin, bytes));
+  ctx->pin_bytes = bytes;
+  return TRR_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+extern "C" int trr_ctx_create(int device, trr_ctx** out) {
+  if (!out) return trr_fail(TRR_ERR_INVALID_ARG, "trr_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return trr_fail(TRR_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  }
+  if (device < 0 || device >= n) return trr_fail(TRR_ERR_INVALID_ARG, "trr_ctx_create: bad device index");
+  cudaDeviceProp prop;
+  TRR_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return trr_fail(TRR_ERR_UNSUPPORTED, "this library is built for sm_100a (B200) only");
+  TRR_CUDA(cudaSetDevice(device));
+  trr_ctx* c = new trr_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  c->ws = new CtxExtra();
+  TRR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (auto& e : c->ev) TRR_CUDA(cudaEventCreate(&e));
+  *out = c;
+  return TRR_OK;
+}
+
+extern "C" int trr_ctx_destroy(trr_ctx* c) {
+  if (!c) return TRR_OK;
+  DeviceGuard g(c->device);
+  cudaStreamSynchronize(c->stream);
+  CtxExtra* x = extra(c);
+  x->scratch.release(); x->io.release(); x->hy.release(); x->flush.release();
+  delete x;
+  if (c->pin) cudaFreeHost(c->pin);
+  for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return TRR_OK;
+}
+
+extern "C" int trr_ctx_sync(trr_ctx* c) {
+  if (!c) return trr_fail(TRR_ERR_INVALID_ARG, "ctx is NULL");
+  DeviceGuard g(c->device);
+  TRR_CUDA(cudaStreamSynchronize(c->stream));
+  return TRR_OK;
+}
+extern "C" int trr_ctx_stream(trr_ctx* c, void** out) {
+  if (!c || !out) return trr_fail(TRR_ERR_INVALID_ARG, "NULL argument");
+  *out = c->stream;
+  return TRR_OK;
+}
+extern "C" int trr_ctx_sm_count(trr_ctx* c, int* out) {
+  if (!c || !out) return trr_fail(TRR_ERR_INVALID_ARG, "NULL argument");
+  *out = c->sm_count;
+  return TRR_OK;
+}
+extern "C" int trr_ctx_flush_l2(trr_ctx* c, size_t bytes) {
+  if (!c) return trr_fail(TRR_ERR_INVALID_ARG, "ctx is NULL");
+  DeviceGuard g(c->device);
+  TRR_CHECK(extra(c)->flush.reserve(bytes));
+  TRR_CUDA(trr_launch_flush(extra(c)->flush.p, bytes, c->stream));
+  return TRR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense store
+// ------------------------------------------------------------------------------------------------
+struct trr_dense {
+  trr_ctx* ctx = nullptr;
+  uint32_t dim = 0;
+  int metric = 0, dtype = 0;
+  uint32_t elem = 4, row_bytes = 0;
+  uint64_t n = 0, cap = 0, n_dead = 0;
+  uint32_t base = 0;
+  uint8_t* rows = nullptr;
+  float* norms = nullptr;
+  uint8_t* dead = nullptr;
+  uint64_t frozen_n = 0;
+  // tensor-core path operands
+  bool gemm_ready = false;
+  DevBuf shadow, scale_bias, max_norm, qbuf;
+  uint32_t dim_pad = 0;
+  uint64_t n_tiles = 0;
+  alignas(64) uint8_t map_d[128];
+  int mode = TRR_DENSE_AUTO;
+  trr_stats stats{};
+};
+
+static int dense_grow(trr_dense* h, uint64_t need) {
+  if (need <= h->cap) return TRR_OK;
+  uint64_t ncap = std::max<uint64_t>(need, h->cap ? h->cap * 2 : 1024);
+  uint8_t* nrows = nullptr; float* nnorms = nullptr; uint8_t* ndead = nullptr;
+  TRR_CUDA(cudaMalloc(&nrows, ncap * h->row_bytes + 256));
+  TRR_CUDA(cudaMalloc(&nnorms, ncap * sizeof(float)));
+  TRR_CUDA(cudaMalloc(&ndead, ncap));
+  cudaStream_t st = h->ctx->stream;
+  TRR_CUDA(cudaMemsetAsync(ndead, 0, ncap, st));
+  if (h->n) {
+    TRR_CUDA(cudaMemcpyAsync(nrows, h->rows, h->n * h->row_bytes, cudaMemcpyDeviceToDevice, st));
+    TRR_CUDA(cudaMemcpyAsync(nnorms, h->norms, h->n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TRR_CUDA(cudaMemcpyAsync(ndead, h->dead, h->n, cudaMemcpyDeviceToDevice, st));
+  }
+  TRR_CUDA(cudaStreamSynchronize(st));
+  if (h->rows) cudaFree(h->rows);
+  if (h->norms) cudaFree(h->norms);
+  if (h->dead) cudaFree(h->dead);
+  h->rows = nrows; h->norms = nnorms; h->dead = ndead; h->cap = ncap;
+  return TRR_OK;
+}
+
+extern "C" int trr_dense_create(trr_ctx* ctx, uint32_t dim, int metric, int dtype, uint64_t capacity_hint,
+                                trr_dense** out) {
+  if (!ctx || !out) return trr_fail(TRR_ERR_INVALID_ARG, "trr_dense_create: NULL argument");
+  *out = nullptr;
+  if (dim == 0) return trr_fail(TRR_ERR_INVALID_ARG, "trr_dense_create: dimension must be > 0");
+  if (metric < 0 || metric > 2) return trr_fail(TRR_ERR_INVALID_ARG, "trr_dense_create: bad metric");
+  if (dtype != TRR_DTYPE_F32 && dtype != TRR_DTYPE_BF16) return trr_fail(TRR_ERR_INVALID_ARG, "bad dtype");
+  DeviceGuard g(ctx->device);
+  trr_dense* h = new trr_dense();
+  h->ctx = ctx; h->dim = dim; h->metric = metric; h->dtype = dtype;
+  h->elem = dtype == TRR_DTYPE_BF16 ? 2 : 4;
+  h->row_bytes = dim * h->elem;
+  if (capacity_hint) {
+    int s = dense_grow(h, capacity_hint);
+    if (s != TRR_OK) { delete h; return s; }
+  }
+  *out = h;
+  return TRR_OK;
+}
+
+extern "C" int trr_dense_destroy(trr_dense* h) {
+  if (!h) return TRR_OK;
+  DeviceGuard g(h->ctx->device);
+  cudaStreamSynchronize(h->ctx->stream);
+  if (h->rows) cudaFree(h->rows);
+  if (h->norms) cudaFree(h->norms);
+  if (h->dead) cudaFree(h->dead);
+  h->shadow.release(); h->scale_bias.release(); h->max_norm.release(); h->qbuf.release();
+  delete h;
+  return TRR_OK;
+}
+
+extern "C" int trr_dense_set_base(trr_dense* h, uint32_t base) {
+  if (!h) return trr_fail(TRR_ERR_INVALID_ARG, "handle is NULL");
+  h->base = base;
+  return TRR_OK;
+}
+extern "C" int trr_dense_set_mode(trr_dense* h, int mode) {
+  if (!h || mode < 0 || mode > 2) return trr_fail(TRR_ERR_INVALID_ARG, "bad mode");
+  h->mode = mode;
+  return TRR_OK;
+}
+extern "C" int trr_dense_len(trr_dense* h, uint64_t* out) {
+  if (!h || !out) return trr_fail(TRR_ERR_INVALID_ARG, "NULL argument");
+  *out = h->n - h->n_dead;
+  return TRR_OK;
+}
+
+static int dense_append_common(trr_dense* h, const void* src, uint64_t n, int src_kind /*0 f32 host,1 bf16 host,2 dev*/) {
+  if (!h || (!src && n)) return trr_fail(TRR_ERR_INVALID_ARG, "trr_dense_append: NULL argument");
+  if (n == 0) return TRR_OK;
+  if (h->n + n + h->base > 0xFFFFFFFEull) return trr_fail(TRR_ERR_UNSUPPORTED, "more than 2^32-2 ordinals");
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  TRR_CHECK(dense_grow(h, h->n + n));
+  cudaStream_t st = h->ctx->stream;
+  uint8_t* dst = h->rows + h->n * h->row_bytes;
+  if (src_kind == 2) {
+    TRR_CUDA(cudaMemcpyAsync(dst, src, n * h->row_bytes, cudaMemcpyDeviceToDevice, st));
+  } else if ((src_kind == 0 && h->dtype == TRR_DTYPE_F32) || (src_kind == 1 && h->dtype == TRR_DTYPE_BF16)) {
+    TRR_CUDA(cudaMemcpyAsync(dst, src, n * h->row_bytes, cudaMemcpyHostToDevice, st));
+  } else if (src_kind == 0 && h->dtype == TRR_DTYPE_BF16) {
+    // f32 host rows into a bf16 store: upload in chunks, round to nearest even on the device
+    const uint64_t chunk = std::max<uint64_t>(1, (64ull << 20) / ((uint64_t)h->dim * 4));
+    TRR_CHECK(extra(h->ctx)->io.reserve(chunk * h->dim * 4));
+    for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
+      const uint64_t m = std::min(chunk, n - r0);
+      TRR_CUDA(cudaMemcpyAsync(extra(h->ctx)->io.p, static_cast<const float*>(src) + r0 * h->dim, m * h->dim * 4,
+                               cudaMemcpyHostToDevice, st));
+      trr_launch_shadow(extra(h->ctx)->io.p, 0, h->dim, h->dim, 0, m,
+                        reinterpret_cast<uint16_t*>(dst + r0 * h->row_bytes), st);
+      h->ctx->launches++;
+      TRR_CUDA(cudaStreamSynchronize(st));
+    }
+  } else {
+    return trr_fail(TRR_ERR_INVALID_ARG, "bf16 rows can only be appended to a bf16 store");
+  }
+  TRR_CUDA(cudaStreamSynchronize(st));
+  h->n += n;
+  h->gemm_ready = false;
+  return TRR_OK;
+}
+
+extern "C" int trr_dense_append(trr_dense* h, const float* rows, uint64_t n) { return dense_append_common(h, rows, n, 0); }
+extern "C" int trr_dense_append_bf16(trr_dense* h, const uint16_t* rows, uint64_t n) {
+  return dense_append_common(h, rows, n, 1);
+}
+extern "C" int trr_dense_append_device(trr_dense* h, const void* d_rows, uint64_t n) {
+  return dense_append_common(h, d_rows, n, 2);
+}
+
+extern "C" int trr_dense_append_synth(trr_dense* h, uint64_t seed, uint64_t first_row, uint64_t n, int dups) {
+  if (!h) return trr_fail(TRR_ERR_INVALID_ARG, "handle is NULL");
+  if (n == 0) return TRR_OK;
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  TRR_CHECK(dense_grow(h, h->n + n));
+  TRR_CUDA(trr_launch_synth_rows(seed, first_row, n, h->dim, dups, h->dtype == TRR_DTYPE_BF16,
+                                 h->rows + h->n * h->row_bytes, h->ctx->stream));
+  h->ctx->launches++;
+  TRR_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  h->n += n;
+  h->gemm_ready = false;
+  return TRR_OK;
+}
+
+extern "C" int trr_dense_remove(trr_dense* h, uint32_t ordinal) {
+  if (!h) return trr_fail(TRR_ERR_INVALID_ARG, "handle is NULL");
+  if (ordinal >= h->n) return trr_fail(TRR_ERR_INVALID_ARG, "trr_dense_remove: ordinal out of range");
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  uint8_t was = 0;
+  TRR_CUDA(cudaMemcpy(&was, h->dead + ordinal, 1, cudaMemcpyDeviceToHost));
+  if (!was) {
+    const uint8_t one = 1;
+    TRR_CUDA(cudaMemcpy(h->dead + ordinal, &one, 1, cudaMemcpyHostToDevice));
+    h->n_dead++;
+    h->gemm_ready = false;
+  }
+  return TRR_OK;
+}
+
+static int dense_freeze_locked(trr_dense* h) {
+  if (h->frozen_n < h->n) {
+    trr_launch_norms(h->dtype == TRR_DTYPE_BF16, h->rows, h->dim, h->frozen_n, h->n - h->frozen_n, h->norms,
+                     h->ctx->stream);
+    h->ctx->launches++;
+    TRR_CUDA(cudaGetLastError());
+    h->frozen_n = h->n;
+  }
+  return TRR_OK;
+}
+
+extern "C" int trr_dense_freeze(trr_dense* h) {
+  if (!h) return trr_fail(TRR_ERR_INVALID_ARG, "handle is NULL");
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  TRR_CHECK(dense_freeze_locked(h));
+  TRR_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  return TRR_OK;
+}
+
+extern "C" int trr_dense_copy_norms(trr_dense* h, float* out, uint64_t n) {
+  if (!h || !out) return trr_fail(TRR_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  TRR_CHECK(dense_freeze_locked(h));
+  TRR_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  TRR_CUDA(cudaMemcpy(out, h->norms, std::min<uint64_t>(n, h->n) * sizeof(float), cudaMemcpyDeviceToHost));
+  return TRR_OK;
+}
+
+// builds the operands of the tensor-core pass: bf16 shadow (if the slab cannot be used in place),
+// per-document scale/bias, max norm, TMA descriptor
+static int dense_prepare_gemm(trr_dense* h) {
+  if (h->gemm_ready) return TRR_OK;
+  cudaStream_t st = h->ctx->stream;
+  h->n_tiles = (h->n + TRR_GEMM_TILE_N - 1) / TRR_GEMM_TILE_N;
+  const uint64_t n_padded = h->n_tiles * TRR_GEMM_TILE_N;
+  const void* operand = h->rows;
+  uint64_t cols = h->dim;
+  if (h->dtype != TRR_DTYPE_BF16 || (h->dim % 8) != 0) {
+    h->dim_pad = (h->dim + 63) / 64 * 64;
+    TRR_CHECK(h->shadow.reserve(h->n * (uint64_t)h->dim_pad * 2));
+    trr_launch_shadow(h->rows, h->dtype == TRR_DTYPE_BF16, h->dim, h->dim_pad, 0, h->n,
+                      reinterpret_cast<uint16_t*>(h->shadow.p), st);
+    h->ctx->launches++;
+    operand = h->shadow.p;
+    cols = h->dim_pad;
+  } else {
+    h->dim_pad = h->dim;
+  }
+  TRR_CHECK(h->scale_bias.reserve(n_padded * sizeof(float2)));
+  TRR_CHECK(h->max_norm.reserve(256));
+  TRR_CUDA(cudaMemsetAsync(h->max_norm.p, 0, 4, st));
+  trr_launch_gemm_operands(h->norms, h->dead, h->n, n_padded, h->metric, reinterpret_cast<float2*>(h->scale_bias.p),
+                           reinterpret_cast<float*>(h->max_norm.p), st);
+  h->ctx->launches++;
+  TRR_CUDA(cudaGetLastError());
+  TRR_CHECK(trr_make_tensor_map(h->map_d, operand, h->n, cols, TRR_GEMM_TILE_N));
+  h->gemm_ready = true;
+  return TRR_OK;
+}
+
+struct ScanPlan {
+  bool bulk;
+  unsigned grid;
+  uint32_t warps, cap, ch_bytes, n_chunks;
+  size_t smem;
+};
+
+static int plan_scan(trr_dense* h, uint32_t k, ScanPlan* p) {
+  p->cap = trr_pow2_ceil(k + 32);
+  if (p->cap < 64) p->cap = 64;
+  const uint32_t q_bytes = (h->dim * 4 + 127) & ~127u;
+  const size_t optin = h->ctx->smem_optin;
+  p->bulk = (h->row_bytes % 16 == 0) && h->n >= 4096;
+  if (p->bulk) {
+    const size_t fixed = q_bytes + 128 + (size_t)4 * p->cap * 8;
+    if (fixed + 128 * 32 > optin) p->bulk = false;
+    else {
+      size_t per_row = (optin - fixed) / 128;                 // bytes of pitch available per staged row
+      uint32_t max_ch = (uint32_t)((per_row - 16) & ~size_t(15));
+      if (max_ch > 4096) max_ch = 4096;
+      if (max_ch < 64) p->bulk = false;
+      else {
+        p->n_chunks = (h->row_bytes + max_ch - 1) / max_ch;
+        p->ch_bytes = ((h->row_bytes + p->n_chunks - 1) / p->n_chunks + 15) & ~15u;
+        p->n_chunks = (h->row_bytes + p->ch_bytes - 1) / p->ch_bytes;
+        p->warps = 4;
+        p->grid = (unsigned)h->ctx->sm_count;
+        p->smem = fixed + (size_t)128 * (p->ch_bytes + 16);
+      }
+    }
+  }
+  if (!p->bulk) {
+    p->warps = 8;
+    p->ch_bytes = 0; p->n_chunks = 0;
+    p->smem = q_bytes + (size_t)8 * p->cap * 8;
+    if (p->smem > optin) return trr_fail(TRR_ERR_UNSUPPORTED, "dimension / k too large for the scan kernel");
+    const uint64_t groups = (h->n + 255) / 256;
+    p->grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(groups, (uint64_t)h->ctx->sm_count * 4));
+  }
+  return TRR_OK;
+}
+
+// exact scan (K1) of the queries selected by (d_sel, n_sel) or all B; results into d_ord/d_score/d_n rows
+static int dense_scan_locked(trr_dense* h, const float* d_q, const float* d_qn, uint32_t n_sel, const uint32_t* d_sel,
+                             uint32_t k, uint32_t* d_ord, float* d_score, uint32_t* d_n, uint64_t* d_keys,
+                             size_t scratch_off) {
+  ScanPlan p;
+  TRR_CHECK(plan_scan(h, k, &p));
+  const uint64_t lists = (uint64_t)p.grid * p.warps;
+  const size_t need = scratch_off + WsCarver::need({(size_t)n_sel * lists * k * 8, (size_t)n_sel * lists * 4});
+  TRR_CHECK(extra(h->ctx)->scratch.reserve(need));
+  WsCarver ws(static_cast<char*>(extra(h->ctx)->scratch.p) + scratch_off);
+  uint64_t* partial = ws.take<uint64_t>((size_t)n_sel * lists * k);
+  uint32_t* partial_n = ws.take<uint32_t>((size_t)n_sel * lists);
+  DenseScanArgs a{};
+  a.rows = h->rows; a.row_bytes = h->row_bytes; a.dim = h->dim; a.n_rows = h->n;
+  a.norms = h->norms; a.dead = h->n_dead ? h->dead : nullptr;
+  a.q = d_q; a.q_norms = d_qn; a.sel = d_sel; a.n_sel_ptr = nullptr; a.n_sel = n_sel;
+  a.ch_bytes = p.ch_bytes; a.n_chunks = p.n_chunks; a.k = k; a.cap = p.cap; a.base_ord = h->base;
+  a.partial = partial; a.partial_n = partial_n;
+  cudaStream_t st = h->ctx->stream;
+  TRR_CUDA(cudaEventRecord(h->ctx->ev[2], st));
+  TRR_CUDA(trr_launch_scan(a, h->dtype == TRR_DTYPE_BF16, h->metric, p.bulk, p.grid, p.smem, st));
+  TRR_CUDA(cudaEventRecord(h->ctx->ev[3], st));
+  h->ctx->launches++;
+  TopkMergeArgs m{};
+  m.lists = partial; m.list_n = partial_n; m.n_lists = (uint32_t)lists; m.list_stride = k;
+  m.n_rows = n_sel; m.n_rows_ptr = nullptr; m.row_map = d_sel; m.k = k; m.k2 = trr_pow2_ceil(k);
+  m.out_keys = d_keys; m.out_ord = d_ord; m.out_score = d_score; m.out_n = d_n;
+  TRR_CUDA(trr_launch_topk_merge(m, n_sel, st));
+  h->ctx->launches++;
+  return TRR_OK;
+}
+
+static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint32_t k, uint32_t* d_ord, float* d_score,
+                               uint32_t* d_n, bool sync_stats) {
+  trr_ctx* c = h->ctx;
+  cudaStream_t st = c->stream;
+  const uint32_t launches0 = c->launches;
+  h->stats = trr_stats{};
+  h->stats.n_queries = B;
+  if (B == 0) return TRR_OK;
+  if (k == 0 || h->n == h->n_dead) {
+    TRR_CUDA(cudaMemsetAsync(d_n, 0, (size_t)B * 4, st));
+    return TRR_OK;
+  }
+  if (k > 1024) return trr_fail(TRR_ERR_UNSUPPORTED, "k > 1024 is not supported yet");
+  TRR_CHECK(dense_freeze_locked(h));
+  TRR_CUDA(cudaEventRecord(c->ev[0], st));
+
+  const uint64_t n_live = h->n - h->n_dead;
+  bool use_gemm = false;
+  if (h->mode == TRR_DENSE_GEMM) use_gemm = true;
+  else if (h->mode == TRR_DENSE_AUTO) use_gemm = B >= 16 && h->n >= 16384;
+  if (h->metric == TRR_METRIC_EUCLIDEAN || k > 50) {
+    if (h->mode == TRR_DENSE_GEMM)
+      return trr_fail(TRR_ERR_UNSUPPORTED, "GEMM mode supports cosine/dot metrics with k <= 50");
+    use_gemm = false;
+  }
+  // scratch: query norms first
+  TRR_CHECK(extra(c)->scratch.reserve(WsCarver::need({(size_t)B * 4})));
+  float* d_qn = nullptr;
+  size_t scratch_off = 0;
+  {
+    WsCarver ws(extra(c)->scratch.p);
+    d_qn = ws.take<float>(B);
+    scratch_off = (ws.off + 255) & ~size_t(255);
+  }
+
+  if (!use_gemm) {
+    // the scratch buffer may be re-allocated by dense_scan_locked: compute the norms after reserving there
+    ScanPlan p;
+    TRR_CHECK(plan_scan(h, k, &p));
+    const uint64_t lists = (uint64_t)p.grid * p.warps;
+    TRR_CHECK(extra(c)->scratch.reserve(scratch_off + WsCarver::need({(size_t)B * lists * k * 8, (size_t)B * lists * 4})));
+    d_qn = reinterpret_cast<float*>(extra(c)->scratch.p);
+    trr_launch_query_norms(d_q, h->dim, B, d_qn, st);
+    c->launches++;
+    TRR_CHECK(dense_scan_locked(h, d_q, d_qn, B, nullptr, k, d_ord, d_score, d_n, nullptr, scratch_off));
+    h->stats.mode_used = TRR_DENSE_SCAN;
+  } else {
+    TRR_CHECK(dense_prepare_gemm(h));
+    const uint32_t n_qblocks = (B + TRR_GEMM_TILE_M - 1) / TRR_GEMM_TILE_M;
+    if (n_qblocks > (uint32_t)c->sm_count)
+      return trr_fail(TRR_ERR_UNSUPPORTED, "batch larger than 128 x SM count; split the batch");
+    uint32_t n_slices = (uint32_t)c->sm_count / n_qblocks;
+    if (n_slices > h->n_tiles) n_slices = (uint32_t)h->n_tiles;
+    if (n_slices == 0) n_slices = 1;
+    const uint32_t B_pad = n_qblocks * TRR_GEMM_TILE_M;
+    const uint32_t CP = TRR_GEMM_CP;
+    const size_t n_cand = (size_t)n_slices * n_qblocks * TRR_GEMM_TILE_M * CP;
+    const uint32_t cap2 = trr_pow2_ceil(n_slices * CP);
+    // scratch layout (single reservation so that pointers stay valid)
+    ScanPlan p;
+    TRR_CHECK(plan_scan(h, k, &p));
+    const uint64_t lists = (uint64_t)p.grid * p.warps;
+    const uint32_t fb_chunk = 64;  // fallback queries per scan launch
+    const size_t need = WsCarver::need({(size_t)B * 4, (size_t)B * 4, n_cand * 4, n_cand * 4, (size_t)B_pad * 4,
+                                        (size_t)B * 4, (size_t)B * 4, 256, (size_t)B_pad * h->dim_pad * 2,
+                                        (size_t)fb_chunk * lists * k * 8 + 512, (size_t)fb_chunk * lists * 4 + 512}) +
+                        4096;
+    TRR_CHECK(extra(c)->scratch.reserve(need));
+    WsCarver ws(extra(c)->scratch.p);
+    d_qn = ws.take<float>(B);
+    float* d_qdelta = ws.take<float>(B);
+    float* cand_score = ws.take<float>(n_cand);
+    uint32_t* cand_ord = ws.take<uint32_t>(n_cand);
+    uint32_t* gthr = ws.take<uint32_t>(B_pad);
+    uint32_t* flags = ws.take<uint32_t>(B);
+    uint32_t* flagged = ws.take<uint32_t>(B);
+    uint32_t* counters = ws.take<uint32_t>(64);  // [0] n_flagged, [1] max_gap (float bits)
+    uint16_t* q_bf16 = ws.take<uint16_t>((size_t)B_pad * h->dim_pad);
+    const size_t fb_off = (ws.off + 255) & ~size_t(255);
+
+    trr_launch_query_norms(d_q, h->dim, B, d_qn, st);
+    trr_launch_query_prep(d_q, h->dim, h->dim_pad, B, B_pad, q_bf16, d_qdelta, st);
+    c->launches += 2;
+    TRR_CUDA(cudaMemsetAsync(gthr, 0, (size_t)B_pad * 4, st));
+    TRR_CUDA(cudaMemsetAsync(counters, 0, 256, st));
+    alignas(64) uint8_t map_q[128];
+    TRR_CHECK(trr_make_tensor_map(map_q, q_bf16, B_pad, h->dim_pad, TRR_GEMM_TILE_M));
+    GemmTopkArgs ga{};
+    ga.n_qblocks = n_qblocks; ga.n_slices = n_slices; ga.n_tiles = (uint32_t)h->n_tiles;
+    ga.k_blocks = (h->dim_pad + 63) / 64; ga.base_ord = h->base;
+    ga.scale_bias = reinterpret_cast<const float2*>(h->scale_bias.p);
+    ga.cand_score = cand_score; ga.cand_ord = cand_ord; ga.gthr = gthr; ga.share_thresholds = 1;
+    TRR_CUDA(cudaEventRecord(c->ev[2], st));
+    TRR_CUDA(trr_launch_gemm_topk(ga, map_q, h->map_d, n_slices * n_qblocks, st));
+    TRR_CUDA(cudaEventRecord(c->ev[3], st));
+    c->launches++;
+
+    RescoreArgs ra{};
+    ra.cand_score = cand_score; ra.cand_ord = cand_ord; ra.n_slices = n_slices; ra.n_qblocks = n_qblocks;
+    ra.cp = CP; ra.cap2 = cap2 < CP ? CP : cap2;
+    ra.rows = h->rows; ra.dim = h->dim; ra.norms = h->norms; ra.base_ord = h->base; ra.n_live = n_live;
+    ra.q = d_q; ra.q_norms = d_qn; ra.q_delta = d_qdelta; ra.max_norm = reinterpret_cast<const float*>(h->max_norm.p);
+    ra.B = B; ra.k = k; ra.metric = h->metric;
+    // |fast - exact| <= eps_rel * |q||d|: products of bf16 values are exact in f32; the tensor-core sum and the
+    // reference's sequential sum each carry at most D roundings of relative size 2^-23 on partial sums bounded by
+    // sum|q_i d_i| <= |q||d|; the scale multiply, the division and the norm product add a few more ulps.
+    // A f32 store scored through its bf16 shadow adds the quantisation term 2^-8 * |q||d|.
+    float eps_rel = (2.0f * (float)h->dim + 8.0f) * 1.1920929e-07f;
+    if (h->dtype != TRR_DTYPE_BF16) eps_rel += 0.00390625f;
+    ra.eps_rel = eps_rel;
+    ra.out_keys = nullptr; ra.out_ord = d_ord; ra.out_score = d_score; ra.out_n = d_n;
+    ra.flags = flags; ra.flagged = flagged; ra.n_flagged = counters; ra.max_gap = reinterpret_cast<float*>(counters + 1);
+    TRR_CUDA(trr_launch_rescore(ra, h->dtype == TRR_DTYPE_BF16, st));
+    c->launches++;
+    // the candidate proof can fail (near-ties, adversarial data): those queries take the exact scan
+    uint32_t hc[2] = {0, 0};
+    TRR_CUDA(cudaMemcpyAsync(hc, counters, 8, cudaMemcpyDeviceToHost, st));
+    TRR_CUDA(cudaStreamSynchronize(st));
+    h->stats.n_guard_fallbacks = hc[0];
+    memcpy(&h->stats.max_fast_exact_gap, &hc[1], 4);
+    h->stats.eps_bound = eps_rel;
+    for (uint32_t f0 = 0; f0 < hc[0]; f0 += fb_chunk) {
+      const uint32_t m = std::min(fb_chunk, hc[0] - f0);
+      TRR_CHECK(dense_scan_locked(h, d_q, d_qn, m, flagged + f0, k, d_ord, d_score, d_n, nullptr, fb_off));
+    }
+    h->stats.mode_used = TRR_DENSE_GEMM;
+  }
+  TRR_CUDA(cudaEventRecord(c->ev[1], st));
+  h->stats.n_kernel_launches = c->launches - launches0;
+  if (sync_stats) {
+    TRR_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&h->stats.ms_total, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&h->stats.ms_main_kernel, c->ev[2], c->ev[3]);
+  }
+  return TRR_OK;
+}
+
+extern "C" int trr_dense_search_device(trr_dense* h, const float* d_q, uint32_t B, uint32_t k, uint32_t* d_ord,
+                                       float* d_score, uint32_t* d_n) {
+  if (!h || (B && (!d_q || !d_ord || !d_score || !d_n))) return trr_fail(TRR_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  return dense_search_locked(h, d_q, B, k, d_ord, d_score, d_n, false);
+}
+
+extern "C" int trr_dense_search(trr_dense* h, const float* q, uint32_t B, uint32_t k, uint32_t* out_ord,
+                                float* out_score, uint32_t* out_n) {
+  if (!h || (B && (!q || !out_n)) || (B && k && (!out_ord || !out_score)))
+    return trr_fail(TRR_ERR_INVALID_ARG, "trr_dense_search: NULL argument");
+  if (B == 0) return TRR_OK;
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  trr_ctx* c = h->ctx;
+  cudaStream_t st = c->stream;
+  const size_t kk = std::max<uint32_t>(k, 1);
+  const size_t need = WsCarver::need({(size_t)B * h->dim * 4, (size_t)B * kk * 4, (size_t)B * kk * 4, (size_t)B * 4});
+  TRR_CHECK(extra(c)->io.reserve(need));
+  WsCarver io(extra(c)->io.p);
+  float* d_q = io.take<float>((size_t)B * h->dim);
+  uint32_t* d_ord = io.take<uint32_t>((size_t)B * kk);
+  float* d_score = io.take<float>((size_t)B * kk);
+  uint32_t* d_n = io.take<uint32_t>(B);
+  TRR_CUDA(cudaMemcpyAsync(d_q, q, (size_t)B * h->dim * 4, cudaMemcpyHostToDevice, st));
+  TRR_CHECK(dense_search_locked(h, d_q, B, k, d_ord, d_score, d_n, true));
+  if (k) {
+    TRR_CUDA(cudaMemcpyAsync(out_ord, d_ord, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));
+    TRR_CUDA(cudaMemcpyAsync(out_score, d_score, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));
+  }
+  TRR_CUDA(cudaMemcpyAsync(out_n, d_n, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  TRR_CUDA(cudaStreamSynchronize(st));
+  return TRR_OK;
+}
+
+extern "C" int trr_dense_last_stats(trr_dense* h, trr_stats* out) {
+  if (!h || !out) return trr_fail(TRR_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  cudaStreamSynchronize(h->ctx->stream);
+  if (h->stats.mode_used) {
+    cudaEventElapsedTime(&h->stats.ms_total, h->ctx->ev[0], h->ctx->ev[1]);
+    cudaEventElapsedTime(&h->stats.ms_main_kernel, h->ctx->ev[2], h->ctx->ev[3]);
+    cudaGetLastError();
+  }
+  *out = h->stats;
+  return TRR_OK;
+}
+
+// debug / test hook: raw fast scores of the tensor-core pass for a small problem (B <= 128 * SMs, N small)
+extern "C" TRR_API int trr_debug_gemm_scores(trr_dense* h, const float* q, uint32_t B, float* out, uint32_t out_ld) {
+  if (!h || !q || !out) return trr_fail(TRR_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  trr_ctx* c = h->ctx;
+  cudaStream_t st = c->stream;
+  TRR_CHECK(dense_freeze_locked(h));
+  TRR_CHECK(dense_prepare_gemm(h));
+  const uint32_t n_qblocks = (B + 127) / 128, B_pad = n_qblocks * 128;
+  const uint64_t n_pad = h->n_tiles * TRR_GEMM_TILE_N;
+  if (out_ld < n_pad) return trr_fail(TRR_ERR_INVALID_ARG, "out_ld must be >= padded document count");
+  uint32_t n_slices = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)c->sm_count / n_qblocks, (uint32_t)h->n_tiles));
+  const size_t n_cand = (size_t)n_slices * n_qblocks * 128 * TRR_GEMM_CP;
+  const size_t need = WsCarver::need({(size_t)B * h->dim * 4, (size_t)B * 4, n_cand * 4, n_cand * 4, (size_t)B_pad * 4,
+                                      (size_t)B_pad * h->dim_pad * 2, (size_t)B_pad * out_ld * 4});
+  TRR_CHECK(extra(c)->scratch.reserve(need));
+  WsCarver ws(extra(c)->scratch.p);
+  float* d_q = ws.take<float>((size_t)B * h->dim);
+  float* d_qdelta = ws.take<float>(B);
+  float* cand_score = ws.take<float>(n_cand);
+  uint32_t* cand_ord = ws.take<uint32_t>(n_cand);
+  uint32_t* gthr = ws.take<uint32_t>(B_pad);
+  uint16_t* q_bf16 = ws.take<uint16_t>((size_t)B_pad * h->dim_pad);
+  float* dump = ws.take<float>((size_t)B_pad * out_ld);
+  TRR_CUDA(cudaMemcpyAsync(d_q, q, (size_t)B * h->dim * 4, cudaMemcpyHostToDevice, st));
+  trr_launch_query_prep(d_q, h->dim, h->dim_pad, B, B_pad, q_bf16, d_qdelta, st);
+  TRR_CUDA(cudaMemsetAsync(gthr, 0, (size_t)B_pad * 4, st));
+  TRR_CUDA(cudaMemsetAsync(dump, 0, (size_t)B_pad * out_ld * 4, st));
+  alignas(64) uint8_t map_q[128];
+  TRR_CHECK(trr_make_tensor_map(map_q, q_bf16, B_pad, h->dim_pad, TRR_GEMM_TILE_M));
+  GemmTopkArgs ga{};
+  ga.n_qblocks = n_qblocks; ga.n_slices = n_slices; ga.n_tiles = (uint32_t)h->n_tiles;
+  ga.k_blocks = (h->dim_pad + 63) / 64; ga.base_ord = h->base;
+  ga.scale_bias = reinterpret_cast<const float2*>(h->scale_bias.p);
+  ga.cand_score = cand_score; ga.cand_ord = cand_ord; ga.gthr = gthr; ga.share_thresholds = 0;
+  TRR_CUDA(trr_launch_gemm_topk_dump(ga, map_q, h->map_d, n_slices * n_qblocks, dump, out_ld, st));
+  TRR_CUDA(cudaMemcpyAsync(out, dump, (size_t)B * out_ld * 4, cudaMemcpyDeviceToHost, st));
+  TRR_CUDA(cudaStreamSynchronize(st));
+  return TRR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BM25
+// ------------------------------------------------------------------------------------------------
+struct trr_bm25 {
+  trr_ctx* ctx = nullptr;
+  uint32_t n_docs = 0, n_terms = 0, doc_base = 0;
+  uint64_t n_postings = 0;
+  uint2* post = nullptr;
+  uint32_t* skip = nullptr;
+  uint32_t range_shift = 14, n_ranges = 0, skip_ld = 0;
+  uint32_t stage_cap = 2048;
+  trr_stats stats{};
+};
+
+extern "C" int trr_bm25_build(trr_ctx* ctx, uint32_t n_docs, uint32_t n_terms, const uint64_t* term_off,
+                              const uint32_t* post_doc, const uint32_t* post_tf, const uint32_t* doc_len, float avgdl,
+                              float k1, float b, const float* idf, uint32_t doc_base, trr_bm25** out) {
+  if (!ctx || !out || !term_off) return trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_build: NULL argument");
+  *out = nullptr;
+  const uint64_t P = term_off[n_terms];
+  if (P && (!post_doc || !post_tf || !doc_len || !idf)) return trr_fail(TRR_ERR_INVALID_ARG, "NULL postings");
+  if (P >= 0xFFFFFFFFull) return trr_fail(TRR_ERR_UNSUPPORTED, "more than 2^32-1 postings per shard");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  trr_bm25* h = new trr_bm25();
+  h->ctx = ctx; h->n_docs = n_docs; h->n_terms = n_terms; h->doc_base = doc_base; h->n_postings = P;
+  // documents per range: 16384 (64 KB of f32 accumulators, two CTAs per SM), smaller for tiny indexes
+  uint32_t shift = 14;
+  while (shift > 8 && (1u << (shift - 1)) >= std::max<uint32_t>(n_docs, 1)) --shift;
+  h->range_shift = shift;
+  h->n_ranges = n_docs ? (uint32_t)(((uint64_t)n_docs + (1u << shift) - 1) >> shift) : 0;
+  h->skip_ld = h->n_ranges + 1;
+  cudaStream_t st = ctx->stream;
+  auto fail = [&](int s) { trr_bm25_destroy(h); return s; };
+#define BM_CUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { trr_fail(_e == cudaErrorMemoryAllocation ? TRR_ERR_OOM : TRR_ERR_CUDA, std::string(#e) + ": " + cudaGetErrorString(_e)); return fail(_e == cudaErrorMemoryAllocation ? TRR_ERR_OOM : TRR_ERR_CUDA); } } while (0)
+  BM_CUDA(cudaMalloc(&h->post, std::max<uint64_t>(P, 1) * sizeof(uint2)));
+  BM_CUDA(cudaMalloc(&h->skip, std::max<uint64_t>((uint64_t)n_terms * h->skip_ld, 1) * 4));
+  uint64_t* d_term_off = nullptr; uint32_t *d_pd = nullptr, *d_ptf = nullptr, *d_dl = nullptr; float* d_idf = nullptr;
+  BM_CUDA(cudaMalloc(&d_term_off, ((uint64_t)n_terms + 1) * 8));
+  BM_CUDA(cudaMalloc(&d_pd, std::max<uint64_t>(P, 1) * 4));
+  BM_CUDA(cudaMalloc(&d_ptf, std::max<uint64_t>(P, 1) * 4));
+  BM_CUDA(cudaMalloc(&d_dl, std::max<uint64_t>(n_docs, 1) * 4));
+  BM_CUDA(cudaMalloc(&d_idf, std::max<uint64_t>(n_terms, 1) * 4));
+  BM_CUDA(cudaMemcpyAsync(d_term_off, term_off, ((uint64_t)n_terms + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (P) {
+    BM_CUDA(cudaMemcpyAsync(d_pd, post_doc, P * 4, cudaMemcpyHostToDevice, st));
+    BM_CUDA(cudaMemcpyAsync(d_ptf, post_tf, P * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (n_docs) BM_CUDA(cudaMemcpyAsync(d_dl, doc_len, (uint64_t)n_docs * 4, cudaMemcpyHostToDevice, st));
+  if (n_terms && idf) BM_CUDA(cudaMemcpyAsync(d_idf, idf, (uint64_t)n_terms * 4, cudaMemcpyHostToDevice, st));
+  Bm25BuildArgs a{};
+  a.n_postings = P; a.n_terms = n_terms; a.n_docs = n_docs; a.term_off = d_term_off; a.post_doc = d_pd; a.post_tf = d_ptf;
+  a.doc_len = d_dl; a.idf = d_idf; a.avgdl = avgdl; a.k1 = k1; a.b = b;
+  a.range_shift = h->range_shift; a.n_ranges = h->n_ranges; a.skip_ld = h->skip_ld; a.post = h->post; a.skip = h->skip;
+  BM_CUDA(trr_launch_bm25_build(a, st));
+  ctx->launches += 2;
+  BM_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_term_off); cudaFree(d_pd); cudaFree(d_ptf); cudaFree(d_dl); cudaFree(d_idf);
+#undef BM_CUDA
+  *out = h;
+  return TRR_OK;
+}
+
+extern "C" int trr_bm25_destroy(trr_bm25* h) {
+  if (!h) return TRR_OK;
+  DeviceGuard g(h->ctx->device);
+  cudaStreamSynchronize(h->ctx->stream);
+  if (h->post) cudaFree(h->post);
+  if (h->skip) cudaFree(h->skip);
+  delete h;
+  return TRR_OK;
+}
+
+extern "C" int trr_bm25_n_postings(trr_bm25* h, uint64_t* out) {
+  if (!h || !out) return trr_fail(TRR_ERR_INVALID_ARG, "NULL argument");
+  *out = h->n_postings;
+  return TRR_OK;
+}
+
+extern "C" int trr_bm25_copy_impacts(trr_bm25* h, float* out, uint64_t n) {
+  if (!h || !out) return trr_fail(TRR_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  n = std::min(n, h->n_postings);
+  std::vector<uint2> tmp(n);
+  TRR_CUDA(cudaMemcpy(tmp.data(), h->post, n * sizeof(uint2), cudaMemcpyDeviceToHost));
+  for (uint64_t i = 0; i < n; ++i) memcpy(&out[i], &tmp[i].y, 4);
+  return TRR_OK;
+}
+
+static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint32_t* d_q_off, const uint32_t* h_q_off,
+                              uint32_t B, uint32_t k, uint32_t* d_ord, float* d_score, uint32_t* d_n, size_t scratch_off) {
+  trr_ctx* c = h->ctx;
+  cudaStream_t st = c->stream;
+  h->stats = trr_stats{};
+  h->stats.n_queries = B;
+  if (B == 0) return TRR_OK;
+  if (k == 0 || h->n_postings == 0) {
+    TRR_CUDA(cudaMemsetAsync(d_n, 0, (size_t)B * 4, st));
+    return TRR_OK;
+  }
+  if (k > 1024) return trr_fail(TRR_ERR_UNSUPPORTED, "k > 1024 is not supported yet");
+  for (uint32_t b = 0; b < B; ++b)
+    if (h_q_off[b + 1] - h_q_off[b] > (uint32_t)TRR_BM25_THREADS)
+      return trr_fail(TRR_ERR_UNSUPPORTED, "more than 512 terms in one query");
+  TRR_CHECK(extra(c)->scratch.reserve(scratch_off + 512));
+  uint32_t* counter = reinterpret_cast<uint32_t*>(static_cast<char*>(extra(c)->scratch.p) + scratch_off);
+  TRR_CUDA(cudaMemsetAsync(counter, 0, 4, st));
+  Bm25SearchArgs a{};
+  a.post = h->post; a.skip = h->skip; a.skip_ld = h->skip_ld; a.n_terms = h->n_terms; a.n_docs = h->n_docs;
+  a.n_ranges = h->n_ranges; a.range_shift = h->range_shift; a.doc_base = h->doc_base;
+  a.q_terms = d_q_terms; a.q_off = d_q_off; a.B = B; a.k = k;
+  a.stage_cap = h->stage_cap;
+  a.cand_cap = trr_pow2_ceil(k + TRR_BM25_THREADS);
+  a.counter = counter; a.out_keys = nullptr; a.out_ord = d_ord; a.out_score = d_score; a.out_n = d_n;
+  const unsigned grid = std::min<unsigned>(B, (unsigned)c->sm_count * 2);
+  TRR_CUDA(cudaEventRecord(c->ev[2], st));
+  TRR_CUDA(trr_launch_bm25_search(a, grid, st));
+  TRR_CUDA(cudaEventRecord(c->ev[3], st));
+  c->launches++;
+  h->stats.n_kernel_launches = 1;
+  h->stats.mode_used = 1;
+  return TRR_OK;
+}
+
+extern "C" int trr_bm25_search_device(trr_bm25* h, const uint32_t* d_q_terms, const uint32_t* d_q_off,
+                                      const uint32_t* h_q_off, uint32_t B, uint32_t k, uint32_t* d_ord, float* d_score,
+                                      uint32_t* d_n) {
+  if (!h || (B && (!d_q_off || !h_q_off || !d_ord || !d_score || !d_n)))
+    return trr_fail(TRR_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  return bm25_search_locked(h, d_q_terms, d_q_off, h_q_off, B, k, d_ord, d_score, d_n, 0);
+}
+
+extern "C" int trr_bm25_search(trr_bm25* h, const uint32_t* q_terms, const uint32_t* q_off, uint32_t B, uint32_t k,
+                               uint32_t* out_ord, float* out_score, uint32_t* out_n) {
+  if (!h || (B && (!q_off || !out_n)) || (B && k && (!out_ord || !out_score)))
+    return trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_search: NULL argument");
+  if (B == 0) return TRR_OK;
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  trr_ctx* c = h->ctx;
+  cudaStream_t st = c->stream;
+  const size_t nt = q_off[B], kk = std::max<uint32_t>(k, 1);
+  const size_t need = WsCarver::need({std::max<size_t>(nt, 1) * 4, (size_t)(B + 1) * 4, (size_t)B * kk * 4,
+                                      (size_t)B * kk * 4, (size_t)B * 4});
+  TRR_CHECK(extra(c)->io.reserve(need));
+  WsCarver io(extra(c)->io.p);
+  uint32_t* d_terms = io.take<uint32_t>(std::max<size_t>(nt, 1));
+  uint32_t* d_off = io.take<uint32_t>(B + 1);
+  uint32_t* d_ord = io.take<uint32_t>((size_t)B * kk);
+  float* d_score = io.take<float>((size_t)B * kk);
+  uint32_t* d_n = io.take<uint32_t>(B);
+  if (nt) TRR_CUDA(cudaMemcpyAsync(d_terms, q_terms, nt * 4, cudaMemcpyHostToDevice, st));
+  TRR_CUDA(cudaMemcpyAsync(d_off, q_off, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
+  TRR_CUDA(cudaEventRecord(c->ev[0], st));
+  TRR_CHECK(bm25_search_locked(h, d_terms, d_off, q_off, B, k, d_ord, d_score, d_n, 0));
+  TRR_CUDA(cudaEventRecord(c->ev[1], st));
+  if (k) {
+    TRR_CUDA(cudaMemcpyAsync(out_ord, d_ord, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));
+    TRR_CUDA(cudaMemcpyAsync(out_score, d_score, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));
+  }
+  TRR_CUDA(cudaMemcpyAsync(out_n, d_n, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  TRR_CUDA(cudaStreamSynchronize(st));
+  if (h->stats.mode_used) {
+    cudaEventElapsedTime(&h->stats.ms_total, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&h->stats.ms_main_kernel, c->ev[2], c->ev[3]);
+  }
+  return TRR_OK;
+}
+
+extern "C" int trr_bm25_last_stats(trr_bm25* h, trr_stats* out) {
+  if (!h || !out) return trr_fail(TRR_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  cudaStreamSynchronize(h->ctx->stream);
+  if (h->stats.mode_used) {
+    cudaEventElapsedTime(&h->stats.ms_main_kernel, h->ctx->ev[2], h->ctx->ev[3]);
+    cudaGetLastError();
+  }
+  *out = h->stats;
+  return TRR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fusion / hybrid
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t trr_exchange_bytes(uint32_t B, uint32_t C) { return ((size_t)4 * B * C + (size_t)2 * B) * 4; }
+
+struct ExchangeView {
+  uint32_t* ord[2];
+  float* score[2];
+  uint32_t* n[2];
+};
+static ExchangeView exchange_view(void* rec, uint32_t B, uint32_t C) {
+  ExchangeView v;
+  uint32_t* w = static_cast<uint32_t*>(rec);
+  const size_t bc = (size_t)B * C;
+  v.ord[0] = w; v.ord[1] = w + bc;
+  v.score[0] = reinterpret_cast<float*>(w + 2 * bc); v.score[1] = reinterpret_cast<float*>(w + 3 * bc);
+  v.n[0] = w + 4 * bc; v.n[1] = w + 4 * bc + B;
+  return v;
+}
+
+static int fuse_locked(trr_ctx* c, const ExchangeView& v, uint64_t shard_stride, uint32_t G, uint32_t B, uint32_t C,
+                       int strategy, float param, uint32_t k, bool have_dense, bool have_sparse, uint32_t* d_out_ord,
+                       float* d_out_fused, float* d_out_dense, float* d_out_sparse, uint32_t* d_out_n) {
+  if (strategy < 0 || strategy > 5) return trr_fail(TRR_ERR_INVALID_ARG, "bad fusion strategy");
+  if (C == 0 || C > 1024) return trr_fail(TRR_ERR_UNSUPPORTED, "candidates per source must be in 1..1024");
+  if ((uint64_t)G * C > 8192) return trr_fail(TRR_ERR_UNSUPPORTED, "shards x candidates > 8192");
+  FuseArgs a{};
+  for (int s = 0; s < 2; ++s) { a.ord[s] = v.ord[s]; a.score[s] = v.score[s]; a.n[s] = v.n[s]; }
+  if (!have_dense) a.n[0] = nullptr;
+  if (!have_sparse) a.n[1] = nullptr;
+  a.shard_stride = shard_stride; a.G = G; a.B = B; a.C = C; a.strategy = strategy; a.param = param; a.k = k;
+  a.mcap = trr_pow2_ceil(std::max<uint32_t>(G * C, 2)); a.fcap = trr_pow2_ceil(2 * C);
+  a.out_ord = d_out_ord; a.out_fused = d_out_fused; a.out_dense = d_out_dense; a.out_sparse = d_out_sparse;
+  a.out_n = d_out_n;
+  if (trr_fuse_smem(a) > c->smem_optin) return trr_fail(TRR_ERR_UNSUPPORTED, "fusion lists exceed shared memory");
+  TRR_CUDA(trr_launch_fuse(a, c->stream));
+  c->launches++;
+  return TRR_OK;
+}
+
+// device outputs -> host outputs helper
+static int fuse_download(trr_ctx* c, uint32_t B, uint32_t k, const uint32_t* d_ord, const float* d_f, const float* d_d,
+                         const float* d_s, const uint32_t* d_n, uint32_t* out_ord, float* out_fused, float* out_dense,
+                         float* out_sparse, uint32_t* out_n) {
+  cudaStream_t st = c->stream;
+  const size_t bk = (size_t)B * k * 4;
+  TRR_CUDA(cudaMemcpyAsync(out_ord, d_ord, bk, cudaMemcpyDeviceToHost, st));
+  TRR_CUDA(cudaMemcpyAsync(out_fused, d_f, bk, cudaMemcpyDeviceToHost, st));
+  if (out_dense) TRR_CUDA(cudaMemcpyAsync(out_dense, d_d, bk, cudaMemcpyDeviceToHost, st));
+  if (out_sparse) TRR_CUDA(cudaMemcpyAsync(out_sparse, d_s, bk, cudaMemcpyDeviceToHost, st));
+  TRR_CUDA(cudaMemcpyAsync(out_n, d_n, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  TRR_CUDA(cudaStreamSynchronize(st));
+  return TRR_OK;
+}
+
+extern "C" int trr_fuse(trr_ctx* c, int strategy, float param, const uint32_t* d_ord, const float* d_score,
+                        const uint32_t* d_n, const uint32_t* s_ord, const float* s_score, const uint32_t* s_n, uint32_t B,
+                        uint32_t C, uint32_t k_out, uint32_t* out_ord, float* out_fused, float* out_dense,
+                        float* out_sparse, uint32_t* out_n) {
+  if (!c || (B && (!out_ord || !out_fused || !out_n))) return trr_fail(TRR_ERR_INVALID_ARG, "trr_fuse: NULL argument");
+  if (B == 0) return TRR_OK;
+  if (k_out == 0) return trr_fail(TRR_ERR_INVALID_ARG, "trr_fuse: k_out must be >= 1");
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard g(c->device);
+  cudaStream_t st = c->stream;
+  const size_t rec = trr_exchange_bytes(B, C);
+  const size_t bk = (size_t)B * k_out;
+  TRR_CHECK(extra(c)->io.reserve(WsCarver::need({rec, bk * 4, bk * 4, bk * 4, bk * 4, (size_t)B * 4})));
+  WsCarver io(extra(c)->io.p);
+  uint8_t* d_rec = io.take<uint8_t>(rec);
+  uint32_t* o_ord = io.take<uint32_t>(bk);
+  float* o_f = io.take<float>(bk);
+  float* o_d = io.take<float>(bk);
+  float* o_s = io.take<float>(bk);
+  uint32_t* o_n = io.take<uint32_t>(B);
+  ExchangeView v = exchange_view(d_rec, B, C);
+  const size_t bc = (size_t)B * C * 4;
+  const bool have_d = d_ord && d_score && d_n, have_s = s_ord && s_score && s_n;
+  if (have_d) {
+    TRR_CUDA(cudaMemcpyAsync(v.ord[0], d_ord, bc, cudaMemcpyHostToDevice, st));
+    TRR_CUDA(cudaMemcpyAsync(v.score[0], d_score, bc, cudaMemcpyHostToDevice, st));
+    TRR_CUDA(cudaMemcpyAsync(v.n[0], d_n, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (have_s) {
+    TRR_CUDA(cudaMemcpyAsync(v.ord[1], s_ord, bc, cudaMemcpyHostToDevice, st));
+    TRR_CUDA(cudaMemcpyAsync(v.score[1], s_score, bc, cudaMemcpyHostToDevice, st));
+    TRR_CUDA(cudaMemcpyAsync(v.n[1], s_n, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  }
+  TRR_CHECK(fuse_locked(c, v, 0, 1, B, C, strategy, param, k_out, have_d, have_s, o_ord, o_f, o_d, o_s, o_n));
+  return fuse_download(c, B, k_out, o_ord, o_f, o_d, o_s, o_n, out_ord, out_fused, out_dense, out_sparse, out_n);
+}
+
+// shard-local stage into a device exchange record (locks taken by the caller)
+static int hybrid_local_locked(trr_dense* dense, trr_bm25* bm25, trr_ctx* c, const float* q, const uint32_t* q_terms,
+                               const uint32_t* q_off, uint32_t B, uint32_t C, bool use_dense, bool use_sparse,
+                               void* d_exchange) {
+  cudaStream_t st = c->stream;
+  ExchangeView v = exchange_view(d_exchange, B, C);
+  const uint32_t dim = dense ? dense->dim : 0;
+  const size_t nt = (use_sparse && q_off) ? q_off[B] : 0;
+  TRR_CHECK(extra(c)->io.reserve(WsCarver::need({(size_t)B * dim * 4, std::max<size_t>(nt, 1) * 4, (size_t)(B + 1) * 4})));
+  WsCarver io(extra(c)->io.p);
+  float* d_q = io.take<float>((size_t)B * dim);
+  uint32_t* d_terms = io.take<uint32_t>(std::max<size_t>(nt, 1));
+  uint32_t* d_off = io.take<uint32_t>(B + 1);
+  if (use_dense) {
+    TRR_CUDA(cudaMemcpyAsync(d_q, q, (size_t)B * dim * 4, cudaMemcpyHostToDevice, st));
+    TRR_CHECK(dense_search_locked(dense, d_q, B, C, v.ord[0], v.score[0], v.n[0], false));
+  } else {
+    TRR_CUDA(cudaMemsetAsync(v.n[0], 0, (size_t)B * 4, st));
+  }
+  if (use_sparse) {
+    if (nt) TRR_CUDA(cudaMemcpyAsync(d_terms, q_terms, nt * 4, cudaMemcpyHostToDevice, st));
+    TRR_CUDA(cudaMemcpyAsync(d_off, q_off, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
+    TRR_CHECK(bm25_search_locked(bm25, d_terms, d_off, q_off, B, C, v.ord[1], v.score[1], v.n[1], 0));
+  } else {
+    TRR_CUDA(cudaMemsetAsync(v.n[1], 0, (size_t)B * 4, st));
+  }
+  return TRR_OK;
+}
+
+static int hybrid_check(trr_dense* dense, trr_bm25* bm25, const float* q, const uint32_t* q_off, uint32_t B, uint32_t C,
+                        int use_dense, int use_sparse, trr_ctx** c) {
+  if (use_dense && (!dense || (B && !q))) return trr_fail(TRR_ERR_INVALID_ARG, "hybrid: dense store / queries missing");
+  if (use_sparse && (!bm25 || (B && !q_off))) return trr_fail(TRR_ERR_INVALID_ARG, "hybrid: sparse index / query terms missing");
+  if (!dense && !bm25) return trr_fail(TRR_ERR_INVALID_ARG, "hybrid: no index given");
+  *c = dense ? dense->ctx : bm25->ctx;
+  if (dense && bm25 && dense->ctx != bm25->ctx) return trr_fail(TRR_ERR_INVALID_ARG, "hybrid: indexes live on different contexts");
+  if (C == 0 || C > 1024) return trr_fail(TRR_ERR_UNSUPPORTED, "candidates per source must be in 1..1024");
+  return TRR_OK;
+}
+
+extern "C" int trr_hybrid_local(trr_dense* dense, trr_bm25* bm25, const float* q, const uint32_t* q_terms,
+                                const uint32_t* q_off, uint32_t B, uint32_t C, int use_dense, int use_sparse,
+                                void* d_exchange) {
+  trr_ctx* c = nullptr;
+  TRR_CHECK(hybrid_check(dense, bm25, q, q_off, B, C, use_dense, use_sparse, &c));
+  if (!d_exchange) return trr_fail(TRR_ERR_INVALID_ARG, "hybrid: exchange buffer is NULL");
+  if (B == 0) return TRR_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard g(c->device);
+  TRR_CHECK(hybrid_local_locked(dense, bm25, c, q, q_terms, q_off, B, C, use_dense != 0, use_sparse != 0, d_exchange));
+  TRR_CUDA(cudaStreamSynchronize(c->stream));
+  return TRR_OK;
+}
+
+static int hybrid_merge_locked(trr_ctx* c, const void* d_gathered, uint32_t G, uint32_t B, uint32_t C, int strategy,
+                               float param, uint32_t k, uint32_t* out_ord, float* out_fused, float* out_dense,
+                               float* out_sparse, uint32_t* out_n) {
+  const size_t bk = (size_t)B * k;
+  TRR_CHECK(extra(c)->scratch.reserve(WsCarver::need({bk * 4, bk * 4, bk * 4, bk * 4, (size_t)B * 4})));
+  WsCarver ws(extra(c)->scratch.p);
+  uint32_t* o_ord = ws.take<uint32_t>(bk);
+  float* o_f = ws.take<float>(bk);
+  float* o_d = ws.take<float>(bk);
+  float* o_s = ws.take<float>(bk);
+  uint32_t* o_n = ws.take<uint32_t>(B);
+  ExchangeView v = exchange_view(const_cast<void*>(d_gathered), B, C);
+  TRR_CHECK(fuse_locked(c, v, trr_exchange_bytes(B, C) / 4, G, B, C, strategy, param, k, true, true, o_ord, o_f, o_d, o_s,
+                        o_n));
+  return fuse_download(c, B, k, o_ord, o_f, o_d, o_s, o_n, out_ord, out_fused, out_dense, out_sparse, out_n);
+}
+
+extern "C" int trr_hybrid_merge(trr_ctx* c, const void* d_gathered, uint32_t G, uint32_t B, uint32_t C, int strategy,
+                                float param, uint32_t k, uint32_t* out_ord, float* out_fused, float* out_dense,
+                                float* out_sparse, uint32_t* out_n) {
+  if (!c || !d_gathered || (B && (!out_ord || !out_fused || !out_n))) return trr_fail(TRR_ERR_INVALID_ARG, "NULL argument");
+  if (B == 0) return TRR_OK;
+  if (k == 0 || G == 0) return trr_fail(TRR_ERR_INVALID_ARG, "hybrid merge: k and G must be >= 1");
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard g(c->device);
+  return hybrid_merge_locked(c, d_gathered, G, B, C, strategy, param, k, out_ord, out_fused, out_dense, out_sparse, out_n);
+}
+
+extern "C" int trr_hybrid_search(trr_dense* dense, trr_bm25* bm25, const float* q, const uint32_t* q_terms,
+                                 const uint32_t* q_off, uint32_t B, uint32_t C, int strategy, float param, uint32_t k,
+                                 int use_dense, int use_sparse, uint32_t* out_ord, float* out_fused, float* out_dense,
+                                 float* out_sparse, uint32_t* out_n) {
+  trr_ctx* c = nullptr;
+  TRR_CHECK(hybrid_check(dense, bm25, q, q_off, B, C, use_dense, use_sparse, &c));
+  if (B && (!out_ord || !out_fused || !out_n)) return trr_fail(TRR_ERR_INVALID_ARG, "hybrid: NULL output");
+  if (B == 0) return TRR_OK;
+  if (k == 0) return trr_fail(TRR_ERR_INVALID_ARG, "hybrid: k must be >= 1");
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard g(c->device);
+  TRR_CHECK(extra(c)->hy.reserve(trr_exchange_bytes(B, C)));
+  TRR_CHECK(hybrid_local_locked(dense, bm25, c, q, q_terms, q_off, B, C, use_dense != 0, use_sparse != 0, extra(c)->hy.p));
+  return hybrid_merge_locked(c, extra(c)->hy.p, 1, B, C, strategy, param, k, out_ord, out_fused, out_dense, out_sparse,
+                             out_n);
+}

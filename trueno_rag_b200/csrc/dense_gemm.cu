@@ -1,0 +1,405 @@
+// dense_gemm.cu — K2: batched query x corpus scoring on the 5th-generation tensor cores with a fused
+// per-row top-k selection, so that the B x N score matrix never reaches HBM.
+//
+// Replaces, for batches of queries, the per-vector scoring loop of VectorStore::search (reference
+// src/index.rs:394-405).  This is the FAST pass only: it selects candidates by
+//     fast(q, d) = dot_bf16(q, d) * scale[d] + bias[d]
+// (cosine: scale = 1/|d|; dot: scale = 1) with fp32 accumulation in TMEM.  Reported scores and the final
+// order come from the exact rescoring + candidate proof in dense_scan.cu (rescore_select_kernel), which
+// reproduces the reference arithmetic bit for bit.
+//
+// Kernel shape (sm_100a, cta_group::1):
+//   grid  = n_slices x n_qblocks persistent CTAs (<= one per SM); a CTA owns 128 queries (rows of A) and a
+//           contiguous range of 256-document tiles (rows of B), so its per-query candidate lists live in
+//           shared memory for the whole kernel.
+//   warp 0   TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) of Q [128 x 64] and docs [256 x 64]
+//            into a 3-stage ring, completion on mbarriers.
+//   warp 1   TMEM allocator + MMA issuer: 4 x tcgen05.mma (M128 N256 K16, bf16 -> f32) per k-block, commits
+//            release the smem stage and, after the last k-block, publish the accumulator stage.
+//   warps 2-5 epilogue: tcgen05.ld of the accumulator (lane == query row), fused scale/bias, threshold test
+//            against the row's running CP-th best, warp-cooperative replace-min insertion into the row's list.
+//            Two accumulator stages (2 x 256 TMEM columns) overlap epilogue(t) with MMA(t+1).
+//   CTAs working on different document slices of the same queries share their thresholds through a global
+//   atomicMax table, which cuts list insertions by an order of magnitude.
+#include <cuda.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "dense.cuh"
+
+namespace {
+
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+constexpr uint32_t BM = TRR_GEMM_TILE_M;  // 128 queries
+constexpr uint32_t BN = TRR_GEMM_TILE_N;  // 256 documents
+constexpr uint32_t BK = 64;               // bf16 elements per k-block = one 128-byte swizzle atom
+constexpr uint32_t UMMA_K = 16;
+constexpr uint32_t STAGES = 3;
+constexpr uint32_t CP = TRR_GEMM_CP;
+constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KB
+constexpr uint32_t B_BYTES = BN * BK * 2;  // 32 KB
+constexpr uint32_t LIST_BYTES = BM * CP * 4;
+constexpr uint32_t SMEM_A = 0;
+constexpr uint32_t SMEM_B = SMEM_A + STAGES * A_BYTES;
+constexpr uint32_t SMEM_LS = SMEM_B + STAGES * B_BYTES;
+constexpr uint32_t SMEM_LO = SMEM_LS + LIST_BYTES;
+constexpr uint32_t SMEM_BAR = SMEM_LO + LIST_BYTES;
+constexpr uint32_t SMEM_TOTAL = SMEM_BAR + 256;
+constexpr uint32_t GEMM_THREADS = 192;
+
+// instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), both K-major
+// (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
+
+__device__ unsigned int g_gemm_timeout_flag = 0;
+
+// bounded mbarrier wait: a protocol bug must surface as an error, never as a hung GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity, int site) {
+  if (trr_mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!trr_mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      atomicExch(&g_gemm_timeout_flag, 0x100u + (unsigned)site);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(const void* map, void* smem_dst, uint64_t* bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(trr_smem_u32(smem_dst)), "l"(map), "r"(trr_smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor: start address >> 4 in bits 0-13, leading byte
+// offset unused for a single swizzle atom along K, stride byte offset (8 rows x 128 B = 1024) >> 4 in bits
+// 32-45, descriptor version 1 at bit 46, layout type SWIZZLE_128B (2) in bits 61-63.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(trr_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// per-row running state of the epilogue (lives in the registers of the lane that owns the row)
+struct RowState {
+  float thr;       // max(list_min, threshold shared by the other slices)
+  float list_min;  // smallest fast score in the row's candidate list
+  uint32_t minpos; // its position
+};
+
+// Warp-cooperative replace-min insertion.  `m` = lanes whose value `s` (document `doc`) beats their row's
+// threshold.  For each such lane in turn the warp overwrites the minimum entry of that row's list and
+// recomputes the minimum with a two-entries-per-lane scan + warp arg-min.  Kept out of line: it is rare
+// in steady state and would otherwise be replicated 256 times in the unrolled column loop.
+__device__ __noinline__ RowState insert_events(uint32_t m, float s, uint32_t doc, RowState st, float* ls_warp,
+                                               uint32_t* lo_warp, uint32_t lane) {
+  while (m) {
+    const uint32_t src = __ffs(m) - 1;
+    m &= m - 1;
+    const float nv = __shfl_sync(FULL, s, src);
+    const uint32_t mp = __shfl_sync(FULL, st.minpos, src);
+    float* rs = ls_warp + src * CP;
+    uint32_t* ro = lo_warp + src * CP;
+    if (lane == 0) { rs[mp] = nv; ro[mp] = doc; }
+    __syncwarp();
+    const float e0 = rs[lane], e1 = rs[lane + 32];
+    float mn = e0;
+    uint32_t pos = lane;
+    if (e1 < mn) { mn = e1; pos = lane + 32; }
+#pragma unroll
+    for (uint32_t o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(FULL, mn, o);
+      const uint32_t op = __shfl_xor_sync(FULL, pos, o);
+      if (om < mn || (om == mn && op < pos)) { mn = om; pos = op; }
+    }
+    if (lane == src) { st.list_min = mn; st.minpos = pos; if (mn > st.thr) st.thr = mn; }
+    __syncwarp();
+  }
+  return st;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d,
+                       GemmTopkArgs a, float* __restrict__ dump, uint32_t dump_ld) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const uint32_t qb = blockIdx.x % a.n_qblocks;
+  const uint32_t slice = blockIdx.x / a.n_qblocks;
+  const uint32_t t0 = (uint32_t)(((uint64_t)slice * a.n_tiles) / a.n_slices);
+  const uint32_t t1 = (uint32_t)(((uint64_t)(slice + 1) * a.n_tiles) / a.n_slices);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_d) : "memory");
+    for (uint32_t s = 0; s < STAGES; ++s) { trr_mbar_init(&full_bar[s], 1); trr_mbar_init(&empty_bar[s], 1); }
+    for (uint32_t s = 0; s < 2; ++s) { trr_mbar_init(&tfull_bar[s], 1); trr_mbar_init(&tempty_bar[s], 128); }
+    trr_fence_mbar_init();
+  }
+  if (warp == 1) {  // TMEM: 512 columns = 2 accumulator stages of 256 f32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(trr_smem_u32(tmem_ptr_smem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t t = t0; t < t1; ++t) {
+        for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
+          mbar_wait_bounded(&empty_bar[stage], phase ^ 1, 1);
+          trr_mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+          tma_load_2d(&map_q, smem + SMEM_A + stage * A_BYTES, &full_bar[stage], (int32_t)(kb * BK), (int32_t)(qb * BM));
+          tma_load_2d(&map_d, smem + SMEM_B + stage * B_BYTES, &full_bar[stage], (int32_t)(kb * BK), (int32_t)(t * BN));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t t = t0, it = 0; t < t1; ++t, ++it) {
+      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      mbar_wait_bounded(&tempty_bar[as], aphase ^ 1, 2);
+      tc_fence_after();
+      for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
+        mbar_wait_bounded(&full_bar[stage], phase, 3);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t da = make_smem_desc(trr_smem_u32(smem + SMEM_A + stage * A_BYTES));
+          const uint64_t db = make_smem_desc(trr_smem_u32(smem + SMEM_B + stage * B_BYTES));
+#pragma unroll
+          for (uint32_t k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(tmem_base + as * BN, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                        // frees the smem stage once the MMAs retire
+          if (kb == a.k_blocks - 1) umma_commit(&tfull_bar[as]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const uint32_t quarter = warp & 3;            // TMEM lane group this warp may access
+    const uint32_t row = quarter * 32 + lane;     // query row inside the block
+    float* ls_all = reinterpret_cast<float*>(smem + SMEM_LS);
+    uint32_t* lo_all = reinterpret_cast<uint32_t*>(smem + SMEM_LO);
+    float* my_ls = ls_all + row * CP;
+    uint32_t* my_lo = lo_all + row * CP;
+    for (uint32_t j = 0; j < CP; ++j) { my_ls[j] = -CUDART_INF_F; my_lo[j] = 0xFFFFFFFFu; }
+    __syncwarp();
+    RowState st;
+    st.list_min = -CUDART_INF_F;      // smallest score in this row's list
+    st.minpos = 0;
+    st.thr = -CUDART_INF_F;           // max(list_min, shared threshold)
+    uint32_t* gthr = a.gthr + (qb * BM + row);
+    float* ls_warp = ls_all + quarter * 32 * CP;
+    uint32_t* lo_warp = lo_all + quarter * 32 * CP;
+
+    for (uint32_t t = t0, it = 0; t < t1; ++t, ++it) {
+      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      if (a.share_thresholds) {
+        const uint32_t g = *reinterpret_cast<volatile uint32_t*>(gthr);
+        if (g > trr_f32_orderable(st.thr)) st.thr = trr_orderable_f32(g);
+      }
+      mbar_wait_bounded(&tfull_bar[as], aphase, 4);
+      tc_fence_after();
+      const uint32_t doc0 = t * BN;
+      const float2* sbp = a.scale_bias + doc0;
+#pragma unroll 1
+      for (uint32_t c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((quarter * 32u) << 16) + as * BN + c * 32, v);
+#pragma unroll
+        for (uint32_t j = 0; j < 32; j += 2) {
+          const float4 sb = __ldg(reinterpret_cast<const float4*>(sbp + c * 32 + j));
+          const float s0 = fmaf(__uint_as_float(v[j]), sb.x, sb.y);
+          const float s1 = fmaf(__uint_as_float(v[j + 1]), sb.z, sb.w);
+          if (dump) {
+            dump[(uint64_t)(qb * BM + row) * dump_ld + doc0 + c * 32 + j] = s0;
+            dump[(uint64_t)(qb * BM + row) * dump_ld + doc0 + c * 32 + j + 1] = s1;
+          }
+          const uint32_t m0 = __ballot_sync(FULL, s0 > st.thr);
+          if (m0) st = insert_events(m0, s0, a.base_ord + doc0 + c * 32 + j, st, ls_warp, lo_warp, lane);
+          const uint32_t m1 = __ballot_sync(FULL, s1 > st.thr);
+          if (m1) st = insert_events(m1, s1, a.base_ord + doc0 + c * 32 + j + 1, st, ls_warp, lo_warp, lane);
+        }
+      }
+      // accumulator stage drained: hand it back to the MMA warp
+      tc_fence_before();
+      trr_mbar_arrive(&tempty_bar[as]);
+      if (a.share_thresholds && st.list_min > -CUDART_INF_F) atomicMax(gthr, trr_f32_orderable(st.list_min));
+    }
+    // publish this slice's candidates
+    const uint64_t base = (((uint64_t)slice * a.n_qblocks + qb) * BM + row) * CP;
+    for (uint32_t j = 0; j < CP; ++j) { a.cand_score[base + j] = my_ls[j]; a.cand_ord[base + j] = my_lo[j]; }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// operand preparation
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint16_t f32_to_bf16_rne(float f) {
+  uint32_t u = __float_as_uint(f);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// one CTA per (padded) query row
+__global__ void query_prep_kernel(const float* __restrict__ q, uint32_t dim, uint32_t dim_pad, uint32_t B,
+                                  uint16_t* __restrict__ q_bf16, float* __restrict__ q_delta) {
+  const uint32_t b = blockIdx.x;
+  float d2 = 0.0f;
+  for (uint32_t j = threadIdx.x; j < dim_pad; j += blockDim.x) {
+    uint16_t h = 0;
+    if (b < B && j < dim) {
+      const float x = q[(uint64_t)b * dim + j];
+      h = f32_to_bf16_rne(x);
+      const float r = x - __uint_as_float(((uint32_t)h) << 16);
+      d2 += r * r;
+    }
+    q_bf16[(uint64_t)b * dim_pad + j] = h;
+  }
+  __shared__ float red[32];
+  for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(FULL, d2, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d2;
+  __syncthreads();
+  if (threadIdx.x == 0 && b < B) {
+    float s = 0.0f;
+    for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) s += red[w];
+    q_delta[b] = sqrtf(s) * 1.0001f;  // upper bound on || q - bf16(q) ||
+  }
+}
+
+__global__ void shadow_kernel(const void* __restrict__ rows, int is_bf16, uint32_t dim, uint32_t dim_pad,
+                              uint64_t row0, uint64_t n, uint16_t* __restrict__ shadow) {
+  const uint64_t total = n * dim_pad;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = row0 + i / dim_pad;
+    const uint32_t j = (uint32_t)(i % dim_pad);
+    uint16_t h = 0;
+    if (j < dim) {
+      h = is_bf16 ? reinterpret_cast<const uint16_t*>(rows)[r * dim + j]
+                  : f32_to_bf16_rne(reinterpret_cast<const float*>(rows)[r * dim + j]);
+    }
+    shadow[r * dim_pad + j] = h;
+  }
+}
+
+void trr_launch_query_prep(const float* q, uint32_t dim, uint32_t dim_pad, uint32_t B, uint32_t B_pad, uint16_t* q_bf16,
+                           float* q_delta, cudaStream_t st) {
+  if (B_pad == 0) return;
+  query_prep_kernel<<<B_pad, 256, 0, st>>>(q, dim, dim_pad, B, q_bf16, q_delta);
+}
+
+void trr_launch_shadow(const void* rows, int is_bf16, uint32_t dim, uint32_t dim_pad, uint64_t row0, uint64_t n,
+                       uint16_t* shadow, cudaStream_t st) {
+  if (n == 0) return;
+  shadow_kernel<<<1184, 256, 0, st>>>(rows, is_bf16, dim, dim_pad, row0, n, shadow);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA descriptors (driver entry point fetched through the runtime: no link-time libcuda dependency)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int trr_make_tensor_map(void* out_map128, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p)
+      return trr_fail(TRR_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+  CUtensorMap* m = reinterpret_cast<CUtensorMap*>(out_map128);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};  // bytes between rows
+  cuuint32_t box[2] = {BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return trr_fail(TRR_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return TRR_OK;
+}
+
+cudaError_t trr_launch_gemm_topk(const GemmTopkArgs& a, const void* map_q128, const void* map_d128, unsigned grid,
+                                 cudaStream_t st) {
+  if (grid == 0) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(dense_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)SMEM_TOTAL);
+  if (e != cudaSuccess) return e;
+  CUtensorMap mq, md;
+  memcpy(&mq, map_q128, 128);
+  memcpy(&md, map_d128, 128);
+  dense_gemm_topk_kernel<<<grid, GEMM_THREADS, SMEM_TOTAL, st>>>(mq, md, a, nullptr, 0);
+  return cudaGetLastError();
+}
+
+// debug: additionally dumps every fast score to dump[(q) * dump_ld + doc] (small problems only)
+cudaError_t trr_launch_gemm_topk_dump(const GemmTopkArgs& a, const void* map_q128, const void* map_d128, unsigned grid,
+                                      float* dump, uint32_t dump_ld, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(dense_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)SMEM_TOTAL);
+  if (e != cudaSuccess) return e;
+  CUtensorMap mq, md;
+  memcpy(&mq, map_q128, 128);
+  memcpy(&md, map_d128, 128);
+  dense_gemm_topk_kernel<<<grid, GEMM_THREADS, SMEM_TOTAL, st>>>(mq, md, a, dump, dump_ld);
+  return cudaGetLastError();
+}

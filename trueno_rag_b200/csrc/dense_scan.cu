@@ -1,0 +1,533 @@
+// dense_scan.cu — strict-f32 dense kernels (compiled with -fmad=false -prec-div=true -prec-sqrt=true).
+//
+// Replaces the exhaustive scan of VectorStore::search (reference src/index.rs:386-412) and the
+// distance functions it calls (src/index.rs:440-462).  Everything in this translation unit
+// reproduces the reference's f32 arithmetic bit for bit: sums are sequential in dimension order,
+// starting from 0.0, with separate multiply and add (no FMA).
+//
+//   K1  dense_scan_bulk_kernel     HBM-bound scan, one row per lane, rows staged into shared memory by
+//                                  the TMA engine (cp.async.bulk, one bulk copy per row and chunk)
+//       dense_scan_generic_kernel  any dimension / tiny stores (rows not 16-byte multiples)
+//       dense_norms_kernel         per-row sqrt(sum x*x) in reference order + GEMM epilogue operands
+//       topk_merge_kernel          merges per-warp partial top-k lists (canonical order)
+//       rescore_select_kernel      exact rescoring + candidate proof for the tensor-core fast pass
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "dense.cuh"
+
+namespace {
+
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+
+// ---------------------------------------------------------------------------------------------
+// warp-private bounded top-k buffer in shared memory (capacity = power of two >= k + 32)
+// ---------------------------------------------------------------------------------------------
+struct WarpTopK {
+  uint64_t* buf;
+  uint32_t cap, k, cnt;
+  uint64_t thr;  // k-th best key so far (TRR_KEY_EMPTY while fewer than k were seen)
+
+  __device__ __forceinline__ void init(uint64_t* b, uint32_t cap_, uint32_t k_) {
+    buf = b; cap = cap_; k = k_; cnt = 0; thr = TRR_KEY_EMPTY;
+  }
+  __device__ __forceinline__ void compact(uint32_t lane) {
+    for (uint32_t i = cnt + lane; i < cap; i += 32) buf[i] = TRR_KEY_EMPTY;
+    trr_bitonic_sort_desc(buf, cap, lane, 32u, WarpSync());
+    if (cnt > k) cnt = k;
+    if (cnt == k && k > 0) thr = buf[k - 1];
+    __syncwarp();
+  }
+  // every lane of the warp must call this (valid == false for lanes without a candidate)
+  __device__ __forceinline__ void push(uint64_t key, bool valid, uint32_t lane) {
+    bool pass = valid && key > thr;
+    uint32_t m = __ballot_sync(FULL, pass);
+    if (m == 0) return;
+    if (cnt + __popc(m) > cap) {
+      compact(lane);
+      pass = pass && key > thr;
+      m = __ballot_sync(FULL, pass);
+      if (m == 0) return;
+    }
+    if (pass) buf[cnt + __popc(m & ((1u << lane) - 1u))] = key;
+    cnt += __popc(m);
+    __syncwarp();
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// element access
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+template <int METRIC>
+__device__ __forceinline__ void acc_step(float& acc, float q, float x) {
+  if (METRIC == TRR_METRIC_EUCLIDEAN) {
+    float t = q - x;       // (x - y) with x = query, y = stored vector   (src/index.rs:455)
+    acc = acc + t * t;     // .powi(2) == t*t, then sequential sum
+  } else {
+    acc = acc + q * x;     // src/index.rs:441,461
+  }
+}
+
+// src/index.rs:398-402 + :445-449 — turns the accumulated sum into the ranking score
+template <int METRIC>
+__device__ __forceinline__ float finish_score(float acc, float q_norm, float d_norm) {
+  if (METRIC == TRR_METRIC_COSINE) {
+    if (q_norm == 0.0f || d_norm == 0.0f) return 0.0f;
+    return acc / (q_norm * d_norm);
+  } else if (METRIC == TRR_METRIC_EUCLIDEAN) {
+    return -sqrtf(acc);
+  }
+  return acc;
+}
+
+}  // namespace
+
+// =============================================================================================
+// norms + GEMM epilogue operands
+// =============================================================================================
+template <int IS_BF16>
+__global__ void dense_norms_kernel(const void* __restrict__ rows, uint32_t dim, uint64_t row0, uint64_t n_rows,
+                                   float* __restrict__ norms) {
+  uint64_t r = row0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= row0 + n_rows) return;
+  float s = 0.0f;
+  if (IS_BF16) {
+    const uint16_t* p = reinterpret_cast<const uint16_t*>(rows) + r * dim;
+    for (uint32_t j = 0; j < dim; ++j) {
+      float x = __uint_as_float(((uint32_t)p[j]) << 16);
+      s = s + x * x;  // src/index.rs:442-443
+    }
+  } else {
+    const float* p = reinterpret_cast<const float*>(rows) + r * dim;
+    for (uint32_t j = 0; j < dim; ++j) {
+      float x = p[j];
+      s = s + x * x;
+    }
+  }
+  norms[r] = sqrtf(s);
+}
+
+// fast-pass operands of the tensor-core path: fast = dot * scale + bias (see dense_gemm.cu)
+__global__ void dense_gemm_operands_kernel(const float* __restrict__ norms, const uint8_t* __restrict__ dead,
+                                           uint64_t n_rows, uint64_t n_padded, int metric,
+                                           float2* __restrict__ scale_bias, float* __restrict__ max_norm) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float nrm = 0.0f;
+  if (r < n_padded) {
+    float2 sb = make_float2(0.0f, -CUDART_INF_F);  // padding rows and tombstones can never be selected
+    if (r < n_rows && !(dead && dead[r])) {
+      nrm = norms[r];
+      if (metric == TRR_METRIC_COSINE) sb = make_float2(nrm == 0.0f ? 0.0f : 1.0f / nrm, 0.0f);
+      else if (metric == TRR_METRIC_DOT) sb = make_float2(1.0f, 0.0f);
+      else sb = make_float2(2.0f, -(nrm * nrm));
+    }
+    scale_bias[r] = sb;
+  }
+  // block max of the norms -> global max (norms are >= 0, so the int ordering of the bits is the float ordering)
+  for (int o = 16; o > 0; o >>= 1) nrm = fmaxf(nrm, __shfl_xor_sync(FULL, nrm, o));
+  if ((threadIdx.x & 31) == 0 && nrm > 0.0f) atomicMax(reinterpret_cast<int*>(max_norm), __float_as_int(nrm));
+}
+
+// query norms in reference order (src/index.rs:442), one thread per query
+__global__ void dense_query_norms_kernel(const float* __restrict__ q, uint32_t dim, uint32_t B, float* __restrict__ qn) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* p = q + (uint64_t)b * dim;
+  float s = 0.0f;
+  for (uint32_t j = 0; j < dim; ++j) s = s + p[j] * p[j];
+  qn[b] = sqrtf(s);
+}
+
+// =============================================================================================
+// K1: bulk scan.  128 threads = 4 independent warps; each warp owns one shared-memory stage of
+// 32 rows x ch_bytes (row pitch ch_bytes + 16 so that the per-lane LDS.128 are conflict-free),
+// refilled by 32 TMA bulk copies that complete on the warp's mbarrier.
+// =============================================================================================
+template <int IS_BF16, int METRIC>
+__global__ void __launch_bounds__(128, 1)
+dense_scan_bulk_kernel(DenseScanArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t pitch = a.ch_bytes + 16;
+  // layout: [query f32 (q_bytes)] [4 mbarriers] [4 x topk cap*8] [4 x stage 32*pitch]
+  float* qs = reinterpret_cast<float*>(smem);
+  const uint32_t q_bytes = (a.dim * 4 + 127) & ~127u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + q_bytes);
+  uint64_t* tk_buf = reinterpret_cast<uint64_t*>(smem + q_bytes + 128) + (size_t)warp * a.cap;
+  uint8_t* stage = smem + q_bytes + 128 + (size_t)4 * a.cap * 8 + (size_t)warp * 32 * pitch;
+
+  if (lane == 0) trr_mbar_init(&bars[warp], 1);
+  trr_fence_mbar_init();
+  __syncthreads();
+
+  const uint32_t n_sel = a.n_sel_ptr ? *a.n_sel_ptr : a.n_sel;
+  const uint64_t n_groups = (a.n_rows + 31) / 32;
+  const uint64_t gwarp = (uint64_t)blockIdx.x * 4 + warp, gstride = (uint64_t)gridDim.x * 4;
+  uint32_t parity = 0;
+  uint8_t* my_row = stage + (size_t)lane * pitch;
+
+  for (uint32_t si = 0; si < n_sel; ++si) {
+    const uint32_t qi = a.sel ? a.sel[si] : si;
+    __syncthreads();  // previous query's reads of qs are done
+    for (uint32_t j = threadIdx.x; j < a.dim; j += blockDim.x) qs[j] = a.q[(uint64_t)qi * a.dim + j];
+    __syncthreads();
+    const float q_norm = a.q_norms[qi];
+    WarpTopK tk;
+    tk.init(tk_buf, a.cap, a.k);
+
+    for (uint64_t g = gwarp; g < n_groups; g += gstride) {
+      const uint64_t row = g * 32 + lane;
+      const bool in_range = row < a.n_rows;
+      float acc = 0.0f;
+      for (uint32_t c = 0; c < a.n_chunks; ++c) {
+        const uint32_t off = c * a.ch_bytes;
+        const uint32_t bytes = min(a.ch_bytes, a.row_bytes - off);
+        const uint64_t rows_left = a.n_rows - g * 32;
+        const uint32_t valid_rows = rows_left < 32 ? (uint32_t)rows_left : 32u;
+        trr_fence_proxy_async();  // order this warp's earlier generic reads of the stage before the async writes
+        if (lane == 0) trr_mbar_expect_tx(&bars[warp], bytes * valid_rows);
+        __syncwarp();
+        if (in_range) trr_bulk_g2s(my_row, a.rows + row * a.row_bytes + off, bytes, &bars[warp]);
+        trr_mbar_wait(&bars[warp], parity);
+        parity ^= 1;
+        if (in_range) {
+          const uint4* rp = reinterpret_cast<const uint4*>(my_row);
+          const uint32_t nvec = bytes >> 4;
+          if (IS_BF16) {
+            const float4* qp = reinterpret_cast<const float4*>(qs + (off >> 1));
+#pragma unroll 4
+            for (uint32_t i = 0; i < nvec; ++i) {
+              const uint4 v = rp[i];
+              const float4 q0 = qp[2 * i], q1 = qp[2 * i + 1];
+              acc_step<METRIC>(acc, q0.x, bf16lo(v.x)); acc_step<METRIC>(acc, q0.y, bf16hi(v.x));
+              acc_step<METRIC>(acc, q0.z, bf16lo(v.y)); acc_step<METRIC>(acc, q0.w, bf16hi(v.y));
+              acc_step<METRIC>(acc, q1.x, bf16lo(v.z)); acc_step<METRIC>(acc, q1.y, bf16hi(v.z));
+              acc_step<METRIC>(acc, q1.z, bf16lo(v.w)); acc_step<METRIC>(acc, q1.w, bf16hi(v.w));
+            }
+          } else {
+            const float4* qp = reinterpret_cast<const float4*>(qs + (off >> 2));
+#pragma unroll 4
+            for (uint32_t i = 0; i < nvec; ++i) {
+              const uint4 v = rp[i];
+              const float4 qq = qp[i];
+              acc_step<METRIC>(acc, qq.x, __uint_as_float(v.x)); acc_step<METRIC>(acc, qq.y, __uint_as_float(v.y));
+              acc_step<METRIC>(acc, qq.z, __uint_as_float(v.z)); acc_step<METRIC>(acc, qq.w, __uint_as_float(v.w));
+            }
+          }
+        }
+        __syncwarp();
+      }
+      bool valid = in_range && !(a.dead && a.dead[row]);
+      float score = 0.0f;
+      if (valid) score = finish_score<METRIC>(acc, q_norm, METRIC == TRR_METRIC_COSINE ? a.norms[row] : 0.0f);
+      tk.push(trr_make_key(score, a.base_ord + (uint32_t)row), valid, lane);
+    }
+    tk.compact(lane);
+    uint64_t* out = a.partial + ((uint64_t)si * gstride + gwarp) * a.k;
+    for (uint32_t i = lane; i < tk.cnt; i += 32) out[i] = tk.buf[i];
+    if (lane == 0) a.partial_n[(uint64_t)si * gstride + gwarp] = tk.cnt;
+    __syncwarp();
+  }
+}
+
+// generic scan: one row per thread straight from global memory; any dimension.  256 threads.
+template <int IS_BF16, int METRIC>
+__global__ void __launch_bounds__(256)
+dense_scan_generic_kernel(DenseScanArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* qs = reinterpret_cast<float*>(smem);
+  const uint32_t q_bytes = (a.dim * 4 + 127) & ~127u;
+  uint64_t* tk_buf = reinterpret_cast<uint64_t*>(smem + q_bytes) + (size_t)warp * a.cap;
+  const uint32_t n_sel = a.n_sel_ptr ? *a.n_sel_ptr : a.n_sel;
+  const uint64_t n_groups = (a.n_rows + 31) / 32;
+  const uint64_t gwarp = (uint64_t)blockIdx.x * 8 + warp, gstride = (uint64_t)gridDim.x * 8;
+
+  for (uint32_t si = 0; si < n_sel; ++si) {
+    const uint32_t qi = a.sel ? a.sel[si] : si;
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < a.dim; j += blockDim.x) qs[j] = a.q[(uint64_t)qi * a.dim + j];
+    __syncthreads();
+    const float q_norm = a.q_norms[qi];
+    WarpTopK tk;
+    tk.init(tk_buf, a.cap, a.k);
+    for (uint64_t g = gwarp; g < n_groups; g += gstride) {
+      const uint64_t row = g * 32 + lane;
+      bool valid = row < a.n_rows && !(a.dead && a.dead[row]);
+      float score = 0.0f;
+      if (valid) {
+        float acc = 0.0f;
+        if (IS_BF16) {
+          const uint16_t* p = reinterpret_cast<const uint16_t*>(a.rows) + row * a.dim;
+          for (uint32_t j = 0; j < a.dim; ++j) acc_step<METRIC>(acc, qs[j], __uint_as_float(((uint32_t)p[j]) << 16));
+        } else {
+          const float* p = reinterpret_cast<const float*>(a.rows) + row * a.dim;
+          for (uint32_t j = 0; j < a.dim; ++j) acc_step<METRIC>(acc, qs[j], p[j]);
+        }
+        score = finish_score<METRIC>(acc, q_norm, METRIC == TRR_METRIC_COSINE ? a.norms[row] : 0.0f);
+      }
+      tk.push(trr_make_key(score, a.base_ord + (uint32_t)row), valid, lane);
+    }
+    tk.compact(lane);
+    uint64_t* out = a.partial + ((uint64_t)si * gstride + gwarp) * a.k;
+    for (uint32_t i = lane; i < tk.cnt; i += 32) out[i] = tk.buf[i];
+    if (lane == 0) a.partial_n[(uint64_t)si * gstride + gwarp] = tk.cnt;
+    __syncwarp();
+  }
+}
+
+// =============================================================================================
+// merge of partial lists: one CTA per output row.  lists[row][l][0..n[row][l]) hold keys; the CTA
+// keeps the best k in the first half of a 2*K2 shared buffer and streams the rest through the
+// second half.  Writes ordinals/scores in canonical order.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(TopkMergeArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);
+  const uint32_t n_rows = a.n_rows_ptr ? *a.n_rows_ptr : a.n_rows;
+  for (uint32_t ri = blockIdx.x; ri < n_rows; ri += gridDim.x) {
+    const uint32_t out_row = a.row_map ? a.row_map[ri] : ri;
+    const uint32_t K2 = a.k2;  // power of two >= k
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 2 * K2; i += blockDim.x) buf[i] = TRR_KEY_EMPTY;
+    __syncthreads();
+    uint32_t fill = 0;  // entries staged in the second half (uniform across the CTA)
+    for (uint32_t l = 0; l < a.n_lists; ++l) {
+      const uint64_t* src = a.lists + ((uint64_t)ri * a.n_lists + l) * a.list_stride;
+      const uint32_t cnt = a.list_n ? min(a.list_n[(uint64_t)ri * a.n_lists + l], a.list_stride) : a.list_stride;
+      uint32_t done = 0;
+      while (done < cnt) {
+        const uint32_t take = min(cnt - done, K2 - fill);
+        for (uint32_t i = threadIdx.x; i < take; i += blockDim.x) buf[K2 + fill + i] = src[done + i];
+        done += take;
+        fill += take;
+        if (fill == K2) {
+          trr_bitonic_sort_desc(buf, 2 * K2, threadIdx.x, blockDim.x, BlockSync());
+          for (uint32_t i = threadIdx.x; i < K2; i += blockDim.x) buf[K2 + i] = TRR_KEY_EMPTY;
+          fill = 0;
+          __syncthreads();
+        }
+      }
+    }
+    trr_bitonic_sort_desc(buf, 2 * K2, threadIdx.x, blockDim.x, BlockSync());
+    // count valid entries among the first k
+    __shared__ uint32_t s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    uint32_t local = 0;
+    for (uint32_t i = threadIdx.x; i < a.k; i += blockDim.x) {
+      uint64_t key = buf[i];
+      if (key != TRR_KEY_EMPTY) {
+        ++local;
+        if (a.out_keys) a.out_keys[(uint64_t)out_row * a.k + i] = key;
+        if (a.out_ord) a.out_ord[(uint64_t)out_row * a.k + i] = trr_key_ord(key);
+        if (a.out_score) a.out_score[(uint64_t)out_row * a.k + i] = trr_key_score(key);
+      } else {
+        if (a.out_keys) a.out_keys[(uint64_t)out_row * a.k + i] = TRR_KEY_EMPTY;
+        if (a.out_ord) a.out_ord[(uint64_t)out_row * a.k + i] = 0xFFFFFFFFu;
+        if (a.out_score) a.out_score[(uint64_t)out_row * a.k + i] = 0.0f;
+      }
+    }
+    if (local) atomicAdd(&s_cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0 && a.out_n) a.out_n[out_row] = s_cnt;
+  }
+}
+
+// =============================================================================================
+// exact rescoring + candidate proof for the tensor-core fast pass (dense_gemm.cu).
+// One CTA (256 threads) per query:
+//   1. gather the query's fast candidates from every slice, keep the best CP by (fast, ordinal);
+//   2. recompute those CP scores exactly as the reference does (one thread per candidate, sequential);
+//   3. sort by the canonical key and emit the top k;
+//   4. proof: every document that was NOT rescored has fast score <= f_min (the smallest fast score kept
+//      by any full per-slice list, or the CP-th best after the merge); with |fast - exact| <= eps for every
+//      document, none of them can reach or tie the k-th exact score if  f_min + eps < exact_k.  If the
+//      proof fails the query is flagged and re-run through the exact scan (K1).
+// =============================================================================================
+template <int IS_BF16>
+__global__ void __launch_bounds__(256)
+rescore_select_kernel(RescoreArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);            // cap2 fast keys
+  uint64_t* ekeys = keys + a.cap2;                                     // CP exact keys (CP power of two)
+  float* efast = reinterpret_cast<float*>(ekeys + a.cp);              // fast score of each kept candidate
+  __shared__ float s_gap;
+  __shared__ uint32_t s_total;
+  const uint32_t b = blockIdx.x;
+  if (b >= a.B) return;
+  const uint32_t tid = threadIdx.x;
+  if (tid == 0) { s_gap = 0.0f; s_total = 0; }
+  for (uint32_t i = tid; i < a.cap2; i += blockDim.x) keys[i] = TRR_KEY_EMPTY;
+  __syncthreads();
+  // 1. gather: slice s of query block qb = b / 128, row r = b % 128
+  const uint32_t qb = b / 128, r = b % 128;
+  uint32_t local_total = 0;
+  for (uint32_t i = tid; i < a.n_slices * a.cp; i += blockDim.x) {
+    const uint32_t s = i / a.cp, j = i % a.cp;
+    const uint64_t base = (((uint64_t)s * a.n_qblocks + qb) * 128 + r) * a.cp + j;
+    const float sc = a.cand_score[base];
+    const uint32_t od = a.cand_ord[base];
+    if (od != 0xFFFFFFFFu) { keys[i] = trr_make_key(sc, od); ++local_total; }
+  }
+  if (local_total) atomicAdd(&s_total, local_total);
+  __syncthreads();
+  trr_bitonic_sort_desc(keys, a.cap2, tid, blockDim.x, BlockSync());
+  const uint32_t n_cand = min(s_total, a.cp);
+  // 2. exact rescoring, strict reference order
+  const float* qv = a.q + (uint64_t)b * a.dim;
+  const float q_norm = a.q_norms[b];
+  if (tid < a.cp) {
+    uint64_t ek = TRR_KEY_EMPTY;
+    float fast = 0.0f;
+    if (tid < n_cand) {
+      const uint64_t fk = keys[tid];
+      const uint32_t od = trr_key_ord(fk);
+      fast = trr_key_score(fk);
+      const uint64_t row = od - a.base_ord;
+      float acc = 0.0f;
+      if (IS_BF16) {
+        const uint16_t* p = reinterpret_cast<const uint16_t*>(a.rows) + row * a.dim;
+        for (uint32_t j = 0; j < a.dim; ++j) acc = acc + qv[j] * __uint_as_float(((uint32_t)p[j]) << 16);
+      } else {
+        const float* p = reinterpret_cast<const float*>(a.rows) + row * a.dim;
+        for (uint32_t j = 0; j < a.dim; ++j) acc = acc + qv[j] * p[j];
+      }
+      float score;
+      if (a.metric == TRR_METRIC_COSINE) {
+        const float dn = a.norms[row];
+        score = (q_norm == 0.0f || dn == 0.0f) ? 0.0f : acc / (q_norm * dn);
+      } else {
+        score = acc;
+      }
+      ek = trr_make_key(score, od);
+      // fast score in score units
+      float fs = (a.metric == TRR_METRIC_COSINE) ? (q_norm > 0.0f ? fast / q_norm : 0.0f) : fast;
+      atomicMax(reinterpret_cast<int*>(&s_gap), __float_as_int(fabsf(fs - score)));
+    }
+    ekeys[tid] = ek;
+    efast[tid] = fast;
+  }
+  __syncthreads();
+  trr_bitonic_sort_desc(ekeys, a.cp, tid, blockDim.x, BlockSync());
+  // 3. emit
+  const uint32_t n_out = min(n_cand, a.k);
+  for (uint32_t i = tid; i < a.k; i += blockDim.x) {
+    const bool ok = i < n_out;
+    const uint64_t key = ok ? ekeys[i] : TRR_KEY_EMPTY;
+    if (a.out_keys) a.out_keys[(uint64_t)b * a.k + i] = key;
+    if (a.out_ord) a.out_ord[(uint64_t)b * a.k + i] = ok ? trr_key_ord(key) : 0xFFFFFFFFu;
+    if (a.out_score) a.out_score[(uint64_t)b * a.k + i] = ok ? trr_key_score(key) : 0.0f;
+  }
+  // 4. proof
+  if (tid == 0) {
+    if (a.out_n) a.out_n[b] = n_out;
+    bool ok = true;
+    const bool something_excluded = a.n_live > (uint64_t)n_cand;
+    if (something_excluded) {
+      if (n_out < a.k || n_cand < a.cp) {
+        ok = false;  // fewer candidates than needed although documents were excluded (non-finite scores)
+      } else {
+        // largest fast score any excluded document can have: the cp-th best fast score overall
+        const float f_excl = trr_key_score(keys[a.cp - 1]);
+        const float f_excl_s = (a.metric == TRR_METRIC_COSINE) ? (q_norm > 0.0f ? f_excl / q_norm : 0.0f) : f_excl;
+        float eps = a.eps_rel;                                  // cosine units
+        if (a.metric == TRR_METRIC_COSINE) eps += (q_norm > 0.0f ? a.q_delta[b] / q_norm : 0.0f);
+        else eps = (a.eps_rel * q_norm + a.q_delta[b]) * (*a.max_norm);
+        const float exact_k = trr_key_score(ekeys[a.k - 1]);
+        ok = (q_norm > 0.0f || a.metric != TRR_METRIC_COSINE) && (f_excl_s + eps < exact_k);
+      }
+    }
+    a.flags[b] = ok ? 0u : 1u;
+    if (!ok) {
+      const uint32_t slot = atomicAdd(a.n_flagged, 1u);
+      a.flagged[slot] = b;
+    }
+    atomicMax(reinterpret_cast<int*>(a.max_gap), __float_as_int(s_gap));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch helpers (host)
+// ---------------------------------------------------------------------------------------------
+template <int IS_BF16>
+static void launch_norms(const void* rows, uint32_t dim, uint64_t row0, uint64_t n, float* norms, cudaStream_t st) {
+  if (n == 0) return;
+  dense_norms_kernel<IS_BF16><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(rows, dim, row0, n, norms);
+}
+
+void trr_launch_norms(int is_bf16, const void* rows, uint32_t dim, uint64_t row0, uint64_t n, float* norms,
+                      cudaStream_t st) {
+  if (is_bf16) launch_norms<1>(rows, dim, row0, n, norms, st);
+  else launch_norms<0>(rows, dim, row0, n, norms, st);
+}
+
+void trr_launch_gemm_operands(const float* norms, const uint8_t* dead, uint64_t n_rows, uint64_t n_padded, int metric,
+                              float2* scale_bias, float* max_norm, cudaStream_t st) {
+  if (n_padded == 0) return;
+  dense_gemm_operands_kernel<<<(unsigned)((n_padded + 255) / 256), 256, 0, st>>>(norms, dead, n_rows, n_padded, metric,
+                                                                                 scale_bias, max_norm);
+}
+
+void trr_launch_query_norms(const float* q, uint32_t dim, uint32_t B, float* qn, cudaStream_t st) {
+  if (B == 0) return;
+  dense_query_norms_kernel<<<(B + 127) / 128, 128, 0, st>>>(q, dim, B, qn);
+}
+
+template <int IS_BF16, int METRIC>
+static cudaError_t launch_scan_t(const DenseScanArgs& a, bool bulk, unsigned grid, size_t smem, cudaStream_t st) {
+  if (bulk) {
+    auto kern = dense_scan_bulk_kernel<IS_BF16, METRIC>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, 128, smem, st>>>(a);
+  } else {
+    auto kern = dense_scan_generic_kernel<IS_BF16, METRIC>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, 256, smem, st>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t trr_launch_scan(const DenseScanArgs& a, int is_bf16, int metric, bool bulk, unsigned grid, size_t smem,
+                            cudaStream_t st) {
+#define TRR_SCAN_CASE(B, M) \
+  if (is_bf16 == B && metric == M) return launch_scan_t<B, M>(a, bulk, grid, smem, st)
+  TRR_SCAN_CASE(0, TRR_METRIC_COSINE);
+  TRR_SCAN_CASE(0, TRR_METRIC_EUCLIDEAN);
+  TRR_SCAN_CASE(0, TRR_METRIC_DOT);
+  TRR_SCAN_CASE(1, TRR_METRIC_COSINE);
+  TRR_SCAN_CASE(1, TRR_METRIC_EUCLIDEAN);
+  TRR_SCAN_CASE(1, TRR_METRIC_DOT);
+#undef TRR_SCAN_CASE
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t trr_launch_topk_merge(const TopkMergeArgs& a, unsigned grid, cudaStream_t st) {
+  if (grid == 0) return cudaSuccess;
+  size_t smem = (size_t)2 * a.k2 * sizeof(uint64_t);
+  cudaError_t e = cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  topk_merge_kernel<<<grid, 256, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t trr_launch_rescore(const RescoreArgs& a, int is_bf16, cudaStream_t st) {
+  if (a.B == 0) return cudaSuccess;
+  size_t smem = (size_t)a.cap2 * 8 + (size_t)a.cp * 8 + (size_t)a.cp * 4;
+  if (is_bf16) {
+    cudaError_t e = cudaFuncSetAttribute(rescore_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rescore_select_kernel<1><<<a.B, 256, smem, st>>>(a);
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(rescore_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rescore_select_kernel<0><<<a.B, 256, smem, st>>>(a);
+  }
+  return cudaGetLastError();
+}
