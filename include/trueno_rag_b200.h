@@ -88,6 +88,10 @@ TRR_API int trr_ctx_sync(trr_ctx* ctx);
 /* the CUDA stream (cudaStream_t) every `_device` entry point enqueues on */
 TRR_API int trr_ctx_stream(trr_ctx* ctx, void** out_stream);
 TRR_API int trr_ctx_sm_count(trr_ctx* ctx, int* out);
+/* makes the context enqueue on a caller-owned stream (e.g. the host framework's current stream) from now on */
+TRR_API int trr_ctx_set_stream(trr_ctx* ctx, void* stream);
+/* number of kernels of this library launched on the context since it was created (diagnostics / bench) */
+TRR_API int trr_ctx_launch_count(trr_ctx* ctx, uint64_t* out);
 
 /* ---- dense store: VectorStore, src/index.rs:322-437 ------------------------------------------ */
 /* VectorStore::new / with_dimension (src/index.rs:335-350) */
@@ -173,6 +177,10 @@ TRR_API size_t trr_exchange_bytes(uint32_t B, uint32_t C);
 TRR_API int trr_hybrid_local(trr_dense* dense, trr_bm25* bm25, const float* q, const uint32_t* q_terms,
                              const uint32_t* q_off, uint32_t B, uint32_t C, int use_dense, int use_sparse,
                              void* d_exchange);
+/* Same with DEVICE inputs (h_q_off is the host copy of q_off, used for validation only); enqueues, no sync. */
+TRR_API int trr_hybrid_local_device(trr_dense* dense, trr_bm25* bm25, const float* d_q, const uint32_t* d_q_terms,
+                                    const uint32_t* d_q_off, const uint32_t* h_q_off, uint32_t B, uint32_t C,
+                                    int use_dense, int use_sparse, void* d_exchange);
 /* Merge stage: d_gathered holds G exchange records back to back (the all-gather output, DEVICE).  Merges the
  * G sorted lists per source into the global top-C, then fuses and takes k exactly as trr_hybrid_search.
  * Outputs are HOST buffers. */
@@ -180,9 +188,27 @@ TRR_API int trr_hybrid_merge(trr_ctx* ctx, const void* d_gathered, uint32_t G, u
                              float param, uint32_t k, uint32_t* out_ord, float* out_fused, float* out_dense,
                              float* out_sparse, uint32_t* out_n);
 
+/* Same with DEVICE outputs; enqueues, no sync. */
+TRR_API int trr_hybrid_merge_device(trr_ctx* ctx, const void* d_gathered, uint32_t G, uint32_t B, uint32_t C, int strategy,
+                                    float param, uint32_t k, uint32_t* d_out_ord, float* d_out_fused, float* d_out_dense,
+                                    float* d_out_sparse, uint32_t* d_out_n);
+
 /* ---- synthetic inputs for tests and benches (not reference behaviour) ------------- */
 /* appends n rows generated on the device by the counter-based recipe of csrc/synth_spec.h */
 TRR_API int trr_dense_append_synth(trr_dense* h, uint64_t seed, uint64_t first_row, uint64_t n, int dups);
+/* host-side generators of the synthetic hybrid workload (csrc/synth_spec.h): queries, query terms and the BM25
+ * postings of the documents [doc_lo, doc_hi) as a CSR with LOCAL doc ids.  Two passes so that the caller can
+ * all-reduce df / total length across shards before computing term_off and idf:
+ *   count: df_local[n_terms] (documents of this shard containing the term), doc_len[doc_hi-doc_lo], total length;
+ *   fill : post_doc / post_tf given term_off[n_terms+1] = exclusive prefix sum of df_local. */
+TRR_API int trr_synth_queries(uint64_t seed, uint64_t q0, uint64_t n, uint32_t dim, uint64_t n_corpus, int corpus_bf16,
+                              int dups, int round_to_bf16, float* out);
+TRR_API int trr_synth_query_terms(uint64_t seed, const uint64_t* cdf, uint32_t n_terms, uint64_t q0, uint64_t n,
+                                  uint32_t* q_off, uint32_t* out_terms, uint64_t out_cap);
+TRR_API int trr_synth_bm25_count(uint64_t seed, const uint64_t* cdf, uint32_t n_terms, uint64_t doc_lo, uint64_t doc_hi,
+                                 uint32_t* df_local, uint32_t* doc_len, uint64_t* total_len);
+TRR_API int trr_synth_bm25_fill(uint64_t seed, const uint64_t* cdf, uint32_t n_terms, uint64_t doc_lo, uint64_t doc_hi,
+                                const uint64_t* term_off, uint32_t* post_doc, uint32_t* post_tf);
 /* L2 flush helper for benches: writes `bytes` of device memory on the context stream */
 TRR_API int trr_ctx_flush_l2(trr_ctx* ctx, size_t bytes);
 

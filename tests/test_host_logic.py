@@ -125,3 +125,46 @@ def test_exchange_record_layout_roundtrip(api):
     assert w.nbytes == api.exchange_bytes(B, C_)
     ords, scores, n = shard.unpack_exchange(w, B, C_)
     assert np.array_equal(ords[0], d[0]) and np.array_equal(scores[1], s[1]) and np.array_equal(n[1], s[2])
+
+
+# ---------------------------------------------------------------- product-side synthetic generators vs the oracle's
+def test_host_synth_generators_match_oracle(built_lib):
+    import ctypes as C
+    from oracle import oracle as O
+    from trueno_rag_b200._lib import f32p, u32p, u64p
+    L = built_lib
+    seed, V, D = 0x5EED0004, 3000, 48
+    cdf = O.zipf_cdf(V)
+    # queries (with and without bf16 rounding of the result)
+    q = np.zeros((300, D), np.float32)
+    assert L.trr_synth_queries(seed, 5, 300, D, 1000, 1, 1, 0, q.ctypes.data_as(f32p)) == 0
+    assert np.array_equal(q, O.synth_queries(seed, 5, 300, D, 1000, corpus_bf16=True, dups=True))
+    # query terms
+    q_off = np.zeros(41, np.uint32)
+    assert L.trr_synth_query_terms(seed, cdf.ctypes.data_as(u64p), V, 0, 40, q_off.ctypes.data_as(u32p), None, 0) == 0
+    terms = np.zeros(int(q_off[-1]), np.uint32)
+    assert L.trr_synth_query_terms(seed, cdf.ctypes.data_as(u64p), V, 0, 40, q_off.ctypes.data_as(u32p),
+                                   terms.ctypes.data_as(u32p), terms.size) == 0
+    eo, et = O.synth_query_terms(seed, cdf, 0, 40)
+    assert np.array_equal(q_off, eo) and np.array_equal(terms, et)
+    # BM25 shard CSR == CSR of the oracle's index restricted to the shard
+    n_docs, lo, hi = 5000, 1200, 4100
+    doc_off, toks = O.synth_doc_tokens(seed, cdf, 0, n_docs)
+    oix = O.BM25(n_terms=V, doc_off=doc_off, tokens=toks)
+    term_off, post_doc, post_tf, doc_len, df = oix.csr()
+    df_l = np.zeros(V, np.uint32)
+    dl = np.zeros(hi - lo, np.uint32)
+    tot = C.c_uint64()
+    assert L.trr_synth_bm25_count(seed, cdf.ctypes.data_as(u64p), V, lo, hi, df_l.ctypes.data_as(u32p),
+                                  dl.ctypes.data_as(u32p), C.byref(tot)) == 0
+    assert np.array_equal(dl, doc_len[lo:hi]) and tot.value == int(doc_len[lo:hi].sum())
+    keep = (post_doc >= lo) & (post_doc < hi)
+    term_of = np.repeat(np.arange(V), np.diff(term_off).astype(np.int64))
+    assert np.array_equal(df_l, np.bincount(term_of[keep], minlength=V))
+    s_off = np.zeros(V + 1, np.uint64)
+    np.cumsum(df_l, out=s_off[1:])
+    pd = np.zeros(int(s_off[-1]), np.uint32)
+    ptf = np.zeros(int(s_off[-1]), np.uint32)
+    assert L.trr_synth_bm25_fill(seed, cdf.ctypes.data_as(u64p), V, lo, hi, s_off.ctypes.data_as(u64p),
+                                 pd.ctypes.data_as(u32p), ptf.ctypes.data_as(u32p)) == 0
+    assert np.array_equal(pd, post_doc[keep] - lo) and np.array_equal(ptf, post_tf[keep])

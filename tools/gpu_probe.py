@@ -183,5 +183,29 @@ def step_perf_gemm():
     ix.close()
 
 
+def step_perf_bm25():
+    ctx = api.Context(0)
+    n_docs, n_terms, B = 2_000_000, 200_000, 512
+    cdf = O.zipf_cdf(n_terms)
+    t0 = time.time()
+    doc_off, toks = O.synth_doc_tokens(SEED, cdf, 0, n_docs)
+    oix = O.BM25(n_terms=n_terms, doc_off=doc_off, tokens=toks)
+    term_off, post_doc, post_tf, doc_len, df = oix.csr()
+    print("host gen+build s", time.time() - t0, "postings", oix.n_postings)
+    t0 = time.time()
+    dev = api.Bm25Device(ctx, n_docs, term_off, post_doc, post_tf, doc_len, oix.avgdl, api.bm25_idf_host(n_docs, df))
+    print("device build s", time.time() - t0)
+    q_off, q_terms = O.synth_query_terms(SEED, cdf, 0, B)
+    vol = int(np.diff(term_off)[q_terms].sum())
+    for it in range(3):
+        got = dev.search(q_terms, q_off, 100)
+        st = dev.stats()
+        print(f"K3 2M docs B={B}: main {st.ms_main_kernel:.3f} ms  postings/query {vol/B:.0f}  {8*vol/st.ms_main_kernel/1e6:.0f} GB/s "
+              f"{B/st.ms_main_kernel*1e3:.0f} q/s")
+    exp = oix.search_batch(q_terms[:q_off[8]], q_off[:9], 100)
+    cmp_lists("bm25 2M check", (got[0][:8], got[1][:8], got[2][:8]), exp)
+    dev.close()
+
+
 if __name__ == "__main__":
     globals()["step_" + sys.argv[1]]()

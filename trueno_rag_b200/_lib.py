@@ -40,6 +40,16 @@ TRR_PROTOS = {
     "trr_ctx_stream": (C.c_int, [vp, vpp]),
     "trr_ctx_sm_count": (C.c_int, [vp, C.POINTER(C.c_int)]),
     "trr_ctx_flush_l2": (C.c_int, [vp, C.c_size_t]),
+    "trr_ctx_set_stream": (C.c_int, [vp, vp]),
+    "trr_ctx_launch_count": (C.c_int, [vp, u64p]),
+    "trr_hybrid_local_device": (C.c_int, [vp, vp, vp, vp, vp, u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, vp]),
+    "trr_hybrid_merge_device": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.c_uint32, vp,
+                                          vp, vp, vp, vp]),
+    "trr_synth_queries": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                    f32p]),
+    "trr_synth_query_terms": (C.c_int, [C.c_uint64, u64p, C.c_uint32, C.c_uint64, C.c_uint64, u32p, u32p, C.c_uint64]),
+    "trr_synth_bm25_count": (C.c_int, [C.c_uint64, u64p, C.c_uint32, C.c_uint64, C.c_uint64, u32p, u32p, u64p]),
+    "trr_synth_bm25_fill": (C.c_int, [C.c_uint64, u64p, C.c_uint32, C.c_uint64, C.c_uint64, u64p, u32p, u32p]),
     "trr_dense_create": (C.c_int, [vp, C.c_uint32, C.c_int, C.c_int, C.c_uint64, vpp]),
     "trr_dense_destroy": (C.c_int, [vp]),
     "trr_dense_set_base": (C.c_int, [vp, C.c_uint32]),

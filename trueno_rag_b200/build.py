@@ -27,7 +27,7 @@ STRICT = ["-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]
 
 CU_STRICT = ["dense_scan.cu", "bm25.cu", "fusion.cu", "synth.cu"]
 CU_FAST = ["dense_gemm.cu", "capi.cu"]
-CPP = ["host/host_mirror.cpp", "host/host_capi.cpp"]
+CPP = ["host/host_mirror.cpp", "host/host_capi.cpp", "host/synth_host.cpp"]
 
 
 def _nvcc() -> str:
@@ -77,7 +77,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         jobs.append([nvcc, "-ccbin", cxx, *ARCH, *COMMON, "-c", os.path.join(CSRC, src), "-o",
                      os.path.join(OBJ, src.replace("/", "_") + ".o")])
     for src in CPP:
-        jobs.append([cxx, "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-fvisibility=hidden",
+        jobs.append([cxx, "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-fvisibility=hidden", "-fopenmp",
                      "-I/usr/local/cuda/include", "-c", os.path.join(CSRC, src), "-o",
                      os.path.join(OBJ, src.replace("/", "_") + ".o")])
 
@@ -92,7 +92,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
         list(ex.map(run, jobs))
     objs = [j[-1] for j in jobs]
-    run([nvcc, "-ccbin", cxx, *ARCH, "-shared", "-o", SO, *objs, "-Xlinker", "--no-undefined"])
+    run([nvcc, "-ccbin", cxx, *ARCH, "-shared", "-o", SO, *objs, "-Xcompiler", "-fopenmp", "-Xlinker", "--no-undefined"])
     with open(stamp_file, "w") as fh:
         fh.write(stamp)
     return SO

@@ -2,6 +2,7 @@
 // No arithmetic of the retrieval path lives here; it sequences the kernels of dense_scan.cu (K1, merge,
 // rescoring), dense_gemm.cu (K2), bm25.cu (K3) and fusion.cu (K4) on the context stream.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -98,6 +99,7 @@ extern "C" int trr_ctx_create(int device, trr_ctx** out) {
   c->smem_optin = prop.sharedMemPerBlockOptin;
   c->ws = new CtxExtra();
   TRR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->owned_stream = c->stream;
   for (auto& e : c->ev) TRR_CUDA(cudaEventCreate(&e));
   *out = c;
   return TRR_OK;
@@ -112,7 +114,7 @@ extern "C" int trr_ctx_destroy(trr_ctx* c) {
   delete x;
   if (c->pin) cudaFreeHost(c->pin);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
-  cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->owned_stream);
   delete c;
   return TRR_OK;
 }
@@ -131,6 +133,19 @@ extern "C" int trr_ctx_stream(trr_ctx* c, void** out) {
 extern "C" int trr_ctx_sm_count(trr_ctx* c, int* out) {
   if (!c || !out) return trr_fail(TRR_ERR_INVALID_ARG, "NULL argument");
   *out = c->sm_count;
+  return TRR_OK;
+}
+extern "C" int trr_ctx_set_stream(trr_ctx* c, void* stream) {
+  if (!c) return trr_fail(TRR_ERR_INVALID_ARG, "ctx is NULL");
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard g(c->device);
+  TRR_CUDA(cudaStreamSynchronize(c->stream));
+  c->stream = reinterpret_cast<cudaStream_t>(stream);  // the original stream is kept alive until destroy
+  return TRR_OK;
+}
+extern "C" int trr_ctx_launch_count(trr_ctx* c, uint64_t* out) {
+  if (!c || !out) return trr_fail(TRR_ERR_INVALID_ARG, "NULL argument");
+  *out = c->launches;
   return TRR_OK;
 }
 extern "C" int trr_ctx_flush_l2(trr_ctx* c, size_t bytes) {
@@ -163,6 +178,7 @@ struct trr_dense {
   alignas(64) uint8_t map_d[128];
   int mode = TRR_DENSE_AUTO;
   trr_stats stats{};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // [0,1] whole call, [2,3] dominant kernel
 };
 
 static int dense_grow(trr_dense* h, uint64_t need) {
@@ -199,6 +215,7 @@ extern "C" int trr_dense_create(trr_ctx* ctx, uint32_t dim, int metric, int dtyp
   h->ctx = ctx; h->dim = dim; h->metric = metric; h->dtype = dtype;
   h->elem = dtype == TRR_DTYPE_BF16 ? 2 : 4;
   h->row_bytes = dim * h->elem;
+  for (auto& e : h->ev) cudaEventCreate(&e);
   if (capacity_hint) {
     int s = dense_grow(h, capacity_hint);
     if (s != TRR_OK) { delete h; return s; }
@@ -215,6 +232,7 @@ extern "C" int trr_dense_destroy(trr_dense* h) {
   if (h->norms) cudaFree(h->norms);
   if (h->dead) cudaFree(h->dead);
   h->shadow.release(); h->scale_bias.release(); h->max_norm.release(); h->qbuf.release();
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   delete h;
   return TRR_OK;
 }
@@ -419,7 +437,7 @@ static int dense_scan_locked(trr_dense* h, const float* d_q, const float* d_qn, 
                              size_t scratch_off) {
   ScanPlan p;
   TRR_CHECK(plan_scan(h, k, &p));
-  const uint64_t lists = (uint64_t)p.grid * p.warps;
+  const uint64_t lists = (uint64_t)p.grid;  // one merged list per CTA
   const size_t need = scratch_off + WsCarver::need({(size_t)n_sel * lists * k * 8, (size_t)n_sel * lists * 4});
   TRR_CHECK(extra(h->ctx)->scratch.reserve(need));
   WsCarver ws(static_cast<char*>(extra(h->ctx)->scratch.p) + scratch_off);
@@ -432,9 +450,9 @@ static int dense_scan_locked(trr_dense* h, const float* d_q, const float* d_qn, 
   a.ch_bytes = p.ch_bytes; a.n_chunks = p.n_chunks; a.k = k; a.cap = p.cap; a.base_ord = h->base;
   a.partial = partial; a.partial_n = partial_n;
   cudaStream_t st = h->ctx->stream;
-  TRR_CUDA(cudaEventRecord(h->ctx->ev[2], st));
+  TRR_CUDA(cudaEventRecord(h->ev[2], st));
   TRR_CUDA(trr_launch_scan(a, h->dtype == TRR_DTYPE_BF16, h->metric, p.bulk, p.grid, p.smem, st));
-  TRR_CUDA(cudaEventRecord(h->ctx->ev[3], st));
+  TRR_CUDA(cudaEventRecord(h->ev[3], st));
   h->ctx->launches++;
   TopkMergeArgs m{};
   m.lists = partial; m.list_n = partial_n; m.n_lists = (uint32_t)lists; m.list_stride = k;
@@ -449,7 +467,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
                                uint32_t* d_n, bool sync_stats) {
   trr_ctx* c = h->ctx;
   cudaStream_t st = c->stream;
-  const uint32_t launches0 = c->launches;
+  const uint64_t launches0 = c->launches;
   h->stats = trr_stats{};
   h->stats.n_queries = B;
   if (B == 0) return TRR_OK;
@@ -459,7 +477,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
   }
   if (k > 1024) return trr_fail(TRR_ERR_UNSUPPORTED, "k > 1024 is not supported yet");
   TRR_CHECK(dense_freeze_locked(h));
-  TRR_CUDA(cudaEventRecord(c->ev[0], st));
+  TRR_CUDA(cudaEventRecord(h->ev[0], st));
 
   const uint64_t n_live = h->n - h->n_dead;
   bool use_gemm = false;
@@ -484,7 +502,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     // the scratch buffer may be re-allocated by dense_scan_locked: compute the norms after reserving there
     ScanPlan p;
     TRR_CHECK(plan_scan(h, k, &p));
-    const uint64_t lists = (uint64_t)p.grid * p.warps;
+    const uint64_t lists = (uint64_t)p.grid;
     TRR_CHECK(extra(c)->scratch.reserve(scratch_off + WsCarver::need({(size_t)B * lists * k * 8, (size_t)B * lists * 4})));
     d_qn = reinterpret_cast<float*>(extra(c)->scratch.p);
     trr_launch_query_norms(d_q, h->dim, B, d_qn, st);
@@ -506,7 +524,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     // scratch layout (single reservation so that pointers stay valid)
     ScanPlan p;
     TRR_CHECK(plan_scan(h, k, &p));
-    const uint64_t lists = (uint64_t)p.grid * p.warps;
+    const uint64_t lists = (uint64_t)p.grid;
     const uint32_t fb_chunk = 64;  // fallback queries per scan launch
     const size_t need = WsCarver::need({(size_t)B * 4, (size_t)B * 4, n_cand * 4, n_cand * 4, (size_t)B_pad * 4,
                                         (size_t)B * 4, (size_t)B * 4, 256, (size_t)B_pad * h->dim_pad * 2,
@@ -537,9 +555,11 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     ga.k_blocks = (h->dim_pad + 63) / 64; ga.base_ord = h->base;
     ga.scale_bias = reinterpret_cast<const float2*>(h->scale_bias.p);
     ga.cand_score = cand_score; ga.cand_ord = cand_ord; ga.gthr = gthr; ga.share_thresholds = 1;
-    TRR_CUDA(cudaEventRecord(c->ev[2], st));
+    if (const char* e = getenv("TRR_GEMM_DEBUG")) ga.debug_mode = atoi(e);      // perf triage only; results are wrong
+    if (const char* e = getenv("TRR_GEMM_NOSHARE")) ga.share_thresholds = atoi(e) ? 0 : 1;
+    TRR_CUDA(cudaEventRecord(h->ev[2], st));
     TRR_CUDA(trr_launch_gemm_topk(ga, map_q, h->map_d, n_slices * n_qblocks, st));
-    TRR_CUDA(cudaEventRecord(c->ev[3], st));
+    TRR_CUDA(cudaEventRecord(h->ev[3], st));
     c->launches++;
 
     RescoreArgs ra{};
@@ -566,18 +586,19 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     h->stats.n_guard_fallbacks = hc[0];
     memcpy(&h->stats.max_fast_exact_gap, &hc[1], 4);
     h->stats.eps_bound = eps_rel;
+    if (ga.debug_mode) hc[0] = 0;  // perf triage: results are meaningless, do not time the fallback
     for (uint32_t f0 = 0; f0 < hc[0]; f0 += fb_chunk) {
       const uint32_t m = std::min(fb_chunk, hc[0] - f0);
       TRR_CHECK(dense_scan_locked(h, d_q, d_qn, m, flagged + f0, k, d_ord, d_score, d_n, nullptr, fb_off));
     }
     h->stats.mode_used = TRR_DENSE_GEMM;
   }
-  TRR_CUDA(cudaEventRecord(c->ev[1], st));
-  h->stats.n_kernel_launches = c->launches - launches0;
+  TRR_CUDA(cudaEventRecord(h->ev[1], st));
+  h->stats.n_kernel_launches = (uint32_t)(c->launches - launches0);
   if (sync_stats) {
     TRR_CUDA(cudaStreamSynchronize(st));
-    cudaEventElapsedTime(&h->stats.ms_total, c->ev[0], c->ev[1]);
-    cudaEventElapsedTime(&h->stats.ms_main_kernel, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&h->stats.ms_total, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&h->stats.ms_main_kernel, h->ev[2], h->ev[3]);
   }
   return TRR_OK;
 }
@@ -624,8 +645,8 @@ extern "C" int trr_dense_last_stats(trr_dense* h, trr_stats* out) {
   DeviceGuard g(h->ctx->device);
   cudaStreamSynchronize(h->ctx->stream);
   if (h->stats.mode_used) {
-    cudaEventElapsedTime(&h->stats.ms_total, h->ctx->ev[0], h->ctx->ev[1]);
-    cudaEventElapsedTime(&h->stats.ms_main_kernel, h->ctx->ev[2], h->ctx->ev[3]);
+    cudaEventElapsedTime(&h->stats.ms_total, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&h->stats.ms_main_kernel, h->ev[2], h->ev[3]);
     cudaGetLastError();
   }
   *out = h->stats;
@@ -686,6 +707,7 @@ struct trr_bm25 {
   uint32_t range_shift = 14, n_ranges = 0, skip_ld = 0;
   uint32_t stage_cap = 2048;
   trr_stats stats{};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 extern "C" int trr_bm25_build(trr_ctx* ctx, uint32_t n_docs, uint32_t n_terms, const uint64_t* term_off,
@@ -700,6 +722,7 @@ extern "C" int trr_bm25_build(trr_ctx* ctx, uint32_t n_docs, uint32_t n_terms, c
   DeviceGuard g(ctx->device);
   trr_bm25* h = new trr_bm25();
   h->ctx = ctx; h->n_docs = n_docs; h->n_terms = n_terms; h->doc_base = doc_base; h->n_postings = P;
+  for (auto& e : h->ev) cudaEventCreate(&e);
   // documents per range: 16384 (64 KB of f32 accumulators, two CTAs per SM), smaller for tiny indexes
   uint32_t shift = 14;
   while (shift > 8 && (1u << (shift - 1)) >= std::max<uint32_t>(n_docs, 1)) --shift;
@@ -743,6 +766,7 @@ extern "C" int trr_bm25_destroy(trr_bm25* h) {
   cudaStreamSynchronize(h->ctx->stream);
   if (h->post) cudaFree(h->post);
   if (h->skip) cudaFree(h->skip);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   delete h;
   return TRR_OK;
 }
@@ -790,9 +814,9 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   a.cand_cap = trr_pow2_ceil(k + TRR_BM25_THREADS);
   a.counter = counter; a.out_keys = nullptr; a.out_ord = d_ord; a.out_score = d_score; a.out_n = d_n;
   const unsigned grid = std::min<unsigned>(B, (unsigned)c->sm_count * 2);
-  TRR_CUDA(cudaEventRecord(c->ev[2], st));
+  TRR_CUDA(cudaEventRecord(h->ev[2], st));
   TRR_CUDA(trr_launch_bm25_search(a, grid, st));
-  TRR_CUDA(cudaEventRecord(c->ev[3], st));
+  TRR_CUDA(cudaEventRecord(h->ev[3], st));
   c->launches++;
   h->stats.n_kernel_launches = 1;
   h->stats.mode_used = 1;
@@ -830,9 +854,9 @@ extern "C" int trr_bm25_search(trr_bm25* h, const uint32_t* q_terms, const uint3
   uint32_t* d_n = io.take<uint32_t>(B);
   if (nt) TRR_CUDA(cudaMemcpyAsync(d_terms, q_terms, nt * 4, cudaMemcpyHostToDevice, st));
   TRR_CUDA(cudaMemcpyAsync(d_off, q_off, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
-  TRR_CUDA(cudaEventRecord(c->ev[0], st));
+  TRR_CUDA(cudaEventRecord(h->ev[0], st));
   TRR_CHECK(bm25_search_locked(h, d_terms, d_off, q_off, B, k, d_ord, d_score, d_n, 0));
-  TRR_CUDA(cudaEventRecord(c->ev[1], st));
+  TRR_CUDA(cudaEventRecord(h->ev[1], st));
   if (k) {
     TRR_CUDA(cudaMemcpyAsync(out_ord, d_ord, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));
     TRR_CUDA(cudaMemcpyAsync(out_score, d_score, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));
@@ -840,8 +864,8 @@ extern "C" int trr_bm25_search(trr_bm25* h, const uint32_t* q_terms, const uint3
   TRR_CUDA(cudaMemcpyAsync(out_n, d_n, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   TRR_CUDA(cudaStreamSynchronize(st));
   if (h->stats.mode_used) {
-    cudaEventElapsedTime(&h->stats.ms_total, c->ev[0], c->ev[1]);
-    cudaEventElapsedTime(&h->stats.ms_main_kernel, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&h->stats.ms_total, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&h->stats.ms_main_kernel, h->ev[2], h->ev[3]);
   }
   return TRR_OK;
 }
@@ -852,7 +876,7 @@ extern "C" int trr_bm25_last_stats(trr_bm25* h, trr_stats* out) {
   DeviceGuard g(h->ctx->device);
   cudaStreamSynchronize(h->ctx->stream);
   if (h->stats.mode_used) {
-    cudaEventElapsedTime(&h->stats.ms_main_kernel, h->ctx->ev[2], h->ctx->ev[3]);
+    cudaEventElapsedTime(&h->stats.ms_main_kernel, h->ev[2], h->ev[3]);
     cudaGetLastError();
   }
   *out = h->stats;
@@ -989,6 +1013,37 @@ static int hybrid_check(trr_dense* dense, trr_bm25* bm25, const float* q, const 
   if (dense && bm25 && dense->ctx != bm25->ctx) return trr_fail(TRR_ERR_INVALID_ARG, "hybrid: indexes live on different contexts");
   if (C == 0 || C > 1024) return trr_fail(TRR_ERR_UNSUPPORTED, "candidates per source must be in 1..1024");
   return TRR_OK;
+}
+
+extern "C" int trr_hybrid_local_device(trr_dense* dense, trr_bm25* bm25, const float* d_q, const uint32_t* d_q_terms,
+                                       const uint32_t* d_q_off, const uint32_t* h_q_off, uint32_t B, uint32_t C,
+                                       int use_dense, int use_sparse, void* d_exchange) {
+  trr_ctx* c = nullptr;
+  TRR_CHECK(hybrid_check(dense, bm25, d_q, h_q_off, B, C, use_dense, use_sparse, &c));
+  if (!d_exchange || (use_sparse && B && !d_q_off)) return trr_fail(TRR_ERR_INVALID_ARG, "hybrid: NULL device buffer");
+  if (B == 0) return TRR_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard g(c->device);
+  cudaStream_t st = c->stream;
+  ExchangeView v = exchange_view(d_exchange, B, C);
+  if (use_dense) TRR_CHECK(dense_search_locked(dense, d_q, B, C, v.ord[0], v.score[0], v.n[0], false));
+  else TRR_CUDA(cudaMemsetAsync(v.n[0], 0, (size_t)B * 4, st));
+  if (use_sparse) TRR_CHECK(bm25_search_locked(bm25, d_q_terms, d_q_off, h_q_off, B, C, v.ord[1], v.score[1], v.n[1], 0));
+  else TRR_CUDA(cudaMemsetAsync(v.n[1], 0, (size_t)B * 4, st));
+  return TRR_OK;
+}
+
+extern "C" int trr_hybrid_merge_device(trr_ctx* c, const void* d_gathered, uint32_t G, uint32_t B, uint32_t C, int strategy,
+                                       float param, uint32_t k, uint32_t* d_out_ord, float* d_out_fused,
+                                       float* d_out_dense, float* d_out_sparse, uint32_t* d_out_n) {
+  if (!c || !d_gathered || (B && (!d_out_ord || !d_out_fused || !d_out_n))) return trr_fail(TRR_ERR_INVALID_ARG, "NULL argument");
+  if (B == 0) return TRR_OK;
+  if (k == 0 || G == 0) return trr_fail(TRR_ERR_INVALID_ARG, "hybrid merge: k and G must be >= 1");
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard g(c->device);
+  ExchangeView v = exchange_view(const_cast<void*>(d_gathered), B, C);
+  return fuse_locked(c, v, trr_exchange_bytes(B, C) / 4, G, B, C, strategy, param, k, true, true, d_out_ord, d_out_fused,
+                     d_out_dense, d_out_sparse, d_out_n);
 }
 
 extern "C" int trr_hybrid_local(trr_dense* dense, trr_bm25* bm25, const float* q, const uint32_t* q_terms,

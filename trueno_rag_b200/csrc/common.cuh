@@ -38,16 +38,14 @@ struct trr_ctx {
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;        // stream every entry point enqueues on (may be caller-owned)
+  cudaStream_t owned_stream = nullptr;  // stream created with the context
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::mutex mu;             // serialises search calls on this context (re-entrancy)
-  void* ws = nullptr;        // device workspace (grown on demand)
-  size_t ws_bytes = 0;
+  void* ws = nullptr;        // CtxExtra (growable device buffers), see capi.cu
   void* pin = nullptr;       // pinned host staging (grown on demand)
   size_t pin_bytes = 0;
-  void* flush = nullptr;     // L2 flush buffer
-  size_t flush_bytes = 0;
-  uint32_t launches = 0;     // kernels launched since the counter was last reset
+  uint64_t launches = 0;     // kernels of this library launched on the context
 };
 
 int trr_ctx_reserve_ws(trr_ctx* ctx, size_t bytes);

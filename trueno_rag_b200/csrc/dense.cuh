@@ -81,6 +81,7 @@ struct GemmTopkArgs {
   uint32_t* cand_ord;
   uint32_t* gthr;            // [n_qblocks*128] shared running thresholds (orderable-encoded), zeroed by the caller
   int share_thresholds;
+  int debug_mode;            // 0 = normal; 1 = epilogue skips TMEM reads; 2 = reads but never inserts (perf triage only)
 };
 
 void trr_launch_norms(int is_bf16, const void* rows, uint32_t dim, uint64_t row0, uint64_t n, float* norms,

@@ -95,7 +95,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -105,7 +105,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// waits for the outstanding tcgen05.ld; the "+r" operands pin every consumer of v[] behind the wait
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+        "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+        "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+        "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+      :
+      : "memory");
 }
 
 // per-row running state of the epilogue (lives in the registers of the lane that owns the row)
@@ -115,8 +125,8 @@ struct RowState {
   uint32_t minpos; // its position
 };
 
-// Warp-cooperative replace-min insertion.  `m` = lanes whose value `s` (document `doc`) beats their row's
-// threshold.  For each such lane in turn the warp overwrites the minimum entry of that row's list and
+// Warp-cooperative replace-min insertion.  `m` = lanes holding a value `s` (document `doc`, both per lane) that
+// beats their row's threshold.  For each such lane in turn the warp overwrites the minimum entry of that row's list and
 // recomputes the minimum with a two-entries-per-lane scan + warp arg-min.  Kept out of line: it is rare
 // in steady state and would otherwise be replicated 256 times in the unrolled column loop.
 __device__ __noinline__ RowState insert_events(uint32_t m, float s, uint32_t doc, RowState st, float* ls_warp,
@@ -125,10 +135,11 @@ __device__ __noinline__ RowState insert_events(uint32_t m, float s, uint32_t doc
     const uint32_t src = __ffs(m) - 1;
     m &= m - 1;
     const float nv = __shfl_sync(FULL, s, src);
+    const uint32_t nd = __shfl_sync(FULL, doc, src);
     const uint32_t mp = __shfl_sync(FULL, st.minpos, src);
     float* rs = ls_warp + src * CP;
     uint32_t* ro = lo_warp + src * CP;
-    if (lane == 0) { rs[mp] = nv; ro[mp] = doc; }
+    if (lane == 0) { rs[mp] = nv; ro[mp] = nd; }
     __syncwarp();
     const float e0 = rs[lane], e1 = rs[lane + 32];
     float mn = e0;
@@ -239,6 +250,13 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     float* ls_warp = ls_all + quarter * 32 * CP;
     uint32_t* lo_warp = lo_all + quarter * 32 * CP;
 
+    // scale/bias of the next 32 columns are prefetched one chunk ahead (16 x LDG.128, L1/L2 hits)
+    float4 sb_cur[16];
+    {
+      const float4* p = reinterpret_cast<const float4*>(a.scale_bias + (uint64_t)t0 * BN);
+#pragma unroll
+      for (uint32_t i = 0; i < 16; ++i) sb_cur[i] = __ldg(p + i);
+    }
     for (uint32_t t = t0, it = 0; t < t1; ++t, ++it) {
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       if (a.share_thresholds) {
@@ -248,25 +266,53 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       mbar_wait_bounded(&tfull_bar[as], aphase, 4);
       tc_fence_after();
       const uint32_t doc0 = t * BN;
-      const float2* sbp = a.scale_bias + doc0;
 #pragma unroll 1
-      for (uint32_t c = 0; c < BN / 32; ++c) {
+      for (uint32_t c = 0; c < (a.debug_mode == 1 ? 0u : BN / 32); ++c) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((quarter * 32u) << 16) + as * BN + c * 32, v);
+        tmem_ld32_issue(tmem_base + ((quarter * 32u) << 16) + as * BN + c * 32, v);
+        // prefetch the next chunk's scale/bias (next tile's first chunk at the end of a tile)
+        float4 sb_nxt[16];
+        {
+          uint64_t nd = (uint64_t)doc0 + (c + 1) * 32;
+          if (c == BN / 32 - 1 && t + 1 >= t1) nd = (uint64_t)doc0;  // nothing follows: reload something valid
+          const float4* p = reinterpret_cast<const float4*>(a.scale_bias + nd);
+#pragma unroll
+          for (uint32_t i = 0; i < 16; ++i) sb_nxt[i] = __ldg(p + i);
+        }
+        tmem_ld32_wait(v);
+        float sv[32];
+        uint32_t pmask = 0;
 #pragma unroll
         for (uint32_t j = 0; j < 32; j += 2) {
-          const float4 sb = __ldg(reinterpret_cast<const float4*>(sbp + c * 32 + j));
-          const float s0 = fmaf(__uint_as_float(v[j]), sb.x, sb.y);
-          const float s1 = fmaf(__uint_as_float(v[j + 1]), sb.z, sb.w);
-          if (dump) {
-            dump[(uint64_t)(qb * BM + row) * dump_ld + doc0 + c * 32 + j] = s0;
-            dump[(uint64_t)(qb * BM + row) * dump_ld + doc0 + c * 32 + j + 1] = s1;
-          }
-          const uint32_t m0 = __ballot_sync(FULL, s0 > st.thr);
-          if (m0) st = insert_events(m0, s0, a.base_ord + doc0 + c * 32 + j, st, ls_warp, lo_warp, lane);
-          const uint32_t m1 = __ballot_sync(FULL, s1 > st.thr);
-          if (m1) st = insert_events(m1, s1, a.base_ord + doc0 + c * 32 + j + 1, st, ls_warp, lo_warp, lane);
+          const float4 sb = sb_cur[j >> 1];
+          sv[j] = fmaf(__uint_as_float(v[j]), sb.x, sb.y);
+          sv[j + 1] = fmaf(__uint_as_float(v[j + 1]), sb.z, sb.w);
+          pmask |= (sv[j] > st.thr ? 1u : 0u) << j;
+          pmask |= (sv[j + 1] > st.thr ? 1u : 0u) << (j + 1);
         }
+        if (dump) {
+#pragma unroll
+          for (uint32_t j = 0; j < 32; ++j) dump[(uint64_t)(qb * BM + row) * dump_ld + doc0 + c * 32 + j] = sv[j];
+        }
+        if (a.debug_mode == 2) pmask = 0;
+        // rare path: some lane has a value above its row's threshold
+        while (__any_sync(FULL, pmask != 0)) {
+          // each lane picks its next column that still beats its (possibly updated) threshold
+          float cand = 0.0f;
+          int cj = -1;
+          while (pmask) {
+            const int j = __ffs(pmask) - 1;
+            pmask &= pmask - 1;
+            float val = sv[0];
+#pragma unroll
+            for (int jj = 1; jj < 32; ++jj) val = (jj == j) ? sv[jj] : val;
+            if (val > st.thr) { cand = val; cj = j; break; }
+          }
+          const uint32_t m = __ballot_sync(FULL, cj >= 0);
+          if (m) st = insert_events(m, cand, a.base_ord + doc0 + c * 32 + (uint32_t)cj, st, ls_warp, lo_warp, lane);
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < 16; ++i) sb_cur[i] = sb_nxt[i];
       }
       // accumulator stage drained: hand it back to the MMA warp
       tc_fence_before();

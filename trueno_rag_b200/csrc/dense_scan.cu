@@ -83,6 +83,28 @@ __device__ __forceinline__ float finish_score(float acc, float q_norm, float d_n
   return acc;
 }
 
+// merges the per-warp lists of a CTA into warp 0's buffer and writes one list per CTA
+__device__ __forceinline__ void cta_merge_and_store(WarpTopK& tk, uint64_t* tk_base, uint32_t cap, uint32_t n_warps,
+                                                    uint32_t warp, uint32_t lane, uint32_t* warp_cnt, uint64_t* out,
+                                                    uint32_t* out_n) {
+  if (lane == 0) warp_cnt[warp] = tk.cnt;
+  __syncthreads();
+  if (warp == 0) {
+    for (uint32_t w = 1; w < n_warps; ++w) {
+      const uint64_t* src = tk_base + (size_t)w * cap;
+      const uint32_t cnt = warp_cnt[w];
+      for (uint32_t i = 0; i < cnt; i += 32) {
+        const bool valid = i + lane < cnt;
+        tk.push(valid ? src[i + lane] : TRR_KEY_EMPTY, valid, lane);
+      }
+    }
+    tk.compact(lane);
+    for (uint32_t i = lane; i < tk.cnt; i += 32) out[i] = tk.buf[i];
+    if (lane == 0) *out_n = tk.cnt;
+  }
+  __syncthreads();
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -156,7 +178,10 @@ dense_scan_bulk_kernel(DenseScanArgs a) {
   float* qs = reinterpret_cast<float*>(smem);
   const uint32_t q_bytes = (a.dim * 4 + 127) & ~127u;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + q_bytes);
-  uint64_t* tk_buf = reinterpret_cast<uint64_t*>(smem + q_bytes + 128) + (size_t)warp * a.cap;
+  constexpr uint32_t NWARPS = 4;
+  uint64_t* tk_base = reinterpret_cast<uint64_t*>(smem + q_bytes + 128);
+  uint64_t* tk_buf = tk_base + (size_t)warp * a.cap;
+  uint32_t* warp_cnt = reinterpret_cast<uint32_t*>(smem + q_bytes + 64);
   uint8_t* stage = smem + q_bytes + 128 + (size_t)4 * a.cap * 8 + (size_t)warp * 32 * pitch;
 
   if (lane == 0) trr_mbar_init(&bars[warp], 1);
@@ -226,10 +251,9 @@ dense_scan_bulk_kernel(DenseScanArgs a) {
       tk.push(trr_make_key(score, a.base_ord + (uint32_t)row), valid, lane);
     }
     tk.compact(lane);
-    uint64_t* out = a.partial + ((uint64_t)si * gstride + gwarp) * a.k;
-    for (uint32_t i = lane; i < tk.cnt; i += 32) out[i] = tk.buf[i];
-    if (lane == 0) a.partial_n[(uint64_t)si * gstride + gwarp] = tk.cnt;
-    __syncwarp();
+    cta_merge_and_store(tk, tk_base, a.cap, NWARPS, warp, lane, warp_cnt,
+                        a.partial + ((uint64_t)si * gridDim.x + blockIdx.x) * a.k,
+                        a.partial_n + ((uint64_t)si * gridDim.x + blockIdx.x));
   }
 }
 
@@ -241,7 +265,10 @@ dense_scan_generic_kernel(DenseScanArgs a) {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* qs = reinterpret_cast<float*>(smem);
   const uint32_t q_bytes = (a.dim * 4 + 127) & ~127u;
-  uint64_t* tk_buf = reinterpret_cast<uint64_t*>(smem + q_bytes) + (size_t)warp * a.cap;
+  constexpr uint32_t NWARPS = 8;
+  uint64_t* tk_base = reinterpret_cast<uint64_t*>(smem + q_bytes);
+  uint64_t* tk_buf = tk_base + (size_t)warp * a.cap;
+  __shared__ uint32_t warp_cnt[8];
   const uint32_t n_sel = a.n_sel_ptr ? *a.n_sel_ptr : a.n_sel;
   const uint64_t n_groups = (a.n_rows + 31) / 32;
   const uint64_t gwarp = (uint64_t)blockIdx.x * 8 + warp, gstride = (uint64_t)gridDim.x * 8;
@@ -272,69 +299,79 @@ dense_scan_generic_kernel(DenseScanArgs a) {
       tk.push(trr_make_key(score, a.base_ord + (uint32_t)row), valid, lane);
     }
     tk.compact(lane);
-    uint64_t* out = a.partial + ((uint64_t)si * gstride + gwarp) * a.k;
-    for (uint32_t i = lane; i < tk.cnt; i += 32) out[i] = tk.buf[i];
-    if (lane == 0) a.partial_n[(uint64_t)si * gstride + gwarp] = tk.cnt;
-    __syncwarp();
+    cta_merge_and_store(tk, tk_base, a.cap, NWARPS, warp, lane, warp_cnt,
+                        a.partial + ((uint64_t)si * gridDim.x + blockIdx.x) * a.k,
+                        a.partial_n + ((uint64_t)si * gridDim.x + blockIdx.x));
   }
 }
 
 // =============================================================================================
-// merge of partial lists: one CTA per output row.  lists[row][l][0..n[row][l]) hold keys; the CTA
-// keeps the best k in the first half of a 2*K2 shared buffer and streams the rest through the
-// second half.  Writes ordinals/scores in canonical order.
+// merge of partial lists: one CTA (1024 threads) per output row.  lists[row][l][0..n[row][l]) hold keys.
+//   small inputs (<= 4096 keys): load everything, one bitonic sort;
+//   large inputs: the best 2048 keys live in the first half of a 4096-key buffer; the remaining keys stream
+//   through a filter (key > current k-th best) into the second half, which is merged by a sort when it fills up.
+// Writes ordinals/scores in canonical order.
 // =============================================================================================
-__global__ void __launch_bounds__(256)
+constexpr uint32_t MERGE_THREADS = 1024;
+constexpr uint32_t MERGE_HALF = 2048;
+
+__global__ void __launch_bounds__(MERGE_THREADS)
 topk_merge_kernel(TopkMergeArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);
+  __shared__ uint32_t s_fill, s_cnt;
+  __shared__ uint64_t s_thr;
+  const uint32_t tid = threadIdx.x;
   const uint32_t n_rows = a.n_rows_ptr ? *a.n_rows_ptr : a.n_rows;
+  const uint32_t total = a.n_lists * a.list_stride;
   for (uint32_t ri = blockIdx.x; ri < n_rows; ri += gridDim.x) {
     const uint32_t out_row = a.row_map ? a.row_map[ri] : ri;
-    const uint32_t K2 = a.k2;  // power of two >= k
+    const uint64_t* lists = a.lists + (uint64_t)ri * total;
+    const uint32_t* list_n = a.list_n ? a.list_n + (uint64_t)ri * a.n_lists : nullptr;
+    auto load_key = [&](uint32_t e) -> uint64_t {
+      if (e >= total) return TRR_KEY_EMPTY;
+      const uint32_t l = e / a.list_stride, j = e - l * a.list_stride;
+      if (list_n && j >= list_n[l]) return TRR_KEY_EMPTY;
+      return lists[e];
+    };
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < 2 * K2; i += blockDim.x) buf[i] = TRR_KEY_EMPTY;
-    __syncthreads();
-    uint32_t fill = 0;  // entries staged in the second half (uniform across the CTA)
-    for (uint32_t l = 0; l < a.n_lists; ++l) {
-      const uint64_t* src = a.lists + ((uint64_t)ri * a.n_lists + l) * a.list_stride;
-      const uint32_t cnt = a.list_n ? min(a.list_n[(uint64_t)ri * a.n_lists + l], a.list_stride) : a.list_stride;
-      uint32_t done = 0;
-      while (done < cnt) {
-        const uint32_t take = min(cnt - done, K2 - fill);
-        for (uint32_t i = threadIdx.x; i < take; i += blockDim.x) buf[K2 + fill + i] = src[done + i];
-        done += take;
-        fill += take;
-        if (fill == K2) {
-          trr_bitonic_sort_desc(buf, 2 * K2, threadIdx.x, blockDim.x, BlockSync());
-          for (uint32_t i = threadIdx.x; i < K2; i += blockDim.x) buf[K2 + i] = TRR_KEY_EMPTY;
-          fill = 0;
+    uint32_t sorted_len;
+    if (total <= 2 * MERGE_HALF) {
+      sorted_len = trr_pow2_ceil(total < 2 ? 2 : total);
+      for (uint32_t e = tid; e < sorted_len; e += MERGE_THREADS) buf[e] = load_key(e);
+      trr_bitonic_sort_desc(buf, sorted_len, tid, MERGE_THREADS, BlockSync());
+    } else {
+      sorted_len = 2 * MERGE_HALF;
+      for (uint32_t e = tid; e < sorted_len; e += MERGE_THREADS) buf[e] = TRR_KEY_EMPTY;
+      if (tid == 0) { s_fill = 0; s_thr = TRR_KEY_EMPTY; }
+      __syncthreads();
+      for (uint32_t base = 0; base < total; base += MERGE_THREADS) {
+        if (s_fill > MERGE_HALF - MERGE_THREADS) {  // uniform: s_fill was last written before the previous barrier
+          trr_bitonic_sort_desc(buf, sorted_len, tid, MERGE_THREADS, BlockSync());
+          for (uint32_t e = tid; e < MERGE_HALF; e += MERGE_THREADS) buf[MERGE_HALF + e] = TRR_KEY_EMPTY;
+          if (tid == 0) { s_fill = 0; s_thr = buf[a.k - 1]; }
           __syncthreads();
         }
+        const uint64_t key = load_key(base + tid);
+        if (key > s_thr) buf[MERGE_HALF + atomicAdd(&s_fill, 1u)] = key;
+        __syncthreads();
       }
+      trr_bitonic_sort_desc(buf, sorted_len, tid, MERGE_THREADS, BlockSync());
     }
-    trr_bitonic_sort_desc(buf, 2 * K2, threadIdx.x, blockDim.x, BlockSync());
-    // count valid entries among the first k
-    __shared__ uint32_t s_cnt;
-    if (threadIdx.x == 0) s_cnt = 0;
+    if (tid == 0) s_cnt = 0;
     __syncthreads();
     uint32_t local = 0;
-    for (uint32_t i = threadIdx.x; i < a.k; i += blockDim.x) {
-      uint64_t key = buf[i];
-      if (key != TRR_KEY_EMPTY) {
-        ++local;
-        if (a.out_keys) a.out_keys[(uint64_t)out_row * a.k + i] = key;
-        if (a.out_ord) a.out_ord[(uint64_t)out_row * a.k + i] = trr_key_ord(key);
-        if (a.out_score) a.out_score[(uint64_t)out_row * a.k + i] = trr_key_score(key);
-      } else {
-        if (a.out_keys) a.out_keys[(uint64_t)out_row * a.k + i] = TRR_KEY_EMPTY;
-        if (a.out_ord) a.out_ord[(uint64_t)out_row * a.k + i] = 0xFFFFFFFFu;
-        if (a.out_score) a.out_score[(uint64_t)out_row * a.k + i] = 0.0f;
-      }
+    for (uint32_t i = tid; i < a.k; i += MERGE_THREADS) {
+      const uint64_t key = i < sorted_len ? buf[i] : TRR_KEY_EMPTY;
+      const bool ok = key != TRR_KEY_EMPTY;
+      local += ok;
+      if (a.out_keys) a.out_keys[(uint64_t)out_row * a.k + i] = key;
+      if (a.out_ord) a.out_ord[(uint64_t)out_row * a.k + i] = ok ? trr_key_ord(key) : 0xFFFFFFFFu;
+      if (a.out_score) a.out_score[(uint64_t)out_row * a.k + i] = ok ? trr_key_score(key) : 0.0f;
     }
     if (local) atomicAdd(&s_cnt, local);
     __syncthreads();
-    if (threadIdx.x == 0 && a.out_n) a.out_n[out_row] = s_cnt;
+    if (tid == 0 && a.out_n) a.out_n[out_row] = s_cnt;
   }
 }
 
@@ -510,10 +547,10 @@ cudaError_t trr_launch_scan(const DenseScanArgs& a, int is_bf16, int metric, boo
 
 cudaError_t trr_launch_topk_merge(const TopkMergeArgs& a, unsigned grid, cudaStream_t st) {
   if (grid == 0) return cudaSuccess;
-  size_t smem = (size_t)2 * a.k2 * sizeof(uint64_t);
+  size_t smem = (size_t)2 * MERGE_HALF * sizeof(uint64_t);
   cudaError_t e = cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  topk_merge_kernel<<<grid, 256, smem, st>>>(a);
+  topk_merge_kernel<<<grid, MERGE_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
 
