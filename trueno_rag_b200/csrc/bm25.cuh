@@ -28,7 +28,11 @@ struct Bm25SearchArgs {
   uint32_t B, k;
   uint32_t stage_cap;  // postings staged per batch
   uint32_t cand_cap;   // power of two >= k + TRR_BM25_THREADS
-  uint32_t* counter;   // dynamic query queue (zeroed by the caller)
+  uint32_t* counter;   // two dynamic work queues (fast kernel, general kernel), zeroed by the caller
+  const uint32_t* fast_list;  // queries served by the fast kernel (<= BM25_FAST_TMAX terms)
+  uint32_t n_fast;
+  uint32_t* slow_list; // queries for the general kernel: host-listed ones first, the fast kernel appends
+  uint32_t* n_slow;    // device count of slow_list
   uint64_t* out_keys;  // nullable [B][k]
   uint32_t* out_ord;   // nullable [B][k]
   float* out_score;    // nullable
@@ -36,5 +40,7 @@ struct Bm25SearchArgs {
 };
 
 cudaError_t trr_launch_bm25_build(const Bm25BuildArgs& a, cudaStream_t st);
-size_t trr_bm25_search_smem(const Bm25SearchArgs& a);
-cudaError_t trr_launch_bm25_search(const Bm25SearchArgs& a, unsigned grid, cudaStream_t st);
+constexpr uint32_t TRR_BM25_FAST_TMAX = 128;
+size_t trr_bm25_general_smem(const Bm25SearchArgs& a);
+size_t trr_bm25_fast_smem(const Bm25SearchArgs& a);
+cudaError_t trr_launch_bm25_search(const Bm25SearchArgs& a, unsigned grid_fast, unsigned grid_slow, cudaStream_t st);

@@ -2,6 +2,7 @@
 // No arithmetic of the retrieval path lives here; it sequences the kernels of dense_scan.cu (K1, merge,
 // rescoring), dense_gemm.cu (K2), bm25.cu (K3) and fusion.cu (K4) on the context stream.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -56,6 +57,8 @@ struct DevBuf {
 };
 
 struct CtxExtra {
+  uint32_t* dbg_host = nullptr;  // pinned + mapped: kernels record the site of a barrier timeout before trapping
+  uint32_t* dbg_dev = nullptr;
   DevBuf scratch;  // kernel-internal scratch of dense / bm25 searches
   DevBuf io;       // device copies of host inputs / outputs of the host-buffer entry points
   DevBuf hy;       // hybrid exchange record (single-GPU path)
@@ -98,6 +101,15 @@ extern "C" int trr_ctx_create(int device, trr_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   c->smem_optin = prop.sharedMemPerBlockOptin;
   c->ws = new CtxExtra();
+  {
+    CtxExtra* x = extra(c);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&x->dbg_host), 64, cudaHostAllocMapped) == cudaSuccess) {
+      memset(x->dbg_host, 0, 64);
+      cudaHostGetDevicePointer(reinterpret_cast<void**>(&x->dbg_dev), x->dbg_host, 0);
+    } else {
+      cudaGetLastError();
+    }
+  }
   TRR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->owned_stream = c->stream;
   for (auto& e : c->ev) TRR_CUDA(cudaEventCreate(&e));
@@ -111,6 +123,7 @@ extern "C" int trr_ctx_destroy(trr_ctx* c) {
   cudaStreamSynchronize(c->stream);
   CtxExtra* x = extra(c);
   x->scratch.release(); x->io.release(); x->hy.release(); x->flush.release();
+  if (x->dbg_host) cudaFreeHost(x->dbg_host);
   delete x;
   if (c->pin) cudaFreeHost(c->pin);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -175,7 +188,8 @@ struct trr_dense {
   DevBuf shadow, scale_bias, max_norm, qbuf;
   uint32_t dim_pad = 0;
   uint64_t n_tiles = 0;
-  alignas(64) uint8_t map_d[128];
+  alignas(64) uint8_t map_d[128];       // documents, 256-row box (1-CTA kernel)
+  alignas(64) uint8_t map_d_half[128];  // documents, 128-row box (2-CTA kernel: each CTA loads half a tile)
   int mode = TRR_DENSE_AUTO;
   trr_stats stats{};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // [0,1] whole call, [2,3] dominant kernel
@@ -385,6 +399,7 @@ static int dense_prepare_gemm(trr_dense* h) {
   h->ctx->launches++;
   TRR_CUDA(cudaGetLastError());
   TRR_CHECK(trr_make_tensor_map(h->map_d, operand, h->n, cols, TRR_GEMM_TILE_N));
+  TRR_CHECK(trr_make_tensor_map(h->map_d_half, operand, h->n, cols, TRR_GEMM_TILE_N / 2));
   h->gemm_ready = true;
   return TRR_OK;
 }
@@ -511,7 +526,11 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     h->stats.mode_used = TRR_DENSE_SCAN;
   } else {
     TRR_CHECK(dense_prepare_gemm(h));
-    const uint32_t n_qblocks = (B + TRR_GEMM_TILE_M - 1) / TRR_GEMM_TILE_M;
+    uint32_t n_qblocks = (B + TRR_GEMM_TILE_M - 1) / TRR_GEMM_TILE_M;
+    // 2-CTA kernel (cta_group::2) whenever there are at least two query blocks; TRR_GEMM_PAIR=0/1 overrides
+    int pair_mode = n_qblocks >= 2 ? 1 : 0;
+    if (const char* e = getenv("TRR_GEMM_PAIR")) pair_mode = atoi(e) ? 1 : 0;
+    if (pair_mode) n_qblocks = (n_qblocks + 1) & ~1u;
     if (n_qblocks > (uint32_t)c->sm_count)
       return trr_fail(TRR_ERR_UNSUPPORTED, "batch larger than 128 x SM count; split the batch");
     uint32_t n_slices = (uint32_t)c->sm_count / n_qblocks;
@@ -555,10 +574,12 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     ga.k_blocks = (h->dim_pad + 63) / 64; ga.base_ord = h->base;
     ga.scale_bias = reinterpret_cast<const float2*>(h->scale_bias.p);
     ga.cand_score = cand_score; ga.cand_ord = cand_ord; ga.gthr = gthr; ga.share_thresholds = 1;
+    ga.pair_mode = pair_mode;
+    ga.dbg = extra(c)->dbg_dev;
     if (const char* e = getenv("TRR_GEMM_DEBUG")) ga.debug_mode = atoi(e);      // perf triage only; results are wrong
     if (const char* e = getenv("TRR_GEMM_NOSHARE")) ga.share_thresholds = atoi(e) ? 0 : 1;
     TRR_CUDA(cudaEventRecord(h->ev[2], st));
-    TRR_CUDA(trr_launch_gemm_topk(ga, map_q, h->map_d, n_slices * n_qblocks, st));
+    TRR_CUDA(trr_launch_gemm_topk(ga, map_q, pair_mode ? h->map_d_half : h->map_d, n_slices * n_qblocks, st));
     TRR_CUDA(cudaEventRecord(h->ev[3], st));
     c->launches++;
 
@@ -582,7 +603,14 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     // the candidate proof can fail (near-ties, adversarial data): those queries take the exact scan
     uint32_t hc[2] = {0, 0};
     TRR_CUDA(cudaMemcpyAsync(hc, counters, 8, cudaMemcpyDeviceToHost, st));
-    TRR_CUDA(cudaStreamSynchronize(st));
+    {
+      cudaError_t se = cudaStreamSynchronize(st);
+      if (se != cudaSuccess) {
+        const uint32_t w = extra(c)->dbg_host ? extra(c)->dbg_host[0] : 0;
+        return trr_fail(TRR_ERR_CUDA, std::string("GEMM path failed: ") + cudaGetErrorString(se) +
+                                          " (barrier-timeout word 0x" + [](uint32_t v) { char b[16]; snprintf(b, 16, "%x", v); return std::string(b); }(w) + ")");
+      }
+    }
     h->stats.n_guard_fallbacks = hc[0];
     memcpy(&h->stats.max_fast_exact_gap, &hc[1], 4);
     h->stats.eps_bound = eps_rel;
@@ -662,7 +690,11 @@ extern "C" TRR_API int trr_debug_gemm_scores(trr_dense* h, const float* q, uint3
   cudaStream_t st = c->stream;
   TRR_CHECK(dense_freeze_locked(h));
   TRR_CHECK(dense_prepare_gemm(h));
-  const uint32_t n_qblocks = (B + 127) / 128, B_pad = n_qblocks * 128;
+  uint32_t n_qblocks = (B + 127) / 128;
+  int pair_mode = 0;
+  if (const char* e = getenv("TRR_GEMM_PAIR")) pair_mode = atoi(e) ? 1 : 0;
+  if (pair_mode) n_qblocks = (n_qblocks + 1) & ~1u;
+  const uint32_t B_pad = n_qblocks * 128;
   const uint64_t n_pad = h->n_tiles * TRR_GEMM_TILE_N;
   if (out_ld < n_pad) return trr_fail(TRR_ERR_INVALID_ARG, "out_ld must be >= padded document count");
   uint32_t n_slices = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)c->sm_count / n_qblocks, (uint32_t)h->n_tiles));
@@ -689,7 +721,10 @@ extern "C" TRR_API int trr_debug_gemm_scores(trr_dense* h, const float* q, uint3
   ga.k_blocks = (h->dim_pad + 63) / 64; ga.base_ord = h->base;
   ga.scale_bias = reinterpret_cast<const float2*>(h->scale_bias.p);
   ga.cand_score = cand_score; ga.cand_ord = cand_ord; ga.gthr = gthr; ga.share_thresholds = 0;
-  TRR_CUDA(trr_launch_gemm_topk_dump(ga, map_q, h->map_d, n_slices * n_qblocks, dump, out_ld, st));
+  ga.pair_mode = pair_mode;
+  ga.dbg = extra(c)->dbg_dev;
+  TRR_CUDA(trr_launch_gemm_topk_dump(ga, map_q, pair_mode ? h->map_d_half : h->map_d, n_slices * n_qblocks, dump, out_ld,
+                                     st));
   TRR_CUDA(cudaMemcpyAsync(out, dump, (size_t)B * out_ld * 4, cudaMemcpyDeviceToHost, st));
   TRR_CUDA(cudaStreamSynchronize(st));
   return TRR_OK;
@@ -803,22 +838,35 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   for (uint32_t b = 0; b < B; ++b)
     if (h_q_off[b + 1] - h_q_off[b] > (uint32_t)TRR_BM25_THREADS)
       return trr_fail(TRR_ERR_UNSUPPORTED, "more than 512 terms in one query");
-  TRR_CHECK(extra(c)->scratch.reserve(scratch_off + 512));
-  uint32_t* counter = reinterpret_cast<uint32_t*>(static_cast<char*>(extra(c)->scratch.p) + scratch_off);
-  TRR_CUDA(cudaMemsetAsync(counter, 0, 4, st));
+  // work lists: queries with <= 128 terms go to the fast kernel; longer ones (and the ones it gives up on) to the
+  // general kernel.  Layout in scratch: [counters: queue0, queue1, n_slow, pad] [fast_list B] [slow_list B]
+  std::vector<uint32_t> lists((size_t)2 * B + 4, 0);
+  uint32_t n_fast = 0, n_slow = 0;
+  for (uint32_t b = 0; b < B; ++b) {
+    if (h_q_off[b + 1] - h_q_off[b] <= TRR_BM25_FAST_TMAX) lists[4 + n_fast++] = b;
+    else lists[4 + (size_t)B + n_slow++] = b;
+  }
+  lists[2] = n_slow;
+  TRR_CHECK(extra(c)->scratch.reserve(scratch_off + lists.size() * 4 + 256));
+  uint32_t* d_lists = reinterpret_cast<uint32_t*>(static_cast<char*>(extra(c)->scratch.p) + scratch_off);
+  TRR_CUDA(cudaMemcpyAsync(d_lists, lists.data(), lists.size() * 4, cudaMemcpyHostToDevice, st));
+  TRR_CUDA(cudaStreamSynchronize(st));  // `lists` is pageable host memory that dies with this frame
   Bm25SearchArgs a{};
   a.post = h->post; a.skip = h->skip; a.skip_ld = h->skip_ld; a.n_terms = h->n_terms; a.n_docs = h->n_docs;
   a.n_ranges = h->n_ranges; a.range_shift = h->range_shift; a.doc_base = h->doc_base;
   a.q_terms = d_q_terms; a.q_off = d_q_off; a.B = B; a.k = k;
   a.stage_cap = h->stage_cap;
   a.cand_cap = trr_pow2_ceil(k + TRR_BM25_THREADS);
-  a.counter = counter; a.out_keys = nullptr; a.out_ord = d_ord; a.out_score = d_score; a.out_n = d_n;
-  const unsigned grid = std::min<unsigned>(B, (unsigned)c->sm_count * 2);
+  a.counter = d_lists; a.n_slow = d_lists + 2; a.fast_list = d_lists + 4; a.n_fast = n_fast;
+  a.slow_list = d_lists + 4 + B;
+  a.out_keys = nullptr; a.out_ord = d_ord; a.out_score = d_score; a.out_n = d_n;
+  const unsigned grid_fast = std::min<unsigned>(n_fast, (unsigned)c->sm_count * 2);
+  const unsigned grid_slow = std::min<unsigned>(B, (unsigned)c->sm_count * 2);
   TRR_CUDA(cudaEventRecord(h->ev[2], st));
-  TRR_CUDA(trr_launch_bm25_search(a, grid, st));
+  TRR_CUDA(trr_launch_bm25_search(a, grid_fast, grid_slow, st));
   TRR_CUDA(cudaEventRecord(h->ev[3], st));
-  c->launches++;
-  h->stats.n_kernel_launches = 1;
+  c->launches += (grid_fast ? 1 : 0) + 1;
+  h->stats.n_kernel_launches = 2;
   h->stats.mode_used = 1;
   return TRR_OK;
 }

@@ -81,6 +81,8 @@ struct GemmTopkArgs {
   uint32_t* cand_ord;
   uint32_t* gthr;            // [n_qblocks*128] shared running thresholds (orderable-encoded), zeroed by the caller
   int share_thresholds;
+  uint32_t* dbg;             // nullable host-mapped word: site of a barrier timeout
+  int pair_mode;             // 1 = 2-CTA kernel (cta_group::2); needs an even n_qblocks
   int debug_mode;            // 0 = normal; 1 = epilogue skips TMEM reads; 2 = reads but never inserts (perf triage only)
 };
 

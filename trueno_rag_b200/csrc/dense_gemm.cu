@@ -51,15 +51,16 @@ constexpr uint32_t GEMM_THREADS = 192;
 // (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
 
-__device__ unsigned int g_gemm_timeout_flag = 0;
+__device__ uint32_t* g_gemm_dbg = nullptr;
 
-// bounded mbarrier wait: a protocol bug must surface as an error, never as a hung GPU
-__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity, int site) {
+// bounded mbarrier wait: a protocol bug must surface as an error, never as a hung GPU.  The site of the timeout
+// (and the CTA) is written to a host-mapped word before trapping so that the host can report it.
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity, int site, uint32_t* dbg = nullptr) {
   if (trr_mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!trr_mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      atomicExch(&g_gemm_timeout_flag, 0x100u + (unsigned)site);
+    if (clock64() - t0 > 2000000000LL) {
+      if (dbg) { *dbg = 0x80000000u | ((uint32_t)site << 16) | (blockIdx.x & 0xFFFFu); __threadfence_system(); }
       __trap();
     }
   }
@@ -199,7 +200,7 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       uint32_t stage = 0, phase = 0;
       for (uint32_t t = t0; t < t1; ++t) {
         for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
-          mbar_wait_bounded(&empty_bar[stage], phase ^ 1, 1);
+          mbar_wait_bounded(&empty_bar[stage], phase ^ 1, 1, a.dbg);
           trr_mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
           tma_load_2d(&map_q, smem + SMEM_A + stage * A_BYTES, &full_bar[stage], (int32_t)(kb * BK), (int32_t)(qb * BM));
           tma_load_2d(&map_d, smem + SMEM_B + stage * B_BYTES, &full_bar[stage], (int32_t)(kb * BK), (int32_t)(t * BN));
@@ -212,10 +213,10 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     uint32_t stage = 0, phase = 0;
     for (uint32_t t = t0, it = 0; t < t1; ++t, ++it) {
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-      mbar_wait_bounded(&tempty_bar[as], aphase ^ 1, 2);
+      mbar_wait_bounded(&tempty_bar[as], aphase ^ 1, 2, a.dbg);
       tc_fence_after();
       for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
-        mbar_wait_bounded(&full_bar[stage], phase, 3);
+        mbar_wait_bounded(&full_bar[stage], phase, 3, a.dbg);
         tc_fence_after();
         if (lane == 0) {
           const uint64_t da = make_smem_desc(trr_smem_u32(smem + SMEM_A + stage * A_BYTES));
@@ -263,7 +264,7 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const uint32_t g = *reinterpret_cast<volatile uint32_t*>(gthr);
         if (g > trr_f32_orderable(st.thr)) st.thr = trr_orderable_f32(g);
       }
-      mbar_wait_bounded(&tfull_bar[as], aphase, 4);
+      mbar_wait_bounded(&tfull_bar[as], aphase, 4, a.dbg);
       tc_fence_after();
       const uint32_t doc0 = t * BN;
 #pragma unroll 1
@@ -329,6 +330,245 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// =============================================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs (two SMs of one TPC) computes a 256-query x 256-document
+// tile.  Each CTA owns 128 query rows (its own A operand and its own 128 x 256 f32 accumulator in its TMEM) and
+// loads HALF of the document tile (128 rows of B); the tensor cores of both SMs read both halves.  Compared with the
+// 1-CTA kernel this cuts the L2 -> shared-memory operand traffic per CTA from 48 KB to 32 KB per k-block and leaves
+// room for a 5-stage ring.  Protocol (barriers at identical shared-memory offsets in both CTAs):
+//   full[s]    lives in the leader CTA: 2 arrivals (one per producer) + 64 KB of TMA transaction bytes;
+//   empty[s]   per CTA, released by the leader's tcgen05.commit multicast to both CTAs;
+//   tfull[a]   per CTA, same multicast commit after the last k-block of a tile;
+//   tempty[a]  lives in the leader: 256 arrivals (the epilogue threads of both CTAs).
+// =============================================================================================
+namespace {
+constexpr uint32_t STAGES2 = 5;
+constexpr uint32_t B2_BYTES = (BN / 2) * BK * 2;  // 16 KB: this CTA's half of the document tile
+constexpr uint32_t STAGE2_BYTES = A_BYTES + B2_BYTES;
+constexpr uint32_t SMEM2_A = 0;
+constexpr uint32_t SMEM2_B = SMEM2_A + STAGES2 * A_BYTES;
+constexpr uint32_t SMEM2_LS = SMEM2_B + STAGES2 * B2_BYTES;
+constexpr uint32_t SMEM2_LO = SMEM2_LS + LIST_BYTES;
+constexpr uint32_t SMEM2_BAR = SMEM2_LO + LIST_BYTES;
+constexpr uint32_t SMEM2_TOTAL = SMEM2_BAR + 256;
+constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((256u >> 4) << 24);  // M = 256
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory object in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const void* map, void* smem_dst, uint32_t bar_cluster_addr, int32_t c0,
+                                                 int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(trr_smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(0x1000000000000000ull)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(trr_smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+}  // namespace
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+dense_gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d,
+                            GemmTopkArgs a, float* __restrict__ dump, uint32_t dump_ld) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM2_BAR);
+  uint64_t* empty_bar = full_bar + STAGES2;
+  uint64_t* tfull_bar = empty_bar + STAGES2;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
+  const uint32_t qb = blockIdx.x % a.n_qblocks;     // n_qblocks is even; the pair owns query blocks (qb & ~1, qb | 1)
+  const uint32_t slice = blockIdx.x / a.n_qblocks;
+  const uint32_t t0 = (uint32_t)(((uint64_t)slice * a.n_tiles) / a.n_slices);
+  const uint32_t t1 = (uint32_t)(((uint64_t)(slice + 1) * a.n_tiles) / a.n_slices);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_d) : "memory");
+    for (uint32_t s = 0; s < STAGES2; ++s) { trr_mbar_init(&full_bar[s], 2); trr_mbar_init(&empty_bar[s], 1); }
+    for (uint32_t s = 0; s < 2; ++s) { trr_mbar_init(&tfull_bar[s], 1); trr_mbar_init(&tempty_bar[s], 256); }
+    trr_fence_mbar_init();
+  }
+  cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / TMA / commit
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(trr_smem_u32(tmem_ptr_smem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t t = t0; t < t1; ++t) {
+        for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
+          mbar_wait_bounded(&empty_bar[stage], phase ^ 1, 11, a.dbg);
+          const uint32_t leader_full = mapa_u32(trr_smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) trr_mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
+          else mbar_arrive_cluster(leader_full);
+          tma_load_2d_pair(&map_q, smem + SMEM2_A + stage * A_BYTES, leader_full, (int32_t)(kb * BK), (int32_t)(qb * BM));
+          tma_load_2d_pair(&map_d, smem + SMEM2_B + stage * B2_BYTES, leader_full, (int32_t)(kb * BK),
+                           (int32_t)(t * BN + rank * (BN / 2)));
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t t = t0, it = 0; t < t1; ++t, ++it) {
+        const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+        mbar_wait_bounded(&tempty_bar[as], aphase ^ 1, 12, a.dbg);
+        tc_fence_after();
+        for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
+          mbar_wait_bounded(&full_bar[stage], phase, 13, a.dbg);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint64_t da = make_smem_desc(trr_smem_u32(smem + SMEM2_A + stage * A_BYTES));
+            const uint64_t db = make_smem_desc(trr_smem_u32(smem + SMEM2_B + stage * B2_BYTES));
+#pragma unroll
+            for (uint32_t k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16_pair(tmem_base + as * BN, da + 2 * k, db + 2 * k, IDESC2, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage]);
+            if (kb == a.k_blocks - 1) umma_commit_pair(&tfull_bar[as]);
+          }
+          __syncwarp();
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs; identical to the 1-CTA kernel except for the tempty arrive) =====
+    const uint32_t quarter = warp & 3;
+    const uint32_t row = quarter * 32 + lane;
+    float* ls_all = reinterpret_cast<float*>(smem + SMEM2_LS);
+    uint32_t* lo_all = reinterpret_cast<uint32_t*>(smem + SMEM2_LO);
+    float* my_ls = ls_all + row * CP;
+    uint32_t* my_lo = lo_all + row * CP;
+    for (uint32_t j = 0; j < CP; ++j) { my_ls[j] = -CUDART_INF_F; my_lo[j] = 0xFFFFFFFFu; }
+    __syncwarp();
+    RowState st;
+    st.list_min = -CUDART_INF_F;
+    st.minpos = 0;
+    st.thr = -CUDART_INF_F;
+    uint32_t* gthr = a.gthr + (qb * BM + row);
+    float* ls_warp = ls_all + quarter * 32 * CP;
+    uint32_t* lo_warp = lo_all + quarter * 32 * CP;
+    const uint32_t leader_tempty[2] = {mapa_u32(trr_smem_u32(&tempty_bar[0]), 0), mapa_u32(trr_smem_u32(&tempty_bar[1]), 0)};
+
+    float4 sb_cur[16];
+    {
+      const float4* p = reinterpret_cast<const float4*>(a.scale_bias + (uint64_t)t0 * BN);
+#pragma unroll
+      for (uint32_t i = 0; i < 16; ++i) sb_cur[i] = __ldg(p + i);
+    }
+    for (uint32_t t = t0, it = 0; t < t1; ++t, ++it) {
+      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      if (a.share_thresholds) {
+        const uint32_t g = *reinterpret_cast<volatile uint32_t*>(gthr);
+        if (g > trr_f32_orderable(st.thr)) st.thr = trr_orderable_f32(g);
+      }
+      mbar_wait_bounded(&tfull_bar[as], aphase, 14, a.dbg);
+      tc_fence_after();
+      const uint32_t doc0 = t * BN;
+#pragma unroll 1
+      for (uint32_t c = 0; c < (a.debug_mode == 1 ? 0u : BN / 32); ++c) {
+        uint32_t v[32];
+        tmem_ld32_issue(tmem_base + ((quarter * 32u) << 16) + as * BN + c * 32, v);
+        float4 sb_nxt[16];
+        {
+          uint64_t nd = (uint64_t)doc0 + (c + 1) * 32;
+          if (c == BN / 32 - 1 && t + 1 >= t1) nd = (uint64_t)doc0;
+          const float4* p = reinterpret_cast<const float4*>(a.scale_bias + nd);
+#pragma unroll
+          for (uint32_t i = 0; i < 16; ++i) sb_nxt[i] = __ldg(p + i);
+        }
+        tmem_ld32_wait(v);
+        float sv[32];
+        uint32_t pmask = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 32; j += 2) {
+          const float4 sb = sb_cur[j >> 1];
+          sv[j] = fmaf(__uint_as_float(v[j]), sb.x, sb.y);
+          sv[j + 1] = fmaf(__uint_as_float(v[j + 1]), sb.z, sb.w);
+          pmask |= (sv[j] > st.thr ? 1u : 0u) << j;
+          pmask |= (sv[j + 1] > st.thr ? 1u : 0u) << (j + 1);
+        }
+        if (dump) {
+#pragma unroll
+          for (uint32_t j = 0; j < 32; ++j) dump[(uint64_t)(qb * BM + row) * dump_ld + doc0 + c * 32 + j] = sv[j];
+        }
+        if (a.debug_mode == 2) pmask = 0;
+        while (__any_sync(FULL, pmask != 0)) {
+          float cand = 0.0f;
+          int cj = -1;
+          while (pmask) {
+            const int j = __ffs(pmask) - 1;
+            pmask &= pmask - 1;
+            float val = sv[0];
+#pragma unroll
+            for (int jj = 1; jj < 32; ++jj) val = (jj == j) ? sv[jj] : val;
+            if (val > st.thr) { cand = val; cj = j; break; }
+          }
+          const uint32_t m = __ballot_sync(FULL, cj >= 0);
+          if (m) st = insert_events(m, cand, a.base_ord + doc0 + c * 32 + (uint32_t)cj, st, ls_warp, lo_warp, lane);
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < 16; ++i) sb_cur[i] = sb_nxt[i];
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(leader_tempty[as]);
+      if (a.share_thresholds && st.list_min > -CUDART_INF_F) atomicMax(gthr, trr_f32_orderable(st.list_min));
+    }
+    const uint64_t base = (((uint64_t)slice * a.n_qblocks + qb) * BM + row) * CP;
+    for (uint32_t j = 0; j < CP; ++j) { a.cand_score[base + j] = my_ls[j]; a.cand_ord[base + j] = my_lo[j]; }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still signal this CTA's barriers
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -424,28 +664,30 @@ int trr_make_tensor_map(void* out_map128, const void* base, uint64_t rows, uint6
   return TRR_OK;
 }
 
+cudaError_t trr_launch_gemm_topk_dump(const GemmTopkArgs& a, const void* map_q128, const void* map_d128, unsigned grid,
+                                      float* dump, uint32_t dump_ld, cudaStream_t st);
 cudaError_t trr_launch_gemm_topk(const GemmTopkArgs& a, const void* map_q128, const void* map_d128, unsigned grid,
                                  cudaStream_t st) {
-  if (grid == 0) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(dense_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)SMEM_TOTAL);
-  if (e != cudaSuccess) return e;
-  CUtensorMap mq, md;
-  memcpy(&mq, map_q128, 128);
-  memcpy(&md, map_d128, 128);
-  dense_gemm_topk_kernel<<<grid, GEMM_THREADS, SMEM_TOTAL, st>>>(mq, md, a, nullptr, 0);
-  return cudaGetLastError();
+  return trr_launch_gemm_topk_dump(a, map_q128, map_d128, grid, nullptr, 0, st);
 }
 
 // debug: additionally dumps every fast score to dump[(q) * dump_ld + doc] (small problems only)
 cudaError_t trr_launch_gemm_topk_dump(const GemmTopkArgs& a, const void* map_q128, const void* map_d128, unsigned grid,
                                       float* dump, uint32_t dump_ld, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(dense_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)SMEM_TOTAL);
-  if (e != cudaSuccess) return e;
+  if (grid == 0) return cudaSuccess;
   CUtensorMap mq, md;
   memcpy(&mq, map_q128, 128);
   memcpy(&md, map_d128, 128);
-  dense_gemm_topk_kernel<<<grid, GEMM_THREADS, SMEM_TOTAL, st>>>(mq, md, a, dump, dump_ld);
+  if (a.pair_mode) {  // grid and a.n_qblocks are even: consecutive CTAs form the 2-CTA clusters
+    cudaError_t e = cudaFuncSetAttribute(dense_gemm_topk_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)SMEM2_TOTAL);
+    if (e != cudaSuccess) return e;
+    dense_gemm_topk_pair_kernel<<<grid, GEMM_THREADS, SMEM2_TOTAL, st>>>(mq, md, a, dump, dump_ld);
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(dense_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)SMEM_TOTAL);
+    if (e != cudaSuccess) return e;
+    dense_gemm_topk_kernel<<<grid, GEMM_THREADS, SMEM_TOTAL, st>>>(mq, md, a, dump, dump_ld);
+  }
   return cudaGetLastError();
 }

@@ -345,16 +345,19 @@ topk_merge_kernel(TopkMergeArgs a) {
       for (uint32_t e = tid; e < sorted_len; e += MERGE_THREADS) buf[e] = TRR_KEY_EMPTY;
       if (tid == 0) { s_fill = 0; s_thr = TRR_KEY_EMPTY; }
       __syncthreads();
+      uint32_t fill = 0;  // register copy of s_fill, uniform across the CTA (advanced by __syncthreads_count)
       for (uint32_t base = 0; base < total; base += MERGE_THREADS) {
-        if (s_fill > MERGE_HALF - MERGE_THREADS) {  // uniform: s_fill was last written before the previous barrier
+        if (fill > MERGE_HALF - MERGE_THREADS) {
           trr_bitonic_sort_desc(buf, sorted_len, tid, MERGE_THREADS, BlockSync());
           for (uint32_t e = tid; e < MERGE_HALF; e += MERGE_THREADS) buf[MERGE_HALF + e] = TRR_KEY_EMPTY;
           if (tid == 0) { s_fill = 0; s_thr = buf[a.k - 1]; }
+          fill = 0;
           __syncthreads();
         }
         const uint64_t key = load_key(base + tid);
-        if (key > s_thr) buf[MERGE_HALF + atomicAdd(&s_fill, 1u)] = key;
-        __syncthreads();
+        int pushed = 0;
+        if (key > s_thr) { buf[MERGE_HALF + atomicAdd(&s_fill, 1u)] = key; pushed = 1; }
+        fill += (uint32_t)__syncthreads_count(pushed);
       }
       trr_bitonic_sort_desc(buf, sorted_len, tid, MERGE_THREADS, BlockSync());
     }
