@@ -11,13 +11,22 @@
 //   skip[t][r] = index of the first posting of term t whose doc id is >= r * R (R = documents per range),
 //              r = 0..n_ranges, so the postings of term t inside range r are [skip[t][r], skip[t][r+1]).
 //
-// Search: one CTA per query (dynamic queue).  The CTA walks the document ranges in order; per range it
-// stages the postings of all query terms into shared memory, then accumulates them term by term IN QUERY
-// ORDER into an R-entry f32 accumulator in shared memory (a document occurs at most once per term, so
-// plain read-modify-write without atomics is race-free inside a term; a barrier separates terms, which
-// makes the sum order deterministic and equal to the reference's).  Touched documents are then harvested
-// with an exchange-with-zero (which also re-zeroes the accumulator), filtered by the query's running k-th
-// best key and appended to a candidate buffer that is compacted by a block-wide bitonic sort.
+// Search (bm25_search_kernel): persistent CTAs, one per SM, fed from a dynamic queue of work items
+// (query, chunk of document ranges) ordered by decreasing posting volume (bm25_plan_kernel).
+//   producer warp   walks the ranges of the item; per range it turns the skip-table entries of the query terms
+//                   into one "pass": one cp.async.bulk (TMA 1-D) per term segment into a 2-stage shared-memory
+//                   ring, completion on an mbarrier, plus a small descriptor (segment bounds inside the stage).
+//   16 consumer warps  each owns a 1/16 sub-range of the R-document f32 accumulator in shared memory.  A warp
+//                   binary-searches every staged segment (sorted by document) for its sub-range and accumulates
+//                   the terms IN QUERY ORDER with plain read-modify-write: a document occurs once per term and
+//                   belongs to exactly one warp, so there are no atomics and no block barriers between terms,
+//                   and the f32 sum order equals the reference's.
+//   harvest         after the last pass of a range each warp scans its accumulators (128-bit loads), keeps the
+//                   documents whose (score, ordinal) key beats the query's running k-th best, and re-zeroes
+//                   them.  Candidates go to a CTA-wide buffer that is compacted by a bitonic sort (named barrier
+//                   over the consumer warps, once per range).
+#include <math_constants.h>
+
 #include "common.cuh"
 #include "bm25.cuh"
 
@@ -68,431 +77,326 @@ __global__ void bm25_skip_empty_kernel(Bm25BuildArgs a) {
 }
 
 // =============================================================================================
-// search
+// planning: posting volume per query -> processing order (largest first), queue reset
 // =============================================================================================
-template <int NT>
-__global__ void __launch_bounds__(NT, 2)
-bm25_search_kernel(Bm25SearchArgs a) {
+__global__ void __launch_bounds__(1024, 1)
+bm25_plan_kernel(Bm25SearchArgs a, uint32_t cap2) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const uint32_t R = 1u << a.range_shift;
-  float* acc = reinterpret_cast<float*>(smem_raw);                              // R
-  uint2* st = reinterpret_cast<uint2*>(acc + R);                                // stage_cap
-  uint64_t* cand = reinterpret_cast<uint64_t*>(st + a.stage_cap);               // cand_cap
-  uint32_t* seg_s = reinterpret_cast<uint32_t*>(cand + a.cand_cap);             // NT
-  uint32_t* seg_l = seg_s + NT;                                                 // NT
-  __shared__ uint32_t s_q, s_cnt;
-  __shared__ uint64_t s_thr;
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);  // cap2 = power of two >= B (0: identity order)
   const uint32_t tid = threadIdx.x;
-
-  for (uint32_t i = tid; i < R; i += NT) acc[i] = 0.0f;
-  __syncthreads();
-
-  // compaction of the candidate buffer (block-wide); afterwards cand[0..cnt) is sorted descending
-  // Every thread carries the candidate count in a register (`n_cand`, uniform across the CTA): it is advanced by
-  // __syncthreads_count at the end of each harvest round, so the decision to compact never races with the pushes
-  // of the round in flight.
-  auto compact = [&](uint32_t cnt) -> uint32_t {
-    __syncthreads();
-    for (uint32_t i = cnt + tid; i < a.cand_cap; i += NT) cand[i] = TRR_KEY_EMPTY;
-    trr_bitonic_sort_desc(cand, a.cand_cap, tid, (uint32_t)NT, BlockSync());
-    const uint32_t c2 = min(cnt, a.k);
-    if (tid == 0) {
-      s_cnt = c2;
-      if (c2 == a.k && a.k > 0) s_thr = cand[a.k - 1];
-    }
-    __syncthreads();
-    return c2;
-  };
-
-  while (true) {
-    __syncthreads();
-    if (tid == 0) s_q = atomicAdd(a.counter + 1, 1u);
-    __syncthreads();
-    const uint32_t bi = s_q;
-    if (bi >= *a.n_slow) break;
-    const uint32_t b = a.slow_list[bi];
-    const uint32_t q0 = a.q_off[b];
-    const uint32_t T = a.q_off[b + 1] - q0;   // host guarantees T <= NT
-    if (tid == 0) { s_cnt = 0; s_thr = TRR_KEY_EMPTY; }
-    uint32_t n_cand = 0;
-    // per-thread cursor of "its" query term through the skip table
-    uint32_t my_term = 0xFFFFFFFFu;
-    const uint32_t* my_skip = nullptr;
-    uint32_t cur = 0, nxt = 0;
-    if (tid < T) {
-      my_term = a.q_terms[q0 + tid];
-      if (my_term < a.n_terms) {
-        my_skip = a.skip + (uint64_t)my_term * a.skip_ld;
-        cur = my_skip[0];
-        nxt = my_skip[1];
-      }
-    }
-    __syncthreads();
-
-    for (uint32_t r = 0; r < a.n_ranges; ++r) {
-      const uint32_t range_base = r << a.range_shift;
-      if (tid < T) {
-        seg_s[tid] = cur;
-        seg_l[tid] = my_skip ? (nxt - cur) : 0u;
-        cur = nxt;
-        if (my_skip && r + 2 <= a.n_ranges) nxt = my_skip[r + 2];
-      }
-      __syncthreads();
-      // ---- ordered accumulation, staged in batches of consecutive terms ----
-      uint32_t i = 0, last_tot = 0, n_any = 0, n_staged_batches = 0, n_direct = 0;
-      while (i < T) {
-        const uint32_t len_i = seg_l[i];
-        if (len_i > a.stage_cap) {
-          // a single term larger than the stage: stream it in pieces (same term: no ordering inside)
-          const uint32_t s0 = seg_s[i];
-          for (uint32_t pos = 0; pos < len_i; pos += a.stage_cap) {
-            const uint32_t take = min(a.stage_cap, len_i - pos);
-            for (uint32_t e = tid; e < take; e += NT) {
-              const uint2 p = a.post[s0 + pos + e];
-              acc[p.x - range_base] = acc[p.x - range_base] + __uint_as_float(p.y);
-            }
-          }
-          __syncthreads();
-          n_any += len_i;
-          ++n_direct;
-          ++i;
-          continue;
-        }
-        uint32_t j = i, tot = 0;
-        while (j < T && tot + seg_l[j] <= a.stage_cap) { tot += seg_l[j]; ++j; }
-        if (tot == 0) { i = j; continue; }
-        // stage the batch
-        uint32_t off = 0;
-        for (uint32_t x = i; x < j; ++x) {
-          const uint32_t len = seg_l[x], s0 = seg_s[x];
-          for (uint32_t e = tid; e < len; e += NT) st[off + e] = a.post[s0 + e];
-          off += len;
-        }
-        __syncthreads();
-        // accumulate term by term, in query order
-        off = 0;
-        for (uint32_t x = i; x < j; ++x) {
-          const uint32_t len = seg_l[x];
-          if (len == 0) continue;
-          for (uint32_t e = tid; e < len; e += NT) {
-            const uint2 p = st[off + e];
-            acc[p.x - range_base] = acc[p.x - range_base] + __uint_as_float(p.y);
-          }
-          off += len;
-          __syncthreads();
-        }
-        ++n_staged_batches;
-        last_tot = tot;
-        n_any += tot;
-        i = j;
-      }
-      if (n_any == 0) { __syncthreads(); continue; }
-      // ---- harvest touched documents ----
-      if (n_staged_batches == 1 && n_direct == 0) {  // every posting of this range is still in the stage
-        for (uint32_t e0 = 0; e0 < last_tot; e0 += NT) {
-          if (n_cand > a.cand_cap - NT) n_cand = compact(n_cand);
-          const uint32_t e = e0 + tid;
-          int pushed = 0;
-          if (e < last_tot) {
-            const uint32_t d = st[e].x;
-            const float v = atomicExch(&acc[d - range_base], 0.0f);
-            if (v > 0.0f) {  // src/index.rs:236 keeps only score > 0.0
-              const uint64_t key = trr_make_key(v, a.doc_base + d);
-              if (key > s_thr) { const uint32_t pos = atomicAdd(&s_cnt, 1u); cand[pos] = key; pushed = 1; }
-            }
-          }
-          n_cand += (uint32_t)__syncthreads_count(pushed);
-        }
-      } else {
-        for (uint32_t x = 0; x < T; ++x) {
-          const uint32_t len = seg_l[x], s0 = seg_s[x];
-          for (uint32_t e0 = 0; e0 < len; e0 += NT) {
-            if (n_cand > a.cand_cap - NT) n_cand = compact(n_cand);
-            const uint32_t e = e0 + tid;
-            int pushed = 0;
-            if (e < len) {
-              const uint32_t d = a.post[s0 + e].x;
-              const float v = atomicExch(&acc[d - range_base], 0.0f);
-              if (v > 0.0f) {
-                const uint64_t key = trr_make_key(v, a.doc_base + d);
-                if (key > s_thr) { const uint32_t pos = atomicAdd(&s_cnt, 1u); cand[pos] = key; pushed = 1; }
-              }
-            }
-            n_cand += (uint32_t)__syncthreads_count(pushed);
-          }
-        }
-      }
-    }
-    // ---- emit the query's top-k ----
-    n_cand = compact(n_cand);
-    const uint32_t n_out = min(n_cand, a.k);
-    for (uint32_t i = tid; i < a.k; i += NT) {
-      const bool ok = i < n_out;
-      const uint64_t key = ok ? cand[i] : TRR_KEY_EMPTY;
-      if (a.out_keys) a.out_keys[(uint64_t)b * a.k + i] = key;
-      if (a.out_ord) a.out_ord[(uint64_t)b * a.k + i] = ok ? trr_key_ord(key) : 0xFFFFFFFFu;
-      if (a.out_score) a.out_score[(uint64_t)b * a.k + i] = ok ? trr_key_score(key) : 0.0f;
-    }
-    if (tid == 0 && a.out_n) a.out_n[b] = n_out;
+  if (tid == 0) { a.queue[0] = 0; a.queue[1] = 0; }
+  if (cap2 == 0) {
+    for (uint32_t b = tid; b < a.B; b += blockDim.x) a.order[b] = b;
+    return;
   }
+  for (uint32_t b = tid; b < cap2; b += blockDim.x) {
+    uint64_t key = 0;
+    if (b < a.B) {
+      uint64_t cost = 0;
+      for (uint32_t i = a.q_off[b]; i < a.q_off[b + 1]; ++i) {
+        const uint32_t t = a.q_terms[i];
+        if (t < a.n_terms) {
+          const uint32_t* row = a.skip + (uint64_t)t * a.skip_ld;
+          cost += row[a.n_ranges] - row[0];
+        }
+      }
+      if (cost > 0xFFFFFFFFull) cost = 0xFFFFFFFFull;
+      key = ((cost + 1) << 32) | (uint64_t)(0xFFFFFFFFu - b);  // never TRR_KEY_EMPTY; ties: smaller b first
+    }
+    keys[b] = key;
+  }
+  trr_bitonic_sort_desc(keys, cap2, tid, blockDim.x, BlockSync());
+  for (uint32_t i = tid; i < a.B; i += blockDim.x) a.order[i] = 0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFu);
 }
 
 // =============================================================================================
-// fast search kernel (queries with at most BM25_FAST_TMAX terms; everything else takes the kernel above)
-//
-// f32 addition is commutative, so the sum over the query terms of a document that matches ONE or TWO terms does
-// not depend on the order of accumulation; only documents matching three or more terms need the reference's
-// query-term order.  Per (query, document range):
-//   phase 1  every posting of every query term bumps a packed 8-bit match counter of its document (shared-memory
-//            atomics); postings stay cached in registers for the later phases;
-//   phase 2  postings of documents with <= 2 matches are added with shared-memory float atomics (order-free, exact);
-//            postings of documents with >= 3 matches are deferred and their term slots recorded in a bit mask;
-//   phase 3  the deferred postings are replayed in query-term order (ascending term slot): normally by ONE warp from
-//            a small shared-memory list (__syncwarp between slots); block-wide from the registers if the list overflows;
-//   harvest  exchange-with-zero of the touched accumulators, threshold filter, candidate buffer.
-// Queries with more than BM25_FAST_TMAX terms are routed to the general kernel by the host.
+// search
 // =============================================================================================
-constexpr int BM25_FAST_TMAX = 128;
-constexpr int BM25_EPT = 8;          // postings cached per thread
-constexpr int BM25_DEF_CAP = 1024;   // deferred postings replayed by a single warp (more: block-wide replay)
+namespace {
 
-template <int NT>
-__global__ void __launch_bounds__(NT, 2)
-bm25_search_fast_kernel(Bm25SearchArgs a) {
+constexpr uint32_t FULLM = 0xFFFFFFFFu;
+constexpr uint32_t CW = TRR_BM25_CONSUMER_WARPS;       // 16
+constexpr uint32_t CT = CW * 32;                       // consumer threads
+constexpr uint32_t F_HARVEST = 1u, F_END_ITEM = 2u, F_QUIT = 4u;
+
+struct PassDesc {
+  uint32_t flags;
+  uint32_t range_base;  // local id of the first document of the range
+  uint32_t item;
+  uint32_t pad;
+  uint32_t seg_begin[32];  // per term slot of the pass: [begin, end) inside the stage buffer
+  uint32_t seg_end[32];
+};
+
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity, uint32_t site, uint32_t* dbg) {
+  if (trr_mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!trr_mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s: a protocol bug must surface as an error, never as a hung GPU
+      if (dbg) { *dbg = 0x40000000u | (site << 16) | (blockIdx.x & 0xFFFFu); __threadfence_system(); }
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory"); }
+struct ConsumerSync { __device__ __forceinline__ void operator()() const { consumer_bar(); } };
+
+__device__ __forceinline__ uint32_t lower_bound_doc(const uint2* st, uint32_t lo, uint32_t hi, uint32_t doc) {
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (st[mid].x < doc) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(TRR_BM25_THREADS, 1)
+bm25_search_kernel(Bm25SearchArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t R = 1u << a.range_shift;
-  float* acc = reinterpret_cast<float*>(smem_raw);                        // R f32
-  uint32_t* cnt32 = reinterpret_cast<uint32_t*>(acc + R);                 // R packed 8-bit counters
-  uint64_t* cand = reinterpret_cast<uint64_t*>(cnt32 + (R >> 2));         // cand_cap keys
-  uint32_t* seg_s = reinterpret_cast<uint32_t*>(cand + a.cand_cap);       // TMAX
-  uint32_t* seg_off = seg_s + BM25_FAST_TMAX;                             // TMAX + 1 (exclusive prefix of lengths)
-  uint32_t* def_doc = seg_off + BM25_FAST_TMAX + 4;                       // DEF_CAP: (local doc << 8) | term slot
-  float* def_imp = reinterpret_cast<float*>(def_doc + BM25_DEF_CAP);      // DEF_CAP
-  __shared__ uint32_t s_q, s_cnt, s_ndef, s_slot_mask[BM25_FAST_TMAX / 32], s_warp_tot[NT / 32];
+  const uint32_t SUB = R / CW;                                                   // documents owned by one consumer warp
+  float* acc = reinterpret_cast<float*>(smem_raw);                                // R
+  uint2* stage_buf = reinterpret_cast<uint2*>(acc + R);                           // 2 x stage_cap
+  uint64_t* cand = reinterpret_cast<uint64_t*>(stage_buf + 2 * (size_t)a.stage_cap);  // cand_cap
+  PassDesc* desc = reinterpret_cast<PassDesc*>(cand + a.cand_cap);                // 2
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(desc + 2);                     // 2
+  uint64_t* empty_bar = full_bar + 2;                                             // 2
+  __shared__ uint32_t s_cnt, s_overflow;
   __shared__ uint64_t s_thr;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint8_t* cnt8 = reinterpret_cast<uint8_t*>(cnt32);
 
-  for (uint32_t i = tid; i < R; i += NT) acc[i] = 0.0f;
-  for (uint32_t i = tid; i < (R >> 2); i += NT) cnt32[i] = 0u;
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { trr_mbar_init(&full_bar[s], 1); trr_mbar_init(&empty_bar[s], CW); }
+    trr_fence_mbar_init();
+    s_cnt = 0; s_overflow = 0; s_thr = TRR_KEY_EMPTY;
+  }
+  if (warp < CW) for (uint32_t i = tid; i < R; i += CT) acc[i] = 0.0f;
   __syncthreads();
 
-  auto compact = [&]() {
-    __syncthreads();
-    const uint32_t cnt = min(s_cnt, a.cand_cap);
-    for (uint32_t i = cnt + tid; i < a.cand_cap; i += NT) cand[i] = TRR_KEY_EMPTY;
-    trr_bitonic_sort_desc(cand, a.cand_cap, tid, (uint32_t)NT, BlockSync());
-    if (tid == 0) {
-      const uint32_t c2 = min(cnt, a.k);
-      s_cnt = c2;
-      if (c2 == a.k && a.k > 0) s_thr = cand[a.k - 1];
-    }
-    __syncthreads();
-  };
-
-  while (true) {
-    __syncthreads();
-    if (tid == 0) s_q = atomicAdd(a.counter, 1u);
-    __syncthreads();
-    const uint32_t bi = s_q;
-    if (bi >= a.n_fast) break;
-    const uint32_t b = a.fast_list[bi];
-    const uint32_t q0 = a.q_off[b];
-    const uint32_t T = a.q_off[b + 1] - q0;  // <= BM25_FAST_TMAX (host-side split)
-    if (tid == 0) { s_cnt = 0; s_thr = TRR_KEY_EMPTY; }
-    const uint32_t* my_skip = nullptr;
-    uint32_t c_lo = 0, c_hi = 0, c_pre = 0;
-    if (tid < T) {
-      const uint32_t term = a.q_terms[q0 + tid];
-      if (term < a.n_terms) {
-        my_skip = a.skip + (uint64_t)term * a.skip_ld;
-        c_lo = my_skip[0];
-        c_hi = my_skip[1];
-        c_pre = a.n_ranges >= 2 ? my_skip[2] : c_hi;
+  if (warp == CW) {
+    // ============================ producer warp ============================
+    uint32_t stage = 0, phase = 0;
+    // publishes one pass: descriptor + bulk copies.  Every lane passes its own slot (len == 0: not in the pass).
+    auto emit = [&](uint32_t flags, uint32_t range_base, uint32_t item, uint32_t off, uint32_t src_al, uint32_t al,
+                    uint32_t begin, uint32_t end, uint32_t total_al) {
+      mbar_wait_or_trap(&empty_bar[stage], phase ^ 1, 1, a.dbg);
+      PassDesc& d = desc[stage];
+      d.seg_begin[lane] = begin;
+      d.seg_end[lane] = end;
+      if (lane == 0) { d.flags = flags; d.range_base = range_base; d.item = item; }
+      __syncwarp();
+      if (lane == 0) {
+        if (total_al) trr_mbar_expect_tx(&full_bar[stage], total_al * 8u);
+        else trr_mbar_arrive(&full_bar[stage]);
       }
-    }
-    __syncthreads();
-
-    for (uint32_t r = 0; r < a.n_ranges; ++r) {
-      const uint32_t range_base = r << a.range_shift;
-      // ---- segment table of this range + exclusive prefix of the lengths (block scan over <= 128 values)
-      uint32_t my_len = 0;
-      if (tid < BM25_FAST_TMAX) {
-        if (tid < T && my_skip) {
-          seg_s[tid] = c_lo;
-          my_len = c_hi - c_lo;
-          c_lo = c_hi;
-          c_hi = c_pre;
-          if (r + 3 <= a.n_ranges) c_pre = my_skip[r + 3];
+      __syncwarp();
+      if (al) trr_bulk_g2s(stage_buf + (size_t)stage * a.stage_cap + off, a.post + src_al, al * 8u, &full_bar[stage]);
+      if (++stage == 2) { stage = 0; phase ^= 1; }
+    };
+    const uint32_t n_items = a.B * a.n_chunks;
+    while (true) {
+      uint32_t item = 0;
+      if (lane == 0) item = atomicAdd(a.queue, 1u);
+      item = __shfl_sync(FULLM, item, 0);
+      if (item >= n_items) { emit(F_QUIT, 0, item, 0, 0, 0, 0, 0, 0); break; }
+      const uint32_t b = a.order[item / a.n_chunks], c = item % a.n_chunks;
+      const uint32_t r0 = (uint32_t)(((uint64_t)c * a.n_ranges) / a.n_chunks);
+      const uint32_t r1 = (uint32_t)(((uint64_t)(c + 1) * a.n_ranges) / a.n_chunks);
+      const uint32_t q0 = a.q_off[b];
+      const uint32_t T = a.q_off[b + 1] - q0;
+      const uint32_t G = (T + 31) >> 5;
+      // G == 1: every lane keeps a cursor through the skip row of its term, fetched one range ahead
+      const uint32_t* row1 = nullptr;
+      uint32_t c_s = 0, c_e = 0, c_n = 0;
+      if (G == 1 && lane < T) {
+        const uint32_t term = a.q_terms[q0 + lane];
+        if (term < a.n_terms) {
+          row1 = a.skip + (uint64_t)term * a.skip_ld;
+          c_s = row1[r0];
+          c_e = r0 < r1 ? row1[r0 + 1] : c_s;
+          c_n = r0 + 2 <= a.n_ranges ? row1[r0 + 2] : c_e;
         }
-        uint32_t incl = my_len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-          if ((int)lane >= o) incl += v;
-        }
-        if (lane == 31) s_warp_tot[warp] = incl;
-        my_len = incl - my_len;  // exclusive prefix inside the warp
       }
-      if (tid < BM25_FAST_TMAX / 32) s_slot_mask[tid] = 0;
-      if (tid == 0) s_ndef = 0;
-      __syncthreads();
-      if (tid < BM25_FAST_TMAX) {
-        uint32_t add = 0;
-        for (uint32_t w = 0; w < warp; ++w) add += s_warp_tot[w];
-        seg_off[tid] = my_len + add;
-      }
-      uint32_t tot = 0;
-#pragma unroll
-      for (uint32_t w = 0; w < BM25_FAST_TMAX / 32; ++w) tot += s_warp_tot[w];
-      if (tid == 0) seg_off[BM25_FAST_TMAX] = tot;
-      __syncthreads();
-      if (tot == 0) continue;
-
-      const bool single = tot <= (uint32_t)(NT * BM25_EPT);
-      uint32_t e_doc[BM25_EPT];   // local doc id, 0xFFFFFFFF = no posting
-      float e_imp[BM25_EPT];
-      uint32_t e_slot[BM25_EPT];  // query term slot
-      // Flattened posting index e -> (term slot, offset).  A warp's postings are contiguous in e, so the slot is found
-      // once per warp by binary search over the 128 prefix sums and then advanced linearly per lane.
-      auto load_chunk = [&](uint32_t base) {
-        const uint32_t e_first = base + warp * 32u;  // posting of lane 0, j = 0
-        uint32_t x = 0;
-        if (e_first < tot) {
-          uint32_t lo = 0, hi = BM25_FAST_TMAX;
-#pragma unroll
-          for (int it = 0; it < 7; ++it) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (seg_off[mid] <= e_first) lo = mid; else hi = mid;
-          }
-          x = lo;
-        }
-#pragma unroll
-        for (int j = 0; j < BM25_EPT; ++j) {
-          const uint32_t e = base + (uint32_t)j * NT + tid;
-          e_doc[j] = 0xFFFFFFFFu;
-          if (e < tot) {
-            while (seg_off[x + 1] <= e) ++x;  // seg_off[TMAX] == tot > e terminates the walk
-            const uint2 p = a.post[seg_s[x] + (e - seg_off[x])];
-            e_doc[j] = p.x - range_base;
-            e_imp[j] = __uint_as_float(p.y);
-            e_slot[j] = x;
-          }
-        }
-      };
-      // ---- phase 1: match counters
-      for (uint32_t base = 0; base < tot; base += NT * BM25_EPT) {
-        load_chunk(base);
-#pragma unroll
-        for (int j = 0; j < BM25_EPT; ++j)
-          if (e_doc[j] != 0xFFFFFFFFu) atomicAdd(&cnt32[e_doc[j] >> 2], 1u << (8 * (e_doc[j] & 3)));
-      }
-      __syncthreads();
-      // ---- phase 2: order-free adds; postings of documents with >= 3 matches are deferred
-      uint32_t deferred = 0;  // bit j: cached posting j belongs to a >= 3-match document (single-chunk case)
-      for (uint32_t base = 0; base < tot; base += NT * BM25_EPT) {
-        if (!single) load_chunk(base);
-#pragma unroll
-        for (int j = 0; j < BM25_EPT; ++j) {
-          if (e_doc[j] == 0xFFFFFFFFu) continue;
-          if (cnt8[e_doc[j]] <= 2) {
-            atomicAdd(&acc[e_doc[j]], e_imp[j]);
+      for (uint32_t r = r0; r < r1; ++r) {
+        const uint32_t range_base = r << a.range_shift;
+        bool pending_harvest = false;  // a pass of this range was emitted without the harvest flag
+        for (uint32_t g = 0; g < G; ++g) {
+          uint32_t s = 0, e = 0;
+          if (G == 1) {
+            s = c_s; e = c_e;
+            c_s = c_e; c_e = c_n;
+            if (row1 && r + 3 <= a.n_ranges) c_n = row1[r + 3];
           } else {
-            deferred |= 1u << j;
-            atomicOr(&s_slot_mask[e_slot[j] >> 5], 1u << (e_slot[j] & 31));
-            const uint32_t pos = atomicAdd(&s_ndef, 1u);
-            if (pos < (uint32_t)BM25_DEF_CAP) { def_doc[pos] = (e_doc[j] << 8) | e_slot[j]; def_imp[pos] = e_imp[j]; }
-          }
-        }
-      }
-      __syncthreads();
-      // ---- phase 3: exact ordered replay of the deferred postings, ascending term slot == query order.  Inside a
-      // slot every posting has a different document, so plain read-modify-write is race-free.
-      const uint32_t n_def = s_ndef;
-      if (n_def != 0 && n_def <= (uint32_t)BM25_DEF_CAP) {
-        // common case: one warp walks the list once per slot, __syncwarp between slots
-        if (warp == 0) {
-#pragma unroll 1
-          for (uint32_t w = 0; w < BM25_FAST_TMAX / 32; ++w) {
-            uint32_t m = s_slot_mask[w];
-            while (m) {
-              const uint32_t x = w * 32 + (__ffs(m) - 1);
-              m &= m - 1;
-              for (uint32_t u = lane; u < n_def; u += 32) {
-                const uint32_t e = def_doc[u];
-                if ((e & 0xFFu) == x) acc[e >> 8] = acc[e >> 8] + def_imp[u];
+            const uint32_t ti = g * 32 + lane;
+            if (ti < T) {
+              const uint32_t term = a.q_terms[q0 + ti];
+              if (term < a.n_terms) {
+                const uint32_t* row = a.skip + (uint64_t)term * a.skip_ld;
+                s = row[r]; e = row[r + 1];
               }
-              __syncwarp();
             }
           }
-        }
-        __syncthreads();
-      } else if (n_def != 0) {
-        // heavy case (e.g. a frequent term repeated in the query): block-wide replay from the registers / postings
-#pragma unroll 1
-        for (uint32_t w = 0; w < BM25_FAST_TMAX / 32; ++w) {
-          uint32_t m = s_slot_mask[w];
-          while (m) {
-            const uint32_t x = w * 32 + (__ffs(m) - 1);
-            m &= m - 1;
-            if (single) {
-              if (deferred) {
+          uint32_t first = 0;  // slots below `first` are done
+          while (first < 32) {
+            const uint32_t len = lane >= first ? e - s : 0u;
+            const uint32_t al = len ? (((s & 1u) + len + 1u) & ~1u) : 0u;  // postings copied: 16-byte aligned both ends
+            uint32_t incl = al;
 #pragma unroll
-                for (int j = 0; j < BM25_EPT; ++j)
-                  if (((deferred >> j) & 1u) && e_slot[j] == x) acc[e_doc[j]] = acc[e_doc[j]] + e_imp[j];
-              }
+            for (int o = 1; o < 32; o <<= 1) {
+              const uint32_t v = __shfl_up_sync(FULLM, incl, o);
+              if ((int)lane >= o) incl += v;
+            }
+            const uint32_t total = __shfl_sync(FULLM, incl, 31);
+            if (total == 0) break;
+            const uint32_t fits = __ballot_sync(FULLM, incl <= a.stage_cap);
+            const uint32_t n_fit = fits == FULLM ? 32u : (uint32_t)(__ffs(~fits) - 1);  // slots [first, n_fit) fit
+            if (n_fit == first) {
+              // slot `first` alone exceeds the stage: stream it in stage-sized pieces (same term: any order is exact)
+              const bool me = lane == first;
+              const uint32_t s_al = s & ~1u;
+              const uint32_t end_idx = min(e, s_al + a.stage_cap);
+              emit(0, range_base, item, 0, me ? s_al : 0u, me ? a.stage_cap : 0u, me ? (s & 1u) : 0u,
+                   me ? end_idx - s_al : 0u, a.stage_cap);
+              if (me) s = end_idx;
+              pending_harvest = true;
             } else {
-              for (uint32_t base = 0; base < tot; base += NT * BM25_EPT) {
-                load_chunk(base);
-#pragma unroll
-                for (int j = 0; j < BM25_EPT; ++j)
-                  if (e_doc[j] != 0xFFFFFFFFu && e_slot[j] == x && cnt8[e_doc[j]] > 2)
-                    acc[e_doc[j]] = acc[e_doc[j]] + e_imp[j];
-              }
+              const bool me = lane >= first && lane < n_fit;
+              const uint32_t taken = __shfl_sync(FULLM, incl, n_fit - 1);
+              const bool last = (G == 1) && (taken == total);
+              const uint32_t off = incl - al;
+              emit(last ? F_HARVEST : 0u, range_base, item, me ? off : 0u, me ? (s & ~1u) : 0u, me ? al : 0u,
+                   me ? off + (s & 1u) : 0u, me ? off + (s & 1u) + len : 0u, taken);
+              pending_harvest = !last;
+              first = n_fit;
             }
-            __syncthreads();
           }
         }
+        if (pending_harvest) emit(F_HARVEST, range_base, item, 0, 0, 0, 0, 0, 0);
       }
-      // ---- harvest (also clears the counters); a full candidate buffer triggers a compaction and a retry
-      for (uint32_t base = 0; base < tot; base += NT * BM25_EPT) {
-        if (!single) load_chunk(base);
-        uint32_t done = 0;
+      emit(F_END_ITEM, 0, item, 0, 0, 0, 0, 0, 0);
+    }
+  } else {
+    // ============================ consumer warps ============================
+    uint32_t stage = 0, phase = 0;
+    bool touched = false;  // this warp accumulated something in the current range
+    float* my_acc = acc + warp * SUB;
+    const uint32_t compact_at = a.k + ((a.cand_cap - a.k) >> 1);
+    // block-wide (consumer warps) compaction: afterwards cand[0..s_cnt) is sorted descending and s_thr is the k-th best
+    auto compact = [&]() {
+      consumer_bar();
+      const uint32_t cnt = min(s_cnt, a.cand_cap);
+      for (uint32_t i = cnt + tid; i < a.cand_cap; i += CT) cand[i] = TRR_KEY_EMPTY;
+      trr_bitonic_sort_desc(cand, a.cand_cap, tid, CT, ConsumerSync());
+      if (tid == 0) {
+        const uint32_t c2 = min(cnt, a.k);
+        s_cnt = c2;
+        s_overflow = 0;
+        if (c2 == a.k && a.k > 0) s_thr = cand[a.k - 1];
+      }
+      consumer_bar();
+    };
+    while (true) {
+      mbar_wait_or_trap(&full_bar[stage], phase, 2, a.dbg);
+      const PassDesc& d = desc[stage];
+      const uint32_t flags = d.flags, range_base = d.range_base, item = d.item;
+      if (flags & F_QUIT) break;
+      const uint2* st = stage_buf + (size_t)stage * a.stage_cap;
+      {
+        const uint32_t sb = d.seg_begin[lane], se = d.seg_end[lane];
+        const uint32_t d0 = range_base + warp * SUB;
+        const uint32_t lo = lower_bound_doc(st, sb, se, d0);
+        const uint32_t hi = lower_bound_doc(st, lo, se, d0 + SUB);
+        uint32_t m = __ballot_sync(FULLM, hi > lo);
+        if (m) touched = true;
+        while (m) {  // ascending slot == query-term order
+          const uint32_t l = __ffs(m) - 1;
+          m &= m - 1;
+          const uint32_t lo_ = __shfl_sync(FULLM, lo, l), hi_ = __shfl_sync(FULLM, hi, l);
+          for (uint32_t p = lo_ + lane; p < hi_; p += 128) {
+            const bool v1 = p + 32 < hi_, v2 = p + 64 < hi_, v3 = p + 96 < hi_;
+            const uint2 e0 = st[p];
+            const uint2 e1 = v1 ? st[p + 32] : e0;
+            const uint2 e2 = v2 ? st[p + 64] : e0;
+            const uint2 e3 = v3 ? st[p + 96] : e0;
+            float* p0 = acc + (e0.x - range_base);
+            float* p1 = acc + (e1.x - range_base);
+            float* p2 = acc + (e2.x - range_base);
+            float* p3 = acc + (e3.x - range_base);
+            const float f0 = *p0, f1 = *p1, f2 = *p2, f3 = *p3;
+            *p0 = f0 + __uint_as_float(e0.y);
+            if (v1) *p1 = f1 + __uint_as_float(e1.y);
+            if (v2) *p2 = f2 + __uint_as_float(e2.y);
+            if (v3) *p3 = f3 + __uint_as_float(e3.y);
+          }
+          __syncwarp();
+        }
+      }
+      __syncwarp();
+      if (lane == 0) trr_mbar_arrive(&empty_bar[stage]);  // stage and descriptor are free again
+      if (++stage == 2) { stage = 0; phase ^= 1; }
+
+      if (flags & F_HARVEST) {
         while (true) {
-          int overflow = 0;
+          const uint64_t thr = *reinterpret_cast<volatile uint64_t*>(&s_thr);
+          const float thr_f = thr == TRR_KEY_EMPTY ? -CUDART_INF_F : trr_key_score(thr);
+          if (touched) {
+            uint4* a4 = reinterpret_cast<uint4*>(my_acc);
+            const uint32_t ord0 = a.doc_base + range_base + warp * SUB;
+            for (uint32_t i = lane; i < (SUB >> 2); i += 32) {
+              uint4 v = a4[i];
+              if ((v.x | v.y | v.z | v.w) == 0u) continue;
+              uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int j = 0; j < BM25_EPT; ++j) {
-            if (e_doc[j] == 0xFFFFFFFFu || (done >> j) & 1u) continue;
-            const float v = atomicExch(&acc[e_doc[j]], 0.0f);
-            cnt8[e_doc[j]] = 0;
-            if (v > 0.0f) {  // src/index.rs:236 keeps only score > 0.0
-              const uint64_t key = trr_make_key(v, a.doc_base + range_base + e_doc[j]);
-              if (key > s_thr) {
-                const uint32_t pos = atomicAdd(&s_cnt, 1u);
-                if (pos < a.cand_cap) cand[pos] = key;
-                else { acc[e_doc[j]] = v; overflow = 1; continue; }  // put it back, retry after the compaction
+              for (int j = 0; j < 4; ++j) {
+                const float f = __uint_as_float(w[j]);
+                if (f >= thr_f && f > 0.0f) {  // src/index.rs:236 keeps only score > 0.0
+                  const uint64_t key = trr_make_key(f, ord0 + i * 4 + j);
+                  if (key > thr) {
+                    const uint32_t pos = atomicAdd(&s_cnt, 1u);
+                    if (pos < a.cand_cap) { cand[pos] = key; w[j] = 0u; }
+                    else s_overflow = 1u;  // stays in the accumulator; retried after the compaction
+                  } else {
+                    w[j] = 0u;
+                  }
+                } else {
+                  w[j] = 0u;
+                }
               }
+              a4[i] = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            done |= 1u << j;
           }
-          if (!__syncthreads_or(overflow)) break;
-          compact();
+          consumer_bar();
+          const uint32_t ovf = s_overflow, cnt = s_cnt;
+          if (ovf || cnt >= compact_at) compact();
+          else consumer_bar();  // nobody may push (and bump s_cnt) before every thread has read it
+          if (!ovf) break;
         }
+        touched = false;
       }
-      __syncthreads();
-      if (s_cnt > (a.cand_cap >> 1)) compact();  // uniform (read after a barrier): keeps the threshold tight
+      if (flags & F_END_ITEM) {
+        compact();
+        const uint32_t n_out = s_cnt;
+        const uint32_t b = a.order[item / a.n_chunks], c = item % a.n_chunks;
+        if (a.n_chunks == 1) {
+          for (uint32_t i = tid; i < a.k; i += CT) {
+            const bool ok = i < n_out;
+            const uint64_t key = ok ? cand[i] : TRR_KEY_EMPTY;
+            if (a.out_keys) a.out_keys[(uint64_t)b * a.k + i] = key;
+            if (a.out_ord) a.out_ord[(uint64_t)b * a.k + i] = ok ? trr_key_ord(key) : 0xFFFFFFFFu;
+            if (a.out_score) a.out_score[(uint64_t)b * a.k + i] = ok ? trr_key_score(key) : 0.0f;
+          }
+          if (tid == 0 && a.out_n) a.out_n[b] = n_out;
+        } else {
+          uint64_t* dst = a.partial + ((uint64_t)b * a.n_chunks + c) * a.k;
+          for (uint32_t i = tid; i < a.k; i += CT) dst[i] = i < n_out ? cand[i] : TRR_KEY_EMPTY;
+        }
+        consumer_bar();
+        if (tid == 0) { s_cnt = 0; s_thr = TRR_KEY_EMPTY; }
+        consumer_bar();
+      }
     }
-    // ---- emit the query's top-k
-    compact();
-    const uint32_t n_out = min(s_cnt, a.k);
-    for (uint32_t i = tid; i < a.k; i += NT) {
-      const bool ok = i < n_out;
-      const uint64_t key = ok ? cand[i] : TRR_KEY_EMPTY;
-      if (a.out_keys) a.out_keys[(uint64_t)b * a.k + i] = key;
-      if (a.out_ord) a.out_ord[(uint64_t)b * a.k + i] = ok ? trr_key_ord(key) : 0xFFFFFFFFu;
-      if (a.out_score) a.out_score[(uint64_t)b * a.k + i] = ok ? trr_key_score(key) : 0.0f;
-    }
-    if (tid == 0 && a.out_n) a.out_n[b] = n_out;
   }
 }
 
@@ -509,33 +413,22 @@ cudaError_t trr_launch_bm25_build(const Bm25BuildArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-size_t trr_bm25_general_smem(const Bm25SearchArgs& a) {
-  return ((size_t)4 << a.range_shift) + (size_t)a.stage_cap * 8 + (size_t)a.cand_cap * 8 + (size_t)TRR_BM25_THREADS * 8;
-}
-size_t trr_bm25_fast_smem(const Bm25SearchArgs& a) {
-  return ((size_t)4 << a.range_shift) + ((size_t)1 << a.range_shift) + (size_t)a.cand_cap * 8 +
-         (size_t)(2 * BM25_FAST_TMAX + 8) * 4 + (size_t)BM25_DEF_CAP * 8 + 64;
+size_t trr_bm25_search_smem(uint32_t range_shift, uint32_t stage_cap, uint32_t cand_cap) {
+  return ((size_t)4 << range_shift) + (size_t)2 * stage_cap * 8 + (size_t)cand_cap * 8 + 2 * sizeof(PassDesc) + 4 * 8;
 }
 
-// fast kernel over a.fast_list, then the general kernel over a.slow_list (host-listed long queries + queries the
-// fast kernel gave up on); the second launch reads its work count from device memory, so no host sync is needed
-cudaError_t trr_launch_bm25_search(const Bm25SearchArgs& a, unsigned grid_fast, unsigned grid_slow, cudaStream_t st) {
-  if (a.B == 0) return cudaSuccess;
-  if (a.n_fast && grid_fast) {
-    const size_t smem = trr_bm25_fast_smem(a);
-    auto kern = bm25_search_fast_kernel<TRR_BM25_THREADS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid_fast, TRR_BM25_THREADS, smem, st>>>(a);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-  }
-  if (grid_slow) {
-    const size_t smem = trr_bm25_general_smem(a);
-    auto kern = bm25_search_kernel<TRR_BM25_THREADS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid_slow, TRR_BM25_THREADS, smem, st>>>(a);
-  }
+cudaError_t trr_launch_bm25_plan(const Bm25SearchArgs& a, cudaStream_t st) {
+  uint32_t cap2 = 0;
+  if (a.B > 1 && a.B <= 4096) cap2 = trr_pow2_ceil(a.B);
+  bm25_plan_kernel<<<1, 1024, (size_t)cap2 * 8, st>>>(a, cap2);
+  return cudaGetLastError();
+}
+
+cudaError_t trr_launch_bm25_search(const Bm25SearchArgs& a, unsigned grid, cudaStream_t st) {
+  if (a.B == 0 || grid == 0) return cudaSuccess;
+  const size_t smem = trr_bm25_search_smem(a.range_shift, a.stage_cap, a.cand_cap);
+  cudaError_t e = cudaFuncSetAttribute(bm25_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  bm25_search_kernel<<<grid, TRR_BM25_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }

@@ -3,7 +3,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-constexpr int TRR_BM25_THREADS = 512;
+constexpr int TRR_BM25_CONSUMER_WARPS = 16;
+constexpr int TRR_BM25_THREADS = (TRR_BM25_CONSUMER_WARPS + 1) * 32;  // 16 consumer warps + 1 producer warp
+constexpr uint32_t TRR_BM25_MAX_QUERY_TERMS = 512;
+constexpr uint32_t TRR_BM25_MIN_RANGE_SHIFT = 11, TRR_BM25_MAX_RANGE_SHIFT = 15;
 
 struct Bm25BuildArgs {
   uint64_t n_postings;
@@ -26,21 +29,20 @@ struct Bm25SearchArgs {
   const uint32_t* q_terms;
   const uint32_t* q_off;
   uint32_t B, k;
-  uint32_t stage_cap;  // postings staged per batch
-  uint32_t cand_cap;   // power of two >= k + TRR_BM25_THREADS
-  uint32_t* counter;   // two dynamic work queues (fast kernel, general kernel), zeroed by the caller
-  const uint32_t* fast_list;  // queries served by the fast kernel (<= BM25_FAST_TMAX terms)
-  uint32_t n_fast;
-  uint32_t* slow_list; // queries for the general kernel: host-listed ones first, the fast kernel appends
-  uint32_t* n_slow;    // device count of slow_list
-  uint64_t* out_keys;  // nullable [B][k]
+  uint32_t stage_cap;  // postings per stage buffer (even)
+  uint32_t cand_cap;   // candidate buffer capacity: power of two > k
+  uint32_t n_chunks;   // work items per query (contiguous chunks of document ranges)
+  uint32_t* order;     // [B] queries by decreasing posting volume (written by the plan kernel)
+  uint32_t* queue;     // [2] dynamic work queue (reset by the plan kernel)
+  uint64_t* partial;   // n_chunks > 1: [B][n_chunks][k] keys, merged by topk_merge_kernel
+  uint64_t* out_keys;  // n_chunks == 1: nullable [B][k]
   uint32_t* out_ord;   // nullable [B][k]
   float* out_score;    // nullable
   uint32_t* out_n;     // nullable
+  uint32_t* dbg;       // nullable host-mapped word: site of a barrier timeout
 };
 
 cudaError_t trr_launch_bm25_build(const Bm25BuildArgs& a, cudaStream_t st);
-constexpr uint32_t TRR_BM25_FAST_TMAX = 128;
-size_t trr_bm25_general_smem(const Bm25SearchArgs& a);
-size_t trr_bm25_fast_smem(const Bm25SearchArgs& a);
-cudaError_t trr_launch_bm25_search(const Bm25SearchArgs& a, unsigned grid_fast, unsigned grid_slow, cudaStream_t st);
+size_t trr_bm25_search_smem(uint32_t range_shift, uint32_t stage_cap, uint32_t cand_cap);
+cudaError_t trr_launch_bm25_plan(const Bm25SearchArgs& a, cudaStream_t st);
+cudaError_t trr_launch_bm25_search(const Bm25SearchArgs& a, unsigned grid, cudaStream_t st);

@@ -527,8 +527,9 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
   } else {
     TRR_CHECK(dense_prepare_gemm(h));
     uint32_t n_qblocks = (B + TRR_GEMM_TILE_M - 1) / TRR_GEMM_TILE_M;
-    // 2-CTA kernel (cta_group::2) whenever there are at least two query blocks; TRR_GEMM_PAIR=0/1 overrides
-    int pair_mode = n_qblocks >= 2 ? 1 : 0;
+    // the 1-CTA kernel (M128 x N256 per CTA) measured faster than the 2-CTA one (cta_group::2) on B200 for this
+    // shape: 16.2 ms vs 24.0 ms at 10M x 768, B = 1024; TRR_GEMM_PAIR=1 selects the 2-CTA kernel
+    int pair_mode = 0;
     if (const char* e = getenv("TRR_GEMM_PAIR")) pair_mode = atoi(e) ? 1 : 0;
     if (pair_mode) n_qblocks = (n_qblocks + 1) & ~1u;
     if (n_qblocks > (uint32_t)c->sm_count)
@@ -739,8 +740,7 @@ struct trr_bm25 {
   uint64_t n_postings = 0;
   uint2* post = nullptr;
   uint32_t* skip = nullptr;
-  uint32_t range_shift = 14, n_ranges = 0, skip_ld = 0;
-  uint32_t stage_cap = 2048;
+  uint32_t range_shift = TRR_BM25_MAX_RANGE_SHIFT, n_ranges = 0, skip_ld = 0;
   trr_stats stats{};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -758,16 +758,19 @@ extern "C" int trr_bm25_build(trr_ctx* ctx, uint32_t n_docs, uint32_t n_terms, c
   trr_bm25* h = new trr_bm25();
   h->ctx = ctx; h->n_docs = n_docs; h->n_terms = n_terms; h->doc_base = doc_base; h->n_postings = P;
   for (auto& e : h->ev) cudaEventCreate(&e);
-  // documents per range: 16384 (64 KB of f32 accumulators, two CTAs per SM), smaller for tiny indexes
-  uint32_t shift = 14;
-  while (shift > 8 && (1u << (shift - 1)) >= std::max<uint32_t>(n_docs, 1)) --shift;
+  // documents per range: 32768 (128 KB of f32 accumulators in shared memory, one CTA per SM), fewer for small indexes
+  uint32_t shift = TRR_BM25_MAX_RANGE_SHIFT;
+  if (const char* e = getenv("TRR_BM25_RANGE_SHIFT")) shift = (uint32_t)atoi(e);
+  shift = std::min(std::max(shift, TRR_BM25_MIN_RANGE_SHIFT), TRR_BM25_MAX_RANGE_SHIFT);
+  while (shift > TRR_BM25_MIN_RANGE_SHIFT && (1u << (shift - 1)) >= std::max<uint32_t>(n_docs, 1)) --shift;
   h->range_shift = shift;
   h->n_ranges = n_docs ? (uint32_t)(((uint64_t)n_docs + (1u << shift) - 1) >> shift) : 0;
   h->skip_ld = h->n_ranges + 1;
   cudaStream_t st = ctx->stream;
   auto fail = [&](int s) { trr_bm25_destroy(h); return s; };
 #define BM_CUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { trr_fail(_e == cudaErrorMemoryAllocation ? TRR_ERR_OOM : TRR_ERR_CUDA, std::string(#e) + ": " + cudaGetErrorString(_e)); return fail(_e == cudaErrorMemoryAllocation ? TRR_ERR_OOM : TRR_ERR_CUDA); } } while (0)
-  BM_CUDA(cudaMalloc(&h->post, std::max<uint64_t>(P, 1) * sizeof(uint2)));
+  BM_CUDA(cudaMalloc(&h->post, (P + 2) * sizeof(uint2)));  // +2: 16-byte aligned bulk copies may read one posting past the end
+  BM_CUDA(cudaMemsetAsync(h->post, 0xFF, (P + 2) * sizeof(uint2), st));
   BM_CUDA(cudaMalloc(&h->skip, std::max<uint64_t>((uint64_t)n_terms * h->skip_ld, 1) * 4));
   uint64_t* d_term_off = nullptr; uint32_t *d_pd = nullptr, *d_ptf = nullptr, *d_dl = nullptr; float* d_idf = nullptr;
   BM_CUDA(cudaMalloc(&d_term_off, ((uint64_t)n_terms + 1) * 8));
@@ -836,37 +839,51 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   }
   if (k > 1024) return trr_fail(TRR_ERR_UNSUPPORTED, "k > 1024 is not supported yet");
   for (uint32_t b = 0; b < B; ++b)
-    if (h_q_off[b + 1] - h_q_off[b] > (uint32_t)TRR_BM25_THREADS)
+    if (h_q_off[b + 1] - h_q_off[b] > TRR_BM25_MAX_QUERY_TERMS)
       return trr_fail(TRR_ERR_UNSUPPORTED, "more than 512 terms in one query");
-  // work lists: queries with <= 128 terms go to the fast kernel; longer ones (and the ones it gives up on) to the
-  // general kernel.  Layout in scratch: [counters: queue0, queue1, n_slow, pad] [fast_list B] [slow_list B]
-  std::vector<uint32_t> lists((size_t)2 * B + 4, 0);
-  uint32_t n_fast = 0, n_slow = 0;
-  for (uint32_t b = 0; b < B; ++b) {
-    if (h_q_off[b + 1] - h_q_off[b] <= TRR_BM25_FAST_TMAX) lists[4 + n_fast++] = b;
-    else lists[4 + (size_t)B + n_slow++] = b;
-  }
-  lists[2] = n_slow;
-  TRR_CHECK(extra(c)->scratch.reserve(scratch_off + lists.size() * 4 + 256));
-  uint32_t* d_lists = reinterpret_cast<uint32_t*>(static_cast<char*>(extra(c)->scratch.p) + scratch_off);
-  TRR_CUDA(cudaMemcpyAsync(d_lists, lists.data(), lists.size() * 4, cudaMemcpyHostToDevice, st));
-  TRR_CUDA(cudaStreamSynchronize(st));  // `lists` is pageable host memory that dies with this frame
   Bm25SearchArgs a{};
   a.post = h->post; a.skip = h->skip; a.skip_ld = h->skip_ld; a.n_terms = h->n_terms; a.n_docs = h->n_docs;
   a.n_ranges = h->n_ranges; a.range_shift = h->range_shift; a.doc_base = h->doc_base;
   a.q_terms = d_q_terms; a.q_off = d_q_off; a.B = B; a.k = k;
-  a.stage_cap = h->stage_cap;
-  a.cand_cap = trr_pow2_ceil(k + TRR_BM25_THREADS);
-  a.counter = d_lists; a.n_slow = d_lists + 2; a.fast_list = d_lists + 4; a.n_fast = n_fast;
-  a.slow_list = d_lists + 4 + B;
+  a.cand_cap = trr_pow2_ceil(k + 512);
+  // stage buffers take what is left of the shared memory (two stages, 8 bytes per posting)
+  {
+    const size_t fixed = trr_bm25_search_smem(a.range_shift, 0, a.cand_cap) + 64;
+    if (fixed + 2 * 8 * 256 > c->smem_optin) return trr_fail(TRR_ERR_UNSUPPORTED, "BM25 kernel does not fit shared memory");
+    size_t cap = (c->smem_optin - fixed) / 16;
+    cap = std::min<size_t>(cap, 8192) & ~size_t(1);
+    a.stage_cap = (uint32_t)cap;
+  }
+  // few queries: split every query into chunks of document ranges so that all SMs have work
+  uint32_t n_chunks = 1;
+  if (B < 2u * (uint32_t)c->sm_count) n_chunks = std::min<uint32_t>(h->n_ranges, (2u * (uint32_t)c->sm_count + B - 1) / B);
+  if (const char* e = getenv("TRR_BM25_CHUNKS")) n_chunks = std::min<uint32_t>(h->n_ranges, std::max(1, atoi(e)));
+  n_chunks = std::max<uint32_t>(n_chunks, 1);
+  a.n_chunks = n_chunks;
+  const size_t need = scratch_off + WsCarver::need({(size_t)B * 4, 64, n_chunks > 1 ? (size_t)B * n_chunks * k * 8 : 8});
+  TRR_CHECK(extra(c)->scratch.reserve(need));
+  WsCarver ws(static_cast<char*>(extra(c)->scratch.p) + scratch_off);
+  a.order = ws.take<uint32_t>(B);
+  a.queue = ws.take<uint32_t>(16);
+  a.partial = ws.take<uint64_t>(n_chunks > 1 ? (size_t)B * n_chunks * k : 1);
   a.out_keys = nullptr; a.out_ord = d_ord; a.out_score = d_score; a.out_n = d_n;
-  const unsigned grid_fast = std::min<unsigned>(n_fast, (unsigned)c->sm_count * 2);
-  const unsigned grid_slow = std::min<unsigned>(B, (unsigned)c->sm_count * 2);
+  a.dbg = extra(c)->dbg_dev;
+  const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)B * n_chunks, (uint64_t)c->sm_count);
+  TRR_CUDA(trr_launch_bm25_plan(a, st));
   TRR_CUDA(cudaEventRecord(h->ev[2], st));
-  TRR_CUDA(trr_launch_bm25_search(a, grid_fast, grid_slow, st));
+  TRR_CUDA(trr_launch_bm25_search(a, grid, st));
   TRR_CUDA(cudaEventRecord(h->ev[3], st));
-  c->launches += (grid_fast ? 1 : 0) + 1;
+  c->launches += 2;
   h->stats.n_kernel_launches = 2;
+  if (n_chunks > 1) {
+    TopkMergeArgs m{};
+    m.lists = a.partial; m.list_n = nullptr; m.n_lists = n_chunks; m.list_stride = k;
+    m.n_rows = B; m.n_rows_ptr = nullptr; m.row_map = nullptr; m.k = k; m.k2 = trr_pow2_ceil(k);
+    m.out_keys = nullptr; m.out_ord = d_ord; m.out_score = d_score; m.out_n = d_n;
+    TRR_CUDA(trr_launch_topk_merge(m, B, st));
+    c->launches++;
+    h->stats.n_kernel_launches = 3;
+  }
   h->stats.mode_used = 1;
   return TRR_OK;
 }
