@@ -207,5 +207,34 @@ def step_perf_bm25():
     dev.close()
 
 
+def step_perf_bm25_big():
+    """cfg4-shaped BM25 leg only (Zipf vocab 1M, B=1024, k=50) on PROBE_DOCS documents (default 4M)."""
+    import ctypes as C
+    from trueno_rag_b200 import _lib
+    from trueno_rag_b200._lib import u32p, u64p
+    L = _lib.load()
+    ctx = api.Context(0)
+    N, V, B, K = int(os.environ.get("PROBE_DOCS", "4000000")), 1_000_000, 1024, 50
+    seed = 0x5EED0004
+    cdf = O.zipf_cdf(V)
+    df = np.zeros(V, np.uint32); dl = np.zeros(N, np.uint32); tot = C.c_uint64()
+    api._check(L.trr_synth_bm25_count(seed, cdf.ctypes.data_as(u64p), V, 0, N, df.ctypes.data_as(u32p), dl.ctypes.data_as(u32p), C.byref(tot)))
+    term_off = np.zeros(V + 1, np.uint64); np.cumsum(df, out=term_off[1:])
+    P = int(term_off[-1])
+    pd = np.zeros(P, np.uint32); ptf = np.zeros(P, np.uint32)
+    api._check(L.trr_synth_bm25_fill(seed, cdf.ctypes.data_as(u64p), V, 0, N, term_off.ctypes.data_as(u64p), pd.ctypes.data_as(u32p), ptf.ctypes.data_as(u32p)))
+    avgdl = float(np.float32(np.uint32(tot.value & 0xFFFFFFFF)) / np.float32(N))
+    dev = api.Bm25Device(ctx, N, term_off, pd, ptf, dl, avgdl, api.bm25_idf_host(N, df))
+    q_off, q_terms = O.synth_query_terms(seed, cdf, 0, B)
+    vol = int(np.diff(term_off)[q_terms].sum())
+    for it in range(4):
+        got = dev.search(q_terms, q_off, K)
+        st = dev.stats()
+        print(f"K3 {N} docs B={B} k={K}: main {st.ms_main_kernel:.3f} ms  postings/query {vol/B:.0f}  {8*vol/st.ms_main_kernel/1e6:.0f} GB/s "
+              f"{B/st.ms_main_kernel*1e3:.0f} q/s", flush=True)
+    print("checksum", int(got[0].astype(np.uint64).sum()), float(got[1].astype(np.float64).sum()), int(got[2].sum()))
+    dev.close()
+
+
 if __name__ == "__main__":
     globals()["step_" + sys.argv[1]]()

@@ -152,7 +152,7 @@ __device__ __forceinline__ uint32_t lower_bound_doc(const uint2* st, uint32_t lo
 
 }  // namespace
 
-__global__ void __launch_bounds__(TRR_BM25_THREADS, 1)
+__global__ void __launch_bounds__(TRR_BM25_THREADS, 2)
 bm25_search_kernel(Bm25SearchArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t R = 1u << a.range_shift;
@@ -306,29 +306,26 @@ bm25_search_kernel(Bm25SearchArgs a) {
       {
         const uint32_t sb = d.seg_begin[lane], se = d.seg_end[lane];
         const uint32_t d0 = range_base + warp * SUB;
-        const uint32_t lo = lower_bound_doc(st, sb, se, d0);
-        const uint32_t hi = lower_bound_doc(st, lo, se, d0 + SUB);
+        // two interleaved binary searches (independent dependency chains): first posting >= d0 and first >= d0 + SUB
+        uint32_t lo = sb, lo_e = se, hi = sb, hi_e = se;
+        const uint32_t d1 = d0 + SUB;
+        while (lo < lo_e || hi < hi_e) {
+          const uint32_t m0 = (lo + lo_e) >> 1, m1 = (hi + hi_e) >> 1;
+          const uint32_t x0 = lo < lo_e ? st[m0].x : 0u, x1 = hi < hi_e ? st[m1].x : 0u;
+          if (lo < lo_e) { if (x0 < d0) lo = m0 + 1; else lo_e = m0; }
+          if (hi < hi_e) { if (x1 < d1) hi = m1 + 1; else hi_e = m1; }
+        }
         uint32_t m = __ballot_sync(FULLM, hi > lo);
         if (m) touched = true;
         while (m) {  // ascending slot == query-term order
           const uint32_t l = __ffs(m) - 1;
           m &= m - 1;
           const uint32_t lo_ = __shfl_sync(FULLM, lo, l), hi_ = __shfl_sync(FULLM, hi, l);
-          for (uint32_t p = lo_ + lane; p < hi_; p += 128) {
-            const bool v1 = p + 32 < hi_, v2 = p + 64 < hi_, v3 = p + 96 < hi_;
+#pragma unroll 1
+          for (uint32_t p = lo_ + lane; p < hi_; p += 32) {
             const uint2 e0 = st[p];
-            const uint2 e1 = v1 ? st[p + 32] : e0;
-            const uint2 e2 = v2 ? st[p + 64] : e0;
-            const uint2 e3 = v3 ? st[p + 96] : e0;
             float* p0 = acc + (e0.x - range_base);
-            float* p1 = acc + (e1.x - range_base);
-            float* p2 = acc + (e2.x - range_base);
-            float* p3 = acc + (e3.x - range_base);
-            const float f0 = *p0, f1 = *p1, f2 = *p2, f3 = *p3;
-            *p0 = f0 + __uint_as_float(e0.y);
-            if (v1) *p1 = f1 + __uint_as_float(e1.y);
-            if (v2) *p2 = f2 + __uint_as_float(e2.y);
-            if (v3) *p3 = f3 + __uint_as_float(e3.y);
+            *p0 = *p0 + __uint_as_float(e0.y);
           }
           __syncwarp();
         }
@@ -344,28 +341,36 @@ bm25_search_kernel(Bm25SearchArgs a) {
           if (touched) {
             uint4* a4 = reinterpret_cast<uint4*>(my_acc);
             const uint32_t ord0 = a.doc_base + range_base + warp * SUB;
-            for (uint32_t i = lane; i < (SUB >> 2); i += 32) {
-              uint4 v = a4[i];
-              if ((v.x | v.y | v.z | v.w) == 0u) continue;
-              uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
+            auto harvest4 = [&](uint32_t i, uint4 v) {
+              if ((v.x | v.y | v.z | v.w) == 0u) return;
+              const float mx = fmaxf(fmaxf(__uint_as_float(v.x), __uint_as_float(v.y)),
+                                     fmaxf(__uint_as_float(v.z), __uint_as_float(v.w)));
+              if (!(mx >= thr_f)) {  // nothing here can enter the top-k (NaN compares false): just re-zero
+                a4[i] = make_uint4(0u, 0u, 0u, 0u);
+                return;
+              }
+#pragma unroll 1
               for (int j = 0; j < 4; ++j) {
-                const float f = __uint_as_float(w[j]);
+                const float f = my_acc[i * 4 + j];
+                bool keep = false;
                 if (f >= thr_f && f > 0.0f) {  // src/index.rs:236 keeps only score > 0.0
                   const uint64_t key = trr_make_key(f, ord0 + i * 4 + j);
                   if (key > thr) {
                     const uint32_t pos = atomicAdd(&s_cnt, 1u);
-                    if (pos < a.cand_cap) { cand[pos] = key; w[j] = 0u; }
-                    else s_overflow = 1u;  // stays in the accumulator; retried after the compaction
-                  } else {
-                    w[j] = 0u;
+                    if (pos < a.cand_cap) cand[pos] = key;
+                    else { s_overflow = 1u; keep = true; }  // stays in the accumulator; retried after the compaction
                   }
-                } else {
-                  w[j] = 0u;
                 }
+                if (!keep) my_acc[i * 4 + j] = 0.0f;
               }
-              a4[i] = make_uint4(w[0], w[1], w[2], w[3]);
+            };
+            const uint32_t n4 = SUB >> 2;  // multiple of 32 (SUB >= 128)
+            uint32_t i = lane;
+            for (; i + 96 < n4; i += 128) {
+              const uint4 v0 = a4[i], v1 = a4[i + 32], v2 = a4[i + 64], v3 = a4[i + 96];
+              harvest4(i, v0); harvest4(i + 32, v1); harvest4(i + 64, v2); harvest4(i + 96, v3);
             }
+            for (; i < n4; i += 32) harvest4(i, a4[i]);
           }
           consumer_bar();
           const uint32_t ovf = s_overflow, cnt = s_cnt;

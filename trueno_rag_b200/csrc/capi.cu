@@ -846,17 +846,24 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   a.n_ranges = h->n_ranges; a.range_shift = h->range_shift; a.doc_base = h->doc_base;
   a.q_terms = d_q_terms; a.q_off = d_q_off; a.B = B; a.k = k;
   a.cand_cap = trr_pow2_ceil(k + 512);
-  // stage buffers take what is left of the shared memory (two stages, 8 bytes per posting)
+  // stage buffers take what is left of the shared memory (two stages, 8 bytes per posting).  Ranges of <= 16K
+  // documents leave room for two CTAs per SM.
+  uint32_t ctas_per_sm = a.range_shift <= 14 ? 2u : 1u;
+  if (const char* e = getenv("TRR_BM25_CTAS_PER_SM")) ctas_per_sm = std::min(2, std::max(1, atoi(e)));
   {
     const size_t fixed = trr_bm25_search_smem(a.range_shift, 0, a.cand_cap) + 64;
-    if (fixed + 2 * 8 * 256 > c->smem_optin) return trr_fail(TRR_ERR_UNSUPPORTED, "BM25 kernel does not fit shared memory");
-    size_t cap = (c->smem_optin - fixed) / 16;
+    size_t budget = c->smem_optin;
+    if (ctas_per_sm == 2) budget = (228 * 1024) / 2 - 1024 - 64;  // 228 KB per SM, 1 KB reserved per CTA
+    if (fixed + 2 * 8 * 256 > budget) { ctas_per_sm = 1; budget = c->smem_optin; }
+    if (fixed + 2 * 8 * 256 > budget) return trr_fail(TRR_ERR_UNSUPPORTED, "BM25 kernel does not fit shared memory");
+    size_t cap = (budget - fixed) / 16;
     cap = std::min<size_t>(cap, 8192) & ~size_t(1);
     a.stage_cap = (uint32_t)cap;
   }
   // few queries: split every query into chunks of document ranges so that all SMs have work
   uint32_t n_chunks = 1;
-  if (B < 2u * (uint32_t)c->sm_count) n_chunks = std::min<uint32_t>(h->n_ranges, (2u * (uint32_t)c->sm_count + B - 1) / B);
+  const uint32_t slots = (uint32_t)c->sm_count * ctas_per_sm;
+  if (B < 2u * slots) n_chunks = std::min<uint32_t>(h->n_ranges, (2u * slots + B - 1) / B);
   if (const char* e = getenv("TRR_BM25_CHUNKS")) n_chunks = std::min<uint32_t>(h->n_ranges, std::max(1, atoi(e)));
   n_chunks = std::max<uint32_t>(n_chunks, 1);
   a.n_chunks = n_chunks;
@@ -868,7 +875,7 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   a.partial = ws.take<uint64_t>(n_chunks > 1 ? (size_t)B * n_chunks * k : 1);
   a.out_keys = nullptr; a.out_ord = d_ord; a.out_score = d_score; a.out_n = d_n;
   a.dbg = extra(c)->dbg_dev;
-  const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)B * n_chunks, (uint64_t)c->sm_count);
+  const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)B * n_chunks, (uint64_t)slots);
   TRR_CUDA(trr_launch_bm25_plan(a, st));
   TRR_CUDA(cudaEventRecord(h->ev[2], st));
   TRR_CUDA(trr_launch_bm25_search(a, grid, st));
