@@ -85,7 +85,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -355,7 +355,8 @@ def run_ours(a):
             "gpu_launches": int(launches.item()),
             "roofline": {"kernel": "dense_gemm_topk_kernel (tcgen05 bf16 GEMM + fused top-k), rank 0 shard",
                          "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": ncu_traffic("gemm", a), "traffic_source": "profiles/r*_gemm_ncu.txt (ncu --set full, same command)",
+                         "peak_source": peak_src,
                          "algorithmic": f"2*B*N_shard*D = {flops:.4g} flop per launch / {g_ms:.3f} ms"},
             "kernels": {"gemm_ms": g_ms, "bm25_ms": b_ms,
                         "bm25": {"bound": "hbm", "achieved": bm_gbs, "peak": peak_hbm, "unit": "GB/s", "frac": bm_gbs / peak_hbm,
@@ -369,6 +370,26 @@ def run_ours(a):
     dense.close(); bm.close(); ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(kind, a):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture of
+    this same command (profiles/rNN_<kind>_ncu.txt, written by tools/make_profiles.py); None when the capture was taken
+    at another size."""
+    import glob
+    import re
+    if (a.docs, a.dim, a.batch, a.gpus) != (10_000_000, 768, 1024, 1):
+        return None
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_{kind}_ncu.txt")))
+    if not files:
+        return None
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    tot = 0.0
+    for line in open(files[-1]):
+        m = re.match(r"\s*dram__bytes_(read|write)\.sum \[(\w+)\] = ([0-9.eE+-]+)", line)
+        if m:
+            tot += float(m.group(3)) * mult.get(m.group(2), 1.0)
+    return tot or None
 
 
 def verify_against_oracle(a, outputs, n_check):
