@@ -167,7 +167,7 @@ def step_perf_scan():
 
 def step_perf_gemm():
     ctx = api.Context(0)
-    n, d, B = 2_000_000, 768, 1024
+    n, d, B = int(os.environ.get("PROBE_DOCS", "2000000")), int(os.environ.get("PROBE_DIM", "768")), int(os.environ.get("PROBE_B", "1024"))
     ix = api.DenseIndex(ctx, d, 0, 1, capacity=n)
     t0 = time.time()
     ix.append_synth(SEED, 0, n)
@@ -178,7 +178,7 @@ def step_perf_gemm():
         ix.search(Q, 50)
         st = ix.stats()
         fl = 2.0 * B * n * d
-        print(f"K2 2Mx768 bf16 B=1024: main {st.ms_main_kernel:.3f} ms total {st.ms_total:.3f} ms "
+        print(f"K2 {n}x{d} bf16 B={B}: main {st.ms_main_kernel:.3f} ms total {st.ms_total:.3f} ms "
               f"{fl/st.ms_main_kernel/1e9:.0f} TFLOP/s fallbacks={st.n_guard_fallbacks} gap={st.max_fast_exact_gap:.2e}")
     ix.close()
 

@@ -539,8 +539,13 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     if (n_slices == 0) n_slices = 1;
     const uint32_t B_pad = n_qblocks * TRR_GEMM_TILE_M;
     const uint32_t CP = TRR_GEMM_CP;
-    const size_t n_cand = (size_t)n_slices * n_qblocks * TRR_GEMM_TILE_M * CP;
-    const uint32_t cap2 = trr_pow2_ceil(n_slices * CP);
+    // list length per (query, slice): the global top-CP is spread over the slices, so short lists suffice when there
+    // are many slices; the candidate proof (rescore_select_kernel) catches the (adversarial) cases where they do not
+    uint32_t cps = n_slices >= 8 ? 16u : (n_slices >= 3 ? 32u : 64u);
+    if (const char* e = getenv("TRR_GEMM_CPS")) { const int v = atoi(e); if (v == 16 || v == 32 || v == 64) cps = (uint32_t)v; }
+    if ((uint64_t)n_slices * cps < CP) cps = CP;
+    const size_t n_cand = (size_t)n_slices * n_qblocks * TRR_GEMM_TILE_M * cps;
+    const uint32_t cap2 = std::max<uint32_t>(trr_pow2_ceil(n_slices * cps), 2 * CP);
     // scratch layout (single reservation so that pointers stay valid)
     ScanPlan p;
     TRR_CHECK(plan_scan(h, k, &p));
@@ -575,7 +580,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     ga.k_blocks = (h->dim_pad + 63) / 64; ga.base_ord = h->base;
     ga.scale_bias = reinterpret_cast<const float2*>(h->scale_bias.p);
     ga.cand_score = cand_score; ga.cand_ord = cand_ord; ga.gthr = gthr; ga.share_thresholds = 1;
-    ga.pair_mode = pair_mode;
+    ga.pair_mode = pair_mode; ga.cps = cps;
     ga.dbg = extra(c)->dbg_dev;
     if (const char* e = getenv("TRR_GEMM_DEBUG")) ga.debug_mode = atoi(e);      // perf triage only; results are wrong
     if (const char* e = getenv("TRR_GEMM_NOSHARE")) ga.share_thresholds = atoi(e) ? 0 : 1;
@@ -586,7 +591,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
 
     RescoreArgs ra{};
     ra.cand_score = cand_score; ra.cand_ord = cand_ord; ra.n_slices = n_slices; ra.n_qblocks = n_qblocks;
-    ra.cp = CP; ra.cap2 = cap2 < CP ? CP : cap2;
+    ra.cps = cps; ra.cp = CP; ra.cap2 = cap2;
     ra.rows = h->rows; ra.dim = h->dim; ra.norms = h->norms; ra.base_ord = h->base; ra.n_live = n_live;
     ra.q = d_q; ra.q_norms = d_qn; ra.q_delta = d_qdelta; ra.max_norm = reinterpret_cast<const float*>(h->max_norm.p);
     ra.B = B; ra.k = k; ra.metric = h->metric;
@@ -722,7 +727,7 @@ extern "C" TRR_API int trr_debug_gemm_scores(trr_dense* h, const float* q, uint3
   ga.k_blocks = (h->dim_pad + 63) / 64; ga.base_ord = h->base;
   ga.scale_bias = reinterpret_cast<const float2*>(h->scale_bias.p);
   ga.cand_score = cand_score; ga.cand_ord = cand_ord; ga.gthr = gthr; ga.share_thresholds = 0;
-  ga.pair_mode = pair_mode;
+  ga.pair_mode = pair_mode; ga.cps = TRR_GEMM_CP;
   ga.dbg = extra(c)->dbg_dev;
   TRR_CUDA(trr_launch_gemm_topk_dump(ga, map_q, pair_mode ? h->map_d_half : h->map_d, n_slices * n_qblocks, dump, out_ld,
                                      st));

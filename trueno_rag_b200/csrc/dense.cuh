@@ -44,9 +44,12 @@ struct TopkMergeArgs {
 
 // exact rescoring + candidate proof (dense_scan.cu)
 struct RescoreArgs {
-  const float* cand_score;   // [n_slices][n_qblocks][128][cp] fast scores
+  const float* cand_score;   // [n_slices][n_qblocks][128][cps] fast scores
   const uint32_t* cand_ord;  // same shape, 0xFFFFFFFF = empty
-  uint32_t n_slices, n_qblocks, cp, cap2;  // cap2 = power of two >= n_slices*cp
+  uint32_t n_slices, n_qblocks;
+  uint32_t cps;              // candidates kept per (query, slice) by the tensor-core pass
+  uint32_t cp;               // candidates re-scored exactly per query (power of two, >= k)
+  uint32_t cap2;             // power of two >= max(n_slices*cps, cp + 1)
   const void* rows;          // slab in the store dtype
   uint32_t dim;
   const float* norms;
@@ -77,7 +80,8 @@ struct GemmTopkArgs {
   uint32_t k_blocks;         // ceil(dim / 64)
   uint32_t base_ord;
   const float2* scale_bias;  // [n_tiles*256]
-  float* cand_score;         // [n_slices][n_qblocks][128][CP]
+  uint32_t cps;              // candidates kept per (query, slice): 16, 32 or 64 (<= TRR_GEMM_CP)
+  float* cand_score;         // [n_slices][n_qblocks][128][cps]
   uint32_t* cand_ord;
   uint32_t* gthr;            // [n_qblocks*128] shared running thresholds (orderable-encoded), zeroed by the caller
   int share_thresholds;
@@ -97,7 +101,7 @@ cudaError_t trr_launch_topk_merge(const TopkMergeArgs& a, unsigned grid, cudaStr
 cudaError_t trr_launch_rescore(const RescoreArgs& a, int is_bf16, cudaStream_t st);
 
 // dense_gemm.cu
-constexpr uint32_t TRR_GEMM_CP = 64;      // fast candidates kept per (query, slice)
+constexpr uint32_t TRR_GEMM_CP = 64;      // exact re-scoring width per query; also the maximum list length per (query, slice)
 constexpr uint32_t TRR_GEMM_TILE_N = 256; // documents per MMA tile
 constexpr uint32_t TRR_GEMM_TILE_M = 128; // queries per CTA
 // converts B x dim f32 queries to a zero-padded [n_qblocks*128][dim_pad] bf16 matrix and reports ||q - bf16(q)||

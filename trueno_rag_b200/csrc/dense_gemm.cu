@@ -38,7 +38,8 @@ constexpr uint32_t STAGES = 3;
 constexpr uint32_t CP = TRR_GEMM_CP;
 constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KB
 constexpr uint32_t B_BYTES = BN * BK * 2;  // 32 KB
-constexpr uint32_t LIST_BYTES = BM * CP * 4;
+constexpr uint32_t LSTRIDE = CP + 1;                 // words per row of a candidate list: odd, so lane == row is conflict-free
+constexpr uint32_t LIST_BYTES = BM * LSTRIDE * 4;
 constexpr uint32_t SMEM_A = 0;
 constexpr uint32_t SMEM_B = SMEM_A + STAGES * A_BYTES;
 constexpr uint32_t SMEM_LS = SMEM_B + STAGES * B_BYTES;
@@ -126,35 +127,25 @@ struct RowState {
   uint32_t minpos; // its position
 };
 
-// Warp-cooperative replace-min insertion.  `m` = lanes holding a value `s` (document `doc`, both per lane) that
-// beats their row's threshold.  For each such lane in turn the warp overwrites the minimum entry of that row's list and
-// recomputes the minimum with a two-entries-per-lane scan + warp arg-min.  Kept out of line: it is rare
-// in steady state and would otherwise be replicated 256 times in the unrolled column loop.
-__device__ __noinline__ RowState insert_events(uint32_t m, float s, uint32_t doc, RowState st, float* ls_warp,
-                                               uint32_t* lo_warp, uint32_t lane) {
-  while (m) {
-    const uint32_t src = __ffs(m) - 1;
-    m &= m - 1;
-    const float nv = __shfl_sync(FULL, s, src);
-    const uint32_t nd = __shfl_sync(FULL, doc, src);
-    const uint32_t mp = __shfl_sync(FULL, st.minpos, src);
-    float* rs = ls_warp + src * CP;
-    uint32_t* ro = lo_warp + src * CP;
-    if (lane == 0) { rs[mp] = nv; ro[mp] = nd; }
-    __syncwarp();
-    const float e0 = rs[lane], e1 = rs[lane + 32];
-    float mn = e0;
-    uint32_t pos = lane;
-    if (e1 < mn) { mn = e1; pos = lane + 32; }
-#pragma unroll
-    for (uint32_t o = 16; o > 0; o >>= 1) {
-      const float om = __shfl_xor_sync(FULL, mn, o);
-      const uint32_t op = __shfl_xor_sync(FULL, pos, o);
-      if (om < mn || (om == mn && op < pos)) { mn = om; pos = op; }
-    }
-    if (lane == src) { st.list_min = mn; st.minpos = pos; if (mn > st.thr) st.thr = mn; }
-    __syncwarp();
+// Lane-private replace-min insertion: every epilogue lane owns one query row and its candidate list of `cps` entries
+// (16 / 32 / 64, chosen by the host from the number of document slices).  The new value overwrites the list minimum and
+// the minimum is found again by a scan of the lane's own list; lanes of a warp insert independently (rows differ), so no
+// warp-level cooperation or synchronisation is needed.  Kept out of line: rare in steady state.
+__device__ __noinline__ RowState insert_private(RowState st, float s, uint32_t doc, float* my_ls, uint32_t* my_lo,
+                                                uint32_t cps) {
+  if (!(s > st.thr)) return st;
+  my_ls[st.minpos] = s;
+  my_lo[st.minpos] = doc;
+  float mn = my_ls[0];
+  uint32_t pos = 0;
+#pragma unroll 8
+  for (uint32_t j = 1; j < cps; ++j) {
+    const float e = my_ls[j];
+    if (e < mn) { mn = e; pos = j; }
   }
+  st.list_min = mn;
+  st.minpos = pos;
+  if (mn > st.thr) st.thr = mn;
   return st;
 }
 
@@ -239,17 +230,15 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     const uint32_t row = quarter * 32 + lane;     // query row inside the block
     float* ls_all = reinterpret_cast<float*>(smem + SMEM_LS);
     uint32_t* lo_all = reinterpret_cast<uint32_t*>(smem + SMEM_LO);
-    float* my_ls = ls_all + row * CP;
-    uint32_t* my_lo = lo_all + row * CP;
-    for (uint32_t j = 0; j < CP; ++j) { my_ls[j] = -CUDART_INF_F; my_lo[j] = 0xFFFFFFFFu; }
-    __syncwarp();
+    float* my_ls = ls_all + row * LSTRIDE;
+    uint32_t* my_lo = lo_all + row * LSTRIDE;
+    const uint32_t cps = a.cps;
+    for (uint32_t j = 0; j < cps; ++j) { my_ls[j] = -CUDART_INF_F; my_lo[j] = 0xFFFFFFFFu; }
     RowState st;
     st.list_min = -CUDART_INF_F;      // smallest score in this row's list
     st.minpos = 0;
     st.thr = -CUDART_INF_F;           // max(list_min, shared threshold)
     uint32_t* gthr = a.gthr + (qb * BM + row);
-    float* ls_warp = ls_all + quarter * 32 * CP;
-    uint32_t* lo_warp = lo_all + quarter * 32 * CP;
 
     // scale/bias of the next 32 columns are prefetched one chunk ahead (16 x LDG.128, L1/L2 hits)
     float4 sb_cur[16];
@@ -296,21 +285,12 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
           for (uint32_t j = 0; j < 32; ++j) dump[(uint64_t)(qb * BM + row) * dump_ld + doc0 + c * 32 + j] = sv[j];
         }
         if (a.debug_mode == 2) pmask = 0;
-        // rare path: some lane has a value above its row's threshold
-        while (__any_sync(FULL, pmask != 0)) {
-          // each lane picks its next column that still beats its (possibly updated) threshold
-          float cand = 0.0f;
-          int cj = -1;
-          while (pmask) {
-            const int j = __ffs(pmask) - 1;
-            pmask &= pmask - 1;
-            float val = sv[0];
+        // rare path: some lane has a value above its row's threshold (re-tested inside: the threshold rises as we insert)
+        if (__any_sync(FULL, pmask != 0)) {
+          const uint32_t dbase = a.base_ord + doc0 + c * 32;
 #pragma unroll
-            for (int jj = 1; jj < 32; ++jj) val = (jj == j) ? sv[jj] : val;
-            if (val > st.thr) { cand = val; cj = j; break; }
-          }
-          const uint32_t m = __ballot_sync(FULL, cj >= 0);
-          if (m) st = insert_events(m, cand, a.base_ord + doc0 + c * 32 + (uint32_t)cj, st, ls_warp, lo_warp, lane);
+          for (uint32_t j = 0; j < 32; ++j)
+            if (pmask & (1u << j)) st = insert_private(st, sv[j], dbase + j, my_ls, my_lo, cps);
         }
 #pragma unroll
         for (uint32_t i = 0; i < 16; ++i) sb_cur[i] = sb_nxt[i];
@@ -321,8 +301,8 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       if (a.share_thresholds && st.list_min > -CUDART_INF_F) atomicMax(gthr, trr_f32_orderable(st.list_min));
     }
     // publish this slice's candidates
-    const uint64_t base = (((uint64_t)slice * a.n_qblocks + qb) * BM + row) * CP;
-    for (uint32_t j = 0; j < CP; ++j) { a.cand_score[base + j] = my_ls[j]; a.cand_ord[base + j] = my_lo[j]; }
+    const uint64_t base = (((uint64_t)slice * a.n_qblocks + qb) * BM + row) * cps;
+    for (uint32_t j = 0; j < cps; ++j) { a.cand_score[base + j] = my_ls[j]; a.cand_ord[base + j] = my_lo[j]; }
   }
 
   tc_fence_before();
@@ -483,17 +463,15 @@ dense_gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     const uint32_t row = quarter * 32 + lane;
     float* ls_all = reinterpret_cast<float*>(smem + SMEM2_LS);
     uint32_t* lo_all = reinterpret_cast<uint32_t*>(smem + SMEM2_LO);
-    float* my_ls = ls_all + row * CP;
-    uint32_t* my_lo = lo_all + row * CP;
-    for (uint32_t j = 0; j < CP; ++j) { my_ls[j] = -CUDART_INF_F; my_lo[j] = 0xFFFFFFFFu; }
-    __syncwarp();
+    float* my_ls = ls_all + row * LSTRIDE;
+    uint32_t* my_lo = lo_all + row * LSTRIDE;
+    const uint32_t cps = a.cps;
+    for (uint32_t j = 0; j < cps; ++j) { my_ls[j] = -CUDART_INF_F; my_lo[j] = 0xFFFFFFFFu; }
     RowState st;
     st.list_min = -CUDART_INF_F;
     st.minpos = 0;
     st.thr = -CUDART_INF_F;
     uint32_t* gthr = a.gthr + (qb * BM + row);
-    float* ls_warp = ls_all + quarter * 32 * CP;
-    uint32_t* lo_warp = lo_all + quarter * 32 * CP;
     const uint32_t leader_tempty[2] = {mapa_u32(trr_smem_u32(&tempty_bar[0]), 0), mapa_u32(trr_smem_u32(&tempty_bar[1]), 0)};
 
     float4 sb_cur[16];
@@ -539,19 +517,11 @@ dense_gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
           for (uint32_t j = 0; j < 32; ++j) dump[(uint64_t)(qb * BM + row) * dump_ld + doc0 + c * 32 + j] = sv[j];
         }
         if (a.debug_mode == 2) pmask = 0;
-        while (__any_sync(FULL, pmask != 0)) {
-          float cand = 0.0f;
-          int cj = -1;
-          while (pmask) {
-            const int j = __ffs(pmask) - 1;
-            pmask &= pmask - 1;
-            float val = sv[0];
+        if (__any_sync(FULL, pmask != 0)) {
+          const uint32_t dbase = a.base_ord + doc0 + c * 32;
 #pragma unroll
-            for (int jj = 1; jj < 32; ++jj) val = (jj == j) ? sv[jj] : val;
-            if (val > st.thr) { cand = val; cj = j; break; }
-          }
-          const uint32_t m = __ballot_sync(FULL, cj >= 0);
-          if (m) st = insert_events(m, cand, a.base_ord + doc0 + c * 32 + (uint32_t)cj, st, ls_warp, lo_warp, lane);
+          for (uint32_t j = 0; j < 32; ++j)
+            if (pmask & (1u << j)) st = insert_private(st, sv[j], dbase + j, my_ls, my_lo, cps);
         }
 #pragma unroll
         for (uint32_t i = 0; i < 16; ++i) sb_cur[i] = sb_nxt[i];
@@ -560,8 +530,8 @@ dense_gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
       mbar_arrive_cluster(leader_tempty[as]);
       if (a.share_thresholds && st.list_min > -CUDART_INF_F) atomicMax(gthr, trr_f32_orderable(st.list_min));
     }
-    const uint64_t base = (((uint64_t)slice * a.n_qblocks + qb) * BM + row) * CP;
-    for (uint32_t j = 0; j < CP; ++j) { a.cand_score[base + j] = my_ls[j]; a.cand_ord[base + j] = my_lo[j]; }
+    const uint64_t base = (((uint64_t)slice * a.n_qblocks + qb) * BM + row) * cps;
+    for (uint32_t j = 0; j < cps; ++j) { a.cand_score[base + j] = my_ls[j]; a.cand_ord[base + j] = my_lo[j]; }
   }
 
   tc_fence_before();

@@ -397,24 +397,36 @@ rescore_select_kernel(RescoreArgs a) {
   uint64_t* ekeys = keys + a.cap2;                                     // CP exact keys (CP power of two)
   float* efast = reinterpret_cast<float*>(ekeys + a.cp);              // fast score of each kept candidate
   __shared__ float s_gap;
-  __shared__ uint32_t s_total;
+  __shared__ uint32_t s_total, s_tmax;
   const uint32_t b = blockIdx.x;
   if (b >= a.B) return;
   const uint32_t tid = threadIdx.x;
-  if (tid == 0) { s_gap = 0.0f; s_total = 0; }
+  if (tid == 0) { s_gap = 0.0f; s_total = 0; s_tmax = 0; }
   for (uint32_t i = tid; i < a.cap2; i += blockDim.x) keys[i] = TRR_KEY_EMPTY;
   __syncthreads();
   // 1. gather: slice s of query block qb = b / 128, row r = b % 128
   const uint32_t qb = b / 128, r = b % 128;
   uint32_t local_total = 0;
-  for (uint32_t i = tid; i < a.n_slices * a.cp; i += blockDim.x) {
-    const uint32_t s = i / a.cp, j = i % a.cp;
-    const uint64_t base = (((uint64_t)s * a.n_qblocks + qb) * 128 + r) * a.cp + j;
+  for (uint32_t i = tid; i < a.n_slices * a.cps; i += blockDim.x) {
+    const uint32_t s = i / a.cps, j = i % a.cps;
+    const uint64_t base = (((uint64_t)s * a.n_qblocks + qb) * 128 + r) * a.cps + j;
     const float sc = a.cand_score[base];
     const uint32_t od = a.cand_ord[base];
     if (od != 0xFFFFFFFFu) { keys[i] = trr_make_key(sc, od); ++local_total; }
   }
   if (local_total) atomicAdd(&s_total, local_total);
+  // a slice whose list is full may have dropped documents: all of them scored at most the list minimum (and the
+  // thresholds shared between slices never exceed a list minimum).  s_tmax = the largest such bound.
+  for (uint32_t s = tid; s < a.n_slices; s += blockDim.x) {
+    const uint64_t base = (((uint64_t)s * a.n_qblocks + qb) * 128 + r) * a.cps;
+    float mn = CUDART_INF_F;
+    bool full = true;
+    for (uint32_t j = 0; j < a.cps; ++j) {
+      if (a.cand_ord[base + j] == 0xFFFFFFFFu) full = false;
+      else mn = fminf(mn, a.cand_score[base + j]);
+    }
+    if (full) atomicMax(&s_tmax, trr_f32_orderable(mn));
+  }
   __syncthreads();
   trr_bitonic_sort_desc(keys, a.cap2, tid, blockDim.x, BlockSync());
   const uint32_t n_cand = min(s_total, a.cp);
@@ -469,11 +481,15 @@ rescore_select_kernel(RescoreArgs a) {
     bool ok = true;
     const bool something_excluded = a.n_live > (uint64_t)n_cand;
     if (something_excluded) {
-      if (n_out < a.k || n_cand < a.cp) {
-        ok = false;  // fewer candidates than needed although documents were excluded (non-finite scores)
+      const bool bounded = s_total > a.cp || s_tmax != 0u;
+      if (n_out < a.k || !bounded) {
+        ok = false;  // fewer results than asked for, or documents vanished without a bound (non-finite scores)
       } else {
-        // largest fast score any excluded document can have: the cp-th best fast score overall
-        const float f_excl = trr_key_score(keys[a.cp - 1]);
+        // largest fast score any excluded document can have: the best gathered candidate that was not re-scored, or
+        // the largest bound on what a slice dropped
+        float f_excl = -CUDART_INF_F;
+        if (s_total > a.cp) f_excl = trr_key_score(keys[a.cp]);
+        if (s_tmax != 0u) f_excl = fmaxf(f_excl, trr_orderable_f32(s_tmax));
         const float f_excl_s = (a.metric == TRR_METRIC_COSINE) ? (q_norm > 0.0f ? f_excl / q_norm : 0.0f) : f_excl;
         float eps = a.eps_rel;                                  // cosine units
         if (a.metric == TRR_METRIC_COSINE) eps += (q_norm > 0.0f ? a.q_delta[b] / q_norm : 0.0f);
