@@ -149,16 +149,17 @@ def step_fusion():
 
 def step_perf_scan():
     ctx = api.Context(0)
-    n, d = 1_000_000, 384
-    ix = api.DenseIndex(ctx, d, 0, 0, capacity=n)
+    n, d = int(os.environ.get("PROBE_DOCS", "1000000")), int(os.environ.get("PROBE_DIM", "384"))
+    dt = int(os.environ.get("PROBE_DTYPE", "0"))
+    ix = api.DenseIndex(ctx, d, 0, dt, capacity=n)
     ix.append_synth(SEED, 0, n)
     ix.set_mode(1)
     Q = O.synth_queries(SEED, 0, 4, d, n)
-    for it in range(3):
+    for it in range(5):
         ix.search(Q[:1], 10)
         st = ix.stats()
-        print(f"K1 1Mx384 f32 B=1: main {st.ms_main_kernel*1e3:.1f} us total {st.ms_total*1e3:.1f} us  "
-              f"{n*d*4/st.ms_main_kernel/1e6:.0f} GB/s")
+        print(f"K1 {n}x{d} dtype={dt} B=1: main {st.ms_main_kernel*1e3:.1f} us total {st.ms_total*1e3:.1f} us  "
+              f"{n*d*(2 if dt else 4)/st.ms_main_kernel/1e6:.0f} GB/s")
     f, _ = O.synth_corpus(SEED, 0, 200000, d)
     got = ix.search(Q[:1], 10)
     print("top1", got[0][0, :5], got[1][0, :5])

@@ -178,11 +178,26 @@ __device__ __forceinline__ void trr_mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!trr_mbar_try_wait(bar, parity)) {
   }
 }
+// bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU
+__device__ __forceinline__ void trr_mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  if (trr_mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!trr_mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
 // 1-D bulk copy global -> shared, completion signalled on an mbarrier (bytes multiple of 16, 16-B aligned)
 __device__ __forceinline__ void trr_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    trr_smem_u32(smem_dst)),
                "l"(gmem_src), "r"(bytes), "r"(trr_smem_u32(bar))
                : "memory");
+}
+// 2-D TMA tile load global -> shared (tensor map in kernel parameter space), completion on an mbarrier
+__device__ __forceinline__ void trr_tma_load_2d(const void* map, void* smem_dst, uint64_t* bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(trr_smem_u32(smem_dst)), "l"(map), "r"(trr_smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
 }
 #endif  // __CUDACC__

@@ -18,6 +18,7 @@ struct DenseScanArgs {
   uint32_t n_sel;
   uint32_t ch_bytes;         // bulk kernel: bytes of a row staged per chunk (multiple of 16)
   uint32_t n_chunks;
+  uint32_t n_slots;          // TMA kernel: 4 KB ring slots per warp
   uint32_t k;
   uint32_t cap;              // per-warp top-k buffer capacity (power of two >= k + 32)
   uint32_t base_ord;
@@ -97,6 +98,10 @@ void trr_launch_gemm_operands(const float* norms, const uint8_t* dead, uint64_t 
 void trr_launch_query_norms(const float* q, uint32_t dim, uint32_t B, float* qn, cudaStream_t st);
 cudaError_t trr_launch_scan(const DenseScanArgs& a, int is_bf16, int metric, bool bulk, unsigned grid, size_t smem,
                             cudaStream_t st);
+// K1 with a 2-D TMA ring (rows of a multiple of 16 bytes): map_rows128 = tensor map of the slab, box 32 rows x 128 bytes
+cudaError_t trr_launch_scan_tma(const DenseScanArgs& a, const void* map_rows128, int is_bf16, int metric, unsigned grid,
+                                unsigned n_warps, size_t smem, cudaStream_t st);
+size_t trr_scan_tma_smem(uint32_t dim, uint32_t cap, uint32_t n_slots, uint32_t n_warps);
 cudaError_t trr_launch_topk_merge(const TopkMergeArgs& a, unsigned grid, cudaStream_t st);
 cudaError_t trr_launch_rescore(const RescoreArgs& a, int is_bf16, cudaStream_t st);
 
@@ -112,5 +117,8 @@ void trr_launch_shadow(const void* rows, int is_bf16, uint32_t dim, uint32_t dim
                        uint16_t* shadow, cudaStream_t st);
 // encodes a 2-D K-major bf16 tensor map (rows x cols, box = box_rows x 64, 128-byte swizzle); 128-byte opaque blob
 int trr_make_tensor_map(void* out_map128, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+// general form: element size 2 (bf16) or 4 (f32), box = box_rows x box_cols elements (box_cols * elem_bytes == 128)
+int trr_make_tensor_map_ex(void* out_map128, const void* base, uint64_t rows, uint64_t cols, uint32_t elem_bytes,
+                           uint32_t box_cols, uint32_t box_rows);
 cudaError_t trr_launch_gemm_topk(const GemmTopkArgs& a, const void* map_q128, const void* map_d128, unsigned grid,
                                  cudaStream_t st);

@@ -611,7 +611,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int trr_make_tensor_map(void* out_map128, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+int trr_make_tensor_map_ex(void* out_map128, const void* base, uint64_t rows, uint64_t cols, uint32_t elem_bytes,
+                           uint32_t box_cols, uint32_t box_rows) {
   static PFN_encodeTiled fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -624,14 +625,18 @@ int trr_make_tensor_map(void* out_map128, const void* base, uint64_t rows, uint6
   static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
   CUtensorMap* m = reinterpret_cast<CUtensorMap*>(out_map128);
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};  // bytes between rows
-  cuuint32_t box[2] = {BK, box_rows};
+  cuuint64_t strides[1] = {cols * elem_bytes};  // bytes between rows
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return trr_fail(TRR_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
   return TRR_OK;
+}
+
+int trr_make_tensor_map(void* out_map128, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  return trr_make_tensor_map_ex(out_map128, base, rows, cols, 2, BK, box_rows);
 }
 
 cudaError_t trr_launch_gemm_topk_dump(const GemmTopkArgs& a, const void* map_q128, const void* map_d128, unsigned grid,

@@ -11,7 +11,9 @@
 //       dense_norms_kernel         per-row sqrt(sum x*x) in reference order + GEMM epilogue operands
 //       topk_merge_kernel          merges per-warp partial top-k lists (canonical order)
 //       rescore_select_kernel      exact rescoring + candidate proof for the tensor-core fast pass
+#include <cuda.h>
 #include <math_constants.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "dense.cuh"
@@ -250,6 +252,127 @@ dense_scan_bulk_kernel(DenseScanArgs a) {
       if (valid) score = finish_score<METRIC>(acc, q_norm, METRIC == TRR_METRIC_COSINE ? a.norms[row] : 0.0f);
       tk.push(trr_make_key(score, a.base_ord + (uint32_t)row), valid, lane);
     }
+    tk.compact(lane);
+    cta_merge_and_store(tk, tk_base, a.cap, NWARPS, warp, lane, warp_cnt,
+                        a.partial + ((uint64_t)si * gridDim.x + blockIdx.x) * a.k,
+                        a.partial_n + ((uint64_t)si * gridDim.x + blockIdx.x));
+  }
+}
+
+// K1, TMA ring: every warp streams its row groups through a private ring of 4 KB slots.  A slot holds one TMA box of
+// 32 rows x 128 bytes (cp.async.bulk.tensor.2d, 128-byte swizzle), so lane r reads row r with conflict-free 128-bit
+// loads (chunk j of row r sits at 16-byte position j ^ (r & 7)); an elected lane refills a slot as soon as the warp has
+// consumed it, which keeps (n_slots - 1) x 4 KB per warp in flight at all times.  Rows past the end of the slab are
+// zero-filled by the TMA unit.  The arithmetic per row is the same strict sequence as everywhere else in this file.
+template <int IS_BF16, int METRIC>
+__global__ void __launch_bounds__(512, 1)
+dense_scan_tma_kernel(const __grid_constant__ CUtensorMap map, DenseScanArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t SLOT = 4096;
+  const uint32_t NWARPS = blockDim.x >> 5;
+  constexpr uint32_t BOX_ELEMS = IS_BF16 ? 64 : 32;
+  const uint32_t S = a.n_slots;
+  uint8_t* smem = smem_dyn + ((1024u - (trr_smem_u32(smem_dyn) & 1023u)) & 1023u);  // swizzle atoms need 1 KB alignment
+  uint8_t* ring = smem + (size_t)warp * S * SLOT;
+  float* qs = reinterpret_cast<float*>(smem + (size_t)NWARPS * S * SLOT);
+  const uint32_t q_bytes = (a.dim * 4 + 127) & ~127u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(qs) + q_bytes) + (size_t)warp * S;
+  uint32_t* warp_cnt = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(qs) + q_bytes + (size_t)NWARPS * S * 8);
+  uint64_t* tk_base = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(warp_cnt) + 64);
+  uint64_t* tk_buf = tk_base + (size_t)warp * a.cap;
+
+  if (lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map) : "memory");
+    for (uint32_t s = 0; s < S; ++s) trr_mbar_init(&bars[s], 1);
+  }
+  trr_fence_mbar_init();
+  __syncthreads();
+
+  const uint32_t n_sel = a.n_sel_ptr ? *a.n_sel_ptr : a.n_sel;
+  const uint32_t n_boxes = (a.row_bytes + 127) >> 7;
+  const uint64_t n_groups = (a.n_rows + 31) / 32;
+  const uint64_t gwarp = (uint64_t)blockIdx.x * NWARPS + warp, gstride = (uint64_t)gridDim.x * NWARPS;
+  const uint64_t n_my = n_groups > gwarp ? (n_groups - gwarp + gstride - 1) / gstride : 0;
+  const uint32_t sw = lane & 7;
+  const uint8_t* lane_base = ring + lane * 128;
+  uint32_t c_slot = 0, c_par = 0;  // consumer position in the ring (persists across queries)
+  uint32_t i_slot = 0;             // producer position
+
+  for (uint32_t si = 0; si < n_sel; ++si) {
+    const uint32_t qi = a.sel ? a.sel[si] : si;
+    __syncthreads();  // previous query's reads of qs are done
+    for (uint32_t j = threadIdx.x; j < a.dim; j += blockDim.x) qs[j] = a.q[(uint64_t)qi * a.dim + j];
+    __syncthreads();
+    const float q_norm = a.q_norms[qi];
+    WarpTopK tk;
+    tk.init(tk_buf, a.cap, a.k);
+
+    // producer state: next box to request = (group i_k, box i_c)
+    uint64_t i_k = 0;
+    uint32_t i_c = 0;
+    auto issue = [&]() {  // lane 0 only
+      if (i_k < n_my) {
+        const uint64_t row0 = (gwarp + i_k * gstride) * 32;
+        trr_fence_proxy_async();  // the warp's generic reads of this slot (ordered by __syncwarp) precede the async write
+        trr_mbar_expect_tx(&bars[i_slot], SLOT);
+        trr_tma_load_2d(&map, ring + (size_t)i_slot * SLOT, &bars[i_slot], (int32_t)(i_c * BOX_ELEMS), (int32_t)row0);
+        if (++i_slot == S) i_slot = 0;
+        if (++i_c == n_boxes) { i_c = 0; ++i_k; }
+      }
+    };
+    if (lane == 0) for (uint32_t s = 0; s < S; ++s) issue();
+
+    for (uint64_t k = 0; k < n_my; ++k) {
+      const uint64_t row = (gwarp + k * gstride) * 32 + lane;
+      float acc = 0.0f;
+      for (uint32_t c = 0; c < n_boxes; ++c) {
+        trr_mbar_wait_bounded(&bars[c_slot], c_par);
+        const uint8_t* rp = lane_base + (size_t)c_slot * SLOT;
+        const uint32_t left = a.row_bytes - (c << 7);
+        const uint32_t nvec = left >= 128 ? 8u : (left >> 4);
+        if (IS_BF16) {
+          const float4* qp = reinterpret_cast<const float4*>(qs + c * 64);
+          auto step = [&](uint32_t j) {
+            const uint4 v = *reinterpret_cast<const uint4*>(rp + ((j ^ sw) << 4));
+            const float4 q0 = qp[2 * j], q1 = qp[2 * j + 1];
+            acc_step<METRIC>(acc, q0.x, bf16lo(v.x)); acc_step<METRIC>(acc, q0.y, bf16hi(v.x));
+            acc_step<METRIC>(acc, q0.z, bf16lo(v.y)); acc_step<METRIC>(acc, q0.w, bf16hi(v.y));
+            acc_step<METRIC>(acc, q1.x, bf16lo(v.z)); acc_step<METRIC>(acc, q1.y, bf16hi(v.z));
+            acc_step<METRIC>(acc, q1.z, bf16lo(v.w)); acc_step<METRIC>(acc, q1.w, bf16hi(v.w));
+          };
+          if (nvec == 8) {
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) step(j);
+          } else {
+            for (uint32_t j = 0; j < nvec; ++j) step(j);
+          }
+        } else {
+          const float4* qp = reinterpret_cast<const float4*>(qs + c * 32);
+          auto step = [&](uint32_t j) {
+            const uint4 v = *reinterpret_cast<const uint4*>(rp + ((j ^ sw) << 4));
+            const float4 qq = qp[j];
+            acc_step<METRIC>(acc, qq.x, __uint_as_float(v.x)); acc_step<METRIC>(acc, qq.y, __uint_as_float(v.y));
+            acc_step<METRIC>(acc, qq.z, __uint_as_float(v.z)); acc_step<METRIC>(acc, qq.w, __uint_as_float(v.w));
+          };
+          if (nvec == 8) {
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) step(j);
+          } else {
+            for (uint32_t j = 0; j < nvec; ++j) step(j);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) issue();  // refill the slot just consumed
+        if (++c_slot == S) { c_slot = 0; c_par ^= 1; }
+      }
+      const bool valid = row < a.n_rows && !(a.dead && a.dead[row]);
+      float score = 0.0f;
+      if (valid) score = finish_score<METRIC>(acc, q_norm, METRIC == TRR_METRIC_COSINE ? a.norms[row] : 0.0f);
+      tk.push(trr_make_key(score, a.base_ord + (uint32_t)row), valid, lane);
+    }
+    // ring is empty here: every box requested for this query has been consumed; i_slot == c_slot
+    i_slot = __shfl_sync(FULL, i_slot, 0);
     tk.compact(lane);
     cta_merge_and_store(tk, tk_base, a.cap, NWARPS, warp, lane, warp_cnt,
                         a.partial + ((uint64_t)si * gridDim.x + blockIdx.x) * a.k,
@@ -554,6 +677,37 @@ cudaError_t trr_launch_scan(const DenseScanArgs& a, int is_bf16, int metric, boo
                             cudaStream_t st) {
 #define TRR_SCAN_CASE(B, M) \
   if (is_bf16 == B && metric == M) return launch_scan_t<B, M>(a, bulk, grid, smem, st)
+  TRR_SCAN_CASE(0, TRR_METRIC_COSINE);
+  TRR_SCAN_CASE(0, TRR_METRIC_EUCLIDEAN);
+  TRR_SCAN_CASE(0, TRR_METRIC_DOT);
+  TRR_SCAN_CASE(1, TRR_METRIC_COSINE);
+  TRR_SCAN_CASE(1, TRR_METRIC_EUCLIDEAN);
+  TRR_SCAN_CASE(1, TRR_METRIC_DOT);
+#undef TRR_SCAN_CASE
+  return cudaErrorInvalidValue;
+}
+
+size_t trr_scan_tma_smem(uint32_t dim, uint32_t cap, uint32_t n_slots, uint32_t n_warps) {
+  return 1024 + (size_t)n_warps * n_slots * 4096 + ((dim * 4 + 127) & ~127u) + (size_t)n_warps * n_slots * 8 + 64 +
+         (size_t)n_warps * cap * 8;
+}
+
+template <int IS_BF16, int METRIC>
+static cudaError_t launch_scan_tma_t(const DenseScanArgs& a, const void* map128, unsigned grid, unsigned n_warps, size_t smem,
+                                     cudaStream_t st) {
+  CUtensorMap m;
+  memcpy(&m, map128, 128);
+  auto kern = dense_scan_tma_kernel<IS_BF16, METRIC>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, 32 * n_warps, smem, st>>>(m, a);
+  return cudaGetLastError();
+}
+
+cudaError_t trr_launch_scan_tma(const DenseScanArgs& a, const void* map128, int is_bf16, int metric, unsigned grid,
+                                unsigned n_warps, size_t smem, cudaStream_t st) {
+#define TRR_SCAN_CASE(B, M) \
+  if (is_bf16 == B && metric == M) return launch_scan_tma_t<B, M>(a, map128, grid, n_warps, smem, st)
   TRR_SCAN_CASE(0, TRR_METRIC_COSINE);
   TRR_SCAN_CASE(0, TRR_METRIC_EUCLIDEAN);
   TRR_SCAN_CASE(0, TRR_METRIC_DOT);
