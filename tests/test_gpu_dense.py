@@ -177,7 +177,8 @@ def test_gemm_fast_scores_match_matmul(api, ctx):
 
 
 @pytest.mark.parametrize("n,d,dtype,B,k", [(20000, 768, 1, 200, 10), (50000, 768, 1, 130, 50), (20000, 384, 0, 64, 10),
-                                            (16500, 100, 1, 17, 5), (33000, 4096, 1, 128, 10), (17000, 72, 0, 16, 3)])
+                                            (16500, 100, 1, 17, 5), (33000, 4096, 1, 128, 10), (17000, 72, 0, 16, 3),
+                                            (60000, 4096, 1, 96, 100), (40000, 256, 1, 1500, 100), (40000, 128, 1, 3000, 50)])
 def test_gemm_path_matches_oracle(api, ctx, n, d, dtype, B, k):
     f, b = O.synth_corpus(SEED + 3, 0, n, d, bf16=bool(dtype), dups=True)
     rows = b if dtype else f

@@ -119,3 +119,32 @@ def test_sharded_flow_on_logical_shards(api, ctx, corpus, G, strategy, param):
     assert_hybrid(got, oracle_hybrid(c, strategy, np.float32(param), C_, k))
     for h in handles:
         h.close()
+
+
+def test_cfg5_shape_linear_top100_eight_shards(api, ctx):
+    """BASELINE.json configs[4] at reduced N: 4096-dim bf16, C = 100 (set explicitly, src/retrieve.rs:128-131), linear
+    fusion dense_weight 0.7 (examples/hybrid_search.rs:27-29), top-100, 8 document shards, tensor-core dense pass."""
+    N, D, V, B, C_, k, G = 24000, 4096, 6000, 40, 100, 100, 8
+    f, b = O.synth_corpus(SEED + 5, 0, N, D, bf16=True)
+    Q = bf16_round(O.synth_queries(SEED + 5, 0, B, D, N, corpus_bf16=True))
+    cdf = O.zipf_cdf(V)
+    doc_off, toks = O.synth_doc_tokens(SEED + 5, cdf, 0, N)
+    q_off, q_terms = O.synth_query_terms(SEED + 5, cdf, 0, B)
+    oix = O.BM25(n_terms=V, doc_off=doc_off, tokens=toks)
+    c = dict(N=N, D=D, V=V, B=B, f=f, b=b, Q=Q, q_off=q_off, q_terms=q_terms, oix=oix)
+    rec_bytes = api.exchange_bytes(B, C_)
+    gathered = torch.zeros(G * rec_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    handles = []
+    for g in range(G):
+        lo, hi = shard.shard_range(N, g, G)
+        dense, bm = make_dense(api, ctx, c, lo, hi), make_bm25(api, ctx, c, lo, hi)
+        dense.set_mode(2)
+        api.hybrid_local(dense, bm, Q, q_terms, q_off, C_, gathered.data_ptr() + g * rec_bytes)
+        assert dense.stats().mode_used == 2
+        handles += [dense, bm]
+    torch.cuda.synchronize()
+    got = api.hybrid_merge(ctx, gathered.data_ptr(), G, B, C_, O.LINEAR, 0.7, k)
+    assert_hybrid(got, oracle_hybrid(c, O.LINEAR, np.float32(0.7), C_, k))
+    for h in handles:
+        h.close()

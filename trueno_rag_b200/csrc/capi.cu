@@ -527,10 +527,20 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
   bool use_gemm = false;
   if (h->mode == TRR_DENSE_GEMM) use_gemm = true;
   else if (h->mode == TRR_DENSE_AUTO) use_gemm = B >= 16 && h->n >= 16384;
-  if (h->metric == TRR_METRIC_EUCLIDEAN || k > 50) {
+  if (h->metric == TRR_METRIC_EUCLIDEAN || k > 100) {
     if (h->mode == TRR_DENSE_GEMM)
-      return trr_fail(TRR_ERR_UNSUPPORTED, "GEMM mode supports cosine/dot metrics with k <= 50");
+      return trr_fail(TRR_ERR_UNSUPPORTED, "GEMM mode supports cosine/dot metrics with k <= 100");
     use_gemm = false;
+  }
+  if (use_gemm && k > 50) {
+    // re-scoring width 128 needs at least two document slices of 64-entry lists
+    const uint32_t n_qb = (B + TRR_GEMM_TILE_M - 1) / TRR_GEMM_TILE_M;
+    const uint64_t tiles = (h->n + TRR_GEMM_TILE_N - 1) / TRR_GEMM_TILE_N;
+    const uint64_t n_sl = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->sm_count / std::max(n_qb, 1u), tiles));
+    if (n_sl * TRR_GEMM_CP < 2 * TRR_GEMM_CP) {
+      if (h->mode == TRR_DENSE_GEMM) return trr_fail(TRR_ERR_UNSUPPORTED, "GEMM mode: batch too large for k > 50");
+      use_gemm = false;
+    }
   }
   // scratch: query norms first
   TRR_CHECK(extra(c)->scratch.reserve(WsCarver::need({(size_t)B * 4})));
@@ -567,12 +577,15 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     if (n_slices > h->n_tiles) n_slices = (uint32_t)h->n_tiles;
     if (n_slices == 0) n_slices = 1;
     const uint32_t B_pad = n_qblocks * TRR_GEMM_TILE_M;
-    const uint32_t CP = TRR_GEMM_CP;
-    // list length per (query, slice): the global top-CP is spread over the slices, so short lists suffice when there
-    // are many slices; the candidate proof (rescore_select_kernel) catches the (adversarial) cases where they do not
-    uint32_t cps = n_slices >= 8 ? 16u : (n_slices >= 3 ? 32u : 64u);
+    // exact re-scoring width per query: k plus a margin of ranks for the candidate proof
+    const uint32_t CP = k <= 50 ? TRR_GEMM_CP : 2 * TRR_GEMM_CP;
+    // list length per (query, slice): the global top-CP by fast score is spread over the slices (about CP / n_slices
+    // per slice), so short lists suffice when there are many slices (Poisson tail < 1e-6 for the choices below); the
+    // candidate proof (rescore_select_kernel) catches the data sets where they do not
+    const float per_slice = (float)CP / (float)n_slices;
+    uint32_t cps = per_slice <= 4.0f ? 16u : (per_slice <= 10.0f ? 32u : 64u);
     if (const char* e = getenv("TRR_GEMM_CPS")) { const int v = atoi(e); if (v == 16 || v == 32 || v == 64) cps = (uint32_t)v; }
-    if ((uint64_t)n_slices * cps < CP) cps = CP;
+    if ((uint64_t)n_slices * cps < CP) cps = TRR_GEMM_CP;  // (n_slices * 64 >= CP is checked before taking this path)
     const size_t n_cand = (size_t)n_slices * n_qblocks * TRR_GEMM_TILE_M * cps;
     const uint32_t cap2 = std::max<uint32_t>(trr_pow2_ceil(n_slices * cps), 2 * CP);
     // scratch layout (single reservation so that pointers stay valid)
