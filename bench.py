@@ -178,6 +178,9 @@ def run_reference(a):
 
 # ------------------------------------------------------------------------------------------------- our arm
 def run_ours(a):
+    # torchrun sets OMP_NUM_THREADS=1; the host-side synthetic generators (OpenMP) should use this rank's share of cores
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(world_env, 1)))
     import torch
     import torch.distributed as dist
     from trueno_rag_b200 import api, shard, _lib
@@ -229,6 +232,7 @@ def run_ours(a):
     api._check(L.trr_synth_bm25_fill(SEED, cdf.ctypes.data_as(u64p), V, lo, hi, term_off.ctypes.data_as(u64p),
                                      post_doc.ctypes.data_as(u32p), post_tf.ctypes.data_as(u32p)))
     bm = api.Bm25Device(ctx, n_loc, term_off, post_doc, post_tf, doc_len[:n_loc], avgdl, idf, doc_base=lo)
+    host_csr = (term_off, post_doc, post_tf, doc_len[:n_loc], df_g, avgdl) if (world == 1 and a.verify > 0) else None
     del post_doc, post_tf
     # ---- queries (bf16-representable, as the corpus): pinned host copies + device copies
     q_pin = torch.empty((B, D), dtype=torch.float32).pin_memory()
@@ -326,7 +330,7 @@ def run_ours(a):
     # ---- correctness spot check against the oracle (outside every timed region)
     verify = None
     if rank == 0 and a.verify > 0:
-        verify = verify_against_oracle(a, last[-1], a.verify)
+        verify = verify_full_size(a, api, dense, bm, q_np, q_terms[:nt], q_off, host_csr, last[-1], world)
 
     if rank == 0:
         peaks = {}
@@ -392,23 +396,54 @@ def ncu_traffic(kind, a):
     return tot or None
 
 
-def verify_against_oracle(a, outputs, n_check):
-    """Exact check of the first n_check queries of the last timed e2e step: the dense top-C needs a full scan of the
-    corpus by the oracle, so it is done on a candidate superset proof: every returned id is re-scored exactly and the
-    lists are compared on the first `cpu_sample_docs` documents only when the corpus is larger than that (size-independent
-    property: restricting corpus AND results to a prefix of ordinals must agree with the oracle on that prefix is NOT
-    implied, so for the full-size run we check internal consistency instead: scores sorted, ids unique, fused score equals
-    the RRF formula of the reported ranks)."""
+def verify_full_size(a, api, dense, bm, q_np, q_terms, q_off, host_csr, outputs, world):
+    """Parity at the FULL bench size, outside every timed region, on the first `--verify` queries:
+      dense   the tensor-core path (K2 + exact re-scoring + proof) must return bit-identical ids and scores to the exact scan
+              kernel K1 over the same 10M-row slab (K1 itself is pinned bit-exactly to the oracle by tests/ at sizes the
+              oracle finishes in seconds; it contains no size-dependent arithmetic);
+      sparse  the BM25 kernel vs the CPU oracle scoring the same host CSR with the same global statistics (single GPU only);
+      fused   the e2e output vs the oracle's RRF fusion + take(k) of those two lists.
+    With several GPUs only the internal-consistency properties are checked (ids unique, fused scores sorted and in range)."""
+    from oracle import oracle as O
     o_ord, o_f, o_d, o_s, o_n = outputs
+    n = int(min(a.verify, o_ord.shape[0]))
+    res = {"checked_queries": n, "ids_unique_sorted_in_range": True}
+    for b in range(n):
+        m = int(o_n[b])
+        ok = len(set(o_ord[b, :m].tolist())) == m and bool(np.all(np.diff(o_f[b, :m]) <= 0))
+        ok &= bool(np.all((o_f[b, :m] > 0) & (o_f[b, :m] <= np.float32(2.0 / 61.0) + 1e-7)))
+        res["ids_unique_sorted_in_range"] &= bool(ok)
+    if world != 1:
+        res["note"] = "multi-GPU run: full-size oracle parity is checked by the 1-GPU run and by tests/ (logical shards)"
+        return res
+    Cn, K = a.cands, a.k
+    dense.set_mode(api.MODE_SCAN)
+    s_ord, s_sc, s_n = dense.search(q_np[:n], Cn)
+    dense.set_mode(api.MODE_GEMM)
+    g_ord, g_sc, g_n = dense.search(q_np[:n], Cn)
+    res["dense_gemm_equals_exact_scan"] = bool(np.array_equal(s_n, g_n) and np.array_equal(s_ord, g_ord) and
+                                                np.array_equal(s_sc, g_sc))
+    term_off, post_doc, post_tf, doc_len, df_g, avgdl = host_csr
+    oix = O.BM25.from_csr(len(doc_len), a.vocab, term_off, post_doc, post_tf, doc_len, df_g, avgdl)
+    qt, qo = q_terms[:int(q_off[n])], q_off[:n + 1]
+    b_ord, b_sc, b_n = bm.search(qt, qo, Cn)
+    e_ord, e_sc, e_n = oix.search_batch(qt, qo, Cn)
+    ok = np.array_equal(b_n, e_n)
+    for b in range(n):
+        m = int(e_n[b])
+        ok = ok and np.array_equal(b_ord[b, :m], e_ord[b, :m]) and np.array_equal(b_sc[b, :m], e_sc[b, :m])
+    res["bm25_equals_oracle"] = bool(ok)
     ok = True
-    for b in range(min(n_check, o_ord.shape[0])):
-        n = int(o_n[b])
-        ids = o_ord[b, :n]
-        ok &= len(set(ids.tolist())) == n
-        ok &= bool(np.all(np.diff(o_f[b, :n]) <= 0))
-        ok &= bool(np.all((o_f[b, :n] > 0) & (o_f[b, :n] <= np.float32(2.0 / 61.0) + 1e-7)))
-    return {"checked_queries": int(min(n_check, o_ord.shape[0])), "consistent": bool(ok),
-            "note": "bit-exact parity vs the oracle is asserted by tests/ (-m gpu) and smoke(); this is a sanity check"}
+    for b in range(n):
+        i, f, dd, ss = O.hybrid_assemble(O.RRF, 60.0, (s_ord[b, :s_n[b]], s_sc[b, :s_n[b]]),
+                                         (e_ord[b, :e_n[b]], e_sc[b, :e_n[b]]), K)
+        m = int(o_n[b])
+        ok = ok and m == len(i) and np.array_equal(o_ord[b, :m], i) and np.array_equal(o_f[b, :m], f) and \
+            np.array_equal(o_d[b, :m], dd, equal_nan=True) and np.array_equal(o_s[b, :m], ss, equal_nan=True)
+    res["fused_equals_oracle"] = bool(ok)
+    res["consistent"] = bool(res["ids_unique_sorted_in_range"] and res["dense_gemm_equals_exact_scan"] and
+                             res["bm25_equals_oracle"] and res["fused_equals_oracle"])
+    return res
 
 
 if __name__ == "__main__":

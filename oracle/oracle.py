@@ -60,6 +60,8 @@ def _proto(L):
                                        C.c_int, u32p, f32p]
     L.orc_bm25_build.restype = C.c_void_p
     L.orc_bm25_build.argtypes = [u64p, u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_float]
+    L.orc_bm25_from_csr.restype = C.c_void_p
+    L.orc_bm25_from_csr.argtypes = [C.c_uint32, C.c_uint32, u64p, u32p, u32p, u32p, u32p, C.c_float, C.c_float, C.c_float]
     L.orc_bm25_free.restype = None
     L.orc_bm25_free.argtypes = [C.c_void_p]
     L.orc_bm25_n_postings.restype = C.c_uint64
@@ -190,6 +192,19 @@ class BM25:
         self.n_terms = int(n_terms)
         self.k1, self.b = k1, b
         self.h = lib().orc_bm25_build(_p(self.doc_off, u64p), _p(self.tokens, u32p), self.n_docs, self.n_terms, k1, b)
+
+    @classmethod
+    def from_csr(cls, n_docs, n_terms, term_off, post_doc, post_tf, doc_len, df, avgdl, k1=1.2, b=0.75):
+        """Oracle index over caller-provided CSR arrays (kept alive by this object, not copied)."""
+        self = cls.__new__(cls)
+        self.n_docs, self.n_terms, self.k1, self.b = int(n_docs), int(n_terms), k1, b
+        self._keep = [np.ascontiguousarray(term_off, np.uint64), np.ascontiguousarray(post_doc, np.uint32),
+                      np.ascontiguousarray(post_tf, np.uint32), np.ascontiguousarray(doc_len, np.uint32),
+                      np.ascontiguousarray(df, np.uint32)]
+        t, pd, ptf, dl, dfa = self._keep
+        self.h = lib().orc_bm25_from_csr(self.n_docs, self.n_terms, _p(t, u64p), _p(pd, u32p), _p(ptf, u32p), _p(dl, u32p),
+                                         _p(dfa, u32p), C.c_float(avgdl), C.c_float(k1), C.c_float(b))
+        return self
 
     def __del__(self):
         try:

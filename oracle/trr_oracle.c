@@ -223,6 +223,7 @@ typedef struct {
   uint32_t* df;        /* :198-200 */
   float avgdl;         /* :157-164 (u32 sum) as f32 / doc_count as f32 */
   float k1, b;
+  int borrowed;        /* arrays belong to the caller (orc_bm25_from_csr) */
 } orc_bm25;
 
 static int orc_u32_cmp(const void* a, const void* b) {
@@ -287,8 +288,20 @@ ORC_API orc_bm25* orc_bm25_build(const uint64_t* doc_off, const uint32_t* tokens
   return ix;
 }
 
+/* Wraps caller-owned CSR arrays (the state orc_bm25_build would have produced) without copying them; used to check the
+ * CUDA path at full corpus size, where N / df / avgdl are the GLOBAL statistics handed to the device index. */
+ORC_API orc_bm25* orc_bm25_from_csr(uint32_t n_docs, uint32_t n_terms, uint64_t* term_off, uint32_t* post_doc,
+                                    uint32_t* post_tf, uint32_t* doc_len, uint32_t* df, float avgdl, float k1, float b) {
+  orc_bm25* ix = (orc_bm25*)calloc(1, sizeof(orc_bm25));
+  ix->n_docs = n_docs; ix->n_terms = n_terms; ix->k1 = k1; ix->b = b; ix->avgdl = avgdl;
+  ix->term_off = term_off; ix->post_doc = post_doc; ix->post_tf = post_tf; ix->doc_len = doc_len; ix->df = df;
+  ix->borrowed = 1;
+  return ix;
+}
+
 ORC_API void orc_bm25_free(orc_bm25* ix) {
   if (!ix) return;
+  if (ix->borrowed) { free(ix); return; }
   free(ix->term_off); free(ix->post_doc); free(ix->post_tf); free(ix->doc_len); free(ix->df); free(ix);
 }
 
