@@ -447,6 +447,10 @@ def verify_full_size(a, api, dense, bm, q_np, q_terms, q_off, host_csr, outputs,
 
 
 if __name__ == "__main__":
+    # stdout carries exactly one JSON line: everything else that writes to fd 1 (e.g. NCCL's version banner) goes to stderr
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
     args = parse()
     if args.impl == "reference":
         run_reference(args)

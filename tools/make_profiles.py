@@ -71,10 +71,10 @@ def kernel_summary(rep, out):
 
 def launches(csv_path, out):
     rows = [r for r in csv.reader(open(csv_path)) if len(r) > 10 and r[0].isdigit()]
-    # the launch list covers setup + (warmup + steps) bench steps; a step starts at each dense_query_norms_kernel
+    # the launch list covers setup + (warmup + steps) bench steps; a step starts at each query_prep_kernel
     names = [r[4] for r in rows]
     ns = [float(r[-1]) for r in rows]
-    starts = [i for i, n in enumerate(names) if n.startswith('dense_query_norms_kernel')]
+    starts = [i for i, n in enumerate(names) if n.startswith('query_prep_kernel')]
     lines = [f"# {os.path.basename(csv_path)}: ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)"]
     if len(starts) >= 2:
         a, b = starts[-2], starts[-1]

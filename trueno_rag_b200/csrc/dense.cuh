@@ -57,7 +57,8 @@ struct RescoreArgs {
   uint32_t base_ord;
   uint64_t n_live;           // live rows in the store
   const float* q;            // B x dim f32
-  const float* q_norms;      // B
+  const float* q_norms;      // B (ignored when q_norms_out is set)
+  float* q_norms_out;        // nullable: the kernel computes ||q|| itself (reference order) and stores it here
   const float* q_delta;      // B: || q - bf16(q) ||  (0 when the query is bf16-exact)
   const float* max_norm;     // device scalar: max row norm
   uint32_t B, k;

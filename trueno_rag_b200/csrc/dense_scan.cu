@@ -519,7 +519,7 @@ rescore_select_kernel(RescoreArgs a) {
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);            // cap2 fast keys
   uint64_t* ekeys = keys + a.cap2;                                     // CP exact keys (CP power of two)
   float* efast = reinterpret_cast<float*>(ekeys + a.cp);              // fast score of each kept candidate
-  __shared__ float s_gap;
+  __shared__ float s_gap, s_qnorm;
   __shared__ uint32_t s_total, s_tmax;
   const uint32_t b = blockIdx.x;
   if (b >= a.B) return;
@@ -553,9 +553,20 @@ rescore_select_kernel(RescoreArgs a) {
   __syncthreads();
   trr_bitonic_sort_desc(keys, a.cap2, tid, blockDim.x, BlockSync());
   const uint32_t n_cand = min(s_total, a.cp);
-  // 2. exact rescoring, strict reference order
+  // 2. exact rescoring, strict reference order (one candidate per thread: the sum is a sequential chain; the loads are
+  //    128-bit and run ahead of it).  The query is staged in shared memory once per CTA.
+  float* qs = efast + a.cp;
   const float* qv = a.q + (uint64_t)b * a.dim;
-  const float q_norm = a.q_norms[b];
+  for (uint32_t j = tid; j < a.dim; j += blockDim.x) qs[j] = qv[j];
+  __syncthreads();
+  if (a.q_norms_out && tid == blockDim.x - 1) {  // src/index.rs:442: sequential f32 sum of squares, then sqrt
+    float s = 0.0f;
+    for (uint32_t j = 0; j < a.dim; ++j) s = s + qs[j] * qs[j];
+    s_qnorm = sqrtf(s);
+    a.q_norms_out[b] = s_qnorm;
+  }
+  if (a.q_norms_out) __syncthreads();
+  const float q_norm = a.q_norms_out ? s_qnorm : a.q_norms[b];
   if (tid < a.cp) {
     uint64_t ek = TRR_KEY_EMPTY;
     float fast = 0.0f;
@@ -567,10 +578,32 @@ rescore_select_kernel(RescoreArgs a) {
       float acc = 0.0f;
       if (IS_BF16) {
         const uint16_t* p = reinterpret_cast<const uint16_t*>(a.rows) + row * a.dim;
-        for (uint32_t j = 0; j < a.dim; ++j) acc = acc + qv[j] * __uint_as_float(((uint32_t)p[j]) << 16);
+        uint32_t j = 0;
+        if ((a.dim & 7u) == 0 && (reinterpret_cast<uintptr_t>(a.rows) & 15u) == 0) {
+          const uint4* p4 = reinterpret_cast<const uint4*>(p);
+#pragma unroll 4
+          for (; j < a.dim; j += 8) {
+            const uint4 v = __ldg(p4 + (j >> 3));
+            acc = acc + qs[j] * bf16lo(v.x);     acc = acc + qs[j + 1] * bf16hi(v.x);
+            acc = acc + qs[j + 2] * bf16lo(v.y); acc = acc + qs[j + 3] * bf16hi(v.y);
+            acc = acc + qs[j + 4] * bf16lo(v.z); acc = acc + qs[j + 5] * bf16hi(v.z);
+            acc = acc + qs[j + 6] * bf16lo(v.w); acc = acc + qs[j + 7] * bf16hi(v.w);
+          }
+        }
+        for (; j < a.dim; ++j) acc = acc + qs[j] * __uint_as_float(((uint32_t)p[j]) << 16);
       } else {
         const float* p = reinterpret_cast<const float*>(a.rows) + row * a.dim;
-        for (uint32_t j = 0; j < a.dim; ++j) acc = acc + qv[j] * p[j];
+        uint32_t j = 0;
+        if ((a.dim & 3u) == 0 && (reinterpret_cast<uintptr_t>(a.rows) & 15u) == 0) {
+          const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll 4
+          for (; j < a.dim; j += 4) {
+            const float4 v = __ldg(p4 + (j >> 2));
+            acc = acc + qs[j] * v.x;     acc = acc + qs[j + 1] * v.y;
+            acc = acc + qs[j + 2] * v.z; acc = acc + qs[j + 3] * v.w;
+          }
+        }
+        for (; j < a.dim; ++j) acc = acc + qs[j] * p[j];
       }
       float score;
       if (a.metric == TRR_METRIC_COSINE) {
@@ -729,7 +762,7 @@ cudaError_t trr_launch_topk_merge(const TopkMergeArgs& a, unsigned grid, cudaStr
 
 cudaError_t trr_launch_rescore(const RescoreArgs& a, int is_bf16, cudaStream_t st) {
   if (a.B == 0) return cudaSuccess;
-  size_t smem = (size_t)a.cap2 * 8 + (size_t)a.cp * 8 + (size_t)a.cp * 4;
+  size_t smem = (size_t)a.cap2 * 8 + (size_t)a.cp * 8 + (size_t)a.cp * 4 + (size_t)a.dim * 4 + 16;
   if (is_bf16) {
     cudaError_t e = cudaFuncSetAttribute(rescore_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
