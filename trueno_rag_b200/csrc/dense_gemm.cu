@@ -131,17 +131,40 @@ struct RowState {
 // (16 / 32 / 64, chosen by the host from the number of document slices).  The new value overwrites the list minimum and
 // the minimum is found again by a scan of the lane's own list; lanes of a warp insert independently (rows differ), so no
 // warp-level cooperation or synchronisation is needed.  Kept out of line: rare in steady state.
+// (value, position) minimum of N list entries by a compare tree of depth log2(N): the scan is on the critical path of
+// every insertion (an epilogue warp is alone on its scheduler), so a sequential compare chain would cost ~10 cycles per entry
+template <uint32_t N>
+__device__ __forceinline__ void list_min_tree(const float* my_ls, uint32_t off, float& mn, uint32_t& pos) {
+  float mv[N];
+  uint32_t mp[N];
+#pragma unroll
+  for (uint32_t i = 0; i < N; ++i) { mv[i] = my_ls[off + i]; mp[i] = off + i; }
+#pragma unroll
+  for (uint32_t w = N / 2; w >= 1; w >>= 1) {
+#pragma unroll
+    for (uint32_t i = 0; i < w; ++i) {
+      const bool hi = mv[i + w] < mv[i];
+      mv[i] = hi ? mv[i + w] : mv[i];
+      mp[i] = hi ? mp[i + w] : mp[i];
+    }
+  }
+  mn = mv[0];
+  pos = mp[0];
+}
+
 __device__ __noinline__ RowState insert_private(RowState st, float s, uint32_t doc, float* my_ls, uint32_t* my_lo,
                                                 uint32_t cps) {
   if (!(s > st.thr)) return st;
   my_ls[st.minpos] = s;
   my_lo[st.minpos] = doc;
-  float mn = my_ls[0];
-  uint32_t pos = 0;
-#pragma unroll 8
-  for (uint32_t j = 1; j < cps; ++j) {
-    const float e = my_ls[j];
-    if (e < mn) { mn = e; pos = j; }
+  float mn;
+  uint32_t pos;
+  list_min_tree<16>(my_ls, 0, mn, pos);
+  for (uint32_t off = 16; off < cps; off += 16) {
+    float m2;
+    uint32_t p2;
+    list_min_tree<16>(my_ls, off, m2, p2);
+    if (m2 < mn) { mn = m2; pos = p2; }
   }
   st.list_min = mn;
   st.minpos = pos;
