@@ -56,6 +56,8 @@ __global__ void bm25_build_kernel(Bm25BuildArgs a) {
     const float tf_norm = (tf * (a.k1 + 1.0f)) / (tf + a.k1 * (1.0f - a.b + a.b * doc_len / a.avgdl));
     const float impact = idf * tf_norm;
     a.post[p] = make_uint2(doc, __float_as_uint(impact));
+    atomicMin(&a.term_min[t], trr_f32_orderable(impact));
+    if (!(impact > 0.0f)) a.flags[0] = 1u;
     // skip table
     const uint64_t t_begin = a.term_off[t], t_end = a.term_off[t + 1];
     const uint32_t r = doc >> a.range_shift;
@@ -85,6 +87,23 @@ bm25_plan_kernel(Bm25SearchArgs a, uint32_t cap2) {
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);  // cap2 = power of two >= B (0: identity order)
   const uint32_t tid = threadIdx.x;
   if (tid == 0) { a.queue[0] = 0; a.queue[1] = 0; }
+  // Threshold bootstrap.  Impacts are positive and f32 addition of non-negative values is monotone, so a document that
+  // contains term t scores at least min_impact(t).  If t has >= k postings in this shard, at least k documents have a
+  // key above K0 = key(min_impact(t), worst ordinal), hence the k-th best key is >= K0 and everything <= K0 - 1 can be
+  // dropped from the first range on (instead of flooding the candidate buffer until the running top-k fills up).
+  for (uint32_t b = tid; b < a.B; b += blockDim.x) {
+    uint32_t best = 0;
+    if (a.n_chunks == 1 && a.flags[0] == 0u) {
+      for (uint32_t i = a.q_off[b]; i < a.q_off[b + 1]; ++i) {
+        const uint32_t t = a.q_terms[i];
+        if (t < a.n_terms) {
+          const uint32_t* row = a.skip + (uint64_t)t * a.skip_ld;
+          if (row[a.n_ranges] - row[0] >= a.k) best = max(best, a.term_min[t]);
+        }
+      }
+    }
+    a.thr0[b] = best ? (((uint64_t)best << 32) - 1ull) : TRR_KEY_EMPTY;
+  }
   if (cap2 == 0) {
     for (uint32_t b = tid; b < a.B; b += blockDim.x) a.order[b] = b;
     return;
@@ -124,6 +143,7 @@ struct PassDesc {
   uint32_t range_base;  // local id of the first document of the range
   uint32_t item;
   uint32_t pad;
+  uint64_t thr0;           // the item's bootstrap threshold (0 = none)
   uint32_t seg_begin[32];  // per term slot of the pass: [begin, end) inside the stage buffer
   uint32_t seg_end[32];
 };
@@ -179,13 +199,14 @@ bm25_search_kernel(Bm25SearchArgs a) {
     // ============================ producer warp ============================
     uint32_t stage = 0, phase = 0;
     // publishes one pass: descriptor + bulk copies.  Every lane passes its own slot (len == 0: not in the pass).
+    uint64_t item_thr0 = TRR_KEY_EMPTY;
     auto emit = [&](uint32_t flags, uint32_t range_base, uint32_t item, uint32_t off, uint32_t src_al, uint32_t al,
                     uint32_t begin, uint32_t end, uint32_t total_al) {
       mbar_wait_or_trap(&empty_bar[stage], phase ^ 1, 1, a.dbg);
       PassDesc& d = desc[stage];
       d.seg_begin[lane] = begin;
       d.seg_end[lane] = end;
-      if (lane == 0) { d.flags = flags; d.range_base = range_base; d.item = item; }
+      if (lane == 0) { d.flags = flags; d.range_base = range_base; d.item = item; d.thr0 = item_thr0; }
       __syncwarp();
       if (lane == 0) {
         if (total_al) trr_mbar_expect_tx(&full_bar[stage], total_al * 8u);
@@ -202,6 +223,7 @@ bm25_search_kernel(Bm25SearchArgs a) {
       item = __shfl_sync(FULLM, item, 0);
       if (item >= n_items) { emit(F_QUIT, 0, item, 0, 0, 0, 0, 0, 0); break; }
       const uint32_t b = a.order[item / a.n_chunks], c = item % a.n_chunks;
+      item_thr0 = a.thr0[b];
       const uint32_t r0 = (uint32_t)(((uint64_t)c * a.n_ranges) / a.n_chunks);
       const uint32_t r1 = (uint32_t)(((uint64_t)(c + 1) * a.n_ranges) / a.n_chunks);
       const uint32_t q0 = a.q_off[b];
@@ -301,6 +323,7 @@ bm25_search_kernel(Bm25SearchArgs a) {
       mbar_wait_or_trap(&full_bar[stage], phase, 2, a.dbg);
       const PassDesc& d = desc[stage];
       const uint32_t flags = d.flags, range_base = d.range_base, item = d.item;
+      const uint64_t thr0 = d.thr0;
       if (flags & F_QUIT) break;
       const uint2* st = stage_buf + (size_t)stage * a.stage_cap;
       {
@@ -336,7 +359,7 @@ bm25_search_kernel(Bm25SearchArgs a) {
 
       if (flags & F_HARVEST) {
         while (true) {
-          const uint64_t thr = *reinterpret_cast<volatile uint64_t*>(&s_thr);
+          const uint64_t thr = max(*reinterpret_cast<volatile uint64_t*>(&s_thr), thr0);
           const float thr_f = thr == TRR_KEY_EMPTY ? -CUDART_INF_F : trr_key_score(thr);
           if (touched) {
             uint4* a4 = reinterpret_cast<uint4*>(my_acc);

@@ -20,6 +20,8 @@ struct Bm25BuildArgs {
   uint32_t range_shift, n_ranges, skip_ld;
   uint2* post;     // out: {doc, impact bits}
   uint32_t* skip;  // out: [n_terms][skip_ld]
+  uint32_t* term_min;  // out: [n_terms] smallest impact of the term (order-preserving u32 image), pre-set to 0xFFFFFFFF
+  uint32_t* flags;     // out: [0] = 1 when some impact is not > 0 (disables the threshold bootstrap), pre-set to 0
 };
 
 struct Bm25SearchArgs {
@@ -32,6 +34,9 @@ struct Bm25SearchArgs {
   uint32_t stage_cap;  // postings per stage buffer (even)
   uint32_t cand_cap;   // candidate buffer capacity: power of two > k
   uint32_t n_chunks;   // work items per query (contiguous chunks of document ranges)
+  const uint32_t* term_min;  // [n_terms] smallest impact per term (orderable image)
+  const uint32_t* flags;     // [0] != 0: impacts are not all positive, no bootstrap
+  uint64_t* thr0;      // [B] initial threshold key per query (written by the plan kernel; 0 = none)
   uint32_t* order;     // [B] queries by decreasing posting volume (written by the plan kernel)
   uint32_t* queue;     // [2] dynamic work queue (reset by the plan kernel)
   uint64_t* partial;   // n_chunks > 1: [B][n_chunks][k] keys, merged by topk_merge_kernel

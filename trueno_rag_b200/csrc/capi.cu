@@ -786,6 +786,7 @@ struct trr_bm25 {
   uint64_t n_postings = 0;
   uint2* post = nullptr;
   uint32_t* skip = nullptr;
+  uint32_t* term_min = nullptr;  // [n_terms + 1]: per-term minimum impact, then one flag word
   uint32_t range_shift = TRR_BM25_MAX_RANGE_SHIFT, n_ranges = 0, skip_ld = 0;
   trr_stats stats{};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -818,6 +819,9 @@ extern "C" int trr_bm25_build(trr_ctx* ctx, uint32_t n_docs, uint32_t n_terms, c
   BM_CUDA(cudaMalloc(&h->post, (P + 2) * sizeof(uint2)));  // +2: 16-byte aligned bulk copies may read one posting past the end
   BM_CUDA(cudaMemsetAsync(h->post, 0xFF, (P + 2) * sizeof(uint2), st));
   BM_CUDA(cudaMalloc(&h->skip, std::max<uint64_t>((uint64_t)n_terms * h->skip_ld, 1) * 4));
+  BM_CUDA(cudaMalloc(&h->term_min, ((uint64_t)n_terms + 1) * 4));
+  BM_CUDA(cudaMemsetAsync(h->term_min, 0xFF, (uint64_t)n_terms * 4, st));
+  BM_CUDA(cudaMemsetAsync(h->term_min + n_terms, 0, 4, st));
   uint64_t* d_term_off = nullptr; uint32_t *d_pd = nullptr, *d_ptf = nullptr, *d_dl = nullptr; float* d_idf = nullptr;
   BM_CUDA(cudaMalloc(&d_term_off, ((uint64_t)n_terms + 1) * 8));
   BM_CUDA(cudaMalloc(&d_pd, std::max<uint64_t>(P, 1) * 4));
@@ -835,6 +839,7 @@ extern "C" int trr_bm25_build(trr_ctx* ctx, uint32_t n_docs, uint32_t n_terms, c
   a.n_postings = P; a.n_terms = n_terms; a.n_docs = n_docs; a.term_off = d_term_off; a.post_doc = d_pd; a.post_tf = d_ptf;
   a.doc_len = d_dl; a.idf = d_idf; a.avgdl = avgdl; a.k1 = k1; a.b = b;
   a.range_shift = h->range_shift; a.n_ranges = h->n_ranges; a.skip_ld = h->skip_ld; a.post = h->post; a.skip = h->skip;
+  a.term_min = h->term_min; a.flags = h->term_min + n_terms;
   BM_CUDA(trr_launch_bm25_build(a, st));
   ctx->launches += 2;
   BM_CUDA(cudaStreamSynchronize(st));
@@ -850,6 +855,7 @@ extern "C" int trr_bm25_destroy(trr_bm25* h) {
   cudaStreamSynchronize(h->ctx->stream);
   if (h->post) cudaFree(h->post);
   if (h->skip) cudaFree(h->skip);
+  if (h->term_min) cudaFree(h->term_min);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   delete h;
   return TRR_OK;
@@ -913,10 +919,12 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   if (const char* e = getenv("TRR_BM25_CHUNKS")) n_chunks = std::min<uint32_t>(h->n_ranges, std::max(1, atoi(e)));
   n_chunks = std::max<uint32_t>(n_chunks, 1);
   a.n_chunks = n_chunks;
-  const size_t need = scratch_off + WsCarver::need({(size_t)B * 4, 64, n_chunks > 1 ? (size_t)B * n_chunks * k * 8 : 8});
+  const size_t need = scratch_off + WsCarver::need({(size_t)B * 4, (size_t)B * 8, 64, n_chunks > 1 ? (size_t)B * n_chunks * k * 8 : 8});
   TRR_CHECK(extra(c)->scratch.reserve(need));
   WsCarver ws(static_cast<char*>(extra(c)->scratch.p) + scratch_off);
+  a.term_min = h->term_min; a.flags = h->term_min + h->n_terms;
   a.order = ws.take<uint32_t>(B);
+  a.thr0 = ws.take<uint64_t>(B);
   a.queue = ws.take<uint32_t>(16);
   a.partial = ws.take<uint64_t>(n_chunks > 1 ? (size_t)B * n_chunks * k : 1);
   a.out_keys = nullptr; a.out_ord = d_ord; a.out_score = d_score; a.out_n = d_n;
