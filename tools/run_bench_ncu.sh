@@ -11,6 +11,6 @@ echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:dense_gemm_topk -s 1 -c 1 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu2.log 2>&1; echo "gemm prof rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:bm25_search -s 1 -c 1 -o gpurun_out/prof_bm25 $CMD > gpurun_out/ncu3.log 2>&1; echo "bm25 prof rc=$?"
 timeout 300 python tools/gpu_probe.py perf_scan > gpurun_out/plain_scan.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:dense_scan_bulk -s 1 -c 1 -o gpurun_out/prof_scan python tools/gpu_probe.py perf_scan > gpurun_out/ncu4.log 2>&1; echo "scan prof rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:dense_scan_tma -s 1 -c 1 -o gpurun_out/prof_scan python tools/gpu_probe.py perf_scan > gpurun_out/ncu4.log 2>&1; echo "scan prof rc=$?"
 cat gpurun_out/plain_scan.log
 ls -la gpurun_out/
