@@ -583,8 +583,8 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     // per slice), so short lists suffice when there are many slices (Poisson tail < 1e-6 for the choices below); the
     // candidate proof (rescore_select_kernel) catches the data sets where they do not
     const float per_slice = (float)CP / (float)n_slices;
-    uint32_t cps = per_slice <= 4.0f ? 16u : (per_slice <= 10.0f ? 32u : 64u);
-    if (const char* e = getenv("TRR_GEMM_CPS")) { const int v = atoi(e); if (v == 16 || v == 32 || v == 64) cps = (uint32_t)v; }
+    uint32_t cps = per_slice <= 1.0f ? 8u : (per_slice <= 4.0f ? 16u : (per_slice <= 10.0f ? 32u : 64u));
+    if (const char* e = getenv("TRR_GEMM_CPS")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32 || v == 64) cps = (uint32_t)v; }
     if ((uint64_t)n_slices * cps < CP) cps = TRR_GEMM_CP;  // (n_slices * 64 >= CP is checked before taking this path)
     const size_t n_cand = (size_t)n_slices * n_qblocks * TRR_GEMM_TILE_M * cps;
     const uint32_t cap2 = std::max<uint32_t>(trr_pow2_ceil(n_slices * cps), 2 * CP);

@@ -82,7 +82,7 @@ struct GemmTopkArgs {
   uint32_t k_blocks;         // ceil(dim / 64)
   uint32_t base_ord;
   const float2* scale_bias;  // [n_tiles*256]
-  uint32_t cps;              // candidates kept per (query, slice): 16, 32 or 64 (<= TRR_GEMM_CP)
+  uint32_t cps;              // candidates kept per (query, slice): 8, 16, 32 or 64 (<= TRR_GEMM_CP)
   float* cand_score;         // [n_slices][n_qblocks][128][cps]
   uint32_t* cand_ord;
   uint32_t* gthr;            // [n_qblocks*128] shared running thresholds (orderable-encoded), zeroed by the caller

@@ -159,7 +159,11 @@ __device__ __noinline__ RowState insert_private(RowState st, float s, uint32_t d
   my_lo[st.minpos] = doc;
   float mn;
   uint32_t pos;
-  list_min_tree<16>(my_ls, 0, mn, pos);
+  if (cps == 8) {
+    list_min_tree<8>(my_ls, 0, mn, pos);
+  } else {
+    list_min_tree<16>(my_ls, 0, mn, pos);
+  }
   for (uint32_t off = 16; off < cps; off += 16) {
     float m2;
     uint32_t p2;
