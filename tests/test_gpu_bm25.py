@@ -134,3 +134,37 @@ def test_bench_shape_topic_keywords(api, ctx):                          # benche
     for k in (10, 100):
         compare(dev, oix, q, np.array([0, len(q)], np.uint32), k)
     dev.close()
+
+
+@pytest.mark.parametrize("k1,b", [(0.0, 0.75), (1.2, 0.0), (1.2, 1.0), (2.5, 0.3), (-0.5, 0.75), (1.2, -2.0)])
+def test_unusual_parameters(api, ctx, k1, b):
+    """BM25Index::with_params (src/index.rs:78-84) accepts any floats: k1 = 0 makes every impact idf, negative values can
+    make impacts negative or non-finite (those documents are dropped by `score > 0.0`, src/index.rs:236) and switch the
+    threshold bootstrap off."""
+    cdf = O.zipf_cdf(2000)
+    doc_off, toks = O.synth_doc_tokens(SEED + 7, cdf, 0, 70000)
+    oix = O.BM25(n_terms=2000, doc_off=doc_off, tokens=toks, k1=k1, b=b)
+    dev = build(api, ctx, oix, 70000, k1=k1, b=b)
+    q_off, q_terms = O.synth_query_terms(SEED + 7, cdf, 0, 24)
+    for k in (10, 100):
+        compare(dev, oix, q_terms, q_off, k)
+    dev.close()
+
+
+def test_range_boundaries_and_many_queries(api, ctx):
+    """Documents exactly at the 32768-document range boundaries and at the 2048-document warp sub-range boundaries; enough
+    queries that every query is one work item (no range chunking) and few enough documents that most ranges are sparse."""
+    n_docs = 3 * 32768 + 1
+    docs = [[] for _ in range(n_docs)]
+    for d in (0, 2047, 2048, 32767, 32768, 65535, 65536, 98303, 98304):
+        docs[d] = [1, 2, 2, 3]
+    for d in range(0, n_docs, 997):
+        docs[d] = docs[d] + [3, 4]
+    oix = O.BM25(docs, 6)
+    dev = build(api, ctx, oix, n_docs)
+    rng = np.random.default_rng(5)
+    qs = [list(rng.integers(0, 6, int(rng.integers(1, 6)))) for _ in range(400)]
+    q_off = np.cumsum([0] + [len(q) for q in qs]).astype(np.uint32)
+    q_terms = np.array([x for q in qs for x in q], np.uint32)
+    compare(dev, oix, q_terms, q_off, 20)
+    dev.close()

@@ -91,39 +91,30 @@ bm25_plan_kernel(Bm25SearchArgs a, uint32_t cap2) {
   // contains term t scores at least min_impact(t).  If t has >= k postings in this shard, at least k documents have a
   // key above K0 = key(min_impact(t), worst ordinal), hence the k-th best key is >= K0 and everything <= K0 - 1 can be
   // dropped from the first range on (instead of flooding the candidate buffer until the running top-k fills up).
-  for (uint32_t b = tid; b < a.B; b += blockDim.x) {
-    uint32_t best = 0;
-    if (a.n_chunks == 1 && a.flags[0] == 0u) {
-      for (uint32_t i = a.q_off[b]; i < a.q_off[b + 1]; ++i) {
-        const uint32_t t = a.q_terms[i];
-        if (t < a.n_terms) {
-          const uint32_t* row = a.skip + (uint64_t)t * a.skip_ld;
-          if (row[a.n_ranges] - row[0] >= a.k) best = max(best, a.term_min[t]);
-        }
-      }
-    }
-    a.thr0[b] = best ? (((uint64_t)best << 32) - 1ull) : TRR_KEY_EMPTY;
-  }
-  if (cap2 == 0) {
-    for (uint32_t b = tid; b < a.B; b += blockDim.x) a.order[b] = b;
-    return;
-  }
-  for (uint32_t b = tid; b < cap2; b += blockDim.x) {
+  const bool boot = a.n_chunks == 1 && a.flags[0] == 0u;
+  const uint32_t n_loop = cap2 ? cap2 : a.B;
+  for (uint32_t b = tid; b < n_loop; b += blockDim.x) {
     uint64_t key = 0;
     if (b < a.B) {
-      uint64_t cost = 0;
+      uint64_t cost = 0;  // postings the query touches in this shard
+      uint32_t best = 0;  // largest min-impact among its terms with >= k postings
       for (uint32_t i = a.q_off[b]; i < a.q_off[b + 1]; ++i) {
         const uint32_t t = a.q_terms[i];
         if (t < a.n_terms) {
           const uint32_t* row = a.skip + (uint64_t)t * a.skip_ld;
-          cost += row[a.n_ranges] - row[0];
+          const uint32_t cnt = row[a.n_ranges] - row[0];
+          cost += cnt;
+          if (boot && cnt >= a.k) best = max(best, a.term_min[t]);
         }
       }
+      a.thr0[b] = best ? (((uint64_t)best << 32) - 1ull) : TRR_KEY_EMPTY;
       if (cost > 0xFFFFFFFFull) cost = 0xFFFFFFFFull;
       key = ((cost + 1) << 32) | (uint64_t)(0xFFFFFFFFu - b);  // never TRR_KEY_EMPTY; ties: smaller b first
+      if (cap2 == 0) a.order[b] = b;
     }
-    keys[b] = key;
+    if (cap2) keys[b] = key;
   }
+  if (cap2 == 0) return;
   trr_bitonic_sort_desc(keys, cap2, tid, blockDim.x, BlockSync());
   for (uint32_t i = tid; i < a.B; i += blockDim.x) a.order[i] = 0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFu);
 }
