@@ -399,8 +399,8 @@ def ncu_traffic(kind, a):
 def verify_full_size(a, api, dense, bm, q_np, q_terms, q_off, host_csr, outputs, world):
     """Parity at the FULL bench size, outside every timed region, on the first `--verify` queries:
       dense   the tensor-core path (K2 + exact re-scoring + proof) must return bit-identical ids and scores to the exact scan
-              kernel K1 over the same 10M-row slab (K1 itself is pinned bit-exactly to the oracle by tests/ at sizes the
-              oracle finishes in seconds; it contains no size-dependent arithmetic);
+              kernel K1 over the same 10M-row slab; K1's returned scores are recomputed by the CPU oracle from the stored
+              rows (bit-exact), its list is in canonical order, and no row of a 20000-row random sample beats its C-th hit;
       sparse  the BM25 kernel vs the CPU oracle scoring the same host CSR with the same global statistics (single GPU only);
       fused   the e2e output vs the oracle's RRF fusion + take(k) of those two lists.
     With several GPUs only the internal-consistency properties are checked (ids unique, fused scores sorted and in range)."""
@@ -423,6 +423,26 @@ def verify_full_size(a, api, dense, bm, q_np, q_terms, q_off, host_csr, outputs,
     g_ord, g_sc, g_n = dense.search(q_np[:n], Cn)
     res["dense_gemm_equals_exact_scan"] = bool(np.array_equal(s_n, g_n) and np.array_equal(s_ord, g_ord) and
                                                 np.array_equal(s_sc, g_sc))
+    # the exact scan itself against the CPU oracle at full size: every returned score is recomputed by the oracle from
+    # the stored rows (downloaded), and a random sample of 20000 other rows must not beat the C-th result
+    rng = np.random.default_rng(1)
+    ok = True
+    for b in range(n):
+        m = int(s_n[b])
+        rows = dense.rows(s_ord[b, :m])
+        f = (rows.astype(np.uint32) << 16).view(np.float32) if rows.dtype == np.uint16 else rows
+        exp = np.array([O.cosine(q_np[b], f[i]) for i in range(m)], np.float32)
+        ok = ok and np.array_equal(exp, s_sc[b, :m])
+        ok = ok and bool(np.all((s_sc[b, :m - 1] > s_sc[b, 1:m]) | ((s_sc[b, :m - 1] == s_sc[b, 1:m]) & (s_ord[b, :m - 1] < s_ord[b, 1:m]))))
+        samp = rng.integers(0, a.docs, 20000).astype(np.uint32)
+        rs = dense.rows(samp)
+        fs = (rs.astype(np.uint32) << 16).view(np.float32) if rs.dtype == np.uint16 else rs
+        o_ids, o_sc, o_cnt = O.dense_search_batch(fs, q_np[b:b + 1], 1)
+        best_ord, best_sc = int(samp[int(o_ids[0, 0])]), float(o_sc[0, 0])
+        kth_sc, kth_ord = float(s_sc[b, m - 1]), int(s_ord[b, m - 1])
+        in_list = best_ord in set(s_ord[b, :m].tolist())
+        ok = ok and (in_list or best_sc < kth_sc or (best_sc == kth_sc and best_ord > kth_ord))
+    res["exact_scan_scores_equal_oracle_and_dominate_sample"] = bool(ok)
     term_off, post_doc, post_tf, doc_len, df_g, avgdl = host_csr
     oix = O.BM25.from_csr(len(doc_len), a.vocab, term_off, post_doc, post_tf, doc_len, df_g, avgdl)
     qt, qo = q_terms[:int(q_off[n])], q_off[:n + 1]
@@ -442,6 +462,7 @@ def verify_full_size(a, api, dense, bm, q_np, q_terms, q_off, host_csr, outputs,
             np.array_equal(o_d[b, :m], dd, equal_nan=True) and np.array_equal(o_s[b, :m], ss, equal_nan=True)
     res["fused_equals_oracle"] = bool(ok)
     res["consistent"] = bool(res["ids_unique_sorted_in_range"] and res["dense_gemm_equals_exact_scan"] and
+                             res["exact_scan_scores_equal_oracle_and_dominate_sample"] and
                              res["bm25_equals_oracle"] and res["fused_equals_oracle"])
     return res
 

@@ -124,6 +124,8 @@ TRR_API int trr_dense_search_device(trr_dense* h, const float* d_q, uint32_t B, 
 TRR_API int trr_dense_last_stats(trr_dense* h, trr_stats* out);
 /* test/diagnostic: copies the stored norms (sqrt of the sequential f32 sum of squares) to the host */
 TRR_API int trr_dense_copy_norms(trr_dense* h, float* out_norms, uint64_t n);
+/* test/diagnostic: copies n stored rows (LOCAL ordinals, in the store's dtype, dim elements each) to the host */
+TRR_API int trr_dense_copy_rows(trr_dense* h, const uint32_t* ordinals, uint64_t n, void* out_rows);
 
 /* ---- sparse index: BM25Index, src/index.rs:30-280 -------------------------------------------- */
 /* Builds the device index from a host CSR over term ids (the tokenizer src/index.rs:111-124 and the

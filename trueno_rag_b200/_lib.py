@@ -65,6 +65,7 @@ TRR_PROTOS = {
     "trr_dense_search_device": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp]),
     "trr_dense_last_stats": (C.c_int, [vp, C.POINTER(Stats)]),
     "trr_dense_copy_norms": (C.c_int, [vp, f32p, C.c_uint64]),
+    "trr_dense_copy_rows": (C.c_int, [vp, u32p, C.c_uint64, vp]),
     "trr_bm25_build": (C.c_int, [vp, C.c_uint32, C.c_uint32, u64p, u32p, u32p, u32p, C.c_float, C.c_float, C.c_float,
                                  f32p, C.c_uint32, vpp]),
     "trr_bm25_destroy": (C.c_int, [vp]),

@@ -143,6 +143,14 @@ class DenseIndex:
         _check(self.L.trr_dense_last_stats(self.h, C.byref(s)))
         return s
 
+    def rows(self, ordinals) -> np.ndarray:
+        """Stored rows (local ordinals) in the store's dtype: float32, or uint16 bf16 bit patterns."""
+        o = np.ascontiguousarray(ordinals, dtype=np.uint32)
+        out = np.zeros((o.size, self.dim), np.uint16 if self.dtype == BF16 else np.float32)
+        if o.size:
+            _check(self.L.trr_dense_copy_rows(self.h, _p(o, u32p), o.size, C.c_void_p(out.ctypes.data)))
+        return out
+
     def norms(self, n: int) -> np.ndarray:
         out = np.zeros(n, np.float32)
         _check(self.L.trr_dense_copy_norms(self.h, _p(out, f32p), n))

@@ -374,6 +374,19 @@ extern "C" int trr_dense_copy_norms(trr_dense* h, float* out, uint64_t n) {
   return TRR_OK;
 }
 
+extern "C" int trr_dense_copy_rows(trr_dense* h, const uint32_t* ordinals, uint64_t n, void* out_rows) {
+  if (!h || (n && (!ordinals || !out_rows))) return trr_fail(TRR_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  TRR_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  for (uint64_t i = 0; i < n; ++i) {
+    if (ordinals[i] >= h->n) return trr_fail(TRR_ERR_INVALID_ARG, "ordinal out of range");
+    TRR_CUDA(cudaMemcpy(static_cast<char*>(out_rows) + i * h->row_bytes, h->rows + (uint64_t)ordinals[i] * h->row_bytes,
+                        h->row_bytes, cudaMemcpyDeviceToHost));
+  }
+  return TRR_OK;
+}
+
 // builds the operands of the tensor-core pass: bf16 shadow (if the slab cannot be used in place),
 // per-document scale/bias, max norm, TMA descriptor
 static int dense_prepare_gemm(trr_dense* h) {
