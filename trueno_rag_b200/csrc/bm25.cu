@@ -127,7 +127,7 @@ namespace {
 constexpr uint32_t FULLM = 0xFFFFFFFFu;
 constexpr uint32_t CW = TRR_BM25_CONSUMER_WARPS;       // 16
 constexpr uint32_t CT = CW * 32;                       // consumer threads
-constexpr uint32_t F_HARVEST = 1u, F_END_ITEM = 2u, F_QUIT = 4u;
+constexpr uint32_t F_HARVEST = 1u, F_END_ITEM = 2u, F_QUIT = 4u, F_HAS_POSTINGS = 8u;
 
 struct PassDesc {
   uint32_t flags;
@@ -174,6 +174,7 @@ bm25_search_kernel(Bm25SearchArgs a) {
   PassDesc* desc = reinterpret_cast<PassDesc*>(cand + a.cand_cap);                // 2
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(desc + 2);                     // 2
   uint64_t* empty_bar = full_bar + 2;                                             // 2
+  uint32_t* bnd_all = reinterpret_cast<uint32_t*>(empty_bar + 2);                 // 2 x 32 x 17 sub-range boundaries
   __shared__ uint32_t s_cnt, s_overflow;
   __shared__ uint64_t s_thr;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -197,7 +198,10 @@ bm25_search_kernel(Bm25SearchArgs a) {
       PassDesc& d = desc[stage];
       d.seg_begin[lane] = begin;
       d.seg_end[lane] = end;
-      if (lane == 0) { d.flags = flags; d.range_base = range_base; d.item = item; d.thr0 = item_thr0; }
+      if (lane == 0) {
+        d.flags = flags | (total_al ? F_HAS_POSTINGS : 0u);
+        d.range_base = range_base; d.item = item; d.thr0 = item_thr0;
+      }
       __syncwarp();
       if (lane == 0) {
         if (total_al) trr_mbar_expect_tx(&full_bar[stage], total_al * 8u);
@@ -318,17 +322,25 @@ bm25_search_kernel(Bm25SearchArgs a) {
       if (flags & F_QUIT) break;
       const uint2* st = stage_buf + (size_t)stage * a.stage_cap;
       {
-        const uint32_t sb = d.seg_begin[lane], se = d.seg_end[lane];
-        const uint32_t d0 = range_base + warp * SUB;
-        // two interleaved binary searches (independent dependency chains): first posting >= d0 and first >= d0 + SUB
-        uint32_t lo = sb, lo_e = se, hi = sb, hi_e = se;
-        const uint32_t d1 = d0 + SUB;
-        while (lo < lo_e || hi < hi_e) {
-          const uint32_t m0 = (lo + lo_e) >> 1, m1 = (hi + hi_e) >> 1;
-          const uint32_t x0 = lo < lo_e ? st[m0].x : 0u, x1 = hi < hi_e ? st[m1].x : 0u;
-          if (lo < lo_e) { if (x0 < d0) lo = m0 + 1; else lo_e = m0; }
-          if (hi < hi_e) { if (x1 < d1) hi = m1 + 1; else hi_e = m1; }
+        // sub-range boundaries of every staged segment, computed once by the 512 consumer threads together:
+        // thread (term slot l = tid / 16, sub-range w = tid % 16) finds the first posting of slot l with doc >= start of
+        // sub-range w; warp w then reads its [lo, hi) per slot from shared memory (one search per boundary instead of
+        // two per (warp, slot)).  The table is double-buffered by stage.
+        uint32_t* bnd = bnd_all + stage * (32 * 17);
+        if (flags & F_HAS_POSTINGS) {
+          const uint32_t l = tid >> 4, w = tid & 15;
+          uint32_t lo_s = d.seg_begin[l], hi_s = d.seg_end[l];
+          const uint32_t dw = range_base + w * SUB;
+          if (w == 0) bnd[l * 17 + 16] = hi_s;
+          while (lo_s < hi_s) {
+            const uint32_t mid = (lo_s + hi_s) >> 1;
+            if (st[mid].x < dw) lo_s = mid + 1; else hi_s = mid;
+          }
+          bnd[l * 17 + w] = lo_s;
+          consumer_bar();
         }
+        uint32_t lo = 0, hi = 0;
+        if (flags & F_HAS_POSTINGS) { lo = bnd[lane * 17 + warp]; hi = bnd[lane * 17 + warp + 1]; }
         uint32_t m = __ballot_sync(FULLM, hi > lo);
         if (m) touched = true;
         while (m) {  // ascending slot == query-term order
@@ -433,7 +445,8 @@ cudaError_t trr_launch_bm25_build(const Bm25BuildArgs& a, cudaStream_t st) {
 }
 
 size_t trr_bm25_search_smem(uint32_t range_shift, uint32_t stage_cap, uint32_t cand_cap) {
-  return ((size_t)4 << range_shift) + (size_t)2 * stage_cap * 8 + (size_t)cand_cap * 8 + 2 * sizeof(PassDesc) + 4 * 8;
+  return ((size_t)4 << range_shift) + (size_t)2 * stage_cap * 8 + (size_t)cand_cap * 8 + 2 * sizeof(PassDesc) + 4 * 8 +
+         (size_t)2 * 32 * 17 * 4;
 }
 
 cudaError_t trr_launch_bm25_plan(const Bm25SearchArgs& a, cudaStream_t st) {
