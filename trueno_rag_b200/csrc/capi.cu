@@ -193,6 +193,8 @@ struct trr_dense {
   alignas(64) uint8_t map_scan[128];    // slab in its own dtype, 32-row x 128-byte box (K1 TMA ring)
   uint64_t map_scan_n = 0;              // rows covered by map_scan (0 = not built)
   const void* map_scan_base = nullptr;
+  uint32_t* stat_dev = nullptr;         // [2] device copy of {n_flagged, max_gap bits} of the last GEMM search
+  bool stat_pending = false;
   int mode = TRR_DENSE_AUTO;
   trr_stats stats{};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // [0,1] whole call, [2,3] dominant kernel
@@ -248,6 +250,7 @@ extern "C" int trr_dense_destroy(trr_dense* h) {
   if (h->rows) cudaFree(h->rows);
   if (h->norms) cudaFree(h->norms);
   if (h->dead) cudaFree(h->dead);
+  if (h->stat_dev) cudaFree(h->stat_dev);
   h->shadow.release(); h->scale_bias.release(); h->max_norm.release(); h->qbuf.release();
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   delete h;
@@ -484,9 +487,10 @@ static int plan_scan(trr_dense* h, uint32_t k, ScanPlan* p) {
 }
 
 // exact scan (K1) of the queries selected by (d_sel, n_sel) or all B; results into d_ord/d_score/d_n rows
+// d_n_sel (nullable): DEVICE count of selected queries (<= n_sel, which then only sizes the buffers and the grids)
 static int dense_scan_locked(trr_dense* h, const float* d_q, const float* d_qn, uint32_t n_sel, const uint32_t* d_sel,
                              uint32_t k, uint32_t* d_ord, float* d_score, uint32_t* d_n, uint64_t* d_keys,
-                             size_t scratch_off) {
+                             size_t scratch_off, const uint32_t* d_n_sel = nullptr, bool record_events = true) {
   ScanPlan p;
   TRR_CHECK(plan_scan(h, k, &p));
   const uint64_t lists = (uint64_t)p.grid;  // one merged list per CTA
@@ -498,7 +502,7 @@ static int dense_scan_locked(trr_dense* h, const float* d_q, const float* d_qn, 
   DenseScanArgs a{};
   a.rows = h->rows; a.row_bytes = h->row_bytes; a.dim = h->dim; a.n_rows = h->n;
   a.norms = h->norms; a.dead = h->n_dead ? h->dead : nullptr;
-  a.q = d_q; a.q_norms = d_qn; a.sel = d_sel; a.n_sel_ptr = nullptr; a.n_sel = n_sel;
+  a.q = d_q; a.q_norms = d_qn; a.sel = d_sel; a.n_sel_ptr = d_n_sel; a.n_sel = n_sel;
   a.ch_bytes = p.ch_bytes; a.n_chunks = p.n_chunks; a.n_slots = p.n_slots; a.k = k; a.cap = p.cap; a.base_ord = h->base;
   a.partial = partial; a.partial_n = partial_n;
   cudaStream_t st = h->ctx->stream;
@@ -506,18 +510,29 @@ static int dense_scan_locked(trr_dense* h, const float* d_q, const float* d_qn, 
     TRR_CHECK(trr_make_tensor_map_ex(h->map_scan, h->rows, h->n, h->dim, h->elem, 128 / h->elem, 32));
     h->map_scan_n = h->n; h->map_scan_base = h->rows;
   }
-  TRR_CUDA(cudaEventRecord(h->ev[2], st));
+  if (record_events) TRR_CUDA(cudaEventRecord(h->ev[2], st));
   if (p.tma) TRR_CUDA(trr_launch_scan_tma(a, h->map_scan, h->dtype == TRR_DTYPE_BF16, h->metric, p.grid, p.warps, p.smem, st));
   else TRR_CUDA(trr_launch_scan(a, h->dtype == TRR_DTYPE_BF16, h->metric, p.bulk, p.grid, p.smem, st));
-  TRR_CUDA(cudaEventRecord(h->ev[3], st));
+  if (record_events) TRR_CUDA(cudaEventRecord(h->ev[3], st));
   h->ctx->launches++;
   TopkMergeArgs m{};
   m.lists = partial; m.list_n = partial_n; m.n_lists = (uint32_t)lists; m.list_stride = k;
-  m.n_rows = n_sel; m.n_rows_ptr = nullptr; m.row_map = d_sel; m.k = k; m.k2 = trr_pow2_ceil(k);
+  m.n_rows = n_sel; m.n_rows_ptr = d_n_sel; m.row_map = d_sel; m.k = k; m.k2 = trr_pow2_ceil(k);
   m.out_keys = d_keys; m.out_ord = d_ord; m.out_score = d_score; m.out_n = d_n;
-  TRR_CUDA(trr_launch_topk_merge(m, n_sel, st));
+  TRR_CUDA(trr_launch_topk_merge(m, d_n_sel ? std::min<uint32_t>(n_sel, 4u * (uint32_t)h->ctx->sm_count) : n_sel, st));
   h->ctx->launches++;
   return TRR_OK;
+}
+
+// reads the fallback count / max gap of the last GEMM search (the stream must be idle)
+static void dense_resolve_stats(trr_dense* h) {
+  if (!h->stat_pending || !h->stat_dev) return;
+  uint32_t hc[2] = {0, 0};
+  if (cudaMemcpy(hc, h->stat_dev, 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+    h->stats.n_guard_fallbacks = hc[0];
+    memcpy(&h->stats.max_fast_exact_gap, &hc[1], 4);
+  }
+  h->stat_pending = false;
 }
 
 static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint32_t k, uint32_t* d_ord, float* d_score,
@@ -605,7 +620,11 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     ScanPlan p;
     TRR_CHECK(plan_scan(h, k, &p));
     const uint64_t lists = (uint64_t)p.grid;
-    const uint32_t fb_chunk = 64;  // fallback queries per scan launch
+    // queries whose candidate proof fails are re-run through the exact scan.  Normally the fallback is DEVICE-DRIVEN (the
+    // scan and merge kernels read the number of flagged queries from device memory and return at once when it is zero), so
+    // the whole search is enqueued without a host round trip; very large B x k falls back to a host-read count and chunks.
+    const bool dev_fallback = (size_t)B * lists * k * 8 <= ((size_t)256 << 20) && !getenv("TRR_GEMM_HOST_FALLBACK");
+    const uint32_t fb_chunk = dev_fallback ? B : 64;  // fallback queries per scan launch
     const size_t need = WsCarver::need({(size_t)B * 4, (size_t)B * 4, n_cand * 4, n_cand * 4, (size_t)B_pad * 4,
                                         (size_t)B * 4, (size_t)B * 4, 256, (size_t)B_pad * h->dim_pad * 2,
                                         (size_t)fb_chunk * lists * k * 8 + 512, (size_t)fb_chunk * lists * 4 + 512}) +
@@ -660,33 +679,45 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     ra.flags = flags; ra.flagged = flagged; ra.n_flagged = counters; ra.max_gap = reinterpret_cast<float*>(counters + 1);
     TRR_CUDA(trr_launch_rescore(ra, h->dtype == TRR_DTYPE_BF16, st));
     c->launches++;
-    // the candidate proof can fail (near-ties, adversarial data): those queries take the exact scan
-    uint32_t hc[2] = {0, 0};
-    TRR_CUDA(cudaMemcpyAsync(hc, counters, 8, cudaMemcpyDeviceToHost, st));
-    {
+    h->stats.eps_bound = eps_rel;
+    if (dev_fallback) {
+      if (!h->stat_dev) TRR_CUDA(cudaMalloc(&h->stat_dev, 64));
+      TRR_CUDA(cudaMemcpyAsync(h->stat_dev, counters, 8, cudaMemcpyDeviceToDevice, st));
+      h->stat_pending = true;
+      if (!ga.debug_mode)
+        TRR_CHECK(dense_scan_locked(h, d_q, d_qn, B, flagged, k, d_ord, d_score, d_n, nullptr, fb_off, counters, false));
+    } else {
+      uint32_t hc[2] = {0, 0};
+      TRR_CUDA(cudaMemcpyAsync(hc, counters, 8, cudaMemcpyDeviceToHost, st));
       cudaError_t se = cudaStreamSynchronize(st);
       if (se != cudaSuccess) {
         const uint32_t w = extra(c)->dbg_host ? extra(c)->dbg_host[0] : 0;
         return trr_fail(TRR_ERR_CUDA, std::string("GEMM path failed: ") + cudaGetErrorString(se) +
                                           " (barrier-timeout word 0x" + [](uint32_t v) { char b[16]; snprintf(b, 16, "%x", v); return std::string(b); }(w) + ")");
       }
-    }
-    h->stats.n_guard_fallbacks = hc[0];
-    memcpy(&h->stats.max_fast_exact_gap, &hc[1], 4);
-    h->stats.eps_bound = eps_rel;
-    if (ga.debug_mode) hc[0] = 0;  // perf triage: results are meaningless, do not time the fallback
-    for (uint32_t f0 = 0; f0 < hc[0]; f0 += fb_chunk) {
-      const uint32_t m = std::min(fb_chunk, hc[0] - f0);
-      TRR_CHECK(dense_scan_locked(h, d_q, d_qn, m, flagged + f0, k, d_ord, d_score, d_n, nullptr, fb_off));
+      h->stats.n_guard_fallbacks = hc[0];
+      memcpy(&h->stats.max_fast_exact_gap, &hc[1], 4);
+      if (ga.debug_mode) hc[0] = 0;  // perf triage: results are meaningless, do not time the fallback
+      for (uint32_t f0 = 0; f0 < hc[0]; f0 += fb_chunk) {
+        const uint32_t m = std::min(fb_chunk, hc[0] - f0);
+        TRR_CHECK(dense_scan_locked(h, d_q, d_qn, m, flagged + f0, k, d_ord, d_score, d_n, nullptr, fb_off, nullptr, false));
+      }
     }
     h->stats.mode_used = TRR_DENSE_GEMM;
   }
   TRR_CUDA(cudaEventRecord(h->ev[1], st));
   h->stats.n_kernel_launches = (uint32_t)(c->launches - launches0);
   if (sync_stats) {
-    TRR_CUDA(cudaStreamSynchronize(st));
+    cudaError_t se = cudaStreamSynchronize(st);
+    if (se != cudaSuccess) {
+      const uint32_t w = extra(c)->dbg_host ? extra(c)->dbg_host[0] : 0;
+      char wb[16]; snprintf(wb, 16, "%x", w);
+      return trr_fail(TRR_ERR_CUDA, std::string("dense search failed: ") + cudaGetErrorString(se) +
+                                        " (barrier-timeout word 0x" + wb + ")");
+    }
     cudaEventElapsedTime(&h->stats.ms_total, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&h->stats.ms_main_kernel, h->ev[2], h->ev[3]);
+    dense_resolve_stats(h);
   }
   return TRR_OK;
 }
@@ -737,6 +768,7 @@ extern "C" int trr_dense_last_stats(trr_dense* h, trr_stats* out) {
     cudaEventElapsedTime(&h->stats.ms_main_kernel, h->ev[2], h->ev[3]);
     cudaGetLastError();
   }
+  dense_resolve_stats(h);
   *out = h->stats;
   return TRR_OK;
 }
