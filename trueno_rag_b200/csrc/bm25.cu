@@ -79,42 +79,54 @@ __global__ void bm25_skip_empty_kernel(Bm25BuildArgs a) {
 }
 
 // =============================================================================================
-// planning: posting volume per query -> processing order (largest first), queue reset
+// planning: posting volume per query -> processing order (largest first), bootstrap thresholds, queue reset
 // =============================================================================================
-__global__ void __launch_bounds__(1024, 1)
-bm25_plan_kernel(Bm25SearchArgs a, uint32_t cap2) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);  // cap2 = power of two >= B (0: identity order)
-  const uint32_t tid = threadIdx.x;
-  if (tid == 0) { a.queue[0] = 0; a.queue[1] = 0; }
+// one warp per query, one lane per query term (strided): the skip-row look-ups of all terms are in flight together
+__global__ void __launch_bounds__(256)
+bm25_cost_kernel(Bm25SearchArgs a, uint64_t* __restrict__ keys, uint32_t cap2) {
+  const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { a.queue[0] = 0; a.queue[1] = 0; }
+  const uint32_t n_loop = cap2 ? cap2 : a.B;
+  if (b >= n_loop) return;
+  if (b >= a.B) {  // padding entries of the sort
+    if (lane == 0) keys[b] = 0;
+    return;
+  }
   // Threshold bootstrap.  Impacts are positive and f32 addition of non-negative values is monotone, so a document that
   // contains term t scores at least min_impact(t).  If t has >= k postings in this shard, at least k documents have a
   // key above K0 = key(min_impact(t), worst ordinal), hence the k-th best key is >= K0 and everything <= K0 - 1 can be
   // dropped from the first range on (instead of flooding the candidate buffer until the running top-k fills up).
   const bool boot = a.n_chunks == 1 && a.flags[0] == 0u;
-  const uint32_t n_loop = cap2 ? cap2 : a.B;
-  for (uint32_t b = tid; b < n_loop; b += blockDim.x) {
-    uint64_t key = 0;
-    if (b < a.B) {
-      uint64_t cost = 0;  // postings the query touches in this shard
-      uint32_t best = 0;  // largest min-impact among its terms with >= k postings
-      for (uint32_t i = a.q_off[b]; i < a.q_off[b + 1]; ++i) {
-        const uint32_t t = a.q_terms[i];
-        if (t < a.n_terms) {
-          const uint32_t* row = a.skip + (uint64_t)t * a.skip_ld;
-          const uint32_t cnt = row[a.n_ranges] - row[0];
-          cost += cnt;
-          if (boot && cnt >= a.k) best = max(best, a.term_min[t]);
-        }
-      }
-      a.thr0[b] = best ? (((uint64_t)best << 32) - 1ull) : TRR_KEY_EMPTY;
-      if (cost > 0xFFFFFFFFull) cost = 0xFFFFFFFFull;
-      key = ((cost + 1) << 32) | (uint64_t)(0xFFFFFFFFu - b);  // never TRR_KEY_EMPTY; ties: smaller b first
-      if (cap2 == 0) a.order[b] = b;
+  uint64_t cost = 0;  // postings the query touches in this shard
+  uint32_t best = 0;  // largest min-impact among its terms with >= k postings
+  for (uint32_t i = a.q_off[b] + lane; i < a.q_off[b + 1]; i += 32) {
+    const uint32_t t = a.q_terms[i];
+    if (t < a.n_terms) {
+      const uint32_t* row = a.skip + (uint64_t)t * a.skip_ld;
+      const uint32_t cnt = row[a.n_ranges] - row[0];
+      cost += cnt;
+      if (boot && cnt >= a.k) best = max(best, a.term_min[t]);
     }
-    if (cap2) keys[b] = key;
   }
-  if (cap2 == 0) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o);
+    best = max(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+  }
+  if (lane == 0) {
+    a.thr0[b] = best ? (((uint64_t)best << 32) - 1ull) : TRR_KEY_EMPTY;
+    if (cost > 0xFFFFFFFFull) cost = 0xFFFFFFFFull;
+    if (cap2) keys[b] = ((cost + 1) << 32) | (uint64_t)(0xFFFFFFFFu - b);  // never TRR_KEY_EMPTY; ties: smaller b first
+    else a.order[b] = b;
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+bm25_order_kernel(Bm25SearchArgs a, const uint64_t* __restrict__ gkeys, uint32_t cap2) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);  // cap2 = power of two >= B
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t i = tid; i < cap2; i += blockDim.x) keys[i] = gkeys[i];
   trr_bitonic_sort_desc(keys, cap2, tid, blockDim.x, BlockSync());
   for (uint32_t i = tid; i < a.B; i += blockDim.x) a.order[i] = 0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFu);
 }
@@ -449,10 +461,12 @@ size_t trr_bm25_search_smem(uint32_t range_shift, uint32_t stage_cap, uint32_t c
          (size_t)2 * 32 * 17 * 4;
 }
 
-cudaError_t trr_launch_bm25_plan(const Bm25SearchArgs& a, cudaStream_t st) {
+cudaError_t trr_launch_bm25_plan(const Bm25SearchArgs& a, uint64_t* plan_keys, cudaStream_t st) {
   uint32_t cap2 = 0;
-  if (a.B > 1 && a.B <= 4096) cap2 = trr_pow2_ceil(a.B);
-  bm25_plan_kernel<<<1, 1024, (size_t)cap2 * 8, st>>>(a, cap2);
+  if (a.B > 1 && a.B <= 4096) cap2 = trr_pow2_ceil(a.B);  // larger batches keep the submission order
+  const uint32_t n = cap2 ? cap2 : a.B;
+  bm25_cost_kernel<<<(n + 7) / 8, 256, 0, st>>>(a, plan_keys, cap2);
+  if (cap2) bm25_order_kernel<<<1, 1024, (size_t)cap2 * 8, st>>>(a, plan_keys, cap2);
   return cudaGetLastError();
 }
 

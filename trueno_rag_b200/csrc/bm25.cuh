@@ -49,5 +49,6 @@ struct Bm25SearchArgs {
 
 cudaError_t trr_launch_bm25_build(const Bm25BuildArgs& a, cudaStream_t st);
 size_t trr_bm25_search_smem(uint32_t range_shift, uint32_t stage_cap, uint32_t cand_cap);
-cudaError_t trr_launch_bm25_plan(const Bm25SearchArgs& a, cudaStream_t st);
+// plan_keys: scratch of max(pow2ceil(B), 1) u64
+cudaError_t trr_launch_bm25_plan(const Bm25SearchArgs& a, uint64_t* plan_keys, cudaStream_t st);
 cudaError_t trr_launch_bm25_search(const Bm25SearchArgs& a, unsigned grid, cudaStream_t st);

@@ -964,7 +964,8 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   if (const char* e = getenv("TRR_BM25_CHUNKS")) n_chunks = std::min<uint32_t>(h->n_ranges, std::max(1, atoi(e)));
   n_chunks = std::max<uint32_t>(n_chunks, 1);
   a.n_chunks = n_chunks;
-  const size_t need = scratch_off + WsCarver::need({(size_t)B * 4, (size_t)B * 8, 64, n_chunks > 1 ? (size_t)B * n_chunks * k * 8 : 8});
+  const size_t need = scratch_off + WsCarver::need({(size_t)B * 4, (size_t)B * 8, 64, n_chunks > 1 ? (size_t)B * n_chunks * k * 8 : 8,
+                                                    (size_t)trr_pow2_ceil(B) * 8});
   TRR_CHECK(extra(c)->scratch.reserve(need));
   WsCarver ws(static_cast<char*>(extra(c)->scratch.p) + scratch_off);
   a.term_min = h->term_min; a.flags = h->term_min + h->n_terms;
@@ -972,15 +973,17 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   a.thr0 = ws.take<uint64_t>(B);
   a.queue = ws.take<uint32_t>(16);
   a.partial = ws.take<uint64_t>(n_chunks > 1 ? (size_t)B * n_chunks * k : 1);
+  uint64_t* plan_keys = ws.take<uint64_t>(trr_pow2_ceil(B));
   a.out_keys = nullptr; a.out_ord = d_ord; a.out_score = d_score; a.out_n = d_n;
   a.dbg = extra(c)->dbg_dev;
   const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)B * n_chunks, (uint64_t)slots);
-  TRR_CUDA(trr_launch_bm25_plan(a, st));
+  TRR_CUDA(trr_launch_bm25_plan(a, plan_keys, st));
   TRR_CUDA(cudaEventRecord(h->ev[2], st));
   TRR_CUDA(trr_launch_bm25_search(a, grid, st));
   TRR_CUDA(cudaEventRecord(h->ev[3], st));
-  c->launches += 2;
-  h->stats.n_kernel_launches = 2;
+  const uint32_t plan_launches = (B > 1 && B <= 4096) ? 2u : 1u;
+  c->launches += plan_launches + 1;
+  h->stats.n_kernel_launches = plan_launches + 1;
   if (n_chunks > 1) {
     TopkMergeArgs m{};
     m.lists = a.partial; m.list_n = nullptr; m.n_lists = n_chunks; m.list_stride = k;
@@ -988,7 +991,7 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
     m.out_keys = nullptr; m.out_ord = d_ord; m.out_score = d_score; m.out_n = d_n;
     TRR_CUDA(trr_launch_topk_merge(m, B, st));
     c->launches++;
-    h->stats.n_kernel_launches = 3;
+    h->stats.n_kernel_launches++;
   }
   h->stats.mode_used = 1;
   return TRR_OK;
