@@ -168,3 +168,14 @@ def test_range_boundaries_and_many_queries(api, ctx):
     q_terms = np.array([x for q in qs for x in q], np.uint32)
     compare(dev, oix, q_terms, q_off, 20)
     dev.close()
+
+
+def test_more_than_4096_queries_keep_submission_order(api, ctx):
+    """Batches above 4096 queries skip the posting-volume sort (identity order); results must not depend on it."""
+    cdf = O.zipf_cdf(1500)
+    doc_off, toks = O.synth_doc_tokens(SEED + 11, cdf, 0, 9000)
+    oix = O.BM25(n_terms=1500, doc_off=doc_off, tokens=toks)
+    dev = build(api, ctx, oix, 9000)
+    q_off, q_terms = O.synth_query_terms(SEED + 11, cdf, 0, 4500)
+    compare(dev, oix, q_terms, q_off, 10)
+    dev.close()

@@ -642,7 +642,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     uint16_t* q_bf16 = ws.take<uint16_t>((size_t)B_pad * h->dim_pad);
     const size_t fb_off = (ws.off + 255) & ~size_t(255);
 
-    trr_launch_query_prep(d_q, h->dim, h->dim_pad, B, B_pad, q_bf16, d_qdelta, st);  // ||q|| comes from the rescoring kernel
+    trr_launch_query_prep(d_q, h->dim, h->dim_pad, B, B_pad, q_bf16, d_qdelta, d_qn, st);  // also ||q|| (reference order)
     c->launches += 1;
     TRR_CUDA(cudaMemsetAsync(gthr, 0, (size_t)B_pad * 4, st));
     TRR_CUDA(cudaMemsetAsync(counters, 0, 256, st));
@@ -666,7 +666,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     ra.cand_score = cand_score; ra.cand_ord = cand_ord; ra.n_slices = n_slices; ra.n_qblocks = n_qblocks;
     ra.cps = cps; ra.cp = CP; ra.cap2 = cap2;
     ra.rows = h->rows; ra.dim = h->dim; ra.norms = h->norms; ra.base_ord = h->base; ra.n_live = n_live;
-    ra.q = d_q; ra.q_norms = nullptr; ra.q_norms_out = d_qn; ra.q_delta = d_qdelta; ra.max_norm = reinterpret_cast<const float*>(h->max_norm.p);
+    ra.q = d_q; ra.q_norms = d_qn; ra.q_norms_out = nullptr; ra.q_delta = d_qdelta; ra.max_norm = reinterpret_cast<const float*>(h->max_norm.p);
     ra.B = B; ra.k = k; ra.metric = h->metric;
     // |fast - exact| <= eps_rel * |q||d|: products of bf16 values are exact in f32; the tensor-core sum and the
     // reference's sequential sum each carry at most D roundings of relative size 2^-23 on partial sums bounded by
@@ -803,7 +803,7 @@ extern "C" TRR_API int trr_debug_gemm_scores(trr_dense* h, const float* q, uint3
   uint16_t* q_bf16 = ws.take<uint16_t>((size_t)B_pad * h->dim_pad);
   float* dump = ws.take<float>((size_t)B_pad * out_ld);
   TRR_CUDA(cudaMemcpyAsync(d_q, q, (size_t)B * h->dim * 4, cudaMemcpyHostToDevice, st));
-  trr_launch_query_prep(d_q, h->dim, h->dim_pad, B, B_pad, q_bf16, d_qdelta, st);
+  trr_launch_query_prep(d_q, h->dim, h->dim_pad, B, B_pad, q_bf16, d_qdelta, nullptr, st);
   TRR_CUDA(cudaMemsetAsync(gthr, 0, (size_t)B_pad * 4, st));
   TRR_CUDA(cudaMemsetAsync(dump, 0, (size_t)B_pad * out_ld * 4, st));
   alignas(64) uint8_t map_q[128];

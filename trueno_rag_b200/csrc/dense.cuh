@@ -112,7 +112,7 @@ constexpr uint32_t TRR_GEMM_TILE_N = 256; // documents per MMA tile
 constexpr uint32_t TRR_GEMM_TILE_M = 128; // queries per CTA
 // converts B x dim f32 queries to a zero-padded [n_qblocks*128][dim_pad] bf16 matrix and reports ||q - bf16(q)||
 void trr_launch_query_prep(const float* q, uint32_t dim, uint32_t dim_pad, uint32_t B, uint32_t B_pad, uint16_t* q_bf16,
-                           float* q_delta, cudaStream_t st);
+                           float* q_delta, float* q_norm, cudaStream_t st);
 // f32 slab -> bf16 shadow (round to nearest even), zero-padded to dim_pad columns
 void trr_launch_shadow(const void* rows, int is_bf16, uint32_t dim, uint32_t dim_pad, uint64_t row0, uint64_t n,
                        uint16_t* shadow, cudaStream_t st);

@@ -580,15 +580,18 @@ __device__ __forceinline__ uint16_t f32_to_bf16_rne(float f) {
   return (uint16_t)(u >> 16);
 }
 
-// one CTA per (padded) query row
+// one CTA per (padded) query row: bf16 operand row, ||q - bf16(q)|| for the proof, and ||q|| in the reference's order
+// (sequential f32 sum of squares, src/index.rs:442; explicit _rn intrinsics because this file allows FMA contraction)
 __global__ void query_prep_kernel(const float* __restrict__ q, uint32_t dim, uint32_t dim_pad, uint32_t B,
-                                  uint16_t* __restrict__ q_bf16, float* __restrict__ q_delta) {
+                                  uint16_t* __restrict__ q_bf16, float* __restrict__ q_delta, float* __restrict__ q_norm) {
+  extern __shared__ float qsh[];
   const uint32_t b = blockIdx.x;
   float d2 = 0.0f;
   for (uint32_t j = threadIdx.x; j < dim_pad; j += blockDim.x) {
     uint16_t h = 0;
     if (b < B && j < dim) {
       const float x = q[(uint64_t)b * dim + j];
+      qsh[j] = x;
       h = f32_to_bf16_rne(x);
       const float r = x - __uint_as_float(((uint32_t)h) << 16);
       d2 += r * r;
@@ -603,6 +606,11 @@ __global__ void query_prep_kernel(const float* __restrict__ q, uint32_t dim, uin
     float s = 0.0f;
     for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) s += red[w];
     q_delta[b] = sqrtf(s) * 1.0001f;  // upper bound on || q - bf16(q) ||
+  }
+  if (threadIdx.x == 32 && b < B && q_norm) {
+    float s = 0.0f;
+    for (uint32_t j = 0; j < dim; ++j) s = __fadd_rn(s, __fmul_rn(qsh[j], qsh[j]));
+    q_norm[b] = __fsqrt_rn(s);
   }
 }
 
@@ -622,9 +630,9 @@ __global__ void shadow_kernel(const void* __restrict__ rows, int is_bf16, uint32
 }
 
 void trr_launch_query_prep(const float* q, uint32_t dim, uint32_t dim_pad, uint32_t B, uint32_t B_pad, uint16_t* q_bf16,
-                           float* q_delta, cudaStream_t st) {
+                           float* q_delta, float* q_norm, cudaStream_t st) {
   if (B_pad == 0) return;
-  query_prep_kernel<<<B_pad, 256, 0, st>>>(q, dim, dim_pad, B, q_bf16, q_delta);
+  query_prep_kernel<<<B_pad, 256, (size_t)dim * 4, st>>>(q, dim, dim_pad, B, q_bf16, q_delta, q_norm);
 }
 
 void trr_launch_shadow(const void* rows, int is_bf16, uint32_t dim, uint32_t dim_pad, uint64_t row0, uint64_t n,

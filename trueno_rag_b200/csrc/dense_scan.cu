@@ -581,7 +581,20 @@ rescore_select_kernel(RescoreArgs a) {
         uint32_t j = 0;
         if ((a.dim & 7u) == 0 && (reinterpret_cast<uintptr_t>(a.rows) & 15u) == 0) {
           const uint4* p4 = reinterpret_cast<const uint4*>(p);
-#pragma unroll 4
+          // batches of 8 x 128-bit loads in flight (the rows are scattered over HBM: latency-bound), then the strict chain
+          for (; j + 64 <= a.dim; j += 64) {
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(p4 + (j >> 3) + u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float* qq = qs + j + u * 8;
+              acc = acc + qq[0] * bf16lo(v[u].x); acc = acc + qq[1] * bf16hi(v[u].x);
+              acc = acc + qq[2] * bf16lo(v[u].y); acc = acc + qq[3] * bf16hi(v[u].y);
+              acc = acc + qq[4] * bf16lo(v[u].z); acc = acc + qq[5] * bf16hi(v[u].z);
+              acc = acc + qq[6] * bf16lo(v[u].w); acc = acc + qq[7] * bf16hi(v[u].w);
+            }
+          }
           for (; j < a.dim; j += 8) {
             const uint4 v = __ldg(p4 + (j >> 3));
             acc = acc + qs[j] * bf16lo(v.x);     acc = acc + qs[j + 1] * bf16hi(v.x);
@@ -596,7 +609,17 @@ rescore_select_kernel(RescoreArgs a) {
         uint32_t j = 0;
         if ((a.dim & 3u) == 0 && (reinterpret_cast<uintptr_t>(a.rows) & 15u) == 0) {
           const float4* p4 = reinterpret_cast<const float4*>(p);
-#pragma unroll 4
+          for (; j + 32 <= a.dim; j += 32) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(p4 + (j >> 2) + u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float* qq = qs + j + u * 4;
+              acc = acc + qq[0] * v[u].x; acc = acc + qq[1] * v[u].y;
+              acc = acc + qq[2] * v[u].z; acc = acc + qq[3] * v[u].w;
+            }
+          }
           for (; j < a.dim; j += 4) {
             const float4 v = __ldg(p4 + (j >> 2));
             acc = acc + qs[j] * v.x;     acc = acc + qs[j + 1] * v.y;
