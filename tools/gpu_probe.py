@@ -237,5 +237,67 @@ def step_perf_bm25_big():
     dev.close()
 
 
+def step_corun():
+    """Feasibility probe: tensor-core dense pass and BM25 kernel on two streams of one GPU (needs a build whose GEMM kernel
+    and BM25 kernel each fit half of the shared memory: TRR_BUILD_DEFS='-DTRR_GEMM_STAGES=2 -DTRR_GEMM_LSTRIDE=17',
+    TRR_BM25_RANGE_SHIFT=14 TRR_BM25_CTAS_PER_SM=1)."""
+    import ctypes as C
+    import torch
+    from trueno_rag_b200 import _lib
+    from trueno_rag_b200._lib import u32p, u64p
+    L = _lib.load()
+    ctxA, ctxB = api.Context(0), api.Context(0)
+    N, D, V, B, K = int(os.environ.get("PROBE_DOCS", "4000000")), 768, 1_000_000, 1024, 50
+    seed = 0x5EED0004
+    dense = api.DenseIndex(ctxA, D, 0, 1, capacity=N)
+    dense.append_synth(seed, 0, N)
+    dense.set_mode(2)
+    cdf = O.zipf_cdf(V)
+    df = np.zeros(V, np.uint32); dl = np.zeros(N, np.uint32); tot = C.c_uint64()
+    api._check(L.trr_synth_bm25_count(seed, cdf.ctypes.data_as(u64p), V, 0, N, df.ctypes.data_as(u32p), dl.ctypes.data_as(u32p), C.byref(tot)))
+    term_off = np.zeros(V + 1, np.uint64); np.cumsum(df, out=term_off[1:])
+    P = int(term_off[-1])
+    pd = np.zeros(P, np.uint32); ptf = np.zeros(P, np.uint32)
+    api._check(L.trr_synth_bm25_fill(seed, cdf.ctypes.data_as(u64p), V, 0, N, term_off.ctypes.data_as(u64p), pd.ctypes.data_as(u32p), ptf.ctypes.data_as(u32p)))
+    avgdl = float(np.float32(np.uint32(tot.value & 0xFFFFFFFF)) / np.float32(N))
+    bm = api.Bm25Device(ctxB, N, term_off, pd, ptf, dl, avgdl, api.bm25_idf_host(N, df))
+    Q = bf16_round(O.synth_queries(seed, 0, B, D, N, corpus_bf16=True))
+    q_off, q_terms = O.synth_query_terms(seed, cdf, 0, B)
+    dev = torch.device("cuda", 0)
+    d_q = torch.from_numpy(Q).to(dev)
+    d_terms = torch.from_numpy(q_terms.view(np.int32).copy()).to(dev)
+    d_off = torch.from_numpy(q_off.view(np.int32).copy()).to(dev)
+    outs = [torch.zeros((B, K), dtype=torch.int32, device=dev), torch.zeros((B, K), dtype=torch.float32, device=dev),
+            torch.zeros(B, dtype=torch.int32, device=dev)]
+    outs2 = [torch.zeros((B, K), dtype=torch.int32, device=dev), torch.zeros((B, K), dtype=torch.float32, device=dev),
+             torch.zeros(B, dtype=torch.int32, device=dev)]
+    torch.cuda.synchronize()
+
+    def run_dense():
+        dense.search_device(d_q.data_ptr(), B, K, outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr())
+
+    def run_bm25():
+        api._check(L.trr_bm25_search_device(bm.h, C.c_void_p(d_terms.data_ptr()), C.c_void_p(d_off.data_ptr()),
+                                            q_off.ctypes.data_as(u32p), B, K, C.c_void_p(outs2[0].data_ptr()),
+                                            C.c_void_p(outs2[1].data_ptr()), C.c_void_p(outs2[2].data_ptr())))
+
+    def sync():
+        api._check(L.trr_ctx_sync(ctxA.h)); api._check(L.trr_ctx_sync(ctxB.h))
+
+    for name, fns in (("dense alone", [run_dense]), ("bm25 alone", [run_bm25]), ("both, two streams", [run_dense, run_bm25]),
+                      ("both, bm25 first", [run_bm25, run_dense])):
+        for f in fns:
+            f()
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            for f in fns:
+                f()
+        sync()
+        print(f"{name}: {(time.perf_counter() - t0) / 5 * 1e3:.3f} ms per batch", flush=True)
+    ref = (outs[0].cpu().numpy().copy(), outs2[0].cpu().numpy().copy())
+    print("checksums", int(ref[0].astype(np.int64).sum()), int(ref[1].astype(np.int64).sum()))
+
+
 if __name__ == "__main__":
     globals()["step_" + sys.argv[1]]()

@@ -65,16 +65,17 @@ def _stamp() -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     stamp_file = os.path.join(OBJ, "stamp")
-    stamp = _stamp()
+    stamp = _stamp() + os.environ.get("TRR_BUILD_DEFS", "")
     if not force and os.path.exists(SO) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return SO
     nvcc, cxx = _nvcc(), _host_cxx()
+    extra_defs = os.environ.get("TRR_BUILD_DEFS", "").split()  # experiments only, e.g. "-DTRR_GEMM_STAGES=2"
     jobs = []
     for src in CU_STRICT:
-        jobs.append([nvcc, "-ccbin", cxx, *ARCH, *COMMON, *STRICT, "-c", os.path.join(CSRC, src), "-o",
+        jobs.append([nvcc, "-ccbin", cxx, *ARCH, *COMMON, *STRICT, *extra_defs, "-c", os.path.join(CSRC, src), "-o",
                      os.path.join(OBJ, src.replace("/", "_") + ".o")])
     for src in CU_FAST:
-        jobs.append([nvcc, "-ccbin", cxx, *ARCH, *COMMON, "-c", os.path.join(CSRC, src), "-o",
+        jobs.append([nvcc, "-ccbin", cxx, *ARCH, *COMMON, *extra_defs, "-c", os.path.join(CSRC, src), "-o",
                      os.path.join(OBJ, src.replace("/", "_") + ".o")])
     for src in CPP:
         jobs.append([cxx, "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-fvisibility=hidden", "-fopenmp",

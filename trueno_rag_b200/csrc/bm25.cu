@@ -175,7 +175,10 @@ __device__ __forceinline__ uint32_t lower_bound_doc(const uint2* st, uint32_t lo
 
 }  // namespace
 
-__global__ void __launch_bounds__(TRR_BM25_THREADS, 2)
+#ifndef TRR_BM25_MIN_CTAS
+#define TRR_BM25_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(TRR_BM25_THREADS, TRR_BM25_MIN_CTAS)
 bm25_search_kernel(Bm25SearchArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t R = 1u << a.range_shift;
@@ -475,6 +478,7 @@ cudaError_t trr_launch_bm25_search(const Bm25SearchArgs& a, unsigned grid, cudaS
   const size_t smem = trr_bm25_search_smem(a.range_shift, a.stage_cap, a.cand_cap);
   cudaError_t e = cudaFuncSetAttribute(bm25_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  cudaFuncSetAttribute(bm25_search_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   bm25_search_kernel<<<grid, TRR_BM25_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }

@@ -950,7 +950,7 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   {
     const size_t fixed = trr_bm25_search_smem(a.range_shift, 0, a.cand_cap) + 64;
     size_t budget = c->smem_optin;
-    if (ctas_per_sm == 2) budget = (228 * 1024) / 2 - 1024 - 64;  // 228 KB per SM, 1 KB reserved per CTA
+    if (ctas_per_sm == 2) budget = (228 * 1024) / 2 - 1024 - 1024;  // 228 KB per SM, 1 KB reserved per CTA, 1 KB slack
     if (fixed + 2 * 8 * 256 > budget) { ctas_per_sm = 1; budget = c->smem_optin; }
     if (fixed + 2 * 8 * 256 > budget) return trr_fail(TRR_ERR_UNSUPPORTED, "BM25 kernel does not fit shared memory");
     size_t cap = (budget - fixed) / 16;

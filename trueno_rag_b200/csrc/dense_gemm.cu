@@ -36,11 +36,17 @@ constexpr uint32_t BM = TRR_GEMM_TILE_M;  // 128 queries
 constexpr uint32_t BN = TRR_GEMM_TILE_N;  // 256 documents
 constexpr uint32_t BK = 64;               // bf16 elements per k-block = one 128-byte swizzle atom
 constexpr uint32_t UMMA_K = 16;
-constexpr uint32_t STAGES = 3;
+#ifndef TRR_GEMM_STAGES
+#define TRR_GEMM_STAGES 3
+#endif
+constexpr uint32_t STAGES = TRR_GEMM_STAGES;
 constexpr uint32_t CP = TRR_GEMM_CP;
 constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KB
 constexpr uint32_t B_BYTES = BN * BK * 2;  // 32 KB
-constexpr uint32_t LSTRIDE = CP + 1;                 // words per row of a candidate list: odd, so lane == row is conflict-free
+#ifndef TRR_GEMM_LSTRIDE
+#define TRR_GEMM_LSTRIDE (TRR_GEMM_CP + 1)
+#endif
+constexpr uint32_t LSTRIDE = TRR_GEMM_LSTRIDE;                 // words per row of a candidate list: odd, so lane == row is conflict-free
 constexpr uint32_t LIST_BYTES = BM * LSTRIDE * 4;
 constexpr uint32_t SMEM_A = 0;
 constexpr uint32_t SMEM_B = SMEM_A + STAGES * A_BYTES;
@@ -699,6 +705,7 @@ cudaError_t trr_launch_gemm_topk_dump(const GemmTopkArgs& a, const void* map_q12
     cudaError_t e = cudaFuncSetAttribute(dense_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)SMEM_TOTAL);
     if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(dense_gemm_topk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     dense_gemm_topk_kernel<<<grid, GEMM_THREADS, SMEM_TOTAL, st>>>(mq, md, a, dump, dump_ld);
   }
   return cudaGetLastError();
