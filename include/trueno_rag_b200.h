@@ -195,6 +195,20 @@ TRR_API int trr_hybrid_merge_device(trr_ctx* ctx, const void* d_gathered, uint32
                                     float param, uint32_t k, uint32_t* d_out_ord, float* d_out_fused, float* d_out_dense,
                                     float* d_out_sparse, uint32_t* d_out_n);
 
+/* ---- persistence -> device load --------------------------------------------- */
+/* The reference can serialise only BM25Index (bincode + LZ4/ZSTD, src/compressed.rs:71-108); VectorStore is not
+ * serialisable (src/compressed.rs:9-10) and the CLI dumps embeddings as JSON (crates/trueno-rag-cli/src/main.rs:135-146).
+ * These entry points add flat little-endian snapshot files of the DEVICE structures, so that a 10M-document index is back
+ * in HBM at file-read speed instead of being re-inserted / re-built: header, then the arrays exactly as they live on the
+ * device (embedding slab + tombstones; postings with impacts + skip table + per-term minimum impacts).  The ChunkId <->
+ * ordinal map, chunk texts and the term dictionary stay with the host language, as everywhere else in this ABI. */
+/* configuration of a store (e.g. one restored from a snapshot): dimension, trr_metric, trr_dtype, base ordinal */
+TRR_API int trr_dense_info(trr_dense* h, uint32_t* out_dim, int* out_metric, int* out_dtype, uint32_t* out_base);
+TRR_API int trr_dense_save(trr_dense* h, const char* path);
+TRR_API int trr_dense_load(trr_ctx* ctx, const char* path, trr_dense** out);
+TRR_API int trr_bm25_save(trr_bm25* h, const char* path);
+TRR_API int trr_bm25_load(trr_ctx* ctx, const char* path, trr_bm25** out);
+
 /* ---- synthetic inputs for tests and benches (not reference behaviour) ------------- */
 /* appends n rows generated on the device by the counter-based recipe of csrc/synth_spec.h */
 TRR_API int trr_dense_append_synth(trr_dense* h, uint64_t seed, uint64_t first_row, uint64_t n, int dups);

@@ -1,0 +1,97 @@
+"""Persistence -> device load: snapshots of the device stores restore bit-identical search results."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+SEED = 0x5EED0006
+
+
+@pytest.fixture(scope="module")
+def api(ctx):
+    from trueno_rag_b200 import api as a
+    return a
+
+
+def bf16_round(x):
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32)
+    return ((u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32).view(np.float32)
+
+
+@pytest.mark.parametrize("dtype,metric", [(0, 0), (1, 0), (0, 1), (1, 2)])
+def test_dense_snapshot_round_trip(api, ctx, tmp_path, dtype, metric):
+    n, d = 21000, 256
+    f, b = O.synth_corpus(SEED, 0, n, d, bf16=bool(dtype), dups=True)
+    rows = b if dtype else f
+    ix = api.DenseIndex(ctx, d, metric, dtype, base=5000)
+    ix.append(rows)
+    for dead in (3, 77, n - 1):
+        ix.remove(dead)
+    Q = O.synth_queries(SEED, 0, 40, d, n, corpus_bf16=bool(dtype), dups=True)
+    if dtype:
+        Q = bf16_round(Q)
+    before = ix.search(Q, 25)
+    path = os.path.join(tmp_path, "dense.trr")
+    ix.save(path)
+    ix.close()
+    ix2 = api.DenseIndex.load(ctx, path)
+    assert (ix2.dim, ix2.metric, ix2.dtype) == (d, metric, dtype) and len(ix2) == n - 3
+    for mode in ((1, 2) if metric != 1 else (1,)):
+        ix2.set_mode(mode)
+        after = ix2.search(Q, 25)
+        assert all(np.array_equal(x, y) for x, y in zip(before, after)), mode
+    alive = np.ones(n, bool)
+    alive[[3, 77, n - 1]] = False
+    eo, es, en = O.dense_search_batch(rows, Q, 25, metric=metric, alive=alive)
+    assert np.array_equal(after[0], eo + 5000) and np.array_equal(after[1], es)
+    ix2.append(rows[:10])                                              # a restored store keeps accepting inserts
+    assert len(ix2) == n - 3 + 10
+    ix2.close()
+
+
+def test_bm25_snapshot_round_trip(api, ctx, tmp_path):
+    cdf = O.zipf_cdf(4000)
+    doc_off, toks = O.synth_doc_tokens(SEED, cdf, 0, 50000)
+    oix = O.BM25(n_terms=4000, doc_off=doc_off, tokens=toks)
+    term_off, post_doc, post_tf, doc_len, df = oix.csr()
+    dev = api.Bm25Device(ctx, 50000, term_off, post_doc, post_tf, doc_len, oix.avgdl, api.bm25_idf_host(50000, df),
+                         doc_base=700)
+    q_off, q_terms = O.synth_query_terms(SEED, cdf, 0, 64)
+    before = dev.search(q_terms, q_off, 50)
+    path = os.path.join(tmp_path, "bm25.trr")
+    dev.save(path)
+    n_post = dev.n_postings
+    dev.close()
+    dev2 = api.Bm25Device.load(ctx, path)
+    assert dev2.n_postings == n_post
+    after = dev2.search(q_terms, q_off, 50)
+    assert all(np.array_equal(x, y) for x, y in zip(before, after))
+    eo, es, en = oix.search_batch(q_terms, q_off, 50)
+    assert np.array_equal(after[2], en)
+    for b in range(64):
+        m = int(en[b])
+        assert np.array_equal(after[0][b, :m], eo[b, :m] + 700) and np.array_equal(after[1][b, :m], es[b, :m])
+    dev2.close()
+
+
+def test_snapshot_rejects_foreign_and_truncated_files(api, ctx, tmp_path):
+    bad = os.path.join(tmp_path, "bad.trr")
+    open(bad, "wb").write(b"not a snapshot at all, just some bytes" * 4)
+    with pytest.raises(api.TrrError):
+        api.DenseIndex.load(ctx, bad)
+    with pytest.raises(api.TrrError):
+        api.Bm25Device.load(ctx, bad)
+    with pytest.raises(api.TrrError):
+        api.DenseIndex.load(ctx, os.path.join(tmp_path, "missing.trr"))
+    ix = api.DenseIndex(ctx, 64)
+    ix.append(np.ones((5000, 64), np.float32))
+    good = os.path.join(tmp_path, "good.trr")
+    ix.save(good)
+    ix.close()
+    data = open(good, "rb").read()
+    open(bad, "wb").write(data[: len(data) // 2])
+    with pytest.raises(api.TrrError):
+        api.DenseIndex.load(ctx, bad)

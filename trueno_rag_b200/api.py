@@ -90,6 +90,21 @@ class DenseIndex:
             self.L.trr_dense_destroy(self.h)
             self.h = C.c_void_p()
 
+    def save(self, path: str):
+        """Snapshot of the device store (slab + tombstones + configuration) in a flat file."""
+        _check(self.L.trr_dense_save(self.h, str(path).encode()))
+
+    @classmethod
+    def load(cls, ctx: Context, path: str) -> "DenseIndex":
+        self = cls.__new__(cls)
+        self.ctx, self.L = ctx, ctx.L
+        self.h = C.c_void_p()
+        _check(self.L.trr_dense_load(ctx.h, str(path).encode(), C.byref(self.h)))
+        dim, metric, dtype, base = C.c_uint32(), C.c_int(), C.c_int(), C.c_uint32()
+        _check(self.L.trr_dense_info(self.h, C.byref(dim), C.byref(metric), C.byref(dtype), C.byref(base)))
+        self.dim, self.metric, self.dtype = dim.value, metric.value, dtype.value
+        return self
+
     def append(self, rows: np.ndarray):
         if rows.dtype == np.uint16:
             rows = np.ascontiguousarray(rows)
@@ -198,6 +213,19 @@ class Bm25Device:
         if self.h:
             self.L.trr_bm25_destroy(self.h)
             self.h = C.c_void_p()
+
+    def save(self, path: str):
+        """Snapshot of the device index (postings with impacts, skip table, per-term minimum impacts)."""
+        _check(self.L.trr_bm25_save(self.h, str(path).encode()))
+
+    @classmethod
+    def load(cls, ctx: Context, path: str) -> "Bm25Device":
+        self = cls.__new__(cls)
+        self.ctx, self.L = ctx, ctx.L
+        self.h = C.c_void_p()
+        _check(self.L.trr_bm25_load(ctx.h, str(path).encode(), C.byref(self.h)))
+        self.n_terms = None
+        return self
 
     @property
     def n_postings(self) -> int:

@@ -1058,6 +1058,145 @@ extern "C" int trr_bm25_last_stats(trr_bm25* h, trr_stats* out) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// snapshots: device structures <-> flat little-endian files (chunked through pinned staging)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct FileCloser {
+  FILE* f;
+  ~FileCloser() { if (f) fclose(f); }
+};
+constexpr size_t SNAP_CHUNK = (size_t)64 << 20;
+
+int snap_write_dev(trr_ctx* c, FILE* f, const void* d_src, size_t bytes) {
+  TRR_CHECK(trr_ctx_reserve_pin(c, SNAP_CHUNK));
+  for (size_t off = 0; off < bytes; off += SNAP_CHUNK) {
+    const size_t n = std::min(SNAP_CHUNK, bytes - off);
+    TRR_CUDA(cudaMemcpy(c->pin, static_cast<const char*>(d_src) + off, n, cudaMemcpyDeviceToHost));
+    if (fwrite(c->pin, 1, n, f) != n) return trr_fail(TRR_ERR_INVALID_ARG, "snapshot: short write");
+  }
+  return TRR_OK;
+}
+int snap_read_dev(trr_ctx* c, FILE* f, void* d_dst, size_t bytes) {
+  TRR_CHECK(trr_ctx_reserve_pin(c, SNAP_CHUNK));
+  for (size_t off = 0; off < bytes; off += SNAP_CHUNK) {
+    const size_t n = std::min(SNAP_CHUNK, bytes - off);
+    if (fread(c->pin, 1, n, f) != n) return trr_fail(TRR_ERR_INVALID_ARG, "snapshot: truncated file");
+    TRR_CUDA(cudaMemcpy(static_cast<char*>(d_dst) + off, c->pin, n, cudaMemcpyHostToDevice));
+  }
+  return TRR_OK;
+}
+struct DenseSnapHeader {
+  char magic[8];  // "TRRDNS01"
+  uint32_t dim; int32_t metric, dtype; uint32_t base;
+  uint64_t n, n_dead;
+};
+struct Bm25SnapHeader {
+  char magic[8];  // "TRRBM251"
+  uint32_t n_docs, n_terms, doc_base, range_shift, n_ranges, skip_ld;
+  uint64_t n_postings;
+};
+}  // namespace
+
+extern "C" int trr_dense_info(trr_dense* h, uint32_t* out_dim, int* out_metric, int* out_dtype, uint32_t* out_base) {
+  if (!h) return trr_fail(TRR_ERR_INVALID_ARG, "handle is NULL");
+  if (out_dim) *out_dim = h->dim;
+  if (out_metric) *out_metric = h->metric;
+  if (out_dtype) *out_dtype = h->dtype;
+  if (out_base) *out_base = h->base;
+  return TRR_OK;
+}
+
+extern "C" int trr_dense_save(trr_dense* h, const char* path) {
+  if (!h || !path) return trr_fail(TRR_ERR_INVALID_ARG, "trr_dense_save: NULL argument");
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  TRR_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  FileCloser fc{fopen(path, "wb")};
+  if (!fc.f) return trr_fail(TRR_ERR_INVALID_ARG, std::string("trr_dense_save: cannot open ") + path);
+  DenseSnapHeader hd{};
+  memcpy(hd.magic, "TRRDNS01", 8);
+  hd.dim = h->dim; hd.metric = h->metric; hd.dtype = h->dtype; hd.base = h->base; hd.n = h->n; hd.n_dead = h->n_dead;
+  if (fwrite(&hd, sizeof(hd), 1, fc.f) != 1) return trr_fail(TRR_ERR_INVALID_ARG, "snapshot: short write");
+  TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->rows, h->n * h->row_bytes));
+  TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->dead, h->n));
+  return TRR_OK;
+}
+
+extern "C" int trr_dense_load(trr_ctx* ctx, const char* path, trr_dense** out) {
+  if (!ctx || !path || !out) return trr_fail(TRR_ERR_INVALID_ARG, "trr_dense_load: NULL argument");
+  *out = nullptr;
+  FileCloser fc{fopen(path, "rb")};
+  if (!fc.f) return trr_fail(TRR_ERR_INVALID_ARG, std::string("trr_dense_load: cannot open ") + path);
+  DenseSnapHeader hd{};
+  if (fread(&hd, sizeof(hd), 1, fc.f) != 1 || memcmp(hd.magic, "TRRDNS01", 8) != 0)
+    return trr_fail(TRR_ERR_INVALID_ARG, "trr_dense_load: not a dense snapshot");
+  if (hd.n_dead > hd.n) return trr_fail(TRR_ERR_INVALID_ARG, "trr_dense_load: corrupt header");
+  trr_dense* h = nullptr;
+  TRR_CHECK(trr_dense_create(ctx, hd.dim, hd.metric, hd.dtype, std::max<uint64_t>(hd.n, 1), &h));
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  h->base = hd.base;
+  int s = snap_read_dev(ctx, fc.f, h->rows, hd.n * h->row_bytes);
+  if (s == TRR_OK) s = snap_read_dev(ctx, fc.f, h->dead, hd.n);
+  if (s != TRR_OK) { trr_dense_destroy(h); return s; }
+  h->n = hd.n; h->n_dead = hd.n_dead; h->frozen_n = 0; h->gemm_ready = false;  // norms / GEMM operands rebuilt lazily
+  *out = h;
+  return TRR_OK;
+}
+
+extern "C" int trr_bm25_save(trr_bm25* h, const char* path) {
+  if (!h || !path) return trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_save: NULL argument");
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  TRR_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  FileCloser fc{fopen(path, "wb")};
+  if (!fc.f) return trr_fail(TRR_ERR_INVALID_ARG, std::string("trr_bm25_save: cannot open ") + path);
+  Bm25SnapHeader hd{};
+  memcpy(hd.magic, "TRRBM251", 8);
+  hd.n_docs = h->n_docs; hd.n_terms = h->n_terms; hd.doc_base = h->doc_base; hd.range_shift = h->range_shift;
+  hd.n_ranges = h->n_ranges; hd.skip_ld = h->skip_ld; hd.n_postings = h->n_postings;
+  if (fwrite(&hd, sizeof(hd), 1, fc.f) != 1) return trr_fail(TRR_ERR_INVALID_ARG, "snapshot: short write");
+  TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->post, (h->n_postings + 2) * sizeof(uint2)));
+  TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->skip, (uint64_t)h->n_terms * h->skip_ld * 4));
+  TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->term_min, ((uint64_t)h->n_terms + 1) * 4));
+  return TRR_OK;
+}
+
+extern "C" int trr_bm25_load(trr_ctx* ctx, const char* path, trr_bm25** out) {
+  if (!ctx || !path || !out) return trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_load: NULL argument");
+  *out = nullptr;
+  FileCloser fc{fopen(path, "rb")};
+  if (!fc.f) return trr_fail(TRR_ERR_INVALID_ARG, std::string("trr_bm25_load: cannot open ") + path);
+  Bm25SnapHeader hd{};
+  if (fread(&hd, sizeof(hd), 1, fc.f) != 1 || memcmp(hd.magic, "TRRBM251", 8) != 0)
+    return trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_load: not a BM25 snapshot");
+  if (hd.range_shift < TRR_BM25_MIN_RANGE_SHIFT || hd.range_shift > TRR_BM25_MAX_RANGE_SHIFT || hd.skip_ld != hd.n_ranges + 1 ||
+      hd.n_postings >= 0xFFFFFFFFull ||
+      hd.n_ranges != (hd.n_docs ? (uint32_t)(((uint64_t)hd.n_docs + (1u << hd.range_shift) - 1) >> hd.range_shift) : 0u))
+    return trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_load: corrupt header");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  trr_bm25* h = new trr_bm25();
+  h->ctx = ctx; h->n_docs = hd.n_docs; h->n_terms = hd.n_terms; h->doc_base = hd.doc_base; h->n_postings = hd.n_postings;
+  h->range_shift = hd.range_shift; h->n_ranges = hd.n_ranges; h->skip_ld = hd.skip_ld;
+  for (auto& e : h->ev) cudaEventCreate(&e);
+  auto fail = [&](int s) { trr_bm25_destroy(h); return s; };
+  if (cudaMalloc(&h->post, (hd.n_postings + 2) * sizeof(uint2)) != cudaSuccess ||
+      cudaMalloc(&h->skip, std::max<uint64_t>((uint64_t)hd.n_terms * hd.skip_ld, 1) * 4) != cudaSuccess ||
+      cudaMalloc(&h->term_min, ((uint64_t)hd.n_terms + 1) * 4) != cudaSuccess) {
+    cudaGetLastError();
+    trr_fail(TRR_ERR_OOM, "trr_bm25_load: out of device memory");
+    return fail(TRR_ERR_OOM);
+  }
+  int s = snap_read_dev(ctx, fc.f, h->post, (hd.n_postings + 2) * sizeof(uint2));
+  if (s == TRR_OK) s = snap_read_dev(ctx, fc.f, h->skip, (uint64_t)hd.n_terms * hd.skip_ld * 4);
+  if (s == TRR_OK) s = snap_read_dev(ctx, fc.f, h->term_min, ((uint64_t)hd.n_terms + 1) * 4);
+  if (s != TRR_OK) return fail(s);
+  *out = h;
+  return TRR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // fusion / hybrid
 // ------------------------------------------------------------------------------------------------
 extern "C" size_t trr_exchange_bytes(uint32_t B, uint32_t C) { return ((size_t)4 * B * C + (size_t)2 * B) * 4; }
