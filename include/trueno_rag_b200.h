@@ -137,6 +137,13 @@ TRR_API int trr_dense_copy_rows(trr_dense* h, const uint32_t* ordinals, uint64_t
 TRR_API int trr_bm25_build(trr_ctx* ctx, uint32_t n_docs, uint32_t n_terms, const uint64_t* term_off,
                            const uint32_t* post_doc, const uint32_t* post_tf, const uint32_t* doc_len, float avgdl,
                            float k1, float b, const float* idf, uint32_t doc_base, trr_bm25** out);
+/* BM25Index::add after the index was built (src/index.rs:176-204): appends n_new_docs documents given as a CSR over
+ * term ids with doc ids RELATIVE to the first new document (0..n_new_docs-1); n_terms_new >= the current vocabulary
+ * size (new terms get the next ids).  avgdl / idf are the NEW global statistics; all impacts are re-weighted on the
+ * device (they depend on N, df and avgdl), so the result is bit-identical to trr_bm25_build over all documents. */
+TRR_API int trr_bm25_append(trr_bm25* h, uint32_t n_new_docs, uint32_t n_terms_new, const uint64_t* delta_term_off,
+                            const uint32_t* delta_post_doc, const uint32_t* delta_post_tf, const uint32_t* delta_doc_len,
+                            float avgdl, float k1, float b, const float* idf);
 TRR_API int trr_bm25_destroy(trr_bm25* h);
 TRR_API int trr_bm25_n_postings(trr_bm25* h, uint64_t* out);
 /* BM25Index::search (src/index.rs:212-243) for B tokenised queries: q_terms holds the term ids of all

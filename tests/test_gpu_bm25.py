@@ -179,3 +179,52 @@ def test_more_than_4096_queries_keep_submission_order(api, ctx):
     q_off, q_terms = O.synth_query_terms(SEED + 11, cdf, 0, 4500)
     compare(dev, oix, q_terms, q_off, 10)
     dev.close()
+
+
+def _csr_of(doc_off, toks, n_terms, lo, hi):
+    """CSR over term ids of documents [lo, hi) with doc ids relative to lo, plus the documents' lengths."""
+    sub_off = (doc_off[lo:hi + 1] - doc_off[lo]).astype(np.uint64)
+    sub = O.BM25(n_terms=n_terms, doc_off=sub_off, tokens=toks[int(doc_off[lo]):int(doc_off[hi])])
+    term_off, post_doc, post_tf, doc_len, df = sub.csr()
+    return term_off, post_doc, post_tf, doc_len, df
+
+
+def test_append_reweights_on_device_and_equals_full_build(api, ctx):
+    """BM25Index::add after the first search (src/index.rs:176-204): trr_bm25_append merges the postings of the new
+    documents on the device and re-weights everything with the new N / df / avgdl; impacts, ids and scores must equal
+    a from-scratch build over all documents (and therefore the oracle) bit for bit.  The vocabulary grows on the way."""
+    V_all, n_all = 3000, 60000
+    cdf = O.zipf_cdf(V_all)
+    doc_off, toks = O.synth_doc_tokens(SEED + 21, cdf, 0, n_all)
+    cuts = [0, 20000, 20001, 45000, n_all]                    # a single-document append included
+    vocab = [1200, 1200, 2500, V_all]                         # terms >= vocab[i] do not exist yet in step i
+    toks = toks.copy()
+    for i in range(len(cuts) - 1):                            # restrict early documents to the early vocabulary
+        seg = slice(int(doc_off[cuts[i]]), int(doc_off[cuts[i + 1]]))
+        toks[seg] = toks[seg] % vocab[i]
+    q_off, q_terms = O.synth_query_terms(SEED + 21, cdf, 0, 48)
+    dev = None
+    df_tot = np.zeros(V_all, np.uint64)
+    len_tot = 0
+    for i in range(len(cuts) - 1):
+        lo, hi, V = cuts[i], cuts[i + 1], vocab[i]
+        t_off, pd, ptf, dl, df = _csr_of(doc_off, toks, V, lo, hi)
+        df_tot[:V] += df
+        len_tot += int(dl.sum())
+        n_now = hi
+        avgdl = float(np.float32(np.uint32(len_tot & 0xFFFFFFFF)) / np.float32(n_now))
+        idf = api.bm25_idf_host(n_now, df_tot[:V].astype(np.uint32))
+        if dev is None:
+            dev = api.Bm25Device(ctx, hi - lo, t_off, pd, ptf, dl, avgdl, idf)
+        else:
+            dev.append(hi - lo, t_off, pd, ptf, dl, avgdl, idf)
+        full = O.BM25(n_terms=V, doc_off=doc_off[:hi + 1], tokens=toks[:int(doc_off[hi])])
+        assert abs(full.avgdl - avgdl) == 0.0
+        qt = np.where(q_terms < V, q_terms, 0xFFFFFFFF).astype(np.uint32)
+        compare(dev, full, qt, q_off, 50)
+        f_off, f_pd, f_ptf, f_dl, f_df = full.csr()
+        ref = build(api, ctx, full, hi)
+        assert np.array_equal(dev.impacts(), ref.impacts())
+        assert dev.n_postings == ref.n_postings
+        ref.close()
+    dev.close()

@@ -193,6 +193,35 @@ def test_bm25_remove_updates_statistics(api):
     assert [r[1] for r in res] == [float(x) for x in s]
 
 
+def test_bm25_incremental_adds_between_searches(api):
+    """RagPipeline::index_document interleaves with queries (src/pipeline.rs:333-347): every add after a search goes
+    through trr_bm25_append (device-side merge + re-weighting) and must equal the oracle rebuilt from scratch, including
+    new vocabulary, a removal in the middle (full rebuild) and adds after it."""
+    words = "rust memory safety python data science compiler borrow rules go concurrency tensor kernel index search".split()
+    rng = np.random.default_rng(9)
+    ix, ti, cs = api.BM25Index(), TextIndex(), []
+    removed = set()
+    for step in range(60):
+        text = " ".join(rng.choice(words[: 4 + step // 4], int(rng.integers(2, 9))))
+        c = chunk(api, text)
+        ix.add(c)
+        cs.append(c)
+        if step == 30:
+            ix.remove(cs[7].id)
+            removed.add(7)
+        if step % 3 == 0 or step in (30, 31, 32):
+            ti2, kept = TextIndex(), []
+            for i, cc in enumerate(cs):
+                if i not in removed:
+                    ti2.add(cc.content)
+                    kept.append(cc)
+            for q in ("rust compiler", "python data data", "tensor kernel search index"):
+                o, sc = ti2.build().search(ti2.query_ids(q), 10)
+                res = ix.search(q, 10)
+                assert [r[0] for r in res] == [kept[i].id for i in o], (step, q)
+                assert [r[1] for r in res] == [float(x) for x in sc], (step, q)
+
+
 def test_bm25_avg_doc_length_and_idf(api):
     ix, cs, ti = bm25(api, ["short text", "this is a longer piece of text about programming"])
     assert ix.avg_doc_length == ti.build().avgdl > 0

@@ -214,6 +214,20 @@ class Bm25Device:
             self.L.trr_bm25_destroy(self.h)
             self.h = C.c_void_p()
 
+    def append(self, n_new_docs: int, term_off, post_doc, post_tf, doc_len, avgdl: float, idf, k1: float = 1.2, b: float = 0.75):
+        """Appends documents (CSR with doc ids relative to the first new document); idf / avgdl are the new global statistics."""
+        term_off = np.ascontiguousarray(term_off, dtype=np.uint64)
+        post_doc = np.ascontiguousarray(post_doc, dtype=np.uint32)
+        post_tf = np.ascontiguousarray(post_tf, dtype=np.uint32)
+        doc_len = np.ascontiguousarray(doc_len, dtype=np.uint32)
+        idf = np.ascontiguousarray(idf, dtype=np.float32)
+        pd = post_doc if post_doc.size else np.zeros(1, np.uint32)
+        pt = post_tf if post_tf.size else np.zeros(1, np.uint32)
+        dl = doc_len if doc_len.size else np.zeros(1, np.uint32)
+        _check(self.L.trr_bm25_append(self.h, n_new_docs, len(term_off) - 1, _p(term_off, u64p), _p(pd, u32p), _p(pt, u32p),
+                                      _p(dl, u32p), avgdl, k1, b, _p(idf, f32p)))
+        self.n_terms = len(term_off) - 1
+
     def save(self, path: str):
         """Snapshot of the device index (postings with impacts, skip table, per-term minimum impacts)."""
         _check(self.L.trr_bm25_save(self.h, str(path).encode()))

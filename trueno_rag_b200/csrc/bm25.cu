@@ -27,6 +27,8 @@
 //                   over the consumer warps, once per range).
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "bm25.cuh"
 
@@ -48,7 +50,8 @@ __global__ void bm25_build_kernel(Bm25BuildArgs a) {
   const uint64_t total = a.n_postings;
   for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t t = term_of_posting(a.term_off, a.n_terms, p);
-    const uint32_t doc = a.post_doc[p];
+    // document ids come from the host CSR (build) or are already in place in post[].x (append / re-weighting)
+    const uint32_t doc = a.post_doc ? a.post_doc[p] : a.post[p].x;
     // src/index.rs:137-153
     const float tf = (float)a.post_tf[p];
     const float doc_len = (float)a.doc_len[doc];
@@ -61,11 +64,34 @@ __global__ void bm25_build_kernel(Bm25BuildArgs a) {
     // skip table
     const uint64_t t_begin = a.term_off[t], t_end = a.term_off[t + 1];
     const uint32_t r = doc >> a.range_shift;
-    const int64_t r_prev = (p == t_begin) ? -1 : (int64_t)(a.post_doc[p - 1] >> a.range_shift);
+    const int64_t r_prev = (p == t_begin) ? -1 : (int64_t)((a.post_doc ? a.post_doc[p - 1] : a.post[p - 1].x) >> a.range_shift);
     uint32_t* row = a.skip + (uint64_t)t * a.skip_ld;
     for (int64_t rr = r_prev + 1; rr <= (int64_t)r; ++rr) row[rr] = (uint32_t)p;
     if (p + 1 == t_end)
       for (uint32_t rr = r + 1; rr <= a.n_ranges; ++rr) row[rr] = (uint32_t)t_end;
+  }
+}
+
+// append: postings of term t in the new index = its old postings followed by the postings of the appended documents
+// (their ordinals are larger, so the per-term doc order is kept).  One thread per new posting slot.
+__global__ void bm25_merge_kernel(Bm25MergeArgs a) {
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.n_postings_new;
+       p += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t t = term_of_posting(a.new_off, a.n_terms_new, p);
+    const uint64_t j = p - a.new_off[t];
+    const uint64_t old_len = t < a.n_terms_old ? a.old_off[t + 1] - a.old_off[t] : 0;
+    uint32_t doc, tf;
+    if (j < old_len) {
+      const uint64_t q = a.old_off[t] + j;
+      doc = a.old_post[q].x;
+      tf = a.old_tf[q];
+    } else {
+      const uint64_t q = a.delta_off[t] + (j - old_len);
+      doc = a.n_docs_old + a.delta_doc[q];
+      tf = a.delta_tf[q];
+    }
+    a.new_post[p] = make_uint2(doc, 0u);
+    a.new_tf[p] = tf;
   }
 }
 
@@ -449,6 +475,13 @@ bm25_search_kernel(Bm25SearchArgs a) {
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
+cudaError_t trr_launch_bm25_merge(const Bm25MergeArgs& a, cudaStream_t st) {
+  if (a.n_postings_new == 0) return cudaSuccess;
+  unsigned grid = (unsigned)std::min<uint64_t>((a.n_postings_new + 255) / 256, 148u * 32u);
+  bm25_merge_kernel<<<grid, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t trr_launch_bm25_build(const Bm25BuildArgs& a, cudaStream_t st) {
   if (a.n_terms) bm25_skip_empty_kernel<<<(a.n_terms + 255) / 256, 256, 0, st>>>(a);
   if (a.n_postings) {

@@ -12,7 +12,7 @@ struct Bm25BuildArgs {
   uint64_t n_postings;
   uint32_t n_terms, n_docs;
   const uint64_t* term_off;  // n_terms + 1
-  const uint32_t* post_doc;
+  const uint32_t* post_doc;  // nullable: document ids are then read from post[].x
   const uint32_t* post_tf;
   const uint32_t* doc_len;
   const float* idf;
@@ -22,6 +22,20 @@ struct Bm25BuildArgs {
   uint32_t* skip;  // out: [n_terms][skip_ld]
   uint32_t* term_min;  // out: [n_terms] smallest impact of the term (order-preserving u32 image), pre-set to 0xFFFFFFFF
   uint32_t* flags;     // out: [0] = 1 when some impact is not > 0 (disables the threshold bootstrap), pre-set to 0
+};
+
+struct Bm25MergeArgs {  // trr_bm25_append: old CSR + CSR of the appended documents -> new CSR (doc ids and tf only)
+  uint64_t n_postings_new;
+  uint32_t n_terms_new, n_terms_old, n_docs_old;
+  const uint64_t* new_off;    // n_terms_new + 1
+  const uint64_t* old_off;    // n_terms_old + 1
+  const uint64_t* delta_off;  // n_terms_new + 1
+  const uint2* old_post;
+  const uint32_t* old_tf;
+  const uint32_t* delta_doc;  // ids relative to the first appended document
+  const uint32_t* delta_tf;
+  uint2* new_post;
+  uint32_t* new_tf;
 };
 
 struct Bm25SearchArgs {
@@ -48,6 +62,7 @@ struct Bm25SearchArgs {
 };
 
 cudaError_t trr_launch_bm25_build(const Bm25BuildArgs& a, cudaStream_t st);
+cudaError_t trr_launch_bm25_merge(const Bm25MergeArgs& a, cudaStream_t st);
 size_t trr_bm25_search_smem(uint32_t range_shift, uint32_t stage_cap, uint32_t cand_cap);
 // plan_keys: scratch of max(pow2ceil(B), 1) u64
 cudaError_t trr_launch_bm25_plan(const Bm25SearchArgs& a, uint64_t* plan_keys, cudaStream_t st);

@@ -832,10 +832,63 @@ struct trr_bm25 {
   uint2* post = nullptr;
   uint32_t* skip = nullptr;
   uint32_t* term_min = nullptr;  // [n_terms + 1]: per-term minimum impact, then one flag word
+  // raw index kept for trr_bm25_append (every impact depends on the global N / df / avgdl, so an append re-weights all)
+  uint64_t* d_term_off = nullptr;  // [n_terms + 1]
+  uint32_t* tf = nullptr;          // [n_postings] term frequencies
+  uint32_t* doc_len = nullptr;     // [n_docs]
+  std::vector<uint64_t> h_term_off;
   uint32_t range_shift = TRR_BM25_MAX_RANGE_SHIFT, n_ranges = 0, skip_ld = 0;
   trr_stats stats{};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
+
+static uint32_t bm25_pick_shift(uint32_t n_docs) {
+  // documents per range: 32768 (128 KB of f32 accumulators in shared memory, one CTA per SM), fewer for small indexes
+  uint32_t shift = TRR_BM25_MAX_RANGE_SHIFT;
+  if (const char* e = getenv("TRR_BM25_RANGE_SHIFT")) shift = (uint32_t)atoi(e);
+  shift = std::min(std::max(shift, TRR_BM25_MIN_RANGE_SHIFT), TRR_BM25_MAX_RANGE_SHIFT);
+  while (shift > TRR_BM25_MIN_RANGE_SHIFT && (1u << (shift - 1)) >= std::max<uint32_t>(n_docs, 1)) --shift;
+  return shift;
+}
+
+#define BM_TRY(e)                                                                                          \
+  do {                                                                                                     \
+    cudaError_t _e = (e);                                                                                  \
+    if (_e != cudaSuccess)                                                                                 \
+      return trr_fail(_e == cudaErrorMemoryAllocation ? TRR_ERR_OOM : TRR_ERR_CUDA,                        \
+                      std::string(#e) + ": " + cudaGetErrorString(_e));                                    \
+  } while (0)
+
+// (Re)computes everything derived from the raw index held by the handle — h->post[].x (doc ids, or d_post_doc when the
+// ids still sit in a separate array), h->tf, h->doc_len, h->d_term_off — for the statistics given: impacts, skip table,
+// per-term minimum impacts.  Allocates h->skip / h->term_min for the current n_terms / n_docs.
+static int bm25_weight_locked(trr_bm25* h, const uint32_t* d_post_doc, float avgdl, float k1, float b, const float* idf_host) {
+  trr_ctx* ctx = h->ctx;
+  cudaStream_t st = ctx->stream;
+  h->range_shift = bm25_pick_shift(h->n_docs);
+  h->n_ranges = h->n_docs ? (uint32_t)(((uint64_t)h->n_docs + (1u << h->range_shift) - 1) >> h->range_shift) : 0;
+  h->skip_ld = h->n_ranges + 1;
+  if (h->skip) { cudaFree(h->skip); h->skip = nullptr; }
+  if (h->term_min) { cudaFree(h->term_min); h->term_min = nullptr; }
+  BM_TRY(cudaMalloc(&h->skip, std::max<uint64_t>((uint64_t)h->n_terms * h->skip_ld, 1) * 4));
+  BM_TRY(cudaMalloc(&h->term_min, ((uint64_t)h->n_terms + 1) * 4));
+  BM_TRY(cudaMemsetAsync(h->term_min, 0xFF, (uint64_t)h->n_terms * 4, st));
+  BM_TRY(cudaMemsetAsync(h->term_min + h->n_terms, 0, 4, st));
+  float* d_idf = nullptr;
+  BM_TRY(cudaMalloc(&d_idf, std::max<uint64_t>(h->n_terms, 1) * 4));
+  if (h->n_terms && idf_host) BM_TRY(cudaMemcpyAsync(d_idf, idf_host, (uint64_t)h->n_terms * 4, cudaMemcpyHostToDevice, st));
+  Bm25BuildArgs a{};
+  a.n_postings = h->n_postings; a.n_terms = h->n_terms; a.n_docs = h->n_docs; a.term_off = h->d_term_off;
+  a.post_doc = d_post_doc; a.post_tf = h->tf; a.doc_len = h->doc_len; a.idf = d_idf; a.avgdl = avgdl; a.k1 = k1; a.b = b;
+  a.range_shift = h->range_shift; a.n_ranges = h->n_ranges; a.skip_ld = h->skip_ld; a.post = h->post; a.skip = h->skip;
+  a.term_min = h->term_min; a.flags = h->term_min + h->n_terms;
+  cudaError_t e = trr_launch_bm25_build(a, st);
+  ctx->launches += 2;
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_idf);
+  BM_TRY(e);
+  return TRR_OK;
+}
 
 extern "C" int trr_bm25_build(trr_ctx* ctx, uint32_t n_docs, uint32_t n_terms, const uint64_t* term_off,
                               const uint32_t* post_doc, const uint32_t* post_tf, const uint32_t* doc_len, float avgdl,
@@ -850,49 +903,98 @@ extern "C" int trr_bm25_build(trr_ctx* ctx, uint32_t n_docs, uint32_t n_terms, c
   trr_bm25* h = new trr_bm25();
   h->ctx = ctx; h->n_docs = n_docs; h->n_terms = n_terms; h->doc_base = doc_base; h->n_postings = P;
   for (auto& e : h->ev) cudaEventCreate(&e);
-  // documents per range: 32768 (128 KB of f32 accumulators in shared memory, one CTA per SM), fewer for small indexes
-  uint32_t shift = TRR_BM25_MAX_RANGE_SHIFT;
-  if (const char* e = getenv("TRR_BM25_RANGE_SHIFT")) shift = (uint32_t)atoi(e);
-  shift = std::min(std::max(shift, TRR_BM25_MIN_RANGE_SHIFT), TRR_BM25_MAX_RANGE_SHIFT);
-  while (shift > TRR_BM25_MIN_RANGE_SHIFT && (1u << (shift - 1)) >= std::max<uint32_t>(n_docs, 1)) --shift;
-  h->range_shift = shift;
-  h->n_ranges = n_docs ? (uint32_t)(((uint64_t)n_docs + (1u << shift) - 1) >> shift) : 0;
-  h->skip_ld = h->n_ranges + 1;
   cudaStream_t st = ctx->stream;
-  auto fail = [&](int s) { trr_bm25_destroy(h); return s; };
-#define BM_CUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { trr_fail(_e == cudaErrorMemoryAllocation ? TRR_ERR_OOM : TRR_ERR_CUDA, std::string(#e) + ": " + cudaGetErrorString(_e)); return fail(_e == cudaErrorMemoryAllocation ? TRR_ERR_OOM : TRR_ERR_CUDA); } } while (0)
-  BM_CUDA(cudaMalloc(&h->post, (P + 2) * sizeof(uint2)));  // +2: 16-byte aligned bulk copies may read one posting past the end
-  BM_CUDA(cudaMemsetAsync(h->post, 0xFF, (P + 2) * sizeof(uint2), st));
-  BM_CUDA(cudaMalloc(&h->skip, std::max<uint64_t>((uint64_t)n_terms * h->skip_ld, 1) * 4));
-  BM_CUDA(cudaMalloc(&h->term_min, ((uint64_t)n_terms + 1) * 4));
-  BM_CUDA(cudaMemsetAsync(h->term_min, 0xFF, (uint64_t)n_terms * 4, st));
-  BM_CUDA(cudaMemsetAsync(h->term_min + n_terms, 0, 4, st));
-  uint64_t* d_term_off = nullptr; uint32_t *d_pd = nullptr, *d_ptf = nullptr, *d_dl = nullptr; float* d_idf = nullptr;
-  BM_CUDA(cudaMalloc(&d_term_off, ((uint64_t)n_terms + 1) * 8));
-  BM_CUDA(cudaMalloc(&d_pd, std::max<uint64_t>(P, 1) * 4));
-  BM_CUDA(cudaMalloc(&d_ptf, std::max<uint64_t>(P, 1) * 4));
-  BM_CUDA(cudaMalloc(&d_dl, std::max<uint64_t>(n_docs, 1) * 4));
-  BM_CUDA(cudaMalloc(&d_idf, std::max<uint64_t>(n_terms, 1) * 4));
-  BM_CUDA(cudaMemcpyAsync(d_term_off, term_off, ((uint64_t)n_terms + 1) * 8, cudaMemcpyHostToDevice, st));
-  if (P) {
-    BM_CUDA(cudaMemcpyAsync(d_pd, post_doc, P * 4, cudaMemcpyHostToDevice, st));
-    BM_CUDA(cudaMemcpyAsync(d_ptf, post_tf, P * 4, cudaMemcpyHostToDevice, st));
-  }
-  if (n_docs) BM_CUDA(cudaMemcpyAsync(d_dl, doc_len, (uint64_t)n_docs * 4, cudaMemcpyHostToDevice, st));
-  if (n_terms && idf) BM_CUDA(cudaMemcpyAsync(d_idf, idf, (uint64_t)n_terms * 4, cudaMemcpyHostToDevice, st));
-  Bm25BuildArgs a{};
-  a.n_postings = P; a.n_terms = n_terms; a.n_docs = n_docs; a.term_off = d_term_off; a.post_doc = d_pd; a.post_tf = d_ptf;
-  a.doc_len = d_dl; a.idf = d_idf; a.avgdl = avgdl; a.k1 = k1; a.b = b;
-  a.range_shift = h->range_shift; a.n_ranges = h->n_ranges; a.skip_ld = h->skip_ld; a.post = h->post; a.skip = h->skip;
-  a.term_min = h->term_min; a.flags = h->term_min + n_terms;
-  BM_CUDA(trr_launch_bm25_build(a, st));
-  ctx->launches += 2;
-  BM_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_term_off); cudaFree(d_pd); cudaFree(d_ptf); cudaFree(d_dl); cudaFree(d_idf);
-#undef BM_CUDA
+  uint32_t* d_pd = nullptr;
+  auto body = [&]() -> int {
+    BM_TRY(cudaMalloc(&h->post, (P + 2) * sizeof(uint2)));  // +2: 16-byte aligned bulk copies may read one posting past the end
+    BM_TRY(cudaMemsetAsync(h->post, 0xFF, (P + 2) * sizeof(uint2), st));
+    BM_TRY(cudaMalloc(&h->d_term_off, ((uint64_t)n_terms + 1) * 8));
+    BM_TRY(cudaMalloc(&h->tf, std::max<uint64_t>(P, 1) * 4));
+    BM_TRY(cudaMalloc(&h->doc_len, std::max<uint64_t>(n_docs, 1) * 4));
+    BM_TRY(cudaMalloc(&d_pd, std::max<uint64_t>(P, 1) * 4));
+    BM_TRY(cudaMemcpyAsync(h->d_term_off, term_off, ((uint64_t)n_terms + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (P) {
+      BM_TRY(cudaMemcpyAsync(d_pd, post_doc, P * 4, cudaMemcpyHostToDevice, st));
+      BM_TRY(cudaMemcpyAsync(h->tf, post_tf, P * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (n_docs) BM_TRY(cudaMemcpyAsync(h->doc_len, doc_len, (uint64_t)n_docs * 4, cudaMemcpyHostToDevice, st));
+    h->h_term_off.assign(term_off, term_off + n_terms + 1);
+    return bm25_weight_locked(h, d_pd, avgdl, k1, b, idf);
+  };
+  const int s = body();
+  if (d_pd) cudaFree(d_pd);
+  if (s != TRR_OK) { trr_bm25_destroy(h); return s; }
   *out = h;
   return TRR_OK;
 }
+
+// BM25Index::add for documents arriving after the index was built (reference src/index.rs:176-204).  Every impact
+// depends on the global N, df and avgdl, so an append re-weights the whole index; what it saves is the host-side merge and
+// the upload of the existing postings: only the CSR of the NEW documents crosses PCIe, the old and new postings are merged
+// per term on the device, and the weighting pass (the same kernel as trr_bm25_build) runs at HBM speed.
+extern "C" int trr_bm25_append(trr_bm25* h, uint32_t n_new_docs, uint32_t n_terms_new, const uint64_t* delta_term_off,
+                               const uint32_t* delta_post_doc, const uint32_t* delta_post_tf, const uint32_t* delta_doc_len,
+                               float avgdl, float k1, float b, const float* idf) {
+  if (!h || !delta_term_off || (n_terms_new && !idf)) return trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_append: NULL argument");
+  if (n_terms_new < h->n_terms) return trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_append: the vocabulary cannot shrink");
+  if (!h->tf || !h->d_term_off || h->h_term_off.size() != (size_t)h->n_terms + 1)
+    return trr_fail(TRR_ERR_UNSUPPORTED, "trr_bm25_append: this index holds no raw postings");
+  const uint64_t dP = delta_term_off[n_terms_new];
+  if (dP && (!delta_post_doc || !delta_post_tf)) return trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_append: NULL postings");
+  if (n_new_docs && !delta_doc_len) return trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_append: NULL doc lengths");
+  const uint64_t P_new = h->n_postings + dP;
+  if (P_new >= 0xFFFFFFFFull || (uint64_t)h->n_docs + n_new_docs >= 0xFFFFFFFFull)
+    return trr_fail(TRR_ERR_UNSUPPORTED, "more than 2^32-1 postings or documents per shard");
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  cudaStream_t st = h->ctx->stream;
+  // new per-term offsets (host prefix sum over old length + appended length)
+  std::vector<uint64_t> new_off((size_t)n_terms_new + 1, 0);
+  for (uint32_t t = 0; t < n_terms_new; ++t) {
+    const uint64_t old_len = t < h->n_terms ? h->h_term_off[t + 1] - h->h_term_off[t] : 0;
+    new_off[t + 1] = new_off[t] + old_len + (delta_term_off[t + 1] - delta_term_off[t]);
+  }
+  uint64_t *d_new_off = nullptr, *d_delta_off = nullptr;
+  uint32_t *d_dd = nullptr, *d_dtf = nullptr, *new_tf = nullptr, *new_dl = nullptr;
+  uint2* new_post = nullptr;
+  auto body = [&]() -> int {
+    BM_TRY(cudaMalloc(&d_new_off, ((size_t)n_terms_new + 1) * 8));
+    BM_TRY(cudaMalloc(&d_delta_off, ((size_t)n_terms_new + 1) * 8));
+    BM_TRY(cudaMalloc(&d_dd, std::max<uint64_t>(dP, 1) * 4));
+    BM_TRY(cudaMalloc(&d_dtf, std::max<uint64_t>(dP, 1) * 4));
+    BM_TRY(cudaMalloc(&new_post, (P_new + 2) * sizeof(uint2)));
+    BM_TRY(cudaMalloc(&new_tf, std::max<uint64_t>(P_new, 1) * 4));
+    BM_TRY(cudaMalloc(&new_dl, std::max<uint64_t>((uint64_t)h->n_docs + n_new_docs, 1) * 4));
+    BM_TRY(cudaMemsetAsync(new_post, 0xFF, (P_new + 2) * sizeof(uint2), st));
+    BM_TRY(cudaMemcpyAsync(d_new_off, new_off.data(), new_off.size() * 8, cudaMemcpyHostToDevice, st));
+    BM_TRY(cudaMemcpyAsync(d_delta_off, delta_term_off, ((size_t)n_terms_new + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (dP) {
+      BM_TRY(cudaMemcpyAsync(d_dd, delta_post_doc, dP * 4, cudaMemcpyHostToDevice, st));
+      BM_TRY(cudaMemcpyAsync(d_dtf, delta_post_tf, dP * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (h->n_docs) BM_TRY(cudaMemcpyAsync(new_dl, h->doc_len, (uint64_t)h->n_docs * 4, cudaMemcpyDeviceToDevice, st));
+    if (n_new_docs) BM_TRY(cudaMemcpyAsync(new_dl + h->n_docs, delta_doc_len, (uint64_t)n_new_docs * 4, cudaMemcpyHostToDevice, st));
+    Bm25MergeArgs m{};
+    m.n_postings_new = P_new; m.n_terms_new = n_terms_new; m.n_terms_old = h->n_terms; m.n_docs_old = h->n_docs;
+    m.new_off = d_new_off; m.old_off = h->d_term_off; m.delta_off = d_delta_off; m.old_post = h->post; m.old_tf = h->tf;
+    m.delta_doc = d_dd; m.delta_tf = d_dtf; m.new_post = new_post; m.new_tf = new_tf;
+    BM_TRY(trr_launch_bm25_merge(m, st));
+    h->ctx->launches++;
+    BM_TRY(cudaStreamSynchronize(st));
+    // swap the raw index, then re-weight
+    cudaFree(h->post); cudaFree(h->tf); cudaFree(h->doc_len); cudaFree(h->d_term_off);
+    h->post = new_post; h->tf = new_tf; h->doc_len = new_dl; h->d_term_off = d_new_off;
+    new_post = nullptr; new_tf = nullptr; new_dl = nullptr; d_new_off = nullptr;
+    h->n_docs += n_new_docs; h->n_terms = n_terms_new; h->n_postings = P_new;
+    h->h_term_off.swap(new_off);
+    return bm25_weight_locked(h, nullptr, avgdl, k1, b, idf);
+  };
+  const int s = body();
+  for (void* p : {(void*)d_new_off, (void*)d_delta_off, (void*)d_dd, (void*)d_dtf, (void*)new_post, (void*)new_tf, (void*)new_dl})
+    if (p) cudaFree(p);
+  return s;
+}
+#undef BM_TRY
 
 extern "C" int trr_bm25_destroy(trr_bm25* h) {
   if (!h) return TRR_OK;
@@ -901,6 +1003,9 @@ extern "C" int trr_bm25_destroy(trr_bm25* h) {
   if (h->post) cudaFree(h->post);
   if (h->skip) cudaFree(h->skip);
   if (h->term_min) cudaFree(h->term_min);
+  if (h->d_term_off) cudaFree(h->d_term_off);
+  if (h->tf) cudaFree(h->tf);
+  if (h->doc_len) cudaFree(h->doc_len);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   delete h;
   return TRR_OK;
@@ -1091,7 +1196,7 @@ struct DenseSnapHeader {
   uint64_t n, n_dead;
 };
 struct Bm25SnapHeader {
-  char magic[8];  // "TRRBM251"
+  char magic[8];  // "TRRBM252"
   uint32_t n_docs, n_terms, doc_base, range_shift, n_ranges, skip_ld;
   uint64_t n_postings;
 };
@@ -1152,13 +1257,16 @@ extern "C" int trr_bm25_save(trr_bm25* h, const char* path) {
   FileCloser fc{fopen(path, "wb")};
   if (!fc.f) return trr_fail(TRR_ERR_INVALID_ARG, std::string("trr_bm25_save: cannot open ") + path);
   Bm25SnapHeader hd{};
-  memcpy(hd.magic, "TRRBM251", 8);
+  memcpy(hd.magic, "TRRBM252", 8);
   hd.n_docs = h->n_docs; hd.n_terms = h->n_terms; hd.doc_base = h->doc_base; hd.range_shift = h->range_shift;
   hd.n_ranges = h->n_ranges; hd.skip_ld = h->skip_ld; hd.n_postings = h->n_postings;
   if (fwrite(&hd, sizeof(hd), 1, fc.f) != 1) return trr_fail(TRR_ERR_INVALID_ARG, "snapshot: short write");
   TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->post, (h->n_postings + 2) * sizeof(uint2)));
   TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->skip, (uint64_t)h->n_terms * h->skip_ld * 4));
   TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->term_min, ((uint64_t)h->n_terms + 1) * 4));
+  TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->d_term_off, ((uint64_t)h->n_terms + 1) * 8));
+  TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->tf, h->n_postings * 4));
+  TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->doc_len, (uint64_t)h->n_docs * 4));
   return TRR_OK;
 }
 
@@ -1168,7 +1276,7 @@ extern "C" int trr_bm25_load(trr_ctx* ctx, const char* path, trr_bm25** out) {
   FileCloser fc{fopen(path, "rb")};
   if (!fc.f) return trr_fail(TRR_ERR_INVALID_ARG, std::string("trr_bm25_load: cannot open ") + path);
   Bm25SnapHeader hd{};
-  if (fread(&hd, sizeof(hd), 1, fc.f) != 1 || memcmp(hd.magic, "TRRBM251", 8) != 0)
+  if (fread(&hd, sizeof(hd), 1, fc.f) != 1 || memcmp(hd.magic, "TRRBM252", 8) != 0)
     return trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_load: not a BM25 snapshot");
   if (hd.range_shift < TRR_BM25_MIN_RANGE_SHIFT || hd.range_shift > TRR_BM25_MAX_RANGE_SHIFT || hd.skip_ld != hd.n_ranges + 1 ||
       hd.n_postings >= 0xFFFFFFFFull ||
@@ -1183,7 +1291,10 @@ extern "C" int trr_bm25_load(trr_ctx* ctx, const char* path, trr_bm25** out) {
   auto fail = [&](int s) { trr_bm25_destroy(h); return s; };
   if (cudaMalloc(&h->post, (hd.n_postings + 2) * sizeof(uint2)) != cudaSuccess ||
       cudaMalloc(&h->skip, std::max<uint64_t>((uint64_t)hd.n_terms * hd.skip_ld, 1) * 4) != cudaSuccess ||
-      cudaMalloc(&h->term_min, ((uint64_t)hd.n_terms + 1) * 4) != cudaSuccess) {
+      cudaMalloc(&h->term_min, ((uint64_t)hd.n_terms + 1) * 4) != cudaSuccess ||
+      cudaMalloc(&h->d_term_off, ((uint64_t)hd.n_terms + 1) * 8) != cudaSuccess ||
+      cudaMalloc(&h->tf, std::max<uint64_t>(hd.n_postings, 1) * 4) != cudaSuccess ||
+      cudaMalloc(&h->doc_len, std::max<uint64_t>(hd.n_docs, 1) * 4) != cudaSuccess) {
     cudaGetLastError();
     trr_fail(TRR_ERR_OOM, "trr_bm25_load: out of device memory");
     return fail(TRR_ERR_OOM);
@@ -1191,6 +1302,14 @@ extern "C" int trr_bm25_load(trr_ctx* ctx, const char* path, trr_bm25** out) {
   int s = snap_read_dev(ctx, fc.f, h->post, (hd.n_postings + 2) * sizeof(uint2));
   if (s == TRR_OK) s = snap_read_dev(ctx, fc.f, h->skip, (uint64_t)hd.n_terms * hd.skip_ld * 4);
   if (s == TRR_OK) s = snap_read_dev(ctx, fc.f, h->term_min, ((uint64_t)hd.n_terms + 1) * 4);
+  if (s == TRR_OK) s = snap_read_dev(ctx, fc.f, h->d_term_off, ((uint64_t)hd.n_terms + 1) * 8);
+  if (s == TRR_OK) s = snap_read_dev(ctx, fc.f, h->tf, hd.n_postings * 4);
+  if (s == TRR_OK) s = snap_read_dev(ctx, fc.f, h->doc_len, (uint64_t)hd.n_docs * 4);
+  if (s == TRR_OK) {
+    h->h_term_off.resize((size_t)hd.n_terms + 1);
+    if (cudaMemcpy(h->h_term_off.data(), h->d_term_off, h->h_term_off.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+      s = trr_fail(TRR_ERR_CUDA, "trr_bm25_load: copy failed");
+  }
   if (s != TRR_OK) return fail(s);
   *out = h;
   return TRR_OK;

@@ -344,6 +344,7 @@ void BM25Index::remove(const ChunkId& id) {  // :245-275
     if (pl.size() < before && df_[t] > 0) df_[t] -= 1;  // a term whose df reaches 0 keeps an empty list
   }
   dirty_ = true;
+  needs_rebuild_ = true;  // postings vanished from the middle of the lists: the device index is rebuilt
 }
 
 float BM25Index::avg_doc_length() const {
@@ -358,20 +359,44 @@ void BM25Index::freeze() const {
   for (size_t i = 0; i < doc_len_.size(); ++i) if (live_[i]) total += doc_len_[i];
   avg_doc_length_ = doc_count_ == 0 ? 0.0f : (float)total / (float)doc_count_;
   const uint32_t n_terms = (uint32_t)postings_.size();
-  std::vector<uint64_t> term_off(n_terms + 1, 0);
-  for (uint32_t t = 0; t < n_terms; ++t) term_off[t + 1] = term_off[t] + postings_[t].size();
-  std::vector<uint32_t> pd(term_off[n_terms]), ptf(term_off[n_terms]);
   std::vector<float> idf(n_terms);
   const float n = (float)doc_count_;
   for (uint32_t t = 0; t < n_terms; ++t) {
-    uint64_t p = term_off[t];
-    for (const auto& e : postings_[t]) { pd[p] = e.first; ptf[p] = e.second; ++p; }
     const float df = (float)df_[t];
     idf[t] = logf((n - df + 0.5f) / (df + 0.5f) + 1.0f);  // :147, platform logf == Rust f32::ln here
   }
-  dev_ = std::make_shared<detail::DeviceBm25>();
-  check(trr_bm25_build(default_context(), (uint32_t)doc_len_.size(), n_terms, term_off.data(), pd.data(), ptf.data(),
-                       doc_len_.data(), avg_doc_length_, k1_, b_, idf.data(), 0, &dev_->h));
+  const uint32_t n_docs = (uint32_t)doc_len_.size();
+  if (dev_ && dev_->h && !needs_rebuild_ && n_docs >= frozen_docs_) {
+    // only adds since the last freeze: ship the CSR of the new documents, merge and re-weight on the device
+    frozen_len_.resize(n_terms, 0);
+    std::vector<uint64_t> d_off(n_terms + 1, 0);
+    for (uint32_t t = 0; t < n_terms; ++t) d_off[t + 1] = d_off[t] + (postings_[t].size() - frozen_len_[t]);
+    std::vector<uint32_t> pd(d_off[n_terms]), ptf(d_off[n_terms]);
+    for (uint32_t t = 0; t < n_terms; ++t) {
+      uint64_t p = d_off[t];
+      for (size_t i = frozen_len_[t]; i < postings_[t].size(); ++i, ++p) {
+        pd[p] = postings_[t][i].first - frozen_docs_;
+        ptf[p] = postings_[t][i].second;
+      }
+    }
+    check(trr_bm25_append(dev_->h, n_docs - frozen_docs_, n_terms, d_off.data(), pd.data(), ptf.data(),
+                          doc_len_.data() + frozen_docs_, avg_doc_length_, k1_, b_, idf.data()));
+  } else {
+    std::vector<uint64_t> term_off(n_terms + 1, 0);
+    for (uint32_t t = 0; t < n_terms; ++t) term_off[t + 1] = term_off[t] + postings_[t].size();
+    std::vector<uint32_t> pd(term_off[n_terms]), ptf(term_off[n_terms]);
+    for (uint32_t t = 0; t < n_terms; ++t) {
+      uint64_t p = term_off[t];
+      for (const auto& e : postings_[t]) { pd[p] = e.first; ptf[p] = e.second; ++p; }
+    }
+    dev_ = std::make_shared<detail::DeviceBm25>();
+    check(trr_bm25_build(default_context(), n_docs, n_terms, term_off.data(), pd.data(), ptf.data(), doc_len_.data(),
+                         avg_doc_length_, k1_, b_, idf.data(), 0, &dev_->h));
+  }
+  frozen_docs_ = n_docs;
+  frozen_len_.resize(n_terms);
+  for (uint32_t t = 0; t < n_terms; ++t) frozen_len_[t] = (uint32_t)postings_[t].size();
+  needs_rebuild_ = false;
   dirty_ = false;
 }
 
