@@ -78,6 +78,54 @@ def cfg3(ctx):
     dev.close()
 
 
+def append(ctx):
+    """trr_bm25_append vs a full rebuild: PROBE_DOCS documents on the device (default 10M), then 100k more."""
+    L = _lib.load()
+    N, V, dN = int(os.environ.get("PROBE_DOCS", "10000000")), 1_000_000, 100_000
+    seed = 0x5EED0003
+    cdf = O.zipf_cdf(V)
+
+    def csr(lo, hi):
+        n = hi - lo
+        df = np.zeros(V, np.uint32); dl = np.zeros(n, np.uint32); tot = C.c_uint64()
+        api._check(L.trr_synth_bm25_count(seed, cdf.ctypes.data_as(u64p), V, lo, hi, df.ctypes.data_as(u32p), dl.ctypes.data_as(u32p), C.byref(tot)))
+        off = np.zeros(V + 1, np.uint64); np.cumsum(df, out=off[1:])
+        P = int(off[-1])
+        pd = np.zeros(max(P, 1), np.uint32); ptf = np.zeros(max(P, 1), np.uint32)
+        api._check(L.trr_synth_bm25_fill(seed, cdf.ctypes.data_as(u64p), V, lo, hi, off.ctypes.data_as(u64p), pd.ctypes.data_as(u32p), ptf.ctypes.data_as(u32p)))
+        return off, pd[:P], ptf[:P], dl, df, int(tot.value)
+
+    off0, pd0, ptf0, dl0, df0, tot0 = csr(0, N)
+    off1, pd1, ptf1, dl1, df1, tot1 = csr(N, N + dN)
+    avg0 = float(np.float32(np.uint32(tot0 & 0xFFFFFFFF)) / np.float32(N))
+    t0 = time.perf_counter()
+    dev = api.Bm25Device(ctx, N, off0, pd0, ptf0, dl0, avg0, api.bm25_idf_host(N, df0))
+    t_build = time.perf_counter() - t0
+    df_all = (df0.astype(np.uint64) + df1).astype(np.uint32)
+    avg1 = float(np.float32(np.uint32((tot0 + tot1) & 0xFFFFFFFF)) / np.float32(N + dN))
+    idf1 = api.bm25_idf_host(N + dN, df_all)
+    t0 = time.perf_counter()
+    dev.append(dN, off1, pd1, ptf1, dl1, avg1, idf1)
+    t_app = time.perf_counter() - t0
+    q_off, q_terms = O.synth_query_terms(seed, cdf, 0, 8)
+    got = dev.search(q_terms, q_off, 50)
+    dev.close()
+    # the same index from scratch (what the host layer had to do before): concatenate on the host, upload everything
+    t0 = time.perf_counter()
+    offA = np.zeros(V + 1, np.uint64); np.cumsum(df_all, out=offA[1:])
+    pdA = np.zeros(int(offA[-1]), np.uint32); ptfA = np.zeros(int(offA[-1]), np.uint32)
+    api._check(L.trr_synth_bm25_fill(seed, cdf.ctypes.data_as(u64p), V, 0, N + dN, offA.ctypes.data_as(u64p), pdA.ctypes.data_as(u32p), ptfA.ctypes.data_as(u32p)))
+    t_host = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ref = api.Bm25Device(ctx, N + dN, offA, pdA, ptfA, np.concatenate([dl0, dl1]), avg1, idf1)
+    t_full = time.perf_counter() - t0
+    exp = ref.search(q_terms, q_off, 50)
+    ref.close()
+    ok = all(np.array_equal(a, b) for a, b in zip(got, exp))
+    print(f"append {dN} docs to {N}: trr_bm25_append {t_app*1e3:.1f} ms  vs  full trr_bm25_build {t_full*1e3:.1f} ms "
+          f"(+ {t_host*1e3:.0f} ms host CSR assembly); initial build {t_build*1e3:.1f} ms; identical results: {ok}")
+
+
 if __name__ == "__main__":
     ctx = api.Context(0)
     which = sys.argv[1:] or ["cfg2", "cfg3"]
@@ -85,3 +133,5 @@ if __name__ == "__main__":
         cfg2(ctx)
     if "cfg3" in which:
         cfg3(ctx)
+    if "append" in which:
+        append(ctx)
