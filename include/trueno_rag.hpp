@@ -158,9 +158,11 @@ class BM25Index {  // src/index.rs:30-280 (SparseIndex impl included)
   mutable float avg_doc_length_ = 0.0f;
   mutable std::shared_ptr<detail::DeviceBm25> dev_;
   // incremental device updates: documents [0, frozen_docs_) and the first frozen_len_[t] postings of term t are on the
-  // device; adds since then go through trr_bm25_append, a remove forces a full rebuild
+  // device; adds since then go through trr_bm25_append, removes through trr_bm25_remove (rebuild once a quarter of the postings is dead)
   mutable uint32_t frozen_docs_ = 0;
   mutable std::vector<uint32_t> frozen_len_;
+  mutable std::vector<uint32_t> pending_removed_;  // ordinals removed since the last freeze (all < frozen_docs_)
+  mutable uint64_t frozen_postings_ = 0;
   mutable bool needs_rebuild_ = true;
 };
 

@@ -144,6 +144,12 @@ TRR_API int trr_bm25_build(trr_ctx* ctx, uint32_t n_docs, uint32_t n_terms, cons
 TRR_API int trr_bm25_append(trr_bm25* h, uint32_t n_new_docs, uint32_t n_terms_new, const uint64_t* delta_term_off,
                             const uint32_t* delta_post_doc, const uint32_t* delta_post_tf, const uint32_t* delta_doc_len,
                             float avgdl, float k1, float b, const float* idf);
+/* BM25Index::remove (src/index.rs:245-275) without a rebuild: the removed documents' postings stay in place with weight
+ * +0.0 (such a document scores 0.0 and is dropped by `score > 0.0`, src/index.rs:236); all other postings are re-weighted
+ * with the NEW global statistics (N, df -> idf, avgdl).  Results equal a rebuild without those documents bit for bit.
+ * ordinals are LOCAL doc ids; out_dead_postings (nullable) = postings of removed documents still held by the index. */
+TRR_API int trr_bm25_remove(trr_bm25* h, const uint32_t* ordinals, uint32_t n, float avgdl, float k1, float b,
+                            const float* idf, uint64_t* out_dead_postings);
 TRR_API int trr_bm25_destroy(trr_bm25* h);
 TRR_API int trr_bm25_n_postings(trr_bm25* h, uint64_t* out);
 /* BM25Index::search (src/index.rs:212-243) for B tokenised queries: q_terms holds the term ids of all

@@ -228,3 +228,36 @@ def test_append_reweights_on_device_and_equals_full_build(api, ctx):
         assert dev.n_postings == ref.n_postings
         ref.close()
     dev.close()
+
+
+def test_remove_in_place_equals_rebuild_without_the_documents(api, ctx):
+    """BM25Index::remove (src/index.rs:245-275) on the device: the removed documents' postings are tombstoned (tf = 0) and
+    everything is re-weighted with the new N / df / avgdl; ids and scores must equal an index built without them."""
+    V, n = 1500, 40000
+    cdf = O.zipf_cdf(V)
+    doc_off, toks = O.synth_doc_tokens(SEED + 31, cdf, 0, n)
+    full = O.BM25(n_terms=V, doc_off=doc_off, tokens=toks)
+    dev = build(api, ctx, full, n, doc_base=100)
+    q_off, q_terms = O.synth_query_terms(SEED + 31, cdf, 0, 32)
+    top = dev.search(q_terms, q_off, 5)[0]
+    rng = np.random.default_rng(4)
+    gone = np.unique(np.concatenate([top[:, :2].ravel() - 100, rng.integers(0, n, 3000).astype(np.uint32)]))
+    keep = np.setdiff1d(np.arange(n, dtype=np.uint32), gone)
+    # the oracle without the removed documents (ordinals renumbered; `keep` maps them back, order preserved)
+    lens = np.diff(doc_off).astype(np.int64)
+    k_off = np.zeros(len(keep) + 1, np.uint64)
+    np.cumsum(lens[keep], out=k_off[1:])
+    k_toks = np.concatenate([toks[int(doc_off[d]):int(doc_off[d + 1])] for d in keep])
+    kept = O.BM25(n_terms=V, doc_off=k_off, tokens=k_toks)
+    _, _, _, _, df_kept = kept.csr()
+    dead = dev.remove(gone, kept.avgdl, api.bm25_idf_host(len(keep), df_kept))
+    assert 0 < dead < dev.n_postings
+    for k in (10, 100):
+        ords, scores, cnt = dev.search(q_terms, q_off, k)
+        eo, es, en = kept.search_batch(q_terms, q_off, k)
+        assert np.array_equal(cnt, en)
+        for b in range(len(q_off) - 1):
+            m = int(en[b])
+            assert np.array_equal(ords[b, :m], keep[eo[b, :m]] + 100), b
+            assert np.array_equal(scores[b, :m], es[b, :m]), b
+    dev.close()

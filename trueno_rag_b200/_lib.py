@@ -70,6 +70,7 @@ TRR_PROTOS = {
     "trr_dense_save": (C.c_int, [vp, C.c_char_p]),
     "trr_dense_load": (C.c_int, [vp, C.c_char_p, vpp]),
     "trr_bm25_append": (C.c_int, [vp, C.c_uint32, C.c_uint32, u64p, u32p, u32p, u32p, C.c_float, C.c_float, C.c_float, f32p]),
+    "trr_bm25_remove": (C.c_int, [vp, u32p, C.c_uint32, C.c_float, C.c_float, C.c_float, f32p, u64p]),
     "trr_bm25_save": (C.c_int, [vp, C.c_char_p]),
     "trr_bm25_load": (C.c_int, [vp, C.c_char_p, vpp]),
     "trr_bm25_build": (C.c_int, [vp, C.c_uint32, C.c_uint32, u64p, u32p, u32p, u32p, C.c_float, C.c_float, C.c_float,

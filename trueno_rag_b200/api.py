@@ -228,6 +228,16 @@ class Bm25Device:
                                       _p(dl, u32p), avgdl, k1, b, _p(idf, f32p)))
         self.n_terms = len(term_off) - 1
 
+    def remove(self, ordinals, avgdl: float, idf, k1: float = 1.2, b: float = 0.75) -> int:
+        """Removes documents (local ordinals) in place; idf / avgdl are the new global statistics.  Returns the number of
+        dead postings the index still holds."""
+        o = np.ascontiguousarray(ordinals, dtype=np.uint32)
+        idf = np.ascontiguousarray(idf, dtype=np.float32)
+        dead = C.c_uint64()
+        oo = o if o.size else np.zeros(1, np.uint32)
+        _check(self.L.trr_bm25_remove(self.h, _p(oo, u32p), o.size, avgdl, k1, b, _p(idf, f32p), C.byref(dead)))
+        return dead.value
+
     def save(self, path: str):
         """Snapshot of the device index (postings with impacts, skip table, per-term minimum impacts)."""
         _check(self.L.trr_bm25_save(self.h, str(path).encode()))

@@ -57,10 +57,15 @@ __global__ void bm25_build_kernel(Bm25BuildArgs a) {
     const float doc_len = (float)a.doc_len[doc];
     const float idf = a.idf[t];
     const float tf_norm = (tf * (a.k1 + 1.0f)) / (tf + a.k1 * (1.0f - a.b + a.b * doc_len / a.avgdl));
-    const float impact = idf * tf_norm;
+    // tf == 0 marks the posting of a removed document (trr_bm25_remove): it weighs exactly +0.0, so the document can only
+    // score 0.0 and is dropped by `score > 0.0`; it stays out of the per-term minimum used by the threshold bootstrap
+    const bool dead = a.post_tf[p] == 0u;
+    const float impact = dead ? 0.0f : idf * tf_norm;
     a.post[p] = make_uint2(doc, __float_as_uint(impact));
-    atomicMin(&a.term_min[t], trr_f32_orderable(impact));
-    if (!(impact > 0.0f)) a.flags[0] = 1u;
+    if (!dead) {
+      atomicMin(&a.term_min[t], trr_f32_orderable(impact));
+      if (!(impact > 0.0f)) a.flags[0] = 1u;
+    }
     // skip table
     const uint64_t t_begin = a.term_off[t], t_end = a.term_off[t + 1];
     const uint32_t r = doc >> a.range_shift;
@@ -93,6 +98,17 @@ __global__ void bm25_merge_kernel(Bm25MergeArgs a) {
     a.new_post[p] = make_uint2(doc, 0u);
     a.new_tf[p] = tf;
   }
+}
+
+// remove: zeroes the term frequency of every posting whose document is in the removed set (bitmap over local doc ids)
+__global__ void bm25_kill_kernel(const uint2* __restrict__ post, uint32_t* __restrict__ tf, uint64_t n_postings,
+                                 const uint32_t* __restrict__ dead_bits, uint32_t* __restrict__ n_killed) {
+  uint32_t local = 0;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_postings; p += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t d = post[p].x;
+    if (((dead_bits[d >> 5] >> (d & 31)) & 1u) && tf[p] != 0u) { tf[p] = 0u; ++local; }
+  }
+  if (local) atomicAdd(n_killed, local);
 }
 
 // terms without postings: every boundary is the (empty) term's offset
@@ -475,6 +491,14 @@ bm25_search_kernel(Bm25SearchArgs a) {
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
+cudaError_t trr_launch_bm25_kill(const uint2* post, uint32_t* tf, uint64_t n_postings, const uint32_t* dead_bits,
+                                 uint32_t* n_killed, cudaStream_t st) {
+  if (n_postings == 0) return cudaSuccess;
+  unsigned grid = (unsigned)std::min<uint64_t>((n_postings + 255) / 256, 148u * 32u);
+  bm25_kill_kernel<<<grid, 256, 0, st>>>(post, tf, n_postings, dead_bits, n_killed);
+  return cudaGetLastError();
+}
+
 cudaError_t trr_launch_bm25_merge(const Bm25MergeArgs& a, cudaStream_t st) {
   if (a.n_postings_new == 0) return cudaSuccess;
   unsigned grid = (unsigned)std::min<uint64_t>((a.n_postings_new + 255) / 256, 148u * 32u);

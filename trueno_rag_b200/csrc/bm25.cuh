@@ -63,6 +63,8 @@ struct Bm25SearchArgs {
 
 cudaError_t trr_launch_bm25_build(const Bm25BuildArgs& a, cudaStream_t st);
 cudaError_t trr_launch_bm25_merge(const Bm25MergeArgs& a, cudaStream_t st);
+cudaError_t trr_launch_bm25_kill(const uint2* post, uint32_t* tf, uint64_t n_postings, const uint32_t* dead_bits,
+                                 uint32_t* n_killed, cudaStream_t st);
 size_t trr_bm25_search_smem(uint32_t range_shift, uint32_t stage_cap, uint32_t cand_cap);
 // plan_keys: scratch of max(pow2ceil(B), 1) u64
 cudaError_t trr_launch_bm25_plan(const Bm25SearchArgs& a, uint64_t* plan_keys, cudaStream_t st);

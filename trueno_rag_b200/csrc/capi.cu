@@ -837,6 +837,7 @@ struct trr_bm25 {
   uint32_t* tf = nullptr;          // [n_postings] term frequencies
   uint32_t* doc_len = nullptr;     // [n_docs]
   std::vector<uint64_t> h_term_off;
+  uint64_t n_dead_postings = 0;    // postings of removed documents still in place (tf == 0)
   uint32_t range_shift = TRR_BM25_MAX_RANGE_SHIFT, n_ranges = 0, skip_ld = 0;
   trr_stats stats{};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -884,6 +885,8 @@ static int bm25_weight_locked(trr_bm25* h, const uint32_t* d_post_doc, float avg
   a.term_min = h->term_min; a.flags = h->term_min + h->n_terms;
   cudaError_t e = trr_launch_bm25_build(a, st);
   ctx->launches += 2;
+  // dead postings make the posting count of a term an over-estimate of its live documents: no threshold bootstrap then
+  if (e == cudaSuccess && h->n_dead_postings) e = cudaMemsetAsync(h->term_min + h->n_terms, 1, 4, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFree(d_idf);
   BM_TRY(e);
@@ -992,6 +995,41 @@ extern "C" int trr_bm25_append(trr_bm25* h, uint32_t n_new_docs, uint32_t n_term
   const int s = body();
   for (void* p : {(void*)d_new_off, (void*)d_delta_off, (void*)d_dd, (void*)d_dtf, (void*)new_post, (void*)new_tf, (void*)new_dl})
     if (p) cudaFree(p);
+  return s;
+}
+// BM25Index::remove (reference src/index.rs:245-275) without a rebuild: the postings of the removed documents stay in
+// place with term frequency 0 (they weigh +0.0 and the document is dropped by `score > 0.0`), and every other posting is
+// re-weighted with the new N / df / avgdl supplied by the host.  out_dead_postings (nullable) reports how many postings
+// are dead in total, so that the host can decide when a compacting rebuild pays off.
+extern "C" int trr_bm25_remove(trr_bm25* h, const uint32_t* ordinals, uint32_t n, float avgdl, float k1, float b,
+                               const float* idf, uint64_t* out_dead_postings) {
+  if (!h || (n && !ordinals) || (h->n_terms && !idf)) return trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_remove: NULL argument");
+  if (!h->tf) return trr_fail(TRR_ERR_UNSUPPORTED, "trr_bm25_remove: this index holds no raw postings");
+  std::lock_guard<std::mutex> lk(h->ctx->mu);
+  DeviceGuard g(h->ctx->device);
+  cudaStream_t st = h->ctx->stream;
+  const size_t words = ((size_t)h->n_docs + 31) / 32 + 1;
+  std::vector<uint32_t> bits(words, 0);
+  for (uint32_t i = 0; i < n; ++i) {
+    if (ordinals[i] >= h->n_docs) return trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_remove: ordinal out of range");
+    bits[ordinals[i] >> 5] |= 1u << (ordinals[i] & 31);
+  }
+  uint32_t* d_bits = nullptr;
+  auto body = [&]() -> int {
+    BM_TRY(cudaMalloc(&d_bits, (words + 1) * 4));
+    BM_TRY(cudaMemcpyAsync(d_bits, bits.data(), words * 4, cudaMemcpyHostToDevice, st));
+    BM_TRY(cudaMemsetAsync(d_bits + words, 0, 4, st));
+    BM_TRY(trr_launch_bm25_kill(h->post, h->tf, h->n_postings, d_bits, d_bits + words, st));
+    h->ctx->launches++;
+    uint32_t killed = 0;
+    BM_TRY(cudaMemcpyAsync(&killed, d_bits + words, 4, cudaMemcpyDeviceToHost, st));
+    BM_TRY(cudaStreamSynchronize(st));
+    h->n_dead_postings += killed;
+    return bm25_weight_locked(h, nullptr, avgdl, k1, b, idf);
+  };
+  const int s = body();
+  if (d_bits) cudaFree(d_bits);
+  if (out_dead_postings) *out_dead_postings = h->n_dead_postings;
   return s;
 }
 #undef BM_TRY

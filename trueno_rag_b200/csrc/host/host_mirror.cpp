@@ -338,13 +338,16 @@ void BM25Index::remove(const ChunkId& id) {  // :245-275
   }
   for (size_t t = 0; t < postings_.size(); ++t) {
     auto& pl = postings_[t];
-    const size_t before = pl.size();
-    pl.erase(std::remove_if(pl.begin(), pl.end(), [&](const std::pair<uint32_t, uint32_t>& p) { return p.first == ord; }),
-             pl.end());
-    if (pl.size() < before && df_[t] > 0) df_[t] -= 1;  // a term whose df reaches 0 keeps an empty list
+    for (size_t i = 0; i < pl.size(); ++i) {
+      if (pl[i].first != ord) continue;
+      if (t < frozen_len_.size() && i < frozen_len_[t]) frozen_len_[t] -= 1;  // the device copy keeps it as a dead posting
+      pl.erase(pl.begin() + (long)i);
+      if (df_[t] > 0) df_[t] -= 1;  // a term whose df reaches 0 keeps an empty list
+      break;                        // a document has at most one posting per term
+    }
   }
+  if (ord < frozen_docs_) pending_removed_.push_back(ord);  // otherwise it never reached the device
   dirty_ = true;
-  needs_rebuild_ = true;  // postings vanished from the middle of the lists: the device index is rebuilt
 }
 
 float BM25Index::avg_doc_length() const {
@@ -366,6 +369,16 @@ void BM25Index::freeze() const {
     idf[t] = logf((n - df + 0.5f) / (df + 0.5f) + 1.0f);  // :147, platform logf == Rust f32::ln here
   }
   const uint32_t n_docs = (uint32_t)doc_len_.size();
+  if (dev_ && dev_->h && !needs_rebuild_ && n_docs >= frozen_docs_ && !pending_removed_.empty()) {
+    // removes since the last freeze: tombstone their postings on the device and re-weight (src/index.rs:245-275)
+    uint64_t dead = 0;
+    const bool only_removes = n_docs == frozen_docs_;
+    check(trr_bm25_remove(dev_->h, pending_removed_.data(), (uint32_t)pending_removed_.size(), avg_doc_length_, k1_, b_,
+                          idf.data(), &dead));
+    pending_removed_.clear();
+    if (dead * 4 > frozen_postings_) needs_rebuild_ = true;  // a quarter of the device postings is dead: compact by rebuilding
+    else if (only_removes) { dirty_ = false; return; }
+  }
   if (dev_ && dev_->h && !needs_rebuild_ && n_docs >= frozen_docs_) {
     // only adds since the last freeze: ship the CSR of the new documents, merge and re-weight on the device
     frozen_len_.resize(n_terms, 0);
@@ -396,6 +409,8 @@ void BM25Index::freeze() const {
   frozen_docs_ = n_docs;
   frozen_len_.resize(n_terms);
   for (uint32_t t = 0; t < n_terms; ++t) frozen_len_[t] = (uint32_t)postings_[t].size();
+  pending_removed_.clear();
+  check(trr_bm25_n_postings(dev_->h, &frozen_postings_));
   needs_rebuild_ = false;
   dirty_ = false;
 }
