@@ -219,6 +219,35 @@ def test_gemm_tombstones_and_base(api, ctx):
     check(api, ctx, b, Q, 10, 0, 1, mode=2, alive=alive, base=7_000_000)
 
 
+@pytest.mark.parametrize("dtype", [0, 1])
+def test_gemm_operands_follow_appends_and_removes(api, ctx, dtype):
+    """VectorStore::insert / remove between batched searches (src/index.rs:359-383, 421-424): the tensor-core operands
+    (bf16 shadow, scale/bias, TMA descriptors) are rebuilt lazily and the results track the oracle."""
+    n, d, B = 30000, 128, 40
+    f, b = O.synth_corpus(SEED + 13, 0, n, d, bf16=bool(dtype))
+    rows = b if dtype else f
+    Q = O.synth_queries(SEED + 13, 0, B, d, n, corpus_bf16=bool(dtype))
+    if dtype:
+        Q = bf16_round(Q)
+    ix = api.DenseIndex(ctx, d, api.COSINE, dtype)
+    ix.set_mode(2)
+    alive = np.zeros(n, bool)
+    for lo, hi in ((0, 17000), (17000, 17001), (17001, n)):
+        ix.append(rows[lo:hi])
+        alive[lo:hi] = True
+        got = ix.search(Q, 10)
+        assert ix.stats().mode_used == 2
+        exp = O.dense_search_batch(rows[:hi], Q, 10, alive=alive[:hi])
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp)), hi
+        victim = int(got[0][0, 0])                                     # remove the current winner of query 0
+        ix.remove(victim)
+        alive[victim] = False
+        got = ix.search(Q, 10)
+        exp = O.dense_search_batch(rows[:hi], Q, 10, alive=alive[:hi])
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp)), ("after remove", hi)
+    ix.close()
+
+
 def test_auto_mode_picks_scan_for_single_query_and_gemm_for_batches(api, ctx):
     n, d = 20000, 128
     f, b = O.synth_corpus(SEED, 0, n, d, bf16=True)
