@@ -189,6 +189,17 @@ def test_gemm_path_matches_oracle(api, ctx, n, d, dtype, B, k):
     assert st.max_fast_exact_gap <= st.eps_bound + 1e-3 * (dtype == 0)
 
 
+def test_gemm_two_cta_variant_matches_oracle(api, ctx, monkeypatch):
+    """The cta_group::2 kernel (two SMs of a TPC share one 256 x 256 tile; opt-in, slower than the 1-CTA kernel on this
+    shape) must return the same bit-exact results."""
+    monkeypatch.setenv("TRR_GEMM_PAIR", "1")
+    n, d, B = 40000, 768, 300
+    f, b = O.synth_corpus(SEED + 4, 0, n, d, bf16=True, dups=True)
+    Q = bf16_round(O.synth_queries(SEED + 4, 0, B, d, n, corpus_bf16=True, dups=True))
+    st = check(api, ctx, b, Q, 50, 0, 1, mode=2, expect_mode=2)
+    assert st.n_guard_fallbacks <= 2
+
+
 def test_gemm_path_dot_metric_and_f32_queries(api, ctx):
     n, d, B = 30000, 512, 96
     rng = np.random.default_rng(3)
