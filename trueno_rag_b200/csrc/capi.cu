@@ -668,6 +668,12 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     ra.rows = h->rows; ra.dim = h->dim; ra.norms = h->norms; ra.base_ord = h->base; ra.n_live = n_live;
     ra.q = d_q; ra.q_norms = d_qn; ra.q_norms_out = nullptr; ra.q_delta = d_qdelta; ra.max_norm = reinterpret_cast<const float*>(h->max_norm.p);
     ra.B = B; ra.k = k; ra.metric = h->metric;
+    // candidate rows are staged in shared memory in chunks (28 KB per CTA keeps six CTAs per SM)
+    uint32_t stage_budget = 28u << 10;
+    if (const char* e = getenv("TRR_RESCORE_STAGE_KB")) stage_budget = (uint32_t)std::max(1, atoi(e)) << 10;
+    ra.stage_chunk = (h->row_bytes % 16 == 0 && !getenv("TRR_RESCORE_NO_STAGE"))
+                         ? std::min<uint32_t>(h->row_bytes, (uint32_t)((stage_budget / CP - 16) & ~15u)) : 0u;
+    if (ra.stage_chunk < 64) ra.stage_chunk = 0;
     // |fast - exact| <= eps_rel * |q||d|: products of bf16 values are exact in f32; the tensor-core sum and the
     // reference's sequential sum each carry at most D roundings of relative size 2^-23 on partial sums bounded by
     // sum|q_i d_i| <= |q||d|; the scale multiply, the division and the norm product add a few more ulps.

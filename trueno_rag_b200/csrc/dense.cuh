@@ -63,6 +63,7 @@ struct RescoreArgs {
   const float* max_norm;     // device scalar: max row norm
   uint32_t B, k;
   int metric;
+  uint32_t stage_chunk;      // bytes of each candidate row staged in shared memory per pass (multiple of 16; 0 = read rows from global)
   float eps_rel;             // accumulation error bound relative to |q||d|
   uint64_t* out_keys;        // nullable [B][k]
   uint32_t* out_ord;         // nullable [B][k]

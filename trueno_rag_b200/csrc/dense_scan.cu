@@ -521,6 +521,7 @@ rescore_select_kernel(RescoreArgs a) {
   float* efast = reinterpret_cast<float*>(ekeys + a.cp);              // fast score of each kept candidate
   __shared__ float s_gap, s_qnorm;
   __shared__ uint32_t s_total, s_tmax;
+  __shared__ uint32_t s_smin[160], s_scnt[160];  // per document slice (at most one slice per SM): list minimum, fill count
   const uint32_t b = blockIdx.x;
   if (b >= a.B) return;
   const uint32_t tid = threadIdx.x;
@@ -530,26 +531,27 @@ rescore_select_kernel(RescoreArgs a) {
   // 1. gather: slice s of query block qb = b / 128, row r = b % 128
   const uint32_t qb = b / 128, r = b % 128;
   uint32_t local_total = 0;
+  // a slice whose list is full may have dropped documents: all of them scored at most the list minimum (and the
+  // thresholds shared between slices never exceed a list minimum).  s_tmax = the largest such bound; the per-slice minimum
+  // and fill count are collected with shared-memory atomics while the candidates are gathered.
+  for (uint32_t s = tid; s < a.n_slices; s += blockDim.x) { s_smin[s] = 0xFFFFFFFFu; s_scnt[s] = 0; }
+  __syncthreads();
   for (uint32_t i = tid; i < a.n_slices * a.cps; i += blockDim.x) {
     const uint32_t s = i / a.cps, j = i % a.cps;
     const uint64_t base = (((uint64_t)s * a.n_qblocks + qb) * 128 + r) * a.cps + j;
     const float sc = a.cand_score[base];
     const uint32_t od = a.cand_ord[base];
-    if (od != 0xFFFFFFFFu) { keys[i] = trr_make_key(sc, od); ++local_total; }
+    if (od != 0xFFFFFFFFu) {
+      keys[i] = trr_make_key(sc, od);
+      ++local_total;
+      atomicMin(&s_smin[s], trr_f32_orderable(sc));
+      atomicAdd(&s_scnt[s], 1u);
+    }
   }
   if (local_total) atomicAdd(&s_total, local_total);
-  // a slice whose list is full may have dropped documents: all of them scored at most the list minimum (and the
-  // thresholds shared between slices never exceed a list minimum).  s_tmax = the largest such bound.
-  for (uint32_t s = tid; s < a.n_slices; s += blockDim.x) {
-    const uint64_t base = (((uint64_t)s * a.n_qblocks + qb) * 128 + r) * a.cps;
-    float mn = CUDART_INF_F;
-    bool full = true;
-    for (uint32_t j = 0; j < a.cps; ++j) {
-      if (a.cand_ord[base + j] == 0xFFFFFFFFu) full = false;
-      else mn = fminf(mn, a.cand_score[base + j]);
-    }
-    if (full) atomicMax(&s_tmax, trr_f32_orderable(mn));
-  }
+  __syncthreads();
+  for (uint32_t s = tid; s < a.n_slices; s += blockDim.x)
+    if (s_scnt[s] == a.cps) atomicMax(&s_tmax, s_smin[s]);
   __syncthreads();
   trr_bitonic_sort_desc(keys, a.cap2, tid, blockDim.x, BlockSync());
   const uint32_t n_cand = min(s_total, a.cp);
@@ -567,6 +569,56 @@ rescore_select_kernel(RescoreArgs a) {
   }
   if (a.q_norms_out) __syncthreads();
   const float q_norm = a.q_norms_out ? s_qnorm : a.q_norms[b];
+  // Staged path (rows of a multiple of 16 bytes): the candidate rows are scattered over HBM, so all 256 threads copy them
+  // into shared memory with 16-byte cp.async (row pitch + 16 bytes: lane == candidate reads are conflict-free), chunk by
+  // chunk; then one thread per candidate runs the strict sequential sum out of shared memory.
+  const uint32_t row_bytes = a.dim * (IS_BF16 ? 2u : 4u);
+  const bool staged = a.stage_chunk != 0 && (row_bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(a.rows) & 15u) == 0;
+  float acc_staged = 0.0f;
+  if (staged) {
+    uint8_t* rowbuf = reinterpret_cast<uint8_t*>(qs) + ((a.dim * 4 + 15) & ~15u);
+    const uint32_t pitch = a.stage_chunk + 16;
+    for (uint32_t c0 = 0; c0 < row_bytes; c0 += a.stage_chunk) {
+      const uint32_t cb = min(a.stage_chunk, row_bytes - c0), pieces = cb >> 4;
+      for (uint32_t idx = tid; idx < n_cand * pieces; idx += blockDim.x) {
+        const uint32_t r = idx / pieces, pc = idx - r * pieces;
+        const uint64_t row = trr_key_ord(keys[r]) - a.base_ord;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.rows) + row * row_bytes + c0 + (pc << 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(trr_smem_u32(rowbuf + r * pitch + (pc << 4))), "l"(src)
+                     : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      if (tid < n_cand) {
+        const uint4* rp = reinterpret_cast<const uint4*>(rowbuf + tid * pitch);
+        float acc = acc_staged;
+        if (IS_BF16) {
+          const float* qq = qs + (c0 >> 1);
+#pragma unroll 4
+          for (uint32_t i = 0; i < pieces; ++i) {
+            const uint4 v = rp[i];
+            const float4 q0 = *reinterpret_cast<const float4*>(qq + 8 * i), q1 = *reinterpret_cast<const float4*>(qq + 8 * i + 4);
+            acc = acc + q0.x * bf16lo(v.x); acc = acc + q0.y * bf16hi(v.x);
+            acc = acc + q0.z * bf16lo(v.y); acc = acc + q0.w * bf16hi(v.y);
+            acc = acc + q1.x * bf16lo(v.z); acc = acc + q1.y * bf16hi(v.z);
+            acc = acc + q1.z * bf16lo(v.w); acc = acc + q1.w * bf16hi(v.w);
+          }
+        } else {
+          const float* qq = qs + (c0 >> 2);
+#pragma unroll 4
+          for (uint32_t i = 0; i < pieces; ++i) {
+            const uint4 v = rp[i];
+            const float4 q0 = *reinterpret_cast<const float4*>(qq + 4 * i);
+            acc = acc + q0.x * __uint_as_float(v.x); acc = acc + q0.y * __uint_as_float(v.y);
+            acc = acc + q0.z * __uint_as_float(v.z); acc = acc + q0.w * __uint_as_float(v.w);
+          }
+        }
+        acc_staged = acc;
+      }
+      __syncthreads();
+    }
+  }
   if (tid < a.cp) {
     uint64_t ek = TRR_KEY_EMPTY;
     float fast = 0.0f;
@@ -575,8 +627,10 @@ rescore_select_kernel(RescoreArgs a) {
       const uint32_t od = trr_key_ord(fk);
       fast = trr_key_score(fk);
       const uint64_t row = od - a.base_ord;
-      float acc = 0.0f;
-      if (IS_BF16) {
+      float acc = acc_staged;
+      if (staged) {
+        // sum already complete
+      } else if (IS_BF16) {
         const uint16_t* p = reinterpret_cast<const uint16_t*>(a.rows) + row * a.dim;
         uint32_t j = 0;
         if ((a.dim & 7u) == 0 && (reinterpret_cast<uintptr_t>(a.rows) & 15u) == 0) {
@@ -785,7 +839,8 @@ cudaError_t trr_launch_topk_merge(const TopkMergeArgs& a, unsigned grid, cudaStr
 
 cudaError_t trr_launch_rescore(const RescoreArgs& a, int is_bf16, cudaStream_t st) {
   if (a.B == 0) return cudaSuccess;
-  size_t smem = (size_t)a.cap2 * 8 + (size_t)a.cp * 8 + (size_t)a.cp * 4 + (size_t)a.dim * 4 + 16;
+  size_t smem = (size_t)a.cap2 * 8 + (size_t)a.cp * 8 + (size_t)a.cp * 4 + (((size_t)a.dim * 4 + 15) & ~(size_t)15) + 16 +
+                (a.stage_chunk ? (size_t)a.cp * (a.stage_chunk + 16) : 0);
   if (is_bf16) {
     cudaError_t e = cudaFuncSetAttribute(rescore_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
