@@ -78,6 +78,35 @@ def cfg3(ctx):
     dev.close()
 
 
+def hybrid_small_batches(ctx):
+    """cfg4 corpus (10M x 768 bf16 + Zipf BM25), the reference's own call shape: HybridRetriever::retrieve for ONE query
+    (B = 1), and small batches, through the host-buffer entry point trr_hybrid_search (H2D + kernels + D2H + sync)."""
+    L = _lib.load()
+    N, D, V, Cn, K = int(os.environ.get("PROBE_DOCS", "10000000")), 768, 1_000_000, 50, 10
+    seed = 0x5EED0004
+    dense = api.DenseIndex(ctx, D, api.COSINE, api.BF16, capacity=N)
+    dense.append_synth(seed, 0, N)
+    cdf = O.zipf_cdf(V)
+    df = np.zeros(V, np.uint32); dl = np.zeros(N, np.uint32); tot = C.c_uint64()
+    api._check(L.trr_synth_bm25_count(seed, cdf.ctypes.data_as(u64p), V, 0, N, df.ctypes.data_as(u32p), dl.ctypes.data_as(u32p), C.byref(tot)))
+    term_off = np.zeros(V + 1, np.uint64); np.cumsum(df, out=term_off[1:])
+    pd = np.zeros(int(term_off[-1]), np.uint32); ptf = np.zeros(int(term_off[-1]), np.uint32)
+    api._check(L.trr_synth_bm25_fill(seed, cdf.ctypes.data_as(u64p), V, 0, N, term_off.ctypes.data_as(u64p), pd.ctypes.data_as(u32p), ptf.ctypes.data_as(u32p)))
+    avgdl = float(np.float32(np.uint32(tot.value & 0xFFFFFFFF)) / np.float32(N))
+    bm = api.Bm25Device(ctx, N, term_off, pd, ptf, dl, avgdl, api.bm25_idf_host(N, df))
+    del pd, ptf
+    Q = O.synth_queries(seed, 0, 64, D, N, corpus_bf16=True)
+    u = Q.view(np.uint32)
+    Q = ((u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32).view(np.float32)
+    q_off, q_terms = O.synth_query_terms(seed, cdf, 0, 64)
+    for B in (1, 8, 64):
+        qo, qt = q_off[:B + 1], q_terms[:q_off[B]]
+        w = wall(lambda: api.hybrid_search(dense, bm, Q[:B], qt, qo, Cn, api.RRF, 60.0, K), 5)
+        print(f"cfg4 hybrid B={B:<3d} (10M x 768 bf16 + BM25, RRF k=60, C=50, top-10), host-buffer call: {w*1e3:8.3f} ms -> {B/w:9.1f} q/s "
+              f"(dense path: {'scan' if dense.stats().mode_used == 1 else 'gemm'})")
+    dense.close(); bm.close()
+
+
 def append(ctx):
     """trr_bm25_append vs a full rebuild: PROBE_DOCS documents on the device (default 10M), then 100k more."""
     L = _lib.load()
@@ -135,3 +164,5 @@ if __name__ == "__main__":
         cfg3(ctx)
     if "append" in which:
         append(ctx)
+    if "hybrid" in which:
+        hybrid_small_batches(ctx)
