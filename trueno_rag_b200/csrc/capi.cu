@@ -626,7 +626,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     const bool dev_fallback = (size_t)B * lists * k * 8 <= ((size_t)256 << 20) && !getenv("TRR_GEMM_HOST_FALLBACK");
     const uint32_t fb_chunk = dev_fallback ? B : 64;  // fallback queries per scan launch
     const size_t need = WsCarver::need({(size_t)B * 4, (size_t)B * 4, n_cand * 4, n_cand * 4, (size_t)B_pad * 4,
-                                        (size_t)B * 4, (size_t)B * 4, 256, (size_t)B_pad * h->dim_pad * 2,
+                                        (size_t)B * 4, (size_t)B * 4, (size_t)B * 4, 256, (size_t)B_pad * h->dim_pad * 2,
                                         (size_t)fb_chunk * lists * k * 8 + 512, (size_t)fb_chunk * lists * 4 + 512}) +
                         4096;
     TRR_CHECK(extra(c)->scratch.reserve(need));
@@ -638,7 +638,8 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     uint32_t* gthr = ws.take<uint32_t>(B_pad);
     uint32_t* flags = ws.take<uint32_t>(B);
     uint32_t* flagged = ws.take<uint32_t>(B);
-    uint32_t* counters = ws.take<uint32_t>(64);  // [0] n_flagged, [1] max_gap (float bits)
+    uint32_t* flagged2 = ws.take<uint32_t>(B);
+    uint32_t* counters = ws.take<uint32_t>(64);  // [0] n_flagged (first pass), [1] max_gap (float bits), [4] n_flagged after the wide pass, [5] resolved by it
     uint16_t* q_bf16 = ws.take<uint16_t>((size_t)B_pad * h->dim_pad);
     const size_t fb_off = (ws.off + 255) & ~size_t(255);
 
@@ -685,16 +686,36 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     ra.flags = flags; ra.flagged = flagged; ra.n_flagged = counters; ra.max_gap = reinterpret_cast<float*>(counters + 1);
     TRR_CUDA(trr_launch_rescore(ra, h->dtype == TRR_DTYPE_BF16, st));
     c->launches++;
+    // Second level: a query whose proof failed (rank spacing tighter than the a-priori error bound: large dimensions, large
+    // k) is re-scored over EVERYTHING the slices kept (n_slices x cps candidates instead of the best CP), so that the only
+    // documents left out are the ones the slices dropped, which sit far further down the ranking.  Only the queries that
+    // still fail go to the exact scan.  CTAs beyond the device-side count of flagged queries return at once.
+    const uint32_t cp_wide = trr_pow2_ceil(n_slices * cps);
+    uint32_t* flagged_final = flagged;
+    uint32_t* counters_final = counters;
+    if (cp_wide > CP && cp_wide <= 2048 && !getenv("TRR_GEMM_NO_WIDE")) {
+      RescoreArgs rw = ra;
+      rw.cp = cp_wide; rw.cap2 = std::max(cap2, cp_wide); rw.stage_chunk = 0;
+      rw.sel = flagged; rw.sel_n = counters;
+      rw.flagged = flagged2; rw.n_flagged = counters + 4; rw.n_resolved = counters + 5;
+      rw.max_gap = reinterpret_cast<float*>(counters + 1);
+      TRR_CUDA(trr_launch_rescore(rw, h->dtype == TRR_DTYPE_BF16, st));
+      c->launches++;
+      flagged_final = flagged2;
+      counters_final = counters + 4;
+    }
     h->stats.eps_bound = eps_rel;
     if (dev_fallback) {
       if (!h->stat_dev) TRR_CUDA(cudaMalloc(&h->stat_dev, 64));
-      TRR_CUDA(cudaMemcpyAsync(h->stat_dev, counters, 8, cudaMemcpyDeviceToDevice, st));
+      TRR_CUDA(cudaMemcpyAsync(h->stat_dev, counters_final, 4, cudaMemcpyDeviceToDevice, st));
+      TRR_CUDA(cudaMemcpyAsync(h->stat_dev + 1, counters + 1, 4, cudaMemcpyDeviceToDevice, st));
       h->stat_pending = true;
       if (!ga.debug_mode)
-        TRR_CHECK(dense_scan_locked(h, d_q, d_qn, B, flagged, k, d_ord, d_score, d_n, nullptr, fb_off, counters, false));
+        TRR_CHECK(dense_scan_locked(h, d_q, d_qn, B, flagged_final, k, d_ord, d_score, d_n, nullptr, fb_off, counters_final, false));
     } else {
       uint32_t hc[2] = {0, 0};
-      TRR_CUDA(cudaMemcpyAsync(hc, counters, 8, cudaMemcpyDeviceToHost, st));
+      TRR_CUDA(cudaMemcpyAsync(&hc[0], counters_final, 4, cudaMemcpyDeviceToHost, st));
+      TRR_CUDA(cudaMemcpyAsync(&hc[1], counters + 1, 4, cudaMemcpyDeviceToHost, st));
       cudaError_t se = cudaStreamSynchronize(st);
       if (se != cudaSuccess) {
         const uint32_t w = extra(c)->dbg_host ? extra(c)->dbg_host[0] : 0;
@@ -706,7 +727,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
       if (ga.debug_mode) hc[0] = 0;  // perf triage: results are meaningless, do not time the fallback
       for (uint32_t f0 = 0; f0 < hc[0]; f0 += fb_chunk) {
         const uint32_t m = std::min(fb_chunk, hc[0] - f0);
-        TRR_CHECK(dense_scan_locked(h, d_q, d_qn, m, flagged + f0, k, d_ord, d_score, d_n, nullptr, fb_off, nullptr, false));
+        TRR_CHECK(dense_scan_locked(h, d_q, d_qn, m, flagged_final + f0, k, d_ord, d_score, d_n, nullptr, fb_off, nullptr, false));
       }
     }
     h->stats.mode_used = TRR_DENSE_GEMM;

@@ -69,6 +69,9 @@ struct RescoreArgs {
   uint32_t* out_ord;         // nullable [B][k]
   float* out_score;          // nullable
   uint32_t* out_n;           // nullable
+  const uint32_t* sel;       // nullable: wide pass, CTA i handles query sel[i] ...
+  const uint32_t* sel_n;     // ... for i < *sel_n (device count)
+  uint32_t* n_resolved;      // nullable: counts the queries whose proof holds in this pass (diagnostics)
   uint32_t* flags;           // [B] 1 = proof failed
   uint32_t* flagged;         // [B] compact list of flagged queries
   uint32_t* n_flagged;       // device counter (zeroed by the caller)

@@ -518,11 +518,12 @@ rescore_select_kernel(RescoreArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);            // cap2 fast keys
   uint64_t* ekeys = keys + a.cap2;                                     // CP exact keys (CP power of two)
-  float* efast = reinterpret_cast<float*>(ekeys + a.cp);              // fast score of each kept candidate
   __shared__ float s_gap, s_qnorm;
   __shared__ uint32_t s_total, s_tmax;
   __shared__ uint32_t s_smin[160], s_scnt[160];  // per document slice (at most one slice per SM): list minimum, fill count
-  const uint32_t b = blockIdx.x;
+  // first pass: CTA == query.  Second (wide) pass: CTA i re-scores the i-th query flagged by the first pass
+  if (a.sel_n && blockIdx.x >= *a.sel_n) return;
+  const uint32_t b = a.sel ? a.sel[blockIdx.x] : blockIdx.x;
   if (b >= a.B) return;
   const uint32_t tid = threadIdx.x;
   if (tid == 0) { s_gap = 0.0f; s_total = 0; s_tmax = 0; }
@@ -557,7 +558,7 @@ rescore_select_kernel(RescoreArgs a) {
   const uint32_t n_cand = min(s_total, a.cp);
   // 2. exact rescoring, strict reference order (one candidate per thread: the sum is a sequential chain; the loads are
   //    128-bit and run ahead of it).  The query is staged in shared memory once per CTA.
-  float* qs = efast + a.cp;
+  float* qs = reinterpret_cast<float*>(ekeys + a.cp);
   const float* qv = a.q + (uint64_t)b * a.dim;
   for (uint32_t j = tid; j < a.dim; j += blockDim.x) qs[j] = qv[j];
   __syncthreads();
@@ -619,11 +620,11 @@ rescore_select_kernel(RescoreArgs a) {
       __syncthreads();
     }
   }
-  if (tid < a.cp) {
+  for (uint32_t c = tid; c < a.cp; c += blockDim.x) {  // one iteration unless this is the wide pass (cp > blockDim.x)
     uint64_t ek = TRR_KEY_EMPTY;
     float fast = 0.0f;
-    if (tid < n_cand) {
-      const uint64_t fk = keys[tid];
+    if (c < n_cand) {
+      const uint64_t fk = keys[c];
       const uint32_t od = trr_key_ord(fk);
       fast = trr_key_score(fk);
       const uint64_t row = od - a.base_ord;
@@ -694,8 +695,7 @@ rescore_select_kernel(RescoreArgs a) {
       float fs = (a.metric == TRR_METRIC_COSINE) ? (q_norm > 0.0f ? fast / q_norm : 0.0f) : fast;
       atomicMax(reinterpret_cast<int*>(&s_gap), __float_as_int(fabsf(fs - score)));
     }
-    ekeys[tid] = ek;
-    efast[tid] = fast;
+    ekeys[c] = ek;
   }
   __syncthreads();
   trr_bitonic_sort_desc(ekeys, a.cp, tid, blockDim.x, BlockSync());
@@ -736,6 +736,7 @@ rescore_select_kernel(RescoreArgs a) {
       const uint32_t slot = atomicAdd(a.n_flagged, 1u);
       a.flagged[slot] = b;
     }
+    if (a.n_resolved && ok) atomicAdd(a.n_resolved, 1u);
     atomicMax(reinterpret_cast<int*>(a.max_gap), __float_as_int(s_gap));
   }
 }
@@ -839,7 +840,7 @@ cudaError_t trr_launch_topk_merge(const TopkMergeArgs& a, unsigned grid, cudaStr
 
 cudaError_t trr_launch_rescore(const RescoreArgs& a, int is_bf16, cudaStream_t st) {
   if (a.B == 0) return cudaSuccess;
-  size_t smem = (size_t)a.cap2 * 8 + (size_t)a.cp * 8 + (size_t)a.cp * 4 + (((size_t)a.dim * 4 + 15) & ~(size_t)15) + 16 +
+  size_t smem = (size_t)a.cap2 * 8 + (size_t)a.cp * 8 + (((size_t)a.dim * 4 + 15) & ~(size_t)15) + 16 +
                 (a.stage_chunk ? (size_t)a.cp * (a.stage_chunk + 16) : 0);
   if (is_bf16) {
     cudaError_t e = cudaFuncSetAttribute(rescore_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
