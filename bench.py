@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--cpu-sample-docs", type=int, default=400_000)
     ap.add_argument("--cpu-sample-queries", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bf16-queries", action="store_true", help="round the query embeddings to bf16 (default: full f32 queries, as an embedder emits them)")
     ap.add_argument("--verify", type=int, default=4, help="queries checked against the oracle after the timed region (0 = off)")
     return ap.parse_args()
 
@@ -57,7 +58,8 @@ def config(a, extra=None):
     c = {"workload": f"cfg4 hybrid dense+BM25 RRF k=60: {a.docs}x{a.dim} bf16, Zipf BM25 vocab {a.vocab}, "
                      f"batch {a.batch}, C={a.cands}, top-{a.k}",
          "docs": a.docs, "dim": a.dim, "batch": a.batch, "vocab": a.vocab, "candidates_per_source": a.cands, "k": a.k,
-         "fusion": "RRF k=60", "sharding": f"documents, contiguous ranges over {a.gpus} GPU(s)",
+         "fusion": "RRF k=60", "queries": "bf16-rounded" if getattr(a, "bf16_queries", False) else "f32 (embedder output; the store is bf16)",
+         "sharding": f"documents, contiguous ranges over {a.gpus} GPU(s)",
          "l2": "inputs (>=1.9 GB of embeddings per GPU) exceed the 126 MB L2; no flush needed"}
     if extra:
         c.update(extra)
@@ -234,10 +236,10 @@ def run_ours(a):
     bm = api.Bm25Device(ctx, n_loc, term_off, post_doc, post_tf, doc_len[:n_loc], avgdl, idf, doc_base=lo)
     host_csr = (term_off, post_doc, post_tf, doc_len[:n_loc], df_g, avgdl) if (world == 1 and a.verify > 0) else None
     del post_doc, post_tf
-    # ---- queries (bf16-representable, as the corpus): pinned host copies + device copies
+    # ---- queries: f32 as an embedder emits them (the corpus is bf16); pinned host copies + device copies
     q_pin = torch.empty((B, D), dtype=torch.float32).pin_memory()
     q_np = q_pin.numpy()
-    api._check(L.trr_synth_queries(SEED, 0, B, D, N, 1, 0, 1, q_np.ctypes.data_as(f32p)))
+    api._check(L.trr_synth_queries(SEED, 0, B, D, N, 1, 0, 1 if a.bf16_queries else 0, q_np.ctypes.data_as(f32p)))
     q_off = np.zeros(B + 1, np.uint32)
     api._check(L.trr_synth_query_terms(SEED, cdf.ctypes.data_as(u64p), V, 0, B, q_off.ctypes.data_as(u32p), None, 0))
     nt = int(q_off[-1])
