@@ -189,6 +189,13 @@ def test_gemm_path_matches_oracle(api, ctx, n, d, dtype, B, k):
     assert st.max_fast_exact_gap <= st.eps_bound + 1e-3 * (dtype == 0)
 
 
+def test_batches_above_4096_queries_are_served_in_pieces(api, ctx):
+    n, d, B = 17000, 64, 4500
+    f, b = O.synth_corpus(SEED + 6, 0, n, d, bf16=True)
+    Q = bf16_round(O.synth_queries(SEED + 6, 0, B, d, n, corpus_bf16=True))
+    check(api, ctx, b, Q, 7, 0, 1, mode=0)
+
+
 def test_gemm_two_cta_variant_matches_oracle(api, ctx, monkeypatch):
     """The cta_group::2 kernel (two SMs of a TPC share one 256 x 256 tile; opt-in, slower than the 1-CTA kernel on this
     shape) must return the same bit-exact results."""

@@ -539,6 +539,17 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
                                uint32_t* d_n, bool sync_stats) {
   trr_ctx* c = h->ctx;
   cudaStream_t st = c->stream;
+  // very large batches are served in pieces (scratch and the query-block grid scale with B)
+  constexpr uint32_t kMaxBatch = 4096;
+  if (B > kMaxBatch) {
+    for (uint32_t b0 = 0; b0 < B; b0 += kMaxBatch) {
+      const uint32_t nb = std::min(kMaxBatch, B - b0);
+      TRR_CHECK(dense_search_locked(h, d_q + (size_t)b0 * h->dim, nb, k, d_ord + (size_t)b0 * k, d_score + (size_t)b0 * k,
+                                    d_n + b0, sync_stats));
+    }
+    h->stats.n_queries = B;
+    return TRR_OK;
+  }
   const uint64_t launches0 = c->launches;
   h->stats = trr_stats{};
   h->stats.n_queries = B;
