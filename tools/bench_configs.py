@@ -43,7 +43,7 @@ def cfg2(ctx):
           f"device call {st.ms_total*1e3:7.1f} us  host call {w*1e6:7.1f} us  -> {256/w:8.0f} q/s  fallbacks {st.n_guard_fallbacks}")
     ix.set_mode(api.MODE_SCAN)
     w = wall(lambda: ix.search(Q[:16], 10), 2)
-    print(f"cfg2 B=16  K1 scan : host call {w*1e6:7.1f} us -> {16/w:8.0f} q/s")
+    print(f"cfg2 B=16  K1 scan (4 queries per pass): host call {w*1e6:7.1f} us -> {16/w:8.0f} q/s")
     ix.close()
 
 

@@ -426,13 +426,15 @@ static int dense_prepare_gemm(trr_dense* h) {
 struct ScanPlan {
   bool tma;   // 2-D TMA ring kernel (rows of a multiple of 16 bytes, >= 4096 rows)
   uint32_t n_slots;
+  uint32_t nq;  // queries per pass over the slab (TMA kernel: 1 or 4)
   bool bulk;
   unsigned grid;
   uint32_t warps, cap, ch_bytes, n_chunks;
   size_t smem;
 };
 
-static int plan_scan(trr_dense* h, uint32_t k, ScanPlan* p) {
+static int plan_scan(trr_dense* h, uint32_t k, ScanPlan* p, uint32_t n_queries = 1) {
+  p->nq = 1;
   p->cap = trr_pow2_ceil(k + 32);
   if (p->cap < 64) p->cap = 64;
   const uint32_t q_bytes = (h->dim * 4 + 127) & ~127u;
@@ -444,8 +446,12 @@ static int plan_scan(trr_dense* h, uint32_t k, ScanPlan* p) {
     // ring slots per warp come from what is left of the shared memory (4 KB per slot, at least 3)
     uint32_t nw_first = 16;
     if (const char* e = getenv("TRR_SCAN_WARPS")) nw_first = (uint32_t)std::min(16, std::max(1, atoi(e)));
+    // several queries on the exact path share each pass over the slab four at a time (if the buffers fit with >= 8 warps)
+    uint32_t nq = (n_queries >= 2 && !getenv("TRR_SCAN_NQ1")) ? 4u : 1u;
+    if (nq == 4 && trr_scan_tma_smem(h->dim, p->cap, 3, 8, 4) > optin) nq = 1;
+    p->nq = nq;
     for (uint32_t nw = nw_first; nw >= 1; nw >>= 1) {
-      const size_t fixed = trr_scan_tma_smem(h->dim, p->cap, 0, nw);
+      const size_t fixed = trr_scan_tma_smem(h->dim, p->cap, 0, nw, nq);
       if (fixed + (size_t)nw * 3 * 4104 > optin) continue;
       uint32_t slots = (uint32_t)((optin - fixed) / ((size_t)nw * (4096 + 8)));
       if (slots > 12) slots = 12;
@@ -453,7 +459,7 @@ static int plan_scan(trr_dense* h, uint32_t k, ScanPlan* p) {
       p->tma = true; p->bulk = false; p->n_slots = slots; p->warps = nw;
       p->grid = (unsigned)h->ctx->sm_count;
       p->ch_bytes = 0; p->n_chunks = 0;
-      p->smem = trr_scan_tma_smem(h->dim, p->cap, slots, nw);
+      p->smem = trr_scan_tma_smem(h->dim, p->cap, slots, nw, nq);
       return TRR_OK;
     }
   }
@@ -492,7 +498,7 @@ static int dense_scan_locked(trr_dense* h, const float* d_q, const float* d_qn, 
                              uint32_t k, uint32_t* d_ord, float* d_score, uint32_t* d_n, uint64_t* d_keys,
                              size_t scratch_off, const uint32_t* d_n_sel = nullptr, bool record_events = true) {
   ScanPlan p;
-  TRR_CHECK(plan_scan(h, k, &p));
+  TRR_CHECK(plan_scan(h, k, &p, n_sel));
   const uint64_t lists = (uint64_t)p.grid;  // one merged list per CTA
   const size_t need = scratch_off + WsCarver::need({(size_t)n_sel * lists * k * 8, (size_t)n_sel * lists * 4});
   TRR_CHECK(extra(h->ctx)->scratch.reserve(need));
@@ -511,7 +517,7 @@ static int dense_scan_locked(trr_dense* h, const float* d_q, const float* d_qn, 
     h->map_scan_n = h->n; h->map_scan_base = h->rows;
   }
   if (record_events) TRR_CUDA(cudaEventRecord(h->ev[2], st));
-  if (p.tma) TRR_CUDA(trr_launch_scan_tma(a, h->map_scan, h->dtype == TRR_DTYPE_BF16, h->metric, p.grid, p.warps, p.smem, st));
+  if (p.tma) TRR_CUDA(trr_launch_scan_tma(a, h->map_scan, h->dtype == TRR_DTYPE_BF16, h->metric, p.grid, p.warps, p.nq, p.smem, st));
   else TRR_CUDA(trr_launch_scan(a, h->dtype == TRR_DTYPE_BF16, h->metric, p.bulk, p.grid, p.smem, st));
   if (record_events) TRR_CUDA(cudaEventRecord(h->ev[3], st));
   h->ctx->launches++;
@@ -594,7 +600,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
   if (!use_gemm) {
     // the scratch buffer may be re-allocated by dense_scan_locked: compute the norms after reserving there
     ScanPlan p;
-    TRR_CHECK(plan_scan(h, k, &p));
+    TRR_CHECK(plan_scan(h, k, &p, B));
     const uint64_t lists = (uint64_t)p.grid;
     TRR_CHECK(extra(c)->scratch.reserve(scratch_off + WsCarver::need({(size_t)B * lists * k * 8, (size_t)B * lists * 4})));
     d_qn = reinterpret_cast<float*>(extra(c)->scratch.p);
@@ -629,7 +635,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     const uint32_t cap2 = std::max<uint32_t>(trr_pow2_ceil(n_slices * cps), 2 * CP);
     // scratch layout (single reservation so that pointers stay valid)
     ScanPlan p;
-    TRR_CHECK(plan_scan(h, k, &p));
+    TRR_CHECK(plan_scan(h, k, &p, B));
     const uint64_t lists = (uint64_t)p.grid;
     // queries whose candidate proof fails are re-run through the exact scan.  Normally the fallback is DEVICE-DRIVEN (the
     // scan and merge kernels read the number of flagged queries from device memory and return at once when it is zero), so

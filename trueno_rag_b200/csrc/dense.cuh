@@ -104,9 +104,10 @@ void trr_launch_query_norms(const float* q, uint32_t dim, uint32_t B, float* qn,
 cudaError_t trr_launch_scan(const DenseScanArgs& a, int is_bf16, int metric, bool bulk, unsigned grid, size_t smem,
                             cudaStream_t st);
 // K1 with a 2-D TMA ring (rows of a multiple of 16 bytes): map_rows128 = tensor map of the slab, box 32 rows x 128 bytes
+// nq = 1 or 4: queries sharing one pass over the slab
 cudaError_t trr_launch_scan_tma(const DenseScanArgs& a, const void* map_rows128, int is_bf16, int metric, unsigned grid,
-                                unsigned n_warps, size_t smem, cudaStream_t st);
-size_t trr_scan_tma_smem(uint32_t dim, uint32_t cap, uint32_t n_slots, uint32_t n_warps);
+                                unsigned n_warps, uint32_t nq, size_t smem, cudaStream_t st);
+size_t trr_scan_tma_smem(uint32_t dim, uint32_t cap, uint32_t n_slots, uint32_t n_warps, uint32_t nq);
 cudaError_t trr_launch_topk_merge(const TopkMergeArgs& a, unsigned grid, cudaStream_t st);
 cudaError_t trr_launch_rescore(const RescoreArgs& a, int is_bf16, cudaStream_t st);
 

@@ -264,7 +264,10 @@ dense_scan_bulk_kernel(DenseScanArgs a) {
 // loads (chunk j of row r sits at 16-byte position j ^ (r & 7)); an elected lane refills a slot as soon as the warp has
 // consumed it, which keeps (n_slots - 1) x 4 KB per warp in flight at all times.  Rows past the end of the slab are
 // zero-filled by the TMA unit.  The arithmetic per row is the same strict sequence as everywhere else in this file.
-template <int IS_BF16, int METRIC>
+// NQ queries share one pass over the slab (NQ = 1 for a single query; NQ = 4 when several queries take the exact path:
+// Euclidean or k > 100 batches, queries whose candidate proof failed): every row element is loaded once and feeds NQ
+// independent strict chains, so four queries cost about one pass instead of four.
+template <int IS_BF16, int METRIC, int NQ>
 __global__ void __launch_bounds__(512, 1)
 dense_scan_tma_kernel(const __grid_constant__ CUtensorMap map, DenseScanArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
@@ -277,10 +280,11 @@ dense_scan_tma_kernel(const __grid_constant__ CUtensorMap map, DenseScanArgs a) 
   uint8_t* ring = smem + (size_t)warp * S * SLOT;
   float* qs = reinterpret_cast<float*>(smem + (size_t)NWARPS * S * SLOT);
   const uint32_t q_bytes = (a.dim * 4 + 127) & ~127u;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(qs) + q_bytes) + (size_t)warp * S;
-  uint32_t* warp_cnt = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(qs) + q_bytes + (size_t)NWARPS * S * 8);
-  uint64_t* tk_base = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(warp_cnt) + 64);
-  uint64_t* tk_buf = tk_base + (size_t)warp * a.cap;
+  const uint32_t q_floats = q_bytes >> 2;
+  uint8_t* after_q = reinterpret_cast<uint8_t*>(qs) + (size_t)NQ * q_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after_q) + (size_t)warp * S;
+  uint32_t* warp_cnt = reinterpret_cast<uint32_t*>(after_q + (size_t)NWARPS * S * 8);
+  uint64_t* tk_base = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(warp_cnt) + 64);  // [NQ][NWARPS][cap]
 
   if (lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map) : "memory");
@@ -299,14 +303,20 @@ dense_scan_tma_kernel(const __grid_constant__ CUtensorMap map, DenseScanArgs a) 
   uint32_t c_slot = 0, c_par = 0;  // consumer position in the ring (persists across queries)
   uint32_t i_slot = 0;             // producer position
 
-  for (uint32_t si = 0; si < n_sel; ++si) {
-    const uint32_t qi = a.sel ? a.sel[si] : si;
-    __syncthreads();  // previous query's reads of qs are done
-    for (uint32_t j = threadIdx.x; j < a.dim; j += blockDim.x) qs[j] = a.q[(uint64_t)qi * a.dim + j];
+  for (uint32_t si = 0; si < n_sel; si += NQ) {
+    const uint32_t nq = min((uint32_t)NQ, n_sel - si);
+    __syncthreads();  // previous group's reads of qs are done
+    float q_norm[NQ];
+    WarpTopK tk[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const uint32_t qi = (uint32_t)q < nq ? (a.sel ? a.sel[si + q] : si + q) : 0u;
+      for (uint32_t j = threadIdx.x; j < a.dim; j += blockDim.x)
+        qs[q * q_floats + j] = (uint32_t)q < nq ? a.q[(uint64_t)qi * a.dim + j] : 0.0f;
+      q_norm[q] = (uint32_t)q < nq ? a.q_norms[qi] : 0.0f;
+      tk[q].init(tk_base + ((size_t)q * NWARPS + warp) * a.cap, a.cap, a.k);
+    }
     __syncthreads();
-    const float q_norm = a.q_norms[qi];
-    WarpTopK tk;
-    tk.init(tk_buf, a.cap, a.k);
 
     // producer state: next box to request = (group i_k, box i_c)
     uint64_t i_k = 0;
@@ -325,21 +335,26 @@ dense_scan_tma_kernel(const __grid_constant__ CUtensorMap map, DenseScanArgs a) 
 
     for (uint64_t k = 0; k < n_my; ++k) {
       const uint64_t row = (gwarp + k * gstride) * 32 + lane;
-      float acc = 0.0f;
+      float acc[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) acc[q] = 0.0f;
       for (uint32_t c = 0; c < n_boxes; ++c) {
         trr_mbar_wait_bounded(&bars[c_slot], c_par);
         const uint8_t* rp = lane_base + (size_t)c_slot * SLOT;
         const uint32_t left = a.row_bytes - (c << 7);
         const uint32_t nvec = left >= 128 ? 8u : (left >> 4);
         if (IS_BF16) {
-          const float4* qp = reinterpret_cast<const float4*>(qs + c * 64);
           auto step = [&](uint32_t j) {
             const uint4 v = *reinterpret_cast<const uint4*>(rp + ((j ^ sw) << 4));
-            const float4 q0 = qp[2 * j], q1 = qp[2 * j + 1];
-            acc_step<METRIC>(acc, q0.x, bf16lo(v.x)); acc_step<METRIC>(acc, q0.y, bf16hi(v.x));
-            acc_step<METRIC>(acc, q0.z, bf16lo(v.y)); acc_step<METRIC>(acc, q0.w, bf16hi(v.y));
-            acc_step<METRIC>(acc, q1.x, bf16lo(v.z)); acc_step<METRIC>(acc, q1.y, bf16hi(v.z));
-            acc_step<METRIC>(acc, q1.z, bf16lo(v.w)); acc_step<METRIC>(acc, q1.w, bf16hi(v.w));
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+              const float4* qp = reinterpret_cast<const float4*>(qs + q * q_floats + c * 64);
+              const float4 q0 = qp[2 * j], q1 = qp[2 * j + 1];
+              acc_step<METRIC>(acc[q], q0.x, bf16lo(v.x)); acc_step<METRIC>(acc[q], q0.y, bf16hi(v.x));
+              acc_step<METRIC>(acc[q], q0.z, bf16lo(v.y)); acc_step<METRIC>(acc[q], q0.w, bf16hi(v.y));
+              acc_step<METRIC>(acc[q], q1.x, bf16lo(v.z)); acc_step<METRIC>(acc[q], q1.y, bf16hi(v.z));
+              acc_step<METRIC>(acc[q], q1.z, bf16lo(v.w)); acc_step<METRIC>(acc[q], q1.w, bf16hi(v.w));
+            }
           };
           if (nvec == 8) {
 #pragma unroll
@@ -348,12 +363,14 @@ dense_scan_tma_kernel(const __grid_constant__ CUtensorMap map, DenseScanArgs a) 
             for (uint32_t j = 0; j < nvec; ++j) step(j);
           }
         } else {
-          const float4* qp = reinterpret_cast<const float4*>(qs + c * 32);
           auto step = [&](uint32_t j) {
             const uint4 v = *reinterpret_cast<const uint4*>(rp + ((j ^ sw) << 4));
-            const float4 qq = qp[j];
-            acc_step<METRIC>(acc, qq.x, __uint_as_float(v.x)); acc_step<METRIC>(acc, qq.y, __uint_as_float(v.y));
-            acc_step<METRIC>(acc, qq.z, __uint_as_float(v.z)); acc_step<METRIC>(acc, qq.w, __uint_as_float(v.w));
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+              const float4 qq = reinterpret_cast<const float4*>(qs + q * q_floats + c * 32)[j];
+              acc_step<METRIC>(acc[q], qq.x, __uint_as_float(v.x)); acc_step<METRIC>(acc[q], qq.y, __uint_as_float(v.y));
+              acc_step<METRIC>(acc[q], qq.z, __uint_as_float(v.z)); acc_step<METRIC>(acc[q], qq.w, __uint_as_float(v.w));
+            }
           };
           if (nvec == 8) {
 #pragma unroll
@@ -367,16 +384,27 @@ dense_scan_tma_kernel(const __grid_constant__ CUtensorMap map, DenseScanArgs a) 
         if (++c_slot == S) { c_slot = 0; c_par ^= 1; }
       }
       const bool valid = row < a.n_rows && !(a.dead && a.dead[row]);
-      float score = 0.0f;
-      if (valid) score = finish_score<METRIC>(acc, q_norm, METRIC == TRR_METRIC_COSINE ? a.norms[row] : 0.0f);
-      tk.push(trr_make_key(score, a.base_ord + (uint32_t)row), valid, lane);
+      const float d_norm = (valid && METRIC == TRR_METRIC_COSINE) ? a.norms[row] : 0.0f;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        if ((uint32_t)q < nq) {  // uniform across the warp
+          float score = 0.0f;
+          if (valid) score = finish_score<METRIC>(acc[q], q_norm[q], d_norm);
+          tk[q].push(trr_make_key(score, a.base_ord + (uint32_t)row), valid, lane);
+        }
+      }
     }
-    // ring is empty here: every box requested for this query has been consumed; i_slot == c_slot
+    // ring is empty here: every box requested for this group has been consumed; i_slot == c_slot
     i_slot = __shfl_sync(FULL, i_slot, 0);
-    tk.compact(lane);
-    cta_merge_and_store(tk, tk_base, a.cap, NWARPS, warp, lane, warp_cnt,
-                        a.partial + ((uint64_t)si * gridDim.x + blockIdx.x) * a.k,
-                        a.partial_n + ((uint64_t)si * gridDim.x + blockIdx.x));
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      if ((uint32_t)q < nq) {  // uniform across the CTA
+        tk[q].compact(lane);
+        cta_merge_and_store(tk[q], tk_base + (size_t)q * NWARPS * a.cap, a.cap, NWARPS, warp, lane, warp_cnt,
+                            a.partial + ((uint64_t)(si + q) * gridDim.x + blockIdx.x) * a.k,
+                            a.partial_n + ((uint64_t)(si + q) * gridDim.x + blockIdx.x));
+      }
+    }
   }
 }
 
@@ -798,17 +826,17 @@ cudaError_t trr_launch_scan(const DenseScanArgs& a, int is_bf16, int metric, boo
   return cudaErrorInvalidValue;
 }
 
-size_t trr_scan_tma_smem(uint32_t dim, uint32_t cap, uint32_t n_slots, uint32_t n_warps) {
-  return 1024 + (size_t)n_warps * n_slots * 4096 + ((dim * 4 + 127) & ~127u) + (size_t)n_warps * n_slots * 8 + 64 +
-         (size_t)n_warps * cap * 8;
+size_t trr_scan_tma_smem(uint32_t dim, uint32_t cap, uint32_t n_slots, uint32_t n_warps, uint32_t nq) {
+  return 1024 + (size_t)n_warps * n_slots * 4096 + (size_t)nq * ((dim * 4 + 127) & ~127u) + (size_t)n_warps * n_slots * 8 + 64 +
+         (size_t)nq * n_warps * cap * 8;
 }
 
-template <int IS_BF16, int METRIC>
+template <int IS_BF16, int METRIC, int NQ>
 static cudaError_t launch_scan_tma_t(const DenseScanArgs& a, const void* map128, unsigned grid, unsigned n_warps, size_t smem,
                                      cudaStream_t st) {
   CUtensorMap m;
   memcpy(&m, map128, 128);
-  auto kern = dense_scan_tma_kernel<IS_BF16, METRIC>;
+  auto kern = dense_scan_tma_kernel<IS_BF16, METRIC, NQ>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, 32 * n_warps, smem, st>>>(m, a);
@@ -816,9 +844,11 @@ static cudaError_t launch_scan_tma_t(const DenseScanArgs& a, const void* map128,
 }
 
 cudaError_t trr_launch_scan_tma(const DenseScanArgs& a, const void* map128, int is_bf16, int metric, unsigned grid,
-                                unsigned n_warps, size_t smem, cudaStream_t st) {
-#define TRR_SCAN_CASE(B, M) \
-  if (is_bf16 == B && metric == M) return launch_scan_tma_t<B, M>(a, map128, grid, n_warps, smem, st)
+                                unsigned n_warps, uint32_t nq, size_t smem, cudaStream_t st) {
+#define TRR_SCAN_CASE(B, M)                                                                          \
+  if (is_bf16 == B && metric == M)                                                                   \
+    return nq == 4 ? launch_scan_tma_t<B, M, 4>(a, map128, grid, n_warps, smem, st)                  \
+                   : launch_scan_tma_t<B, M, 1>(a, map128, grid, n_warps, smem, st)
   TRR_SCAN_CASE(0, TRR_METRIC_COSINE);
   TRR_SCAN_CASE(0, TRR_METRIC_EUCLIDEAN);
   TRR_SCAN_CASE(0, TRR_METRIC_DOT);
