@@ -58,7 +58,8 @@ def config(a, extra=None):
     c = {"workload": f"cfg4 hybrid dense+BM25 RRF k=60: {a.docs}x{a.dim} bf16, Zipf BM25 vocab {a.vocab}, "
                      f"batch {a.batch}, C={a.cands}, top-{a.k}",
          "docs": a.docs, "dim": a.dim, "batch": a.batch, "vocab": a.vocab, "candidates_per_source": a.cands, "k": a.k,
-         "fusion": "RRF k=60", "queries": "bf16-rounded" if getattr(a, "bf16_queries", False) else "f32 (embedder output; the store is bf16)",
+         "fusion": "RRF k=60", "exchange": "all-gather + merge of step i on a second stream, overlapped with the shard-local kernels of step i+1" if a.gpus > 1 else "none (one shard)",
+         "queries": "bf16-rounded" if getattr(a, "bf16_queries", False) else "f32 (embedder output; the store is bf16)",
          "sharding": f"documents, contiguous ranges over {a.gpus} GPU(s)",
          "l2": "inputs (>=1.9 GB of embeddings per GPU) exceed the 126 MB L2; no flush needed"}
     if extra:
@@ -266,13 +267,45 @@ def run_ours(a):
             return d_gath
         return d_rec
 
+    # Sharded runs overlap the exchange with compute: the shard-local kernels of step i+1 run on the compute stream while the
+    # all-gather and the merge + fusion kernel of step i run on a second stream (exchange records and gather buffers are
+    # double-buffered; events order record reuse).  This hides the all-gather latency and the skew between ranks.
+    pipelined = world > 1 and not os.environ.get("TRR_BENCH_NO_PIPELINE")
+    if pipelined:
+        s_main = torch.cuda.current_stream()
+        s_xchg = torch.cuda.Stream()
+        ctx_x = api.Context(local_rank)
+        api._check(L.trr_ctx_set_stream(ctx_x.h, C.c_void_p(s_xchg.cuda_stream)))
+        recs = [d_rec, torch.zeros_like(d_rec)]
+        gaths = [d_gath, torch.zeros_like(d_gath)]
+        ev_local = [torch.cuda.Event(), torch.cuda.Event()]
+        ev_gath = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in ev_gath:
+            e.record(s_xchg)
+        step_no = [0]
+
     def step_device():
+        if not pipelined:
+            api._check(L.trr_hybrid_local_device(dense.h, bm.h, C.c_void_p(d_q.data_ptr()), C.c_void_p(d_terms.data_ptr()),
+                                                 C.c_void_p(d_off.data_ptr()), q_off.ctypes.data_as(u32p), B, Cn, 1, 1,
+                                                 C.c_void_p(d_rec.data_ptr())))
+            g = gather()
+            api._check(L.trr_hybrid_merge_device(ctx.h, C.c_void_p(g.data_ptr()), world, B, Cn, api.RRF, 60.0, K,
+                                                 *[C.c_void_p(t.data_ptr()) for t in d_out]))
+            return
+        p = step_no[0] & 1
+        step_no[0] += 1
+        s_main.wait_event(ev_gath[p])                      # the all-gather of step i-2 has consumed recs[p]
         api._check(L.trr_hybrid_local_device(dense.h, bm.h, C.c_void_p(d_q.data_ptr()), C.c_void_p(d_terms.data_ptr()),
                                              C.c_void_p(d_off.data_ptr()), q_off.ctypes.data_as(u32p), B, Cn, 1, 1,
-                                             C.c_void_p(d_rec.data_ptr())))
-        g = gather()
-        api._check(L.trr_hybrid_merge_device(ctx.h, C.c_void_p(g.data_ptr()), world, B, Cn, api.RRF, 60.0, K,
-                                             *[C.c_void_p(t.data_ptr()) for t in d_out]))
+                                             C.c_void_p(recs[p].data_ptr())))
+        ev_local[p].record(s_main)
+        with torch.cuda.stream(s_xchg):
+            s_xchg.wait_event(ev_local[p])
+            dist.all_gather_into_tensor(gaths[p], recs[p])
+            ev_gath[p].record(s_xchg)
+            api._check(L.trr_hybrid_merge_device(ctx_x.h, C.c_void_p(gaths[p].data_ptr()), world, B, Cn, api.RRF, 60.0, K,
+                                                 *[C.c_void_p(t.data_ptr()) for t in d_out]))
 
     def step_e2e():
         api.hybrid_local(dense, bm, q_np, q_terms[:nt], q_off, Cn, d_rec.data_ptr())       # H2D of queries inside
@@ -293,6 +326,8 @@ def run_ours(a):
             r = fn()
             if collect is not None:
                 collect(r)
+        if pipelined:
+            torch.cuda.current_stream().wait_stream(s_xchg)   # the timed region ends when the last merge has finished
         ev1.record()
         barrier()
         ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
@@ -317,6 +352,7 @@ def run_ours(a):
     launches1 = C.c_uint64()
     L.trr_ctx_launch_count(ctx.h, C.byref(launches1))
     clocks = sampler.stop() if rank == 0 else None
+    d_out_snapshot = [t.clone() for t in d_out]       # results of the last timed (device-resident) step
     # per-kernel device times: the library records CUDA events around its dominant kernels on the launching stream at every
     # step; what is read here (the stream is idle after the closing barrier) are the events of the LAST TIMED step
     sd_t, sb_t = dense.stats(), bm.stats()
@@ -337,6 +373,15 @@ def run_ours(a):
     verify = None
     if rank == 0 and a.verify > 0:
         verify = verify_full_size(a, api, dense, bm, q_np, q_terms[:nt], q_off, host_csr, last[-1], world)
+        # the device-resident (and, when sharded, pipelined) step must have produced exactly what the host-buffer call returns
+        dev_out = [t.cpu().numpy() for t in d_out_snapshot]
+        e_ord, e_f, e_d, e_s, e_n = last[-1]
+        same = np.array_equal(dev_out[4].view(np.uint32), e_n)
+        for b in range(B):
+            m = int(e_n[b])
+            same = same and np.array_equal(dev_out[0][b, :m].view(np.uint32), e_ord[b, :m]) and np.array_equal(dev_out[1][b, :m], e_f[b, :m])
+        verify["device_step_equals_host_buffer_call"] = bool(same)
+        verify["consistent"] = bool(verify.get("consistent", True) and same)
 
     if rank == 0:
         peaks = {}
@@ -378,6 +423,7 @@ def run_ours(a):
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a)
         print(json.dumps(line), flush=True)
+    torch.cuda.synchronize()
     dense.close(); bm.close(); ctx.close()
     if world > 1:
         dist.destroy_process_group()
