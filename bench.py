@@ -379,11 +379,16 @@ def run_ours(a):
     for _ in range(min(a.steps, 3)):
         step_device()
         collect_stats(None)
+    # e2e (headline): the blocking host-buffer C-ABI calls, exactly what a host-language shim would call per batch
+    for _ in range(max(1, a.warmup // 2)):
+        step_host_buffers()
+    last = []
+    ms_e2e = timed(step_host_buffers, a.steps, collect=lambda r: last.append(r))
+    # secondary: the same work with asynchronous pinned copies around the device-resident step (a serving loop)
     for _ in range(max(1, a.warmup // 2)):
         step_e2e()
-    ms_e2e = timed(step_e2e, a.steps)
-    e2e_out = [t.numpy().copy() for t in out_pin]     # what the last end-to-end step delivered to the host
-    last = [step_host_buffers()]                      # the blocking host-buffer calls on the same inputs
+    ms_e2e_async = timed(step_e2e, a.steps)
+    e2e_out = [t.numpy().copy() for t in out_pin]     # what the last asynchronous end-to-end step delivered to the host
     launches = torch.tensor([launches1.value - launches0.value], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(launches)
@@ -427,7 +432,9 @@ def run_ours(a):
             "dtype": "bf16", "data": "synthetic",
             "config": config(a, {"setup_s": round(setup_s, 1), "docs_per_gpu": n_loc}),
             "e2e": {"value": B / e2e_ms * 1e3, "unit": "queries/s", "ms_per_step": e2e_ms,
-                    "how": "per step: async H2D of the queries / terms / offsets from pinned memory, device-resident hybrid step, async D2H of the results into pinned memory; verified against the blocking host-buffer C-ABI calls",
+                    "how": "per step: the blocking host-buffer C-ABI calls trr_hybrid_local + (all-gather) + trr_hybrid_merge: H2D of queries / terms / offsets, kernels, D2H of the results, synchronised",
+                    "async_pinned": {"value": B / (ms_e2e_async / a.steps) * 1e3, "unit": "queries/s",
+                                     "how": "same bytes per step with asynchronous copies from / to pinned memory around the device-resident step (copies overlap neighbouring steps); results verified against the blocking calls"},
                     "h2d_bytes_per_step": int(B * D * 4 + nt * 4 + (B + 1) * 4), "d2h_bytes_per_step": int(B * K * 16 + B * 4)},
             "gpu_launches": int(launches.item()),
             "roofline": {"kernel": "dense_gemm_topk_kernel (tcgen05 bf16 GEMM + fused top-k), rank 0 shard",
