@@ -627,12 +627,16 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     // list length per (query, slice): the global top-CP by fast score is spread over the slices (about CP / n_slices
     // per slice), so short lists suffice when there are many slices (Poisson tail < 1e-6 for the choices below); the
     // candidate proof (rescore_select_kernel) catches the data sets where they do not
-    const float per_slice = (float)CP / (float)n_slices;
+    // The 1-CTA kernel keeps one list per HALF slice (its two epilogue warp groups split the columns of every tile), so
+    // the re-scoring kernel sees 2 * n_slices "virtual" slices of at most TRR_GEMM_CPS_MAX entries.
+    const uint32_t vslices = pair_mode ? n_slices : 2 * n_slices;
+    const uint32_t cps_max = pair_mode ? TRR_GEMM_CP : TRR_GEMM_CPS_MAX;
+    const float per_slice = (float)CP / (float)vslices;
     uint32_t cps = per_slice <= 1.0f ? 8u : (per_slice <= 4.0f ? 16u : (per_slice <= 10.0f ? 32u : 64u));
     if (const char* e = getenv("TRR_GEMM_CPS")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32 || v == 64) cps = (uint32_t)v; }
-    if ((uint64_t)n_slices * cps < CP) cps = TRR_GEMM_CP;  // (n_slices * 64 >= CP is checked before taking this path)
-    const size_t n_cand = (size_t)n_slices * n_qblocks * TRR_GEMM_TILE_M * cps;
-    const uint32_t cap2 = std::max<uint32_t>(trr_pow2_ceil(n_slices * cps), 2 * CP);
+    if (cps > cps_max || (uint64_t)vslices * cps < CP) cps = cps_max;  // (vslices * cps_max >= CP is checked before taking this path)
+    const size_t n_cand = (size_t)vslices * n_qblocks * TRR_GEMM_TILE_M * cps;
+    const uint32_t cap2 = std::max<uint32_t>(trr_pow2_ceil(vslices * cps), 2 * CP);
     // scratch layout (single reservation so that pointers stay valid)
     ScanPlan p;
     TRR_CHECK(plan_scan(h, k, &p, B));
@@ -681,7 +685,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     c->launches++;
 
     RescoreArgs ra{};
-    ra.cand_score = cand_score; ra.cand_ord = cand_ord; ra.n_slices = n_slices; ra.n_qblocks = n_qblocks;
+    ra.cand_score = cand_score; ra.cand_ord = cand_ord; ra.n_slices = vslices; ra.n_qblocks = n_qblocks;
     ra.cps = cps; ra.cp = CP; ra.cap2 = cap2;
     ra.rows = h->rows; ra.dim = h->dim; ra.norms = h->norms; ra.base_ord = h->base; ra.n_live = n_live;
     ra.q = d_q; ra.q_norms = d_qn; ra.q_norms_out = nullptr; ra.q_delta = d_qdelta; ra.max_norm = reinterpret_cast<const float*>(h->max_norm.p);
@@ -707,7 +711,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     // k) is re-scored over EVERYTHING the slices kept (n_slices x cps candidates instead of the best CP), so that the only
     // documents left out are the ones the slices dropped, which sit far further down the ranking.  Only the queries that
     // still fail go to the exact scan.  CTAs beyond the device-side count of flagged queries return at once.
-    const uint32_t cp_wide = trr_pow2_ceil(n_slices * cps);
+    const uint32_t cp_wide = trr_pow2_ceil(vslices * cps);
     uint32_t* flagged_final = flagged;
     uint32_t* counters_final = counters;
     if (cp_wide > CP && cp_wide <= 2048 && !getenv("TRR_GEMM_NO_WIDE")) {
@@ -834,7 +838,7 @@ extern "C" TRR_API int trr_debug_gemm_scores(trr_dense* h, const float* q, uint3
   const uint64_t n_pad = h->n_tiles * TRR_GEMM_TILE_N;
   if (out_ld < n_pad) return trr_fail(TRR_ERR_INVALID_ARG, "out_ld must be >= padded document count");
   uint32_t n_slices = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)c->sm_count / n_qblocks, (uint32_t)h->n_tiles));
-  const size_t n_cand = (size_t)n_slices * n_qblocks * 128 * TRR_GEMM_CP;
+  const size_t n_cand = (size_t)2 * n_slices * n_qblocks * 128 * TRR_GEMM_CP;
   const size_t need = WsCarver::need({(size_t)B * h->dim * 4, (size_t)B * 4, n_cand * 4, n_cand * 4, (size_t)B_pad * 4,
                                       (size_t)B_pad * h->dim_pad * 2, (size_t)B_pad * out_ld * 4});
   TRR_CHECK(extra(c)->scratch.reserve(need));
@@ -857,7 +861,7 @@ extern "C" TRR_API int trr_debug_gemm_scores(trr_dense* h, const float* q, uint3
   ga.k_blocks = (h->dim_pad + 63) / 64; ga.base_ord = h->base;
   ga.scale_bias = reinterpret_cast<const float2*>(h->scale_bias.p);
   ga.cand_score = cand_score; ga.cand_ord = cand_ord; ga.gthr = gthr; ga.share_thresholds = 0;
-  ga.pair_mode = pair_mode; ga.cps = TRR_GEMM_CP;
+  ga.pair_mode = pair_mode; ga.cps = pair_mode ? TRR_GEMM_CP : TRR_GEMM_CPS_MAX;
   ga.dbg = extra(c)->dbg_dev;
   TRR_CUDA(trr_launch_gemm_topk_dump(ga, map_q, pair_mode ? h->map_d_half : h->map_d, n_slices * n_qblocks, dump, out_ld,
                                      st));

@@ -48,13 +48,23 @@ constexpr uint32_t B_BYTES = BN * BK * 2;  // 32 KB
 #endif
 constexpr uint32_t LSTRIDE = TRR_GEMM_LSTRIDE;                 // words per row of a candidate list: odd, so lane == row is conflict-free
 constexpr uint32_t LIST_BYTES = BM * LSTRIDE * 4;
+// 1-CTA kernel: 8 epilogue warps; the two warps that share a TMEM lane quarter split the 256 columns of a tile into
+// halves, and every (row, half) owns a candidate list of up to L1MAX entries: [half][row][L1STRIDE] (odd stride: lanes of
+// a warp are consecutive rows of one half, conflict-free).
+constexpr uint32_t L1MAX = TRR_GEMM_CPS_MAX;
+constexpr uint32_t L1STRIDE = L1MAX + 1;
+constexpr uint32_t LIST1_BYTES = 2 * BM * L1STRIDE * 4;
+constexpr uint32_t SB_BYTES = BN * 8;  // scale/bias of one document tile
 constexpr uint32_t SMEM_A = 0;
 constexpr uint32_t SMEM_B = SMEM_A + STAGES * A_BYTES;
 constexpr uint32_t SMEM_LS = SMEM_B + STAGES * B_BYTES;
-constexpr uint32_t SMEM_LO = SMEM_LS + LIST_BYTES;
-constexpr uint32_t SMEM_BAR = SMEM_LO + LIST_BYTES;
+constexpr uint32_t SMEM_LO = SMEM_LS + LIST1_BYTES;
+constexpr uint32_t SMEM_SB = SMEM_LO + LIST1_BYTES;
+constexpr uint32_t SMEM_BAR = SMEM_SB + 2 * SB_BYTES;
 constexpr uint32_t SMEM_TOTAL = SMEM_BAR + 256;
-constexpr uint32_t GEMM_THREADS = 192;
+static_assert(SMEM_TOTAL <= 227 * 1024, "1-CTA GEMM shared memory");
+constexpr uint32_t GEMM_THREADS = 192;   // 2-CTA kernel: TMA, MMA, 4 epilogue warps
+constexpr uint32_t GEMM1_THREADS = 320;  // 1-CTA kernel: TMA, MMA, 8 epilogue warps
 
 // instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), both K-major
 // (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
@@ -186,7 +196,7 @@ __device__ __noinline__ RowState insert_private(RowState st, float s, uint32_t d
 
 }  // namespace
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM1_THREADS, 1)
 dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d,
                        GemmTopkArgs a, float* __restrict__ dump, uint32_t dump_ld) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -195,7 +205,8 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* sbfull_bar = tempty_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sbfull_bar + 2);
 
   const uint32_t qb = blockIdx.x % a.n_qblocks;
   const uint32_t slice = blockIdx.x / a.n_qblocks;
@@ -206,7 +217,11 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_d) : "memory");
     for (uint32_t s = 0; s < STAGES; ++s) { trr_mbar_init(&full_bar[s], 1); trr_mbar_init(&empty_bar[s], 1); }
-    for (uint32_t s = 0; s < 2; ++s) { trr_mbar_init(&tfull_bar[s], 1); trr_mbar_init(&tempty_bar[s], 128); }
+    for (uint32_t s = 0; s < 2; ++s) {
+      trr_mbar_init(&tfull_bar[s], 1);
+      trr_mbar_init(&tempty_bar[s], 8);  // one arrival per epilogue warp
+      trr_mbar_init(&sbfull_bar[s], 1);
+    }
     trr_fence_mbar_init();
   }
   if (warp == 1) {  // TMEM: 512 columns = 2 accumulator stages of 256 f32 columns
@@ -241,6 +256,11 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       mbar_wait_bounded(&tempty_bar[as], aphase ^ 1, 2, a.dbg);
       tc_fence_after();
+      // the epilogue of tile it-2 has let go of this stage's scale/bias buffer as well: refill it for tile t
+      if (lane == 0) {
+        trr_mbar_expect_tx(&sbfull_bar[as], SB_BYTES);
+        trr_bulk_g2s(smem + SMEM_SB + as * SB_BYTES, a.scale_bias + (uint64_t)t * BN, SB_BYTES, &sbfull_bar[as]);
+      }
       for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
         mbar_wait_bounded(&full_bar[stage], phase, 3, a.dbg);
         tc_fence_after();
@@ -260,13 +280,12 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       }
     }
   } else {
-    // ===================== epilogue =====================
+    // ===================== epilogue (8 warps) =====================
     const uint32_t quarter = warp & 3;            // TMEM lane group this warp may access
+    const uint32_t half = (warp - 2) >> 2;        // which 128 columns of every tile this warp reads
     const uint32_t row = quarter * 32 + lane;     // query row inside the block
-    float* ls_all = reinterpret_cast<float*>(smem + SMEM_LS);
-    uint32_t* lo_all = reinterpret_cast<uint32_t*>(smem + SMEM_LO);
-    float* my_ls = ls_all + row * LSTRIDE;
-    uint32_t* my_lo = lo_all + row * LSTRIDE;
+    float* my_ls = reinterpret_cast<float*>(smem + SMEM_LS) + (half * BM + row) * L1STRIDE;
+    uint32_t* my_lo = reinterpret_cast<uint32_t*>(smem + SMEM_LO) + (half * BM + row) * L1STRIDE;
     const uint32_t cps = a.cps;
     for (uint32_t j = 0; j < cps; ++j) { my_ls[j] = -CUDART_INF_F; my_lo[j] = 0xFFFFFFFFu; }
     RowState st;
@@ -274,42 +293,41 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     st.minpos = 0;
     st.thr = -CUDART_INF_F;           // max(list_min, shared threshold)
     uint32_t* gthr = a.gthr + (qb * BM + row);
+    constexpr uint32_t CHUNKS = BN / 64;  // 32-column chunks per warp and tile
 
-    // scale/bias of the next 32 columns are prefetched one chunk ahead (16 x LDG.128, L1/L2 hits)
-    float4 sb_cur[16];
-    {
-      const float4* p = reinterpret_cast<const float4*>(a.scale_bias + (uint64_t)t0 * BN);
-#pragma unroll
-      for (uint32_t i = 0; i < 16; ++i) sb_cur[i] = __ldg(p + i);
-    }
     for (uint32_t t = t0, it = 0; t < t1; ++t, ++it) {
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       if (a.share_thresholds) {
         const uint32_t g = *reinterpret_cast<volatile uint32_t*>(gthr);
         if (g > trr_f32_orderable(st.thr)) st.thr = trr_orderable_f32(g);
       }
+      mbar_wait_bounded(&sbfull_bar[as], aphase, 5, a.dbg);
       mbar_wait_bounded(&tfull_bar[as], aphase, 4, a.dbg);
       tc_fence_after();
-      const uint32_t doc0 = t * BN;
+      const uint32_t doc0 = t * BN + half * (BN / 2);
+      const float4* sbs = reinterpret_cast<const float4*>(smem + SMEM_SB + as * SB_BYTES) + half * (BN / 4);
 #pragma unroll 1
-      for (uint32_t c = 0; c < (a.debug_mode == 1 ? 0u : BN / 32); ++c) {
+      for (uint32_t c = 0; c < (a.debug_mode == 1 ? 0u : CHUNKS); ++c) {
         uint32_t v[32];
-        tmem_ld32_issue(tmem_base + ((quarter * 32u) << 16) + as * BN + c * 32, v);
-        // prefetch the next chunk's scale/bias (next tile's first chunk at the end of a tile)
-        float4 sb_nxt[16];
-        {
-          uint64_t nd = (uint64_t)doc0 + (c + 1) * 32;
-          if (c == BN / 32 - 1 && t + 1 >= t1) nd = (uint64_t)doc0;  // nothing follows: reload something valid
-          const float4* p = reinterpret_cast<const float4*>(a.scale_bias + nd);
+        if (a.debug_mode != 4) {  // (4: perf triage without the TMEM reads)
+          tmem_ld32_issue(tmem_base + ((quarter * 32u) << 16) + as * BN + half * (BN / 2) + c * 32, v);
+          tmem_ld32_wait(v);
+        } else {
 #pragma unroll
-          for (uint32_t i = 0; i < 16; ++i) sb_nxt[i] = __ldg(p + i);
+          for (uint32_t j = 0; j < 32; ++j) v[j] = c + j;
         }
-        tmem_ld32_wait(v);
+        if (a.debug_mode == 3) {  // perf triage: TMEM reads only
+          uint32_t x = 0;
+#pragma unroll
+          for (uint32_t j = 0; j < 32; ++j) x ^= v[j];
+          if (x == 0x7FC12345u) st.thr = 0.0f;
+          continue;
+        }
         float sv[32];
         uint32_t pmask = 0;
 #pragma unroll
         for (uint32_t j = 0; j < 32; j += 2) {
-          const float4 sb = sb_cur[j >> 1];
+          const float4 sb = sbs[c * 16 + (j >> 1)];  // same address in every lane: broadcast
           sv[j] = fmaf(__uint_as_float(v[j]), sb.x, sb.y);
           sv[j + 1] = fmaf(__uint_as_float(v[j + 1]), sb.z, sb.w);
           pmask |= (sv[j] > st.thr ? 1u : 0u) << j;
@@ -327,16 +345,15 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
           for (uint32_t j = 0; j < 32; ++j)
             if (pmask & (1u << j)) st = insert_private(st, sv[j], dbase + j, my_ls, my_lo, cps);
         }
-#pragma unroll
-        for (uint32_t i = 0; i < 16; ++i) sb_cur[i] = sb_nxt[i];
       }
-      // accumulator stage drained: hand it back to the MMA warp
+      // accumulator stage and scale/bias buffer drained: hand them back to the MMA warp
       tc_fence_before();
-      trr_mbar_arrive(&tempty_bar[as]);
+      __syncwarp();
+      if (lane == 0) trr_mbar_arrive(&tempty_bar[as]);
       if (a.share_thresholds && st.list_min > -CUDART_INF_F) atomicMax(gthr, trr_f32_orderable(st.list_min));
     }
-    // publish this slice's candidates
-    const uint64_t base = (((uint64_t)slice * a.n_qblocks + qb) * BM + row) * cps;
+    // publish this half-slice's candidates: virtual slice 2 * slice + half
+    const uint64_t base = (((uint64_t)(slice * 2 + half) * a.n_qblocks + qb) * BM + row) * cps;
     for (uint32_t j = 0; j < cps; ++j) { a.cand_score[base + j] = my_ls[j]; a.cand_ord[base + j] = my_lo[j]; }
   }
 
@@ -707,7 +724,7 @@ cudaError_t trr_launch_gemm_topk_dump(const GemmTopkArgs& a, const void* map_q12
                                          (int)SMEM_TOTAL);
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(dense_gemm_topk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    dense_gemm_topk_kernel<<<grid, GEMM_THREADS, SMEM_TOTAL, st>>>(mq, md, a, dump, dump_ld);
+    dense_gemm_topk_kernel<<<grid, GEMM1_THREADS, SMEM_TOTAL, st>>>(mq, md, a, dump, dump_ld);
   }
   return cudaGetLastError();
 }

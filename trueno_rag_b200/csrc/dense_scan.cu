@@ -548,7 +548,7 @@ rescore_select_kernel(RescoreArgs a) {
   uint64_t* ekeys = keys + a.cap2;                                     // CP exact keys (CP power of two)
   __shared__ float s_gap, s_qnorm;
   __shared__ uint32_t s_total, s_tmax;
-  __shared__ uint32_t s_smin[160], s_scnt[160];  // per document slice (at most one slice per SM): list minimum, fill count
+  __shared__ uint32_t s_smin[320], s_scnt[320];  // per candidate list (at most two half slices per SM): list minimum, fill count
   // first pass: CTA == query.  Second (wide) pass: CTA i re-scores the i-th query flagged by the first pass
   if (a.sel_n && blockIdx.x >= *a.sel_n) return;
   const uint32_t b = a.sel ? a.sel[blockIdx.x] : blockIdx.x;
