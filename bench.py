@@ -437,7 +437,7 @@ def run_ours(a):
                                      "how": "same bytes per step with asynchronous copies from / to pinned memory around the device-resident step (copies overlap neighbouring steps); results verified against the blocking calls"},
                     "h2d_bytes_per_step": int(B * D * 4 + nt * 4 + (B + 1) * 4), "d2h_bytes_per_step": int(B * K * 16 + B * 4)},
             "gpu_launches": int(launches.item()),
-            "roofline": {"kernel": "dense_gemm_topk_kernel (tcgen05 bf16 GEMM + fused top-k), rank 0 shard",
+            "roofline": {"kernel": ("dense_gemm_topk_kernel (tcgen05 bf16 GEMM + fused top-k), rank 0 shard" if os.environ.get("TRR_GEMM_PAIR") == "0" or args.batch <= 128 else "dense_gemm_topk_pair_kernel (tcgen05 cta_group::2 bf16 GEMM + fused top-k), rank 0 shard"),
                          "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
                          "traffic": ncu_traffic("gemm", a), "traffic_source": "profiles/r*_gemm_ncu.txt (ncu --set full, same command)",
                          "peak_source": peak_src,

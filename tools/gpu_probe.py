@@ -175,12 +175,40 @@ def step_perf_gemm():
     print("synth gen s", time.time() - t0)
     ix.set_mode(2)
     Q = bf16_round(O.synth_queries(SEED, 0, B, d, n, corpus_bf16=True))
-    for it in range(3):
+    for it in range(int(os.environ.get("PROBE_ITERS", "3"))):
         ix.search(Q, 50)
         st = ix.stats()
         fl = 2.0 * B * n * d
         print(f"K2 {n}x{d} bf16 B={B}: main {st.ms_main_kernel:.3f} ms total {st.ms_total:.3f} ms "
               f"{fl/st.ms_main_kernel/1e9:.0f} TFLOP/s fallbacks={st.n_guard_fallbacks} gap={st.max_fast_exact_gap:.2e}")
+    ix.close()
+
+
+def step_ab_pair():
+    """alternates GEMM kernel variants in one process (same thermal / power state): (2-CTA?, TRR_GEMM_DEBUG bits)"""
+    ctx = api.Context(0)
+    n, d, B = int(os.environ.get("PROBE_DOCS", "10000000")), 768, 1024
+    ix = api.DenseIndex(ctx, d, 0, 1, capacity=n)
+    ix.append_synth(SEED, 0, n)
+    ix.set_mode(2)
+    Q = bf16_round(O.synth_queries(SEED, 0, B, d, n, corpus_bf16=True))
+    variants = [tuple(int(x) for x in v.split(":")) for v in os.environ.get("PROBE_VARIANTS", "0:0,0:16,1:0,1:16").split(",")]
+    acc = {v: [] for v in variants}
+    ref = None
+    for it in range(int(os.environ.get("PROBE_ITERS", "8")) * len(variants)):
+        v = variants[it % len(variants)]
+        os.environ["TRR_GEMM_PAIR"] = str(v[0])
+        os.environ["TRR_GEMM_DEBUG"] = str(v[1])
+        ids, sc, cnt = ix.search(Q, 50)
+        if (v[1] & 7) == 0:
+            if ref is None:
+                ref = (ids.copy(), sc.copy())
+            elif not (np.array_equal(ref[0], ids) and np.array_equal(ref[1], sc)):
+                print("MISMATCH between variants", v)
+        acc[v].append(ix.stats().ms_main_kernel)
+    for v in variants:
+        x = acc[v][2:]
+        print(f"pair={v[0]} debug={v[1]}: main ms {' '.join('%.2f' % t for t in acc[v])}  mean(after 2) {sum(x)/len(x):.3f}")
     ix.close()
 
 

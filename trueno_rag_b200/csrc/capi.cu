@@ -578,11 +578,11 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     use_gemm = false;
   }
   if (use_gemm && k > 50) {
-    // re-scoring width 128 needs at least two document slices of 64-entry lists
+    // re-scoring width 128 needs at least four half-slice lists of 32 entries
     const uint32_t n_qb = (B + TRR_GEMM_TILE_M - 1) / TRR_GEMM_TILE_M;
     const uint64_t tiles = (h->n + TRR_GEMM_TILE_N - 1) / TRR_GEMM_TILE_N;
     const uint64_t n_sl = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->sm_count / std::max(n_qb, 1u), tiles));
-    if (n_sl * TRR_GEMM_CP < 2 * TRR_GEMM_CP) {
+    if (2 * n_sl * TRR_GEMM_CPS_MAX < 2 * TRR_GEMM_CP) {
       if (h->mode == TRR_DENSE_GEMM) return trr_fail(TRR_ERR_UNSUPPORTED, "GEMM mode: batch too large for k > 50");
       use_gemm = false;
     }
@@ -611,9 +611,11 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
   } else {
     TRR_CHECK(dense_prepare_gemm(h));
     uint32_t n_qblocks = (B + TRR_GEMM_TILE_M - 1) / TRR_GEMM_TILE_M;
-    // the 1-CTA kernel (M128 x N256 per CTA) measured faster than the 2-CTA one (cta_group::2) on B200 for this
-    // shape: 16.2 ms vs 24.0 ms at 10M x 768, B = 1024; TRR_GEMM_PAIR=1 selects the 2-CTA kernel
-    int pair_mode = 0;
+    // The 2-CTA kernel (cta_group::2: each CTA of a pair loads half of the document tile) moves a third less operand
+    // data into shared memory per FLOP; the B200 runs this GEMM against its power cap (SM clock 1.3-1.6 GHz of 1.965), so
+    // the saving is time: 12.9 ms vs 14.1 ms at 10M x 768, B = 1024 under back-to-back launches.  It needs an even number
+    // of query blocks; an odd count is padded only when the padding costs less than the gain (TRR_GEMM_PAIR=0/1 overrides).
+    int pair_mode = n_qblocks >= 2 && (n_qblocks % 2 == 0 || n_qblocks >= 9) ? 1 : 0;
     if (const char* e = getenv("TRR_GEMM_PAIR")) pair_mode = atoi(e) ? 1 : 0;
     if (pair_mode) n_qblocks = (n_qblocks + 1) & ~1u;
     if (n_qblocks > (uint32_t)c->sm_count)
@@ -627,14 +629,14 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     // list length per (query, slice): the global top-CP by fast score is spread over the slices (about CP / n_slices
     // per slice), so short lists suffice when there are many slices (Poisson tail < 1e-6 for the choices below); the
     // candidate proof (rescore_select_kernel) catches the data sets where they do not
-    // The 1-CTA kernel keeps one list per HALF slice (its two epilogue warp groups split the columns of every tile), so
+    // The kernels keep one list per HALF slice (the two epilogue warp groups of a CTA split the columns of every tile), so
     // the re-scoring kernel sees 2 * n_slices "virtual" slices of at most TRR_GEMM_CPS_MAX entries.
-    const uint32_t vslices = pair_mode ? n_slices : 2 * n_slices;
-    const uint32_t cps_max = pair_mode ? TRR_GEMM_CP : TRR_GEMM_CPS_MAX;
+    const uint32_t vslices = 2 * n_slices;
+    const uint32_t cps_max = TRR_GEMM_CPS_MAX;
     const float per_slice = (float)CP / (float)vslices;
-    uint32_t cps = per_slice <= 1.0f ? 8u : (per_slice <= 4.0f ? 16u : (per_slice <= 10.0f ? 32u : 64u));
-    if (const char* e = getenv("TRR_GEMM_CPS")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32 || v == 64) cps = (uint32_t)v; }
-    if (cps > cps_max || (uint64_t)vslices * cps < CP) cps = cps_max;  // (vslices * cps_max >= CP is checked before taking this path)
+    uint32_t cps = per_slice <= 1.0f ? 8u : (per_slice <= 4.0f ? 16u : 32u);
+    if (const char* e = getenv("TRR_GEMM_CPS")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) cps = (uint32_t)v; }
+    if ((uint64_t)vslices * cps < CP) cps = cps_max;  // (vslices * cps_max >= CP is checked before taking this path)
     const size_t n_cand = (size_t)vslices * n_qblocks * TRR_GEMM_TILE_M * cps;
     const uint32_t cap2 = std::max<uint32_t>(trr_pow2_ceil(vslices * cps), 2 * CP);
     // scratch layout (single reservation so that pointers stay valid)
@@ -731,7 +733,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
       TRR_CUDA(cudaMemcpyAsync(h->stat_dev, counters_final, 4, cudaMemcpyDeviceToDevice, st));
       TRR_CUDA(cudaMemcpyAsync(h->stat_dev + 1, counters + 1, 4, cudaMemcpyDeviceToDevice, st));
       h->stat_pending = true;
-      if (!ga.debug_mode)
+      if (!(ga.debug_mode & 7))
         TRR_CHECK(dense_scan_locked(h, d_q, d_qn, B, flagged_final, k, d_ord, d_score, d_n, nullptr, fb_off, counters_final, false));
     } else {
       uint32_t hc[2] = {0, 0};
@@ -745,7 +747,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
       }
       h->stats.n_guard_fallbacks = hc[0];
       memcpy(&h->stats.max_fast_exact_gap, &hc[1], 4);
-      if (ga.debug_mode) hc[0] = 0;  // perf triage: results are meaningless, do not time the fallback
+      if (ga.debug_mode & 7) hc[0] = 0;  // perf triage: results are meaningless, do not time the fallback
       for (uint32_t f0 = 0; f0 < hc[0]; f0 += fb_chunk) {
         const uint32_t m = std::min(fb_chunk, hc[0] - f0);
         TRR_CHECK(dense_scan_locked(h, d_q, d_qn, m, flagged_final + f0, k, d_ord, d_score, d_n, nullptr, fb_off, nullptr, false));
@@ -766,6 +768,11 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     cudaEventElapsedTime(&h->stats.ms_total, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&h->stats.ms_main_kernel, h->ev[2], h->ev[3]);
     dense_resolve_stats(h);
+    if (getenv("TRR_GEMM_DEBUG") && (atoi(getenv("TRR_GEMM_DEBUG")) & 8) && extra(c)->dbg_host)
+      fprintf(stderr, "[trr] K2 CTA 0: %u cycles in %u ns = %.0f MHz; MMA warp waited %u on operands, %u on the epilogue; "
+                      "producer(s) waited %u / %u on free stages\n", extra(c)->dbg_host[8], extra(c)->dbg_host[9],
+              1000.0 * extra(c)->dbg_host[8] / std::max(1u, extra(c)->dbg_host[9]), extra(c)->dbg_host[10],
+              extra(c)->dbg_host[11], extra(c)->dbg_host[12], extra(c)->dbg_host[13]);
   }
   return TRR_OK;
 }
@@ -861,7 +868,7 @@ extern "C" TRR_API int trr_debug_gemm_scores(trr_dense* h, const float* q, uint3
   ga.k_blocks = (h->dim_pad + 63) / 64; ga.base_ord = h->base;
   ga.scale_bias = reinterpret_cast<const float2*>(h->scale_bias.p);
   ga.cand_score = cand_score; ga.cand_ord = cand_ord; ga.gthr = gthr; ga.share_thresholds = 0;
-  ga.pair_mode = pair_mode; ga.cps = pair_mode ? TRR_GEMM_CP : TRR_GEMM_CPS_MAX;
+  ga.pair_mode = pair_mode; ga.cps = TRR_GEMM_CPS_MAX;
   ga.dbg = extra(c)->dbg_dev;
   TRR_CUDA(trr_launch_gemm_topk_dump(ga, map_q, pair_mode ? h->map_d_half : h->map_d, n_slices * n_qblocks, dump, out_ld,
                                      st));

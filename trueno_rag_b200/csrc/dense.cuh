@@ -86,7 +86,7 @@ struct GemmTopkArgs {
   uint32_t k_blocks;         // ceil(dim / 64)
   uint32_t base_ord;
   const float2* scale_bias;  // [n_tiles*256]
-  uint32_t cps;              // candidates kept per (query, list): 8, 16, 32 (1-CTA kernel: one list per half slice) or 64 (2-CTA kernel only)
+  uint32_t cps;              // candidates kept per (query, half slice): 8, 16 or 32
   float* cand_score;         // [n_slices][n_qblocks][128][cps]
   uint32_t* cand_ord;
   uint32_t* gthr;            // [n_qblocks*128] shared running thresholds (orderable-encoded), zeroed by the caller
@@ -112,8 +112,8 @@ cudaError_t trr_launch_topk_merge(const TopkMergeArgs& a, unsigned grid, cudaStr
 cudaError_t trr_launch_rescore(const RescoreArgs& a, int is_bf16, cudaStream_t st);
 
 // dense_gemm.cu
-constexpr uint32_t TRR_GEMM_CP = 64;      // exact re-scoring width per query; also the maximum list length per (query, slice) of the 2-CTA kernel
-constexpr uint32_t TRR_GEMM_CPS_MAX = 32; // maximum list length per (query, half slice) of the 1-CTA kernel
+constexpr uint32_t TRR_GEMM_CP = 64;      // exact re-scoring width per query (doubled for k > 50)
+constexpr uint32_t TRR_GEMM_CPS_MAX = 32; // maximum list length per (query, half slice)
 constexpr uint32_t TRR_GEMM_TILE_N = 256; // documents per MMA tile
 constexpr uint32_t TRR_GEMM_TILE_M = 128; // queries per CTA
 // converts B x dim f32 queries to a zero-padded [n_qblocks*128][dim_pad] bf16 matrix and reports ||q - bf16(q)||

@@ -43,14 +43,9 @@ constexpr uint32_t STAGES = TRR_GEMM_STAGES;
 constexpr uint32_t CP = TRR_GEMM_CP;
 constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KB
 constexpr uint32_t B_BYTES = BN * BK * 2;  // 32 KB
-#ifndef TRR_GEMM_LSTRIDE
-#define TRR_GEMM_LSTRIDE (TRR_GEMM_CP + 1)
-#endif
-constexpr uint32_t LSTRIDE = TRR_GEMM_LSTRIDE;                 // words per row of a candidate list: odd, so lane == row is conflict-free
-constexpr uint32_t LIST_BYTES = BM * LSTRIDE * 4;
-// 1-CTA kernel: 8 epilogue warps; the two warps that share a TMEM lane quarter split the 256 columns of a tile into
-// halves, and every (row, half) owns a candidate list of up to L1MAX entries: [half][row][L1STRIDE] (odd stride: lanes of
-// a warp are consecutive rows of one half, conflict-free).
+// Both kernels run 8 epilogue warps per CTA; the two warps that share a TMEM lane quarter split the 256 columns of a tile
+// into halves, and every (row, half) owns a candidate list of up to L1MAX entries: [half][row][L1STRIDE] (odd stride:
+// lanes of a warp are consecutive rows of one half, conflict-free).
 constexpr uint32_t L1MAX = TRR_GEMM_CPS_MAX;
 constexpr uint32_t L1STRIDE = L1MAX + 1;
 constexpr uint32_t LIST1_BYTES = 2 * BM * L1STRIDE * 4;
@@ -63,8 +58,7 @@ constexpr uint32_t SMEM_SB = SMEM_LO + LIST1_BYTES;
 constexpr uint32_t SMEM_BAR = SMEM_SB + 2 * SB_BYTES;
 constexpr uint32_t SMEM_TOTAL = SMEM_BAR + 256;
 static_assert(SMEM_TOTAL <= 227 * 1024, "1-CTA GEMM shared memory");
-constexpr uint32_t GEMM_THREADS = 192;   // 2-CTA kernel: TMA, MMA, 4 epilogue warps
-constexpr uint32_t GEMM1_THREADS = 320;  // 1-CTA kernel: TMA, MMA, 8 epilogue warps
+constexpr uint32_t GEMM1_THREADS = 320;  // TMA producer, MMA issuer, 8 epilogue warps
 
 // instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), both K-major
 // (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
@@ -83,6 +77,15 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
       __trap();
     }
   }
+}
+
+// perf triage (debug_mode & 8): the wait with the cycles it took added to `acc`
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, int site, uint32_t* dbg, bool timed,
+                                                long long& acc) {
+  if (!timed) { mbar_wait_bounded(bar, parity, site, dbg); return; }
+  const long long t = clock64();
+  mbar_wait_bounded(bar, parity, site, dbg);
+  acc += clock64() - t;
 }
 
 __device__ __forceinline__ void tma_load_2d(const void* map, void* smem_dst, uint64_t* bar, int32_t c0, int32_t c1) {
@@ -194,6 +197,86 @@ __device__ __noinline__ RowState insert_private(RowState st, float s, uint32_t d
   return st;
 }
 
+
+// One 32-column chunk of a finished accumulator stage, for one epilogue warp (lane == query row): read the 32 f32 sums
+// of the lane's row from TMEM, turn them into fast scores with the per-document scale/bias staged in shared memory (sb16:
+// 16 float4 = 32 x {scale, bias}, the same address in every lane: broadcast), and insert the ones above the row's
+// threshold into the lane's candidate list.  PREFILTER: one 3-input max tree and a single compare per chunk instead of
+// a compare + mask bit per element; the per-element tests run only in the (rare) chunks where some lane has a hit.
+// `mode` (perf triage only): 2 no insertions, 3 TMEM reads only, 4 no TMEM reads.
+template <bool PREFILTER>
+__device__ __forceinline__ RowState epilogue_chunk(uint32_t taddr, const float4* sb16, uint32_t dbase, RowState st,
+                                                   float* my_ls, uint32_t* my_lo, uint32_t cps, uint32_t mode,
+                                                   float* dump_row) {
+  uint32_t v[32];
+  if (mode != 4) {
+    tmem_ld32_issue(taddr, v);
+    tmem_ld32_wait(v);
+  } else {
+#pragma unroll
+    for (uint32_t j = 0; j < 32; ++j) v[j] = dbase + j;
+  }
+  if (mode == 3) {
+    uint32_t x = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 32; ++j) x ^= v[j];
+    if (x == 0x7FC12345u) st.thr = 0.0f;
+    return st;
+  }
+  float sv[32];
+  if (PREFILTER) {
+#pragma unroll
+    for (uint32_t j = 0; j < 32; j += 2) {
+      const float4 sb = sb16[j >> 1];
+      sv[j] = fmaf(__uint_as_float(v[j]), sb.x, sb.y);
+      sv[j + 1] = fmaf(__uint_as_float(v[j + 1]), sb.z, sb.w);
+    }
+    float m[4];
+#pragma unroll
+    for (uint32_t g = 0; g < 4; ++g) {  // four independent chains of 3-input maxima (NaN never wins)
+      m[g] = fmaxf(fmaxf(sv[8 * g], sv[8 * g + 1]), sv[8 * g + 2]);
+      m[g] = fmaxf(fmaxf(m[g], sv[8 * g + 3]), sv[8 * g + 4]);
+      m[g] = fmaxf(fmaxf(m[g], sv[8 * g + 5]), sv[8 * g + 6]);
+      m[g] = fmaxf(m[g], sv[8 * g + 7]);
+    }
+    const float mx = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+    if (dump_row) {
+#pragma unroll
+      for (uint32_t j = 0; j < 32; ++j) dump_row[j] = sv[j];
+    }
+    const bool hit = mode != 2 && mx > st.thr;
+    if (__any_sync(FULL, hit)) {
+      if (hit) {
+#pragma unroll
+        for (uint32_t j = 0; j < 32; ++j)
+          if (sv[j] > st.thr) st = insert_private(st, sv[j], dbase + j, my_ls, my_lo, cps);
+      }
+    }
+  } else {
+    uint32_t pmask = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 32; j += 2) {
+      const float4 sb = sb16[j >> 1];
+      sv[j] = fmaf(__uint_as_float(v[j]), sb.x, sb.y);
+      sv[j + 1] = fmaf(__uint_as_float(v[j + 1]), sb.z, sb.w);
+      pmask |= (sv[j] > st.thr ? 1u : 0u) << j;
+      pmask |= (sv[j + 1] > st.thr ? 1u : 0u) << (j + 1);
+    }
+    if (dump_row) {
+#pragma unroll
+      for (uint32_t j = 0; j < 32; ++j) dump_row[j] = sv[j];
+    }
+    if (mode == 2) pmask = 0;
+    // rare path: some lane has a value above its row's threshold (re-tested inside: the threshold rises as we insert)
+    if (__any_sync(FULL, pmask != 0)) {
+#pragma unroll
+      for (uint32_t j = 0; j < 32; ++j)
+        if (pmask & (1u << j)) st = insert_private(st, sv[j], dbase + j, my_ls, my_lo, cps);
+    }
+  }
+  return st;
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(GEMM1_THREADS, 1)
@@ -234,6 +317,15 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // perf triage (debug_mode & 8): SM cycles and nanoseconds spent by CTA 0, i.e. the SM clock this kernel ran at
+  long long dbg_c0 = 0;
+  uint64_t dbg_t0 = 0;
+  const bool timed = (a.debug_mode & 8) && blockIdx.x < 2 && a.dbg != nullptr;
+  long long w_empty = 0, w_full = 0, w_tempty = 0;  // cycles the producer / the MMA warp spent waiting
+  if ((a.debug_mode & 8) && blockIdx.x == 0 && threadIdx.x == 0) {
+    dbg_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -241,20 +333,21 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       uint32_t stage = 0, phase = 0;
       for (uint32_t t = t0; t < t1; ++t) {
         for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
-          mbar_wait_bounded(&empty_bar[stage], phase ^ 1, 1, a.dbg);
+          mbar_wait_timed(&empty_bar[stage], phase ^ 1, 1, a.dbg, timed, w_empty);
           trr_mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
           tma_load_2d(&map_q, smem + SMEM_A + stage * A_BYTES, &full_bar[stage], (int32_t)(kb * BK), (int32_t)(qb * BM));
           tma_load_2d(&map_d, smem + SMEM_B + stage * B_BYTES, &full_bar[stage], (int32_t)(kb * BK), (int32_t)(t * BN));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (timed && blockIdx.x == 0) a.dbg[12] = (uint32_t)w_empty;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     uint32_t stage = 0, phase = 0;
     for (uint32_t t = t0, it = 0; t < t1; ++t, ++it) {
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-      mbar_wait_bounded(&tempty_bar[as], aphase ^ 1, 2, a.dbg);
+      mbar_wait_timed(&tempty_bar[as], aphase ^ 1, 2, a.dbg, timed, w_tempty);
       tc_fence_after();
       // the epilogue of tile it-2 has let go of this stage's scale/bias buffer as well: refill it for tile t
       if (lane == 0) {
@@ -262,7 +355,7 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         trr_bulk_g2s(smem + SMEM_SB + as * SB_BYTES, a.scale_bias + (uint64_t)t * BN, SB_BYTES, &sbfull_bar[as]);
       }
       for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
-        mbar_wait_bounded(&full_bar[stage], phase, 3, a.dbg);
+        mbar_wait_timed(&full_bar[stage], phase, 3, a.dbg, timed, w_full);
         tc_fence_after();
         if (lane == 0) {
           const uint64_t da = make_smem_desc(trr_smem_u32(smem + SMEM_A + stage * A_BYTES));
@@ -279,6 +372,7 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    if (timed && blockIdx.x == 0 && lane == 0) { a.dbg[10] = (uint32_t)w_full; a.dbg[11] = (uint32_t)w_tempty; }
   } else {
     // ===================== epilogue (8 warps) =====================
     const uint32_t quarter = warp & 3;            // TMEM lane group this warp may access
@@ -306,45 +400,16 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       tc_fence_after();
       const uint32_t doc0 = t * BN + half * (BN / 2);
       const float4* sbs = reinterpret_cast<const float4*>(smem + SMEM_SB + as * SB_BYTES) + half * (BN / 4);
+      const uint32_t mode = a.debug_mode & 7;
+      const bool prefilter = !(a.debug_mode & 16);
 #pragma unroll 1
-      for (uint32_t c = 0; c < (a.debug_mode == 1 ? 0u : CHUNKS); ++c) {
-        uint32_t v[32];
-        if (a.debug_mode != 4) {  // (4: perf triage without the TMEM reads)
-          tmem_ld32_issue(tmem_base + ((quarter * 32u) << 16) + as * BN + half * (BN / 2) + c * 32, v);
-          tmem_ld32_wait(v);
-        } else {
-#pragma unroll
-          for (uint32_t j = 0; j < 32; ++j) v[j] = c + j;
-        }
-        if (a.debug_mode == 3) {  // perf triage: TMEM reads only
-          uint32_t x = 0;
-#pragma unroll
-          for (uint32_t j = 0; j < 32; ++j) x ^= v[j];
-          if (x == 0x7FC12345u) st.thr = 0.0f;
-          continue;
-        }
-        float sv[32];
-        uint32_t pmask = 0;
-#pragma unroll
-        for (uint32_t j = 0; j < 32; j += 2) {
-          const float4 sb = sbs[c * 16 + (j >> 1)];  // same address in every lane: broadcast
-          sv[j] = fmaf(__uint_as_float(v[j]), sb.x, sb.y);
-          sv[j + 1] = fmaf(__uint_as_float(v[j + 1]), sb.z, sb.w);
-          pmask |= (sv[j] > st.thr ? 1u : 0u) << j;
-          pmask |= (sv[j + 1] > st.thr ? 1u : 0u) << (j + 1);
-        }
-        if (dump) {
-#pragma unroll
-          for (uint32_t j = 0; j < 32; ++j) dump[(uint64_t)(qb * BM + row) * dump_ld + doc0 + c * 32 + j] = sv[j];
-        }
-        if (a.debug_mode == 2) pmask = 0;
-        // rare path: some lane has a value above its row's threshold (re-tested inside: the threshold rises as we insert)
-        if (__any_sync(FULL, pmask != 0)) {
-          const uint32_t dbase = a.base_ord + doc0 + c * 32;
-#pragma unroll
-          for (uint32_t j = 0; j < 32; ++j)
-            if (pmask & (1u << j)) st = insert_private(st, sv[j], dbase + j, my_ls, my_lo, cps);
-        }
+      for (uint32_t c = 0; c < (mode == 1 ? 0u : CHUNKS); ++c) {
+        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * BN + half * (BN / 2) + c * 32;
+        float* dump_row = dump ? dump + (uint64_t)(qb * BM + row) * dump_ld + doc0 + c * 32 : nullptr;
+        if (prefilter)
+          st = epilogue_chunk<true>(taddr, sbs + c * 16, a.base_ord + doc0 + c * 32, st, my_ls, my_lo, cps, mode, dump_row);
+        else
+          st = epilogue_chunk<false>(taddr, sbs + c * 16, a.base_ord + doc0 + c * 32, st, my_ls, my_lo, cps, mode, dump_row);
       }
       // accumulator stage and scale/bias buffer drained: hand them back to the MMA warp
       tc_fence_before();
@@ -359,6 +424,12 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 
   tc_fence_before();
   __syncthreads();
+  if ((a.debug_mode & 8) && blockIdx.x == 0 && threadIdx.x == 0 && a.dbg) {
+    uint64_t t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    a.dbg[8] = (uint32_t)(clock64() - dbg_c0);
+    a.dbg[9] = (uint32_t)(t1 - dbg_t0);
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -370,22 +441,27 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 // tile.  Each CTA owns 128 query rows (its own A operand and its own 128 x 256 f32 accumulator in its TMEM) and
 // loads HALF of the document tile (128 rows of B); the tensor cores of both SMs read both halves.  Compared with the
 // 1-CTA kernel this cuts the L2 -> shared-memory operand traffic per CTA from 48 KB to 32 KB per k-block and leaves
-// room for a 5-stage ring.  Protocol (barriers at identical shared-memory offsets in both CTAs):
-//   full[s]    lives in the leader CTA: 2 arrivals (one per producer) + 64 KB of TMA transaction bytes;
+// room for a deeper ring in bytes per SM.  Protocol (barriers at identical shared-memory offsets in both CTAs):
+//   full[s]    lives in the leader CTA: 1 arrival (the leader's producer) + 64 KB of TMA transaction bytes from both CTAs
+//              (a remote arrive per k-block from the peer's producer cost ~900 cycles each and halved the throughput);
 //   empty[s]   per CTA, released by the leader's tcgen05.commit multicast to both CTAs;
 //   tfull[a]   per CTA, same multicast commit after the last k-block of a tile;
-//   tempty[a]  lives in the leader: 8 arrivals (one per epilogue warp of both CTAs).
+//   tempty[a]  lives in the leader: 16 arrivals (one per epilogue warp of both CTAs);
+//   sbfull[i] / sbempty[i]  per CTA: ring of three scale/bias buffers between the producer and the epilogue warps.
 // =============================================================================================
 namespace {
-constexpr uint32_t STAGES2 = 5;
+constexpr uint32_t STAGES2 = 4;
 constexpr uint32_t B2_BYTES = (BN / 2) * BK * 2;  // 16 KB: this CTA's half of the document tile
 constexpr uint32_t STAGE2_BYTES = A_BYTES + B2_BYTES;
+constexpr uint32_t SB_RING = 3;                   // scale/bias buffers (filled by the producer a tile ahead)
 constexpr uint32_t SMEM2_A = 0;
 constexpr uint32_t SMEM2_B = SMEM2_A + STAGES2 * A_BYTES;
 constexpr uint32_t SMEM2_LS = SMEM2_B + STAGES2 * B2_BYTES;
-constexpr uint32_t SMEM2_LO = SMEM2_LS + LIST_BYTES;
-constexpr uint32_t SMEM2_BAR = SMEM2_LO + LIST_BYTES;
+constexpr uint32_t SMEM2_LO = SMEM2_LS + LIST1_BYTES;
+constexpr uint32_t SMEM2_SB = SMEM2_LO + LIST1_BYTES;
+constexpr uint32_t SMEM2_BAR = SMEM2_SB + SB_RING * SB_BYTES;
 constexpr uint32_t SMEM2_TOTAL = SMEM2_BAR + 256;
+static_assert(SMEM2_TOTAL <= 227 * 1024, "2-CTA GEMM shared memory");
 constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((256u >> 4) << 24);  // M = 256
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -431,7 +507,7 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 }
 }  // namespace
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM1_THREADS, 1)
 dense_gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d,
                             GemmTopkArgs a, float* __restrict__ dump, uint32_t dump_ld) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -440,7 +516,9 @@ dense_gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
   uint64_t* empty_bar = full_bar + STAGES2;
   uint64_t* tfull_bar = empty_bar + STAGES2;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* sbfull_bar = tempty_bar + 2;
+  uint64_t* sbempty_bar = sbfull_bar + SB_RING;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sbempty_bar + SB_RING);
 
   const uint32_t rank = cluster_ctarank();          // 0 = leader
   const uint32_t qb = blockIdx.x % a.n_qblocks;     // n_qblocks is even; the pair owns query blocks (qb & ~1, qb | 1)
@@ -451,8 +529,9 @@ dense_gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_d) : "memory");
-    for (uint32_t s = 0; s < STAGES2; ++s) { trr_mbar_init(&full_bar[s], 2); trr_mbar_init(&empty_bar[s], 1); }
-    for (uint32_t s = 0; s < 2; ++s) { trr_mbar_init(&tfull_bar[s], 1); trr_mbar_init(&tempty_bar[s], 8); }  // one arrival per epilogue warp of both CTAs
+    for (uint32_t s = 0; s < STAGES2; ++s) { trr_mbar_init(&full_bar[s], 1); trr_mbar_init(&empty_bar[s], 1); }
+    for (uint32_t s = 0; s < 2; ++s) { trr_mbar_init(&tfull_bar[s], 1); trr_mbar_init(&tempty_bar[s], 16); }  // one arrival per epilogue warp of both CTAs
+    for (uint32_t s = 0; s < SB_RING; ++s) { trr_mbar_init(&sbfull_bar[s], 1); trr_mbar_init(&sbempty_bar[s], 8); }
     trr_fence_mbar_init();
   }
   cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / TMA / commit
@@ -466,23 +545,41 @@ dense_gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const bool timed = (a.debug_mode & 8) && blockIdx.x < 2 && a.dbg != nullptr;
+  long long w_empty = 0, w_full = 0, w_tempty = 0;
+  long long dbg_c0 = 0;
+  uint64_t dbg_t0 = 0;
+  if (timed && blockIdx.x == 0 && threadIdx.x == 0) {
+    dbg_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+  }
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (uint32_t t = t0; t < t1; ++t) {
+      for (uint32_t t = t0, it = 0; t < t1; ++t, ++it) {
+        {
+          // scale/bias of this tile's 256 documents for this CTA's epilogue; the buffer was last read for tile it - 3,
+          // whose epilogue finished before the MMAs of tile it - 1 could start, so this wait does not stall the ring
+          const uint32_t sbuf = it % SB_RING, sphase = (it / SB_RING) & 1;
+          mbar_wait_bounded(&sbempty_bar[sbuf], sphase ^ 1, 15, a.dbg);
+          trr_mbar_expect_tx(&sbfull_bar[sbuf], SB_BYTES);
+          trr_bulk_g2s(smem + SMEM2_SB + sbuf * SB_BYTES, a.scale_bias + (uint64_t)t * BN, SB_BYTES, &sbfull_bar[sbuf]);
+        }
         for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
-          mbar_wait_bounded(&empty_bar[stage], phase ^ 1, 11, a.dbg);
+          mbar_wait_timed(&empty_bar[stage], phase ^ 1, 11, a.dbg, timed, w_empty);
           const uint32_t leader_full = mapa_u32(trr_smem_u32(&full_bar[stage]), 0);
+          // the leader alone arrives, expecting the bytes of both CTAs: the peer's copies may complete on the barrier before
+          // the leader's expect_tx (the transaction count goes negative; the phase cannot complete without the arrival)
           if (rank == 0) trr_mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
-          else mbar_arrive_cluster(leader_full);
           tma_load_2d_pair(&map_q, smem + SMEM2_A + stage * A_BYTES, leader_full, (int32_t)(kb * BK), (int32_t)(qb * BM));
           tma_load_2d_pair(&map_d, smem + SMEM2_B + stage * B2_BYTES, leader_full, (int32_t)(kb * BK),
                            (int32_t)(t * BN + rank * (BN / 2)));
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
       }
+      if (timed) a.dbg[12 + blockIdx.x] = (uint32_t)w_empty;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
@@ -490,10 +587,10 @@ dense_gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
       uint32_t stage = 0, phase = 0;
       for (uint32_t t = t0, it = 0; t < t1; ++t, ++it) {
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-        mbar_wait_bounded(&tempty_bar[as], aphase ^ 1, 12, a.dbg);
+        mbar_wait_timed(&tempty_bar[as], aphase ^ 1, 12, a.dbg, timed, w_tempty);
         tc_fence_after();
         for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
-          mbar_wait_bounded(&full_bar[stage], phase, 13, a.dbg);
+          mbar_wait_timed(&full_bar[stage], phase, 13, a.dbg, timed, w_full);
           tc_fence_after();
           if (lane == 0) {
             const uint64_t da = make_smem_desc(trr_smem_u32(smem + SMEM2_A + stage * A_BYTES));
@@ -508,15 +605,15 @@ dense_gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
       }
+      if (timed && blockIdx.x == 0 && lane == 0) { a.dbg[10] = (uint32_t)w_full; a.dbg[11] = (uint32_t)w_tempty; }
     }
   } else {
-    // ===================== epilogue (both CTAs; identical to the 1-CTA kernel except for the tempty arrive) =====
+    // ===================== epilogue (both CTAs, 8 warps each; as in the 1-CTA kernel) =====================
     const uint32_t quarter = warp & 3;
+    const uint32_t half = (warp - 2) >> 2;
     const uint32_t row = quarter * 32 + lane;
-    float* ls_all = reinterpret_cast<float*>(smem + SMEM2_LS);
-    uint32_t* lo_all = reinterpret_cast<uint32_t*>(smem + SMEM2_LO);
-    float* my_ls = ls_all + row * LSTRIDE;
-    uint32_t* my_lo = lo_all + row * LSTRIDE;
+    float* my_ls = reinterpret_cast<float*>(smem + SMEM2_LS) + (half * BM + row) * L1STRIDE;
+    uint32_t* my_lo = reinterpret_cast<uint32_t*>(smem + SMEM2_LO) + (half * BM + row) * L1STRIDE;
     const uint32_t cps = a.cps;
     for (uint32_t j = 0; j < cps; ++j) { my_ls[j] = -CUDART_INF_F; my_lo[j] = 0xFFFFFFFFu; }
     RowState st;
@@ -525,70 +622,52 @@ dense_gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     st.thr = -CUDART_INF_F;
     uint32_t* gthr = a.gthr + (qb * BM + row);
     const uint32_t leader_tempty[2] = {mapa_u32(trr_smem_u32(&tempty_bar[0]), 0), mapa_u32(trr_smem_u32(&tempty_bar[1]), 0)};
+    constexpr uint32_t CHUNKS = BN / 64;
+    const uint32_t mode = a.debug_mode & 7;
+    const bool prefilter = !(a.debug_mode & 16);
 
-    float4 sb_cur[16];
-    {
-      const float4* p = reinterpret_cast<const float4*>(a.scale_bias + (uint64_t)t0 * BN);
-#pragma unroll
-      for (uint32_t i = 0; i < 16; ++i) sb_cur[i] = __ldg(p + i);
-    }
     for (uint32_t t = t0, it = 0; t < t1; ++t, ++it) {
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      const uint32_t sbuf = it % SB_RING, sphase = (it / SB_RING) & 1;
       if (a.share_thresholds) {
         const uint32_t g = *reinterpret_cast<volatile uint32_t*>(gthr);
         if (g > trr_f32_orderable(st.thr)) st.thr = trr_orderable_f32(g);
       }
+      mbar_wait_bounded(&sbfull_bar[sbuf], sphase, 16, a.dbg);
       mbar_wait_bounded(&tfull_bar[as], aphase, 14, a.dbg);
       tc_fence_after();
-      const uint32_t doc0 = t * BN;
+      const uint32_t doc0 = t * BN + half * (BN / 2);
+      const float4* sbs = reinterpret_cast<const float4*>(smem + SMEM2_SB + sbuf * SB_BYTES) + half * (BN / 4);
 #pragma unroll 1
-      for (uint32_t c = 0; c < (a.debug_mode == 1 ? 0u : BN / 32); ++c) {
-        uint32_t v[32];
-        tmem_ld32_issue(tmem_base + ((quarter * 32u) << 16) + as * BN + c * 32, v);
-        float4 sb_nxt[16];
-        {
-          uint64_t nd = (uint64_t)doc0 + (c + 1) * 32;
-          if (c == BN / 32 - 1 && t + 1 >= t1) nd = (uint64_t)doc0;
-          const float4* p = reinterpret_cast<const float4*>(a.scale_bias + nd);
-#pragma unroll
-          for (uint32_t i = 0; i < 16; ++i) sb_nxt[i] = __ldg(p + i);
-        }
-        tmem_ld32_wait(v);
-        float sv[32];
-        uint32_t pmask = 0;
-#pragma unroll
-        for (uint32_t j = 0; j < 32; j += 2) {
-          const float4 sb = sb_cur[j >> 1];
-          sv[j] = fmaf(__uint_as_float(v[j]), sb.x, sb.y);
-          sv[j + 1] = fmaf(__uint_as_float(v[j + 1]), sb.z, sb.w);
-          pmask |= (sv[j] > st.thr ? 1u : 0u) << j;
-          pmask |= (sv[j + 1] > st.thr ? 1u : 0u) << (j + 1);
-        }
-        if (dump) {
-#pragma unroll
-          for (uint32_t j = 0; j < 32; ++j) dump[(uint64_t)(qb * BM + row) * dump_ld + doc0 + c * 32 + j] = sv[j];
-        }
-        if (a.debug_mode == 2) pmask = 0;
-        if (__any_sync(FULL, pmask != 0)) {
-          const uint32_t dbase = a.base_ord + doc0 + c * 32;
-#pragma unroll
-          for (uint32_t j = 0; j < 32; ++j)
-            if (pmask & (1u << j)) st = insert_private(st, sv[j], dbase + j, my_ls, my_lo, cps);
-        }
-#pragma unroll
-        for (uint32_t i = 0; i < 16; ++i) sb_cur[i] = sb_nxt[i];
+      for (uint32_t c = 0; c < (mode == 1 ? 0u : CHUNKS); ++c) {
+        const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * BN + half * (BN / 2) + c * 32;
+        float* dump_row = dump ? dump + (uint64_t)(qb * BM + row) * dump_ld + doc0 + c * 32 : nullptr;
+        if (prefilter)
+          st = epilogue_chunk<true>(taddr, sbs + c * 16, a.base_ord + doc0 + c * 32, st, my_ls, my_lo, cps, mode, dump_row);
+        else
+          st = epilogue_chunk<false>(taddr, sbs + c * 16, a.base_ord + doc0 + c * 32, st, my_ls, my_lo, cps, mode, dump_row);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(leader_tempty[as]);  // 8 arrivals per tile instead of 256 (128 of them remote)
+      if (lane == 0) {
+        mbar_arrive_cluster(leader_tempty[as]);  // accumulator stage free (the leader's MMA warp waits for all 16 warps)
+        trr_mbar_arrive(&sbempty_bar[sbuf]);     // scale/bias buffer free (this CTA's producer)
+      }
       if (a.share_thresholds && st.list_min > -CUDART_INF_F) atomicMax(gthr, trr_f32_orderable(st.list_min));
     }
-    const uint64_t base = (((uint64_t)slice * a.n_qblocks + qb) * BM + row) * cps;
+    // publish this half-slice's candidates: virtual slice 2 * slice + half
+    const uint64_t base = (((uint64_t)(slice * 2 + half) * a.n_qblocks + qb) * BM + row) * cps;
     for (uint32_t j = 0; j < cps; ++j) { a.cand_score[base + j] = my_ls[j]; a.cand_ord[base + j] = my_lo[j]; }
   }
 
   tc_fence_before();
   cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still signal this CTA's barriers
+  if (timed && blockIdx.x == 0 && threadIdx.x == 0) {
+    uint64_t t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    a.dbg[8] = (uint32_t)(clock64() - dbg_c0);
+    a.dbg[9] = (uint32_t)(t1 - dbg_t0);
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -718,7 +797,7 @@ cudaError_t trr_launch_gemm_topk_dump(const GemmTopkArgs& a, const void* map_q12
     cudaError_t e = cudaFuncSetAttribute(dense_gemm_topk_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)SMEM2_TOTAL);
     if (e != cudaSuccess) return e;
-    dense_gemm_topk_pair_kernel<<<grid, GEMM_THREADS, SMEM2_TOTAL, st>>>(mq, md, a, dump, dump_ld);
+    dense_gemm_topk_pair_kernel<<<grid, GEMM1_THREADS, SMEM2_TOTAL, st>>>(mq, md, a, dump, dump_ld);
   } else {
     cudaError_t e = cudaFuncSetAttribute(dense_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)SMEM_TOTAL);
