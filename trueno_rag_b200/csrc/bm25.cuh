@@ -59,6 +59,7 @@ struct Bm25SearchArgs {
   float* out_score;    // nullable
   uint32_t* out_n;     // nullable
   uint32_t* dbg;       // nullable host-mapped word: site of a barrier timeout
+  uint32_t debug_mode; // perf triage (TRR_BM25_DEBUG): 8 = CTA 0 records where its cycles go
 };
 
 cudaError_t trr_launch_bm25_build(const Bm25BuildArgs& a, cudaStream_t st);

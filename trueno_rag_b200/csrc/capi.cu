@@ -1174,6 +1174,7 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   uint64_t* plan_keys = ws.take<uint64_t>(trr_pow2_ceil(B));
   a.out_keys = nullptr; a.out_ord = d_ord; a.out_score = d_score; a.out_n = d_n;
   a.dbg = extra(c)->dbg_dev;
+  if (const char* e = getenv("TRR_BM25_DEBUG")) a.debug_mode = (uint32_t)atoi(e);
   const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)B * n_chunks, (uint64_t)slots);
   TRR_CUDA(trr_launch_bm25_plan(a, plan_keys, st));
   TRR_CUDA(cudaEventRecord(h->ev[2], st));
@@ -1250,6 +1251,12 @@ extern "C" int trr_bm25_last_stats(trr_bm25* h, trr_stats* out) {
   if (h->stats.mode_used) {
     cudaEventElapsedTime(&h->stats.ms_main_kernel, h->ev[2], h->ev[3]);
     cudaGetLastError();
+    const char* e = getenv("TRR_BM25_DEBUG");
+    if (e && (atoi(e) & 8) && extra(h->ctx)->dbg_host) {
+      const uint32_t* w = extra(h->ctx)->dbg_host;
+      fprintf(stderr, "[trr] K3 CTA 0 (x16 cycles): total %u; producer waited %u for a free stage; consumer warp 0: %u waiting "
+                      "for postings, %u boundaries, %u accumulate, %u harvest\n", w[8], w[9], w[10], w[11], w[12], w[13]);
+    }
   }
   *out = h->stats;
   return TRR_OK;
