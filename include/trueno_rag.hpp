@@ -55,7 +55,7 @@ struct Chunk {  // src/chunk.rs:46-61 (metadata omitted: never read on the retri
 
 class Error : public std::runtime_error {  // src/error.rs:9-64 (variants reachable from the path)
  public:
-  enum class Kind { InvalidConfig, DimensionMismatch, VectorStore, Unsupported };
+  enum class Kind { InvalidConfig, DimensionMismatch, VectorStore, Unsupported, Serialization };
   Kind kind;
   size_t expected = 0, actual = 0;  // DimensionMismatch fields
   Error(Kind k, const std::string& msg, size_t exp = 0, size_t act = 0) : std::runtime_error(msg), kind(k), expected(exp), actual(act) {}
@@ -113,6 +113,14 @@ class VectorStore {  // src/index.rs:322-437
   mutable std::shared_ptr<detail::DeviceDense> dev_;
 };
 
+// src/compressed.rs:13-66 — compression of serialised indexes.  LZ4 = lz4_flex 0.11 `compress_prepend_size` /
+// `decompress_size_prepended` (u32 little-endian length + one LZ4 block), implemented here; ZSTD frames need a full
+// entropy decoder and are reported as Error::Unsupported (the reference's default is LZ4).  Empty input <-> empty output.
+enum class Compression { Lz4 = 0, Zstd = 1 };
+const char* compression_as_str(Compression c);                                  // :24-30
+std::vector<uint8_t> compress(Compression c, const uint8_t* data, size_t n);    // :36-47
+std::vector<uint8_t> decompress(Compression c, const uint8_t* data, size_t n);  // :53-66
+
 class BM25Index {  // src/index.rs:30-280 (SparseIndex impl included)
  public:
   BM25Index();
@@ -135,6 +143,16 @@ class BM25Index {  // src/index.rs:30-280 (SparseIndex impl included)
   float avg_doc_length() const;
   bool contains_term(const std::string& term) const { return dict_.count(term) != 0; }
 
+  // Persistence in the REFERENCE's format: `#[derive(Serialize, Deserialize)]` of the struct at
+  // src/index.rs:30-51 through bincode 1.3 default options (little-endian, fixed-width integers, u64 lengths; ChunkId =
+  // uuid bytes with a u64 length of 16), optionally compressed (src/compressed.rs:71-108).  A file written by the
+  // reference loads here and vice versa.  The reference's maps carry no insertion order, so a loaded index numbers its
+  // chunks by ascending ChunkId and its terms by ascending term string (ties in the reference are hash-order anyway).
+  std::vector<uint8_t> to_bytes() const;                                                        // bincode::serialize
+  static BM25Index from_bytes(const uint8_t* data, size_t n);                                   // bincode::deserialize
+  std::vector<uint8_t> to_compressed_bytes(Compression c) const;                                // :92-94
+  static BM25Index from_compressed_bytes(const uint8_t* data, size_t n, Compression c);         // :101-103
+
   // plumbing used by HybridRetriever
   trr_bm25* device_handle() const;  // rebuilds the device index if the host state changed
   std::vector<uint32_t> term_ids(const std::vector<std::string>& tokens) const;
@@ -156,6 +174,7 @@ class BM25Index {  // src/index.rs:30-280 (SparseIndex impl included)
   std::unordered_set<std::string> stopwords_;
   mutable bool dirty_ = true;
   mutable float avg_doc_length_ = 0.0f;
+  std::optional<float> avg_loaded_;  // avg_doc_length of a loaded file that disagrees with its doc_lengths; dropped by add/remove, which recompute (:157-164)
   mutable std::shared_ptr<detail::DeviceBm25> dev_;
   // incremental device updates: documents [0, frozen_docs_) and the first frozen_len_[t] postings of term t are on the
   // device; adds since then go through trr_bm25_append, removes through trr_bm25_remove (rebuild once a quarter of the postings is dead)

@@ -3,7 +3,7 @@
  * reference's own Rust tests drive them.  A Rust integration would NOT use this layer (its host logic is Rust, see
  * INTEGRATION.md); it binds trueno_rag_b200.h directly.
  * Status codes: 0 ok, 1 InvalidConfig, 2 DimensionMismatch (expected/actual via trrh_last_expected/actual),
- * 3 VectorStore (device error), 6 Unsupported. */
+ * 3 VectorStore (device error), 6 Unsupported, 7 SerializationError. */
 #ifndef TRUENO_RAG_HOST_H
 #define TRUENO_RAG_HOST_H
 #include <stdint.h>
@@ -43,6 +43,14 @@ TRRH_API float trrh_bm25_avgdl(trrh_bm25* s);
 TRRH_API float trrh_bm25_k1(trrh_bm25* s);
 TRRH_API float trrh_bm25_b(trrh_bm25* s);
 TRRH_API int trrh_bm25_contains_term(trrh_bm25* s, const char* term);
+/* Persistence in the reference's format (src/compressed.rs:13-108; bincode 1.3 of the struct at src/index.rs:30-51).
+ * compression: -1 = plain bincode, 0 = LZ4 (lz4_flex size-prepended block), 1 = ZSTD (status 6: not built in).
+ * Output buffers are owned by the library until trrh_bytes_free.  Status 7 = SerializationError. */
+TRRH_API int trrh_compress(int compression, const uint8_t* data, uint64_t n, uint8_t** out, uint64_t* out_n);
+TRRH_API int trrh_decompress(int compression, const uint8_t* data, uint64_t n, uint8_t** out, uint64_t* out_n);
+TRRH_API void trrh_bytes_free(uint8_t* p);
+TRRH_API int trrh_bm25_to_bytes(trrh_bm25* s, int compression, uint8_t** out, uint64_t* out_n);
+TRRH_API int trrh_bm25_from_bytes(const uint8_t* data, uint64_t n, int compression, trrh_bm25** out);
 
 /* FusionStrategy::fuse (reference src/fusion.rs:42-63); out buffers hold nd + ns entries */
 TRRH_API int trrh_fuse(int kind, float param, const trrh_id* d_ids, const float* d_sc, uint32_t nd, const trrh_id* s_ids,

@@ -116,6 +116,11 @@ TRRH_PROTOS = {
     "trrh_bm25_k1": (C.c_float, [vp]),
     "trrh_bm25_b": (C.c_float, [vp]),
     "trrh_bm25_contains_term": (C.c_int, [vp, C.c_char_p]),
+    "trrh_compress": (C.c_int, [C.c_int, C.c_char_p, C.c_uint64, C.POINTER(vp), C.POINTER(C.c_uint64)]),
+    "trrh_decompress": (C.c_int, [C.c_int, C.c_char_p, C.c_uint64, C.POINTER(vp), C.POINTER(C.c_uint64)]),
+    "trrh_bytes_free": (None, [vp]),
+    "trrh_bm25_to_bytes": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_uint64)]),
+    "trrh_bm25_from_bytes": (C.c_int, [C.c_char_p, C.c_uint64, C.c_int, vpp]),
     "trrh_fuse": (C.c_int, [C.c_int, C.c_float, idp, f32p, C.c_uint32, idp, f32p, C.c_uint32, idp, f32p, u32p]),
     "trrh_retriever_new": (C.c_int, [vp, vp, C.c_uint32, C.c_int, C.c_float, C.c_int, C.c_int, vpp]),
     "trrh_retriever_free": (None, [vp]),

@@ -364,7 +364,7 @@ class Error(Exception):
         self.kind, self.expected, self.actual = kind, expected, actual
 
 
-_KINDS = {1: "InvalidConfig", 2: "DimensionMismatch", 3: "VectorStore", 6: "Unsupported"}
+_KINDS = {1: "InvalidConfig", 2: "DimensionMismatch", 3: "VectorStore", 6: "Unsupported", 7: "SerializationError"}
 
 
 def _hcheck(status: int):
@@ -477,13 +477,75 @@ class VectorStore:
         return VectorStore(self.dimension, self.metric, _h=h)
 
 
+class Compression:
+    """Reference `Compression` (src/compressed.rs:13-31); `Lz4` is the default."""
+    Lz4, Zstd = 0, 1
+
+    @staticmethod
+    def as_str(c: int) -> str:
+        return "lz4" if c == Compression.Lz4 else "zstd"
+
+    @staticmethod
+    def default() -> int:
+        return Compression.Lz4
+
+
+def _take_bytes(L, out, n) -> bytes:
+    try:
+        return C.string_at(out, n.value) if n.value else b""
+    finally:
+        L.trrh_bytes_free(out)
+
+
+def compress(data: bytes, compression: int = Compression.Lz4) -> bytes:
+    """`Compression::compress` (src/compressed.rs:36-47)."""
+    L = _lib.load()
+    out, n = C.c_void_p(), C.c_uint64()
+    _hcheck(L.trrh_compress(compression, bytes(data), len(data), C.byref(out), C.byref(n)))
+    return _take_bytes(L, out, n)
+
+
+def decompress(data: bytes, compression: int = Compression.Lz4) -> bytes:
+    """`Compression::decompress` (src/compressed.rs:53-66)."""
+    L = _lib.load()
+    out, n = C.c_void_p(), C.c_uint64()
+    _hcheck(L.trrh_decompress(compression, bytes(data), len(data), C.byref(out), C.byref(n)))
+    return _take_bytes(L, out, n)
+
+
 class BM25Index:
     """Reference `BM25Index` + `SparseIndex` impl (src/index.rs:30-280); scoring on the device."""
 
-    def __init__(self, k1: float = 1.2, b: float = 0.75):
+    def __init__(self, k1: float = 1.2, b: float = 0.75, _h=None):
         self.L = _lib.load()
-        self.h = C.c_void_p()
-        _hcheck(self.L.trrh_bm25_new(k1, b, C.byref(self.h)))
+        self.h = _h or C.c_void_p()
+        if _h is None:
+            _hcheck(self.L.trrh_bm25_new(k1, b, C.byref(self.h)))
+
+    def to_bytes(self) -> bytes:
+        """`bincode::serialize(&index)` — the reference's on-disk layout of `BM25Index`."""
+        out, n = C.c_void_p(), C.c_uint64()
+        _hcheck(self.L.trrh_bm25_to_bytes(self.h, -1, C.byref(out), C.byref(n)))
+        return _take_bytes(self.L, out, n)
+
+    @staticmethod
+    def from_bytes(data: bytes) -> "BM25Index":
+        h = C.c_void_p()
+        _hcheck(_lib.load().trrh_bm25_from_bytes(bytes(data), len(data), -1, C.byref(h)))
+        return BM25Index(_h=h)
+
+    def to_compressed_bytes(self, compression: int = Compression.Lz4) -> bytes:
+        """`BM25Index::to_compressed_bytes` (src/compressed.rs:92-94)."""
+        out, n = C.c_void_p(), C.c_uint64()
+        _hcheck(self.L.trrh_bm25_to_bytes(self.h, compression, C.byref(out), C.byref(n)))
+        return _take_bytes(self.L, out, n)
+
+    @staticmethod
+    def from_compressed_bytes(data: bytes, compression: int = Compression.Lz4) -> "BM25Index":
+        """`BM25Index::from_compressed_bytes` (src/compressed.rs:101-103)."""
+        h = C.c_void_p()
+        _hcheck(_lib.load().trrh_bm25_from_bytes(bytes(data), len(data), compression, C.byref(h)))
+        return BM25Index(_h=h)
 
     @staticmethod
     def with_params(k1: float, b: float) -> "BM25Index":

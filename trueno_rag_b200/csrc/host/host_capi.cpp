@@ -1,5 +1,6 @@
 // host_capi.cpp — flat C wrappers over the C++ host mirror (see include/trueno_rag_host.h).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../../include/trueno_rag.hpp"
@@ -21,6 +22,7 @@ static int guarded(F&& f) {
       case Error::Kind::InvalidConfig: return 1;
       case Error::Kind::DimensionMismatch: return 2;
       case Error::Kind::Unsupported: return 6;
+      case Error::Kind::Serialization: return 7;
       default: return 3;
     }
   } catch (const std::exception& e) {
@@ -113,6 +115,31 @@ float trrh_bm25_k1(trrh_bm25* s) { return s->v.k1(); }
 float trrh_bm25_b(trrh_bm25* s) { return s->v.b(); }
 int trrh_bm25_contains_term(trrh_bm25* s, const char* term) { return s->v.contains_term(term) ? 1 : 0; }
 
+static void bytes_out(const std::vector<uint8_t>& v, uint8_t** out, uint64_t* out_n) {
+  uint8_t* p = static_cast<uint8_t*>(malloc(v.size() ? v.size() : 1));
+  if (!p) throw Error(Error::Kind::VectorStore, "out of host memory");
+  if (!v.empty()) memcpy(p, v.data(), v.size());
+  *out = p;
+  *out_n = v.size();
+}
+int trrh_compress(int compression, const uint8_t* data, uint64_t n, uint8_t** out, uint64_t* out_n) {
+  return guarded([&] { bytes_out(compress((Compression)compression, data, n), out, out_n); });
+}
+int trrh_decompress(int compression, const uint8_t* data, uint64_t n, uint8_t** out, uint64_t* out_n) {
+  return guarded([&] { bytes_out(decompress((Compression)compression, data, n), out, out_n); });
+}
+void trrh_bytes_free(uint8_t* p) { free(p); }
+int trrh_bm25_to_bytes(trrh_bm25* s, int compression, uint8_t** out, uint64_t* out_n) {
+  return guarded([&] {
+    bytes_out(compression < 0 ? s->v.to_bytes() : s->v.to_compressed_bytes((Compression)compression), out, out_n);
+  });
+}
+int trrh_bm25_from_bytes(const uint8_t* data, uint64_t n, int compression, trrh_bm25** out) {
+  return guarded([&] {
+    *out = new trrh_bm25{compression < 0 ? BM25Index::from_bytes(data, n)
+                                         : BM25Index::from_compressed_bytes(data, n, (Compression)compression)};
+  });
+}
 int trrh_fuse(int kind, float param, const trrh_id* d_ids, const float* d_sc, uint32_t nd, const trrh_id* s_ids,
               const float* s_sc, uint32_t ns, trrh_id* out_ids, float* out_sc, uint32_t* out_n) {
   return guarded([&] {

@@ -319,6 +319,7 @@ void BM25Index::add(const Chunk& chunk) {  // :176-204
     df_[ids[a]] += 1;
     a = e;
   }
+  avg_loaded_.reset();  // update_avg_doc_length (:203)
   dirty_ = true;
 }
 
@@ -347,20 +348,24 @@ void BM25Index::remove(const ChunkId& id) {  // :245-275
     }
   }
   if (ord < frozen_docs_) pending_removed_.push_back(ord);  // otherwise it never reached the device
+  avg_loaded_.reset();  // update_avg_doc_length (:274)
   dirty_ = true;
 }
 
-float BM25Index::avg_doc_length() const {
-  freeze();
-  return avg_doc_length_;
+static float avg_of(const std::vector<uint32_t>& doc_len, const std::vector<uint8_t>& live, uint32_t doc_count) {
+  // :157-164 — u32 (wrapping) sum of the live lengths, as f32 / count as f32
+  uint32_t total = 0;
+  for (size_t i = 0; i < doc_len.size(); ++i) if (live[i]) total += doc_len[i];
+  return doc_count == 0 ? 0.0f : (float)total / (float)doc_count;
+}
+
+float BM25Index::avg_doc_length() const {  // host only: no device work
+  return avg_loaded_ ? *avg_loaded_ : avg_of(doc_len_, live_, doc_count_);
 }
 
 void BM25Index::freeze() const {
   if (!dirty_) return;
-  // :157-164 — u32 (wrapping) sum of the live lengths, as f32 / count as f32
-  uint32_t total = 0;
-  for (size_t i = 0; i < doc_len_.size(); ++i) if (live_[i]) total += doc_len_[i];
-  avg_doc_length_ = doc_count_ == 0 ? 0.0f : (float)total / (float)doc_count_;
+  avg_doc_length_ = avg_doc_length();
   const uint32_t n_terms = (uint32_t)postings_.size();
   std::vector<float> idf(n_terms);
   const float n = (float)doc_count_;
@@ -445,6 +450,275 @@ std::vector<Scored> BM25Index::search(const std::string& query, size_t k) const 
   out.reserve(n);
   for (uint32_t i = 0; i < n; ++i) out.emplace_back(id_of_[ord[i]], sc[i]);
   return out;
+}
+
+// ================================================================================================
+// Persistence in the reference's format: bincode 1.3 of BM25Index (src/index.rs:30-51), LZ4 (src/compressed.rs)
+// ================================================================================================
+const char* compression_as_str(Compression c) { return c == Compression::Lz4 ? "lz4" : "zstd"; }
+
+namespace {
+[[noreturn]] void ser_fail(const std::string& m) { throw Error(Error::Kind::Serialization, m); }
+
+inline uint32_t load32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+
+// One LZ4 block (the format lz4_flex writes): sequences of [token][literal length bytes][literals][offset u16]
+// [match length bytes]; the block ends with a literals-only sequence, the last match starts at least 12 bytes and ends
+// at least 5 bytes before the end of the input.
+std::vector<uint8_t> lz4_compress_block(const uint8_t* src, size_t n) {
+  std::vector<uint8_t> out;
+  out.reserve(n + n / 255 + 16);
+  auto put_len = [&](size_t v) {  // the part of a length beyond the 15 held by the token nibble
+    while (v >= 255) { out.push_back(255); v -= 255; }
+    out.push_back((uint8_t)v);
+  };
+  auto emit = [&](size_t lit_start, size_t lit_len, size_t match_len, size_t offset) {
+    const size_t ml = match_len ? match_len - 4 : 0;
+    out.push_back((uint8_t)((std::min<size_t>(lit_len, 15) << 4) | (match_len ? std::min<size_t>(ml, 15) : 0)));
+    if (lit_len >= 15) put_len(lit_len - 15);
+    out.insert(out.end(), src + lit_start, src + lit_start + lit_len);
+    if (match_len) {
+      out.push_back((uint8_t)(offset & 0xFF));
+      out.push_back((uint8_t)(offset >> 8));
+      if (ml >= 15) put_len(ml - 15);
+    }
+  };
+  size_t anchor = 0;
+  if (n > 12) {
+    std::vector<int64_t> table((size_t)1 << 16, -1);
+    const size_t match_start_limit = n - 12, match_end_limit = n - 5;
+    size_t i = 0;
+    while (i <= match_start_limit) {
+      const uint32_t v = load32(src + i);
+      const uint32_t h = (v * 2654435761u) >> 16;
+      const int64_t cand = table[h];
+      table[h] = (int64_t)i;
+      if (cand >= 0 && i - (size_t)cand <= 65535 && load32(src + cand) == v) {
+        size_t ml = 4;
+        while (i + ml < match_end_limit && src[(size_t)cand + ml] == src[i + ml]) ++ml;
+        emit(anchor, i - anchor, ml, i - (size_t)cand);
+        i += ml;
+        anchor = i;
+      } else {
+        ++i;
+      }
+    }
+  }
+  emit(anchor, n - anchor, 0, 0);
+  return out;
+}
+
+std::vector<uint8_t> lz4_decompress_block(const uint8_t* src, size_t n, size_t out_size) {
+  std::vector<uint8_t> out;
+  out.reserve(out_size);
+  size_t i = 0;
+  auto get_len = [&](size_t base) {
+    size_t v = base;
+    if (base == 15) {
+      uint8_t b;
+      do {
+        if (i >= n) ser_fail("LZ4 decompression failed: truncated length");
+        b = src[i++];
+        v += b;
+      } while (b == 255);
+    }
+    return v;
+  };
+  while (i < n) {
+    const uint8_t token = src[i++];
+    const size_t lit = get_len(token >> 4);
+    if (lit > n - i || out.size() + lit > out_size) ser_fail("LZ4 decompression failed: literals out of bounds");
+    out.insert(out.end(), src + i, src + i + lit);
+    i += lit;
+    if (i == n) break;  // the last sequence has no match
+    if (n - i < 2) ser_fail("LZ4 decompression failed: truncated offset");
+    const size_t offset = (size_t)src[i] | ((size_t)src[i + 1] << 8);
+    i += 2;
+    const size_t ml = get_len(token & 15) + 4;
+    if (offset == 0 || offset > out.size()) ser_fail("LZ4 decompression failed: offset out of bounds");
+    if (out.size() + ml > out_size) ser_fail("LZ4 decompression failed: output too large");
+    size_t from = out.size() - offset;
+    for (size_t k = 0; k < ml; ++k) out.push_back(out[from + k]);  // may overlap its own output (run-length style)
+  }
+  if (out.size() != out_size) ser_fail("LZ4 decompression failed: size mismatch");
+  return out;
+}
+
+struct BinWriter {
+  std::vector<uint8_t> b;
+  void raw(const void* p, size_t n) { const uint8_t* q = static_cast<const uint8_t*>(p); b.insert(b.end(), q, q + n); }
+  void u8(uint8_t v) { b.push_back(v); }
+  void u32(uint32_t v) { raw(&v, 4); }
+  void u64(uint64_t v) { raw(&v, 8); }
+  void f32(float v) { raw(&v, 4); }
+  void str(const std::string& s) { u64(s.size()); raw(s.data(), s.size()); }
+  void id(const ChunkId& c) {  // uuid::Uuid in a binary format: serialize_bytes(as_bytes()) = u64 length + 16 big-endian bytes
+    u64(16);
+    for (int k = 7; k >= 0; --k) u8((uint8_t)(c.hi >> (8 * k)));
+    for (int k = 7; k >= 0; --k) u8((uint8_t)(c.lo >> (8 * k)));
+  }
+};
+
+struct BinReader {
+  const uint8_t* p;
+  size_t n, i = 0;
+  void need(size_t k) const { if (k > n - i) ser_fail("Bincode deserialization failed: unexpected end of input"); }
+  uint8_t u8() { need(1); return p[i++]; }
+  uint32_t u32() { need(4); uint32_t v; memcpy(&v, p + i, 4); i += 4; return v; }
+  uint64_t u64() { need(8); uint64_t v; memcpy(&v, p + i, 8); i += 8; return v; }
+  float f32() { need(4); float v; memcpy(&v, p + i, 4); i += 4; return v; }
+  uint64_t len(size_t min_elem_bytes) {  // a length prefix that the remaining input can actually hold
+    const uint64_t v = u64();
+    if (min_elem_bytes && v > (n - i) / min_elem_bytes) ser_fail("Bincode deserialization failed: length exceeds input");
+    return v;
+  }
+  std::string str() {
+    const uint64_t l = len(1);
+    std::string s(reinterpret_cast<const char*>(p + i), (size_t)l);
+    i += (size_t)l;
+    return s;
+  }
+  ChunkId id() {
+    if (u64() != 16) ser_fail("Bincode deserialization failed: a ChunkId is 16 bytes");
+    need(16);
+    ChunkId c;
+    for (int k = 0; k < 8; ++k) c.hi = (c.hi << 8) | p[i++];
+    for (int k = 0; k < 8; ++k) c.lo = (c.lo << 8) | p[i++];
+    return c;
+  }
+};
+}  // namespace
+
+std::vector<uint8_t> compress(Compression c, const uint8_t* data, size_t n) {
+  if (n == 0) return {};  // :37-39
+  if (c == Compression::Zstd) throw Error(Error::Kind::Unsupported, "ZSTD compression is not built into this library (use LZ4, the reference's default)");
+  if (n > 0xFFFFFFFFull) ser_fail("LZ4 compression failed: input larger than 4 GiB");
+  std::vector<uint8_t> block = lz4_compress_block(data, n);
+  std::vector<uint8_t> out(4);
+  const uint32_t sz = (uint32_t)n;
+  memcpy(out.data(), &sz, 4);  // compress_prepend_size: u32 little-endian
+  out.insert(out.end(), block.begin(), block.end());
+  return out;
+}
+
+std::vector<uint8_t> decompress(Compression c, const uint8_t* data, size_t n) {
+  if (n == 0) return {};  // :54-56
+  if (c == Compression::Zstd) throw Error(Error::Kind::Unsupported, "ZSTD decompression is not built into this library (use LZ4, the reference's default)");
+  if (n < 4) ser_fail("LZ4 decompression failed: missing size prefix");
+  return lz4_decompress_block(data + 4, n - 4, load32(data));
+}
+
+std::vector<uint8_t> BM25Index::to_bytes() const {
+  BinWriter w;
+  std::vector<const std::string*> term_of(postings_.size(), nullptr);
+  for (const auto& kv : dict_) term_of[kv.second] = &kv.first;
+  uint64_t n_terms = 0;  // the reference drops a term when its df reaches 0 (:262-271); here it keeps an empty list
+  for (size_t t = 0; t < postings_.size(); ++t) n_terms += !postings_[t].empty();
+  // inverted_index: HashMap<String, Vec<(ChunkId, u32)>>
+  w.u64(n_terms);
+  for (size_t t = 0; t < postings_.size(); ++t) {
+    if (postings_[t].empty()) continue;
+    w.str(*term_of[t]);
+    w.u64(postings_[t].size());
+    for (const auto& e : postings_[t]) { w.id(id_of_[e.first]); w.u32(e.second); }
+  }
+  // doc_freqs: HashMap<String, u32>
+  w.u64(n_terms);
+  for (size_t t = 0; t < postings_.size(); ++t) {
+    if (postings_[t].empty()) continue;
+    w.str(*term_of[t]);
+    w.u32(df_[t]);
+  }
+  // doc_lengths: HashMap<ChunkId, u32>
+  uint64_t n_live = 0;
+  for (size_t i = 0; i < live_.size(); ++i) n_live += ord_of_.count(id_of_[i]) && ord_of_.at(id_of_[i]) == i && live_[i];
+  w.u64(n_live);
+  for (size_t i = 0; i < live_.size(); ++i)
+    if (live_[i] && ord_of_.count(id_of_[i]) && ord_of_.at(id_of_[i]) == i) { w.id(id_of_[i]); w.u32(doc_len_[i]); }
+  w.f32(avg_doc_length());
+  w.u32(doc_count_);
+  w.f32(k1_);
+  w.f32(b_);
+  w.u8(lowercase_ ? 1 : 0);
+  w.u64(stopwords_.size());
+  for (const std::string& s : stopwords_) w.str(s);
+  return std::move(w.b);
+}
+
+BM25Index BM25Index::from_bytes(const uint8_t* data, size_t n) {
+  BinReader r{data, n};
+  struct TermIn { std::string term; std::vector<std::pair<ChunkId, uint32_t>> postings; };
+  std::vector<TermIn> terms((size_t)r.len(16));
+  for (TermIn& t : terms) {
+    t.term = r.str();
+    t.postings.resize((size_t)r.len(28));
+    for (auto& e : t.postings) { e.first = r.id(); e.second = r.u32(); }
+  }
+  std::unordered_map<std::string, uint32_t> doc_freqs;
+  for (uint64_t k = r.len(12); k > 0; --k) { std::string t = r.str(); doc_freqs[std::move(t)] = r.u32(); }
+  std::unordered_map<ChunkId, uint32_t, ChunkIdHash> doc_lengths;
+  for (uint64_t k = r.len(28); k > 0; --k) { const ChunkId c = r.id(); doc_lengths[c] = r.u32(); }
+  BM25Index ix;
+  const float avg = r.f32();
+  ix.doc_count_ = r.u32();
+  ix.k1_ = r.f32();
+  ix.b_ = r.f32();
+  const uint8_t lc = r.u8();
+  if (lc > 1) ser_fail("Bincode deserialization failed: invalid bool");
+  ix.lowercase_ = lc != 0;
+  ix.stopwords_.clear();
+  for (uint64_t k = r.len(8); k > 0; --k) ix.stopwords_.insert(r.str());
+  if (r.i != r.n) ser_fail("Bincode deserialization failed: trailing bytes");
+
+  // chunks: every id of doc_lengths plus any id that only occurs in a posting (length 0, :144 unwrap_or(0)), numbered by
+  // ascending ChunkId
+  std::vector<ChunkId> ids;
+  ids.reserve(doc_lengths.size());
+  for (const auto& kv : doc_lengths) ids.push_back(kv.first);
+  {
+    std::unordered_set<ChunkId, ChunkIdHash> extra;
+    for (const TermIn& t : terms)
+      for (const auto& e : t.postings)
+        if (!doc_lengths.count(e.first) && extra.insert(e.first).second) ids.push_back(e.first);
+  }
+  std::sort(ids.begin(), ids.end(), [](const ChunkId& a, const ChunkId& b) { return a.hi != b.hi ? a.hi < b.hi : a.lo < b.lo; });
+  ix.id_of_ = ids;
+  ix.doc_len_.resize(ids.size());
+  ix.live_.assign(ids.size(), 1);
+  for (size_t i = 0; i < ids.size(); ++i) {
+    ix.ord_of_[ids[i]] = (uint32_t)i;
+    auto it = doc_lengths.find(ids[i]);
+    ix.doc_len_[i] = it == doc_lengths.end() ? 0u : it->second;
+  }
+  // terms by ascending string; postings by ascending ordinal, first occurrence of a chunk wins (:128-132 `find`)
+  std::sort(terms.begin(), terms.end(), [](const TermIn& a, const TermIn& b) { return a.term < b.term; });
+  for (size_t t = 0; t < terms.size(); ++t) {
+    if (t && terms[t].term == terms[t - 1].term) ser_fail("Bincode deserialization failed: duplicate term");
+    ix.dict_.emplace(terms[t].term, (uint32_t)t);
+    std::vector<std::pair<uint32_t, uint32_t>> pl;
+    pl.reserve(terms[t].postings.size());
+    for (const auto& e : terms[t].postings) pl.emplace_back(ix.ord_of_.at(e.first), e.second);
+    std::stable_sort(pl.begin(), pl.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    pl.erase(std::unique(pl.begin(), pl.end(), [](const auto& a, const auto& b) { return a.first == b.first; }), pl.end());
+    ix.postings_.push_back(std::move(pl));
+    auto df = doc_freqs.find(terms[t].term);
+    ix.df_.push_back(df == doc_freqs.end() ? 0u : df->second);  // :140 unwrap_or(0)
+  }
+  // the reference scores with the stored average until the next add/remove recomputes it
+  const float recomputed = avg_of(ix.doc_len_, ix.live_, ix.doc_count_);
+  if (memcmp(&recomputed, &avg, 4) != 0) ix.avg_loaded_ = avg;
+  ix.dirty_ = true;
+  return ix;
+}
+
+std::vector<uint8_t> BM25Index::to_compressed_bytes(Compression c) const {
+  const std::vector<uint8_t> b = to_bytes();
+  return compress(c, b.data(), b.size());
+}
+
+BM25Index BM25Index::from_compressed_bytes(const uint8_t* data, size_t n, Compression c) {
+  const std::vector<uint8_t> b = decompress(c, data, n);
+  return from_bytes(b.data(), b.size());
 }
 
 // ================================================================================================
