@@ -185,6 +185,45 @@ class BM25Index {  // src/index.rs:30-280 (SparseIndex impl included)
   mutable bool needs_rebuild_ = true;
 };
 
+// ------------------------------------------------------------------------------------------------
+// The CLI's persisted index (crates/trueno-rag-cli/src/main.rs:133-154): `index.json` written by `trueno-rag index`
+// (serde_json::to_string_pretty, :423) and scanned by `trueno-rag query` (:437-439, 479-492).  SURVEY 8(f) ranks 2 and 4:
+// the file is parsed straight into an embedding slab and the query's brute-force cosine loop runs through K1.
+// ------------------------------------------------------------------------------------------------
+struct PersistedChunk {  // :148-153
+  std::string content;
+  std::optional<std::string> title, source;
+};
+class PersistedIndex {  // :133-146
+ public:
+  std::vector<PersistedChunk> chunks;
+  std::vector<std::vector<float>> embeddings;
+  size_t dimension = 0;
+  std::string embedder_type;               // #[serde(default)]
+  std::optional<std::string> model_name;   // #[serde(default)]
+
+  // serde_json::from_str::<PersistedIndex>: unknown keys ignored, `chunks` / `embeddings` / `dimension` required, numbers
+  // parsed as f64 and narrowed to f32 like serde_json does; malformed input -> Error::Serialization
+  static PersistedIndex from_json(const char* text, size_t n);
+  // run_query's scoring (:479-492): cosine of `query` against every stored embedding (an embedding of another length
+  // scores 0.0, :529-531), stable sort by score descending (ties keep index order), first top_k.  The query embedding comes
+  // from the caller (the embedders are out of scope).  Pairs are (index into `chunks`, score).
+  std::vector<std::pair<size_t, float>> query(const std::vector<float>& query_embedding, size_t top_k) const;
+
+  PersistedIndex();
+  ~PersistedIndex();
+  PersistedIndex(PersistedIndex&&) noexcept;
+  PersistedIndex& operator=(PersistedIndex&&) noexcept;
+
+ private:
+  struct DeviceRows {  // the embeddings of one length on the device, with their indexes into `chunks`
+    std::shared_ptr<detail::DeviceDense> dev;
+    std::vector<uint32_t> index_of;
+    size_t n_other = 0;  // embeddings of any other length (score 0.0)
+  };
+  mutable std::unordered_map<size_t, DeviceRows> by_len_;
+};
+
 struct FusionStrategy {  // src/fusion.rs:9-63
   enum class Kind { RRF = 0, Linear = 1, Convex = 2, DBSF = 3, Union = 4, Intersection = 5 };
   Kind kind = Kind::RRF;

@@ -52,6 +52,22 @@ TRRH_API void trrh_bytes_free(uint8_t* p);
 TRRH_API int trrh_bm25_to_bytes(trrh_bm25* s, int compression, uint8_t** out, uint64_t* out_n);
 TRRH_API int trrh_bm25_from_bytes(const uint8_t* data, uint64_t n, int compression, trrh_bm25** out);
 
+/* The CLI's index.json (reference crates/trueno-rag-cli/src/main.rs:133-154): parse (:437-439) and the brute-force query
+ * scan (:479-492) on the device.  Strings are owned by the handle; NULL = None. */
+typedef struct trrh_cli_index trrh_cli_index;
+TRRH_API int trrh_cli_index_from_json(const char* text, uint64_t n, trrh_cli_index** out);
+TRRH_API void trrh_cli_index_free(trrh_cli_index* h);
+TRRH_API uint64_t trrh_cli_index_len(trrh_cli_index* h);
+TRRH_API uint64_t trrh_cli_index_n_embeddings(trrh_cli_index* h);
+TRRH_API uint64_t trrh_cli_index_dimension(trrh_cli_index* h);
+TRRH_API const char* trrh_cli_index_embedder_type(trrh_cli_index* h);
+TRRH_API const char* trrh_cli_index_model_name(trrh_cli_index* h);
+TRRH_API int trrh_cli_index_chunk(trrh_cli_index* h, uint64_t i, const char** content, uint64_t* content_len,
+                                  const char** title, const char** source);
+TRRH_API int trrh_cli_index_embedding(trrh_cli_index* h, uint64_t i, const float** data, uint64_t* len);
+TRRH_API int trrh_cli_index_query(trrh_cli_index* h, const float* q, uint64_t q_len, uint64_t top_k, uint64_t* out_idx,
+                                  float* out_score, uint64_t* out_n);
+
 /* FusionStrategy::fuse (reference src/fusion.rs:42-63); out buffers hold nd + ns entries */
 TRRH_API int trrh_fuse(int kind, float param, const trrh_id* d_ids, const float* d_sc, uint32_t nd, const trrh_id* s_ids,
                        const float* s_sc, uint32_t ns, trrh_id* out_ids, float* out_sc, uint32_t* out_n);

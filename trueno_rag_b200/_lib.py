@@ -121,6 +121,18 @@ TRRH_PROTOS = {
     "trrh_bytes_free": (None, [vp]),
     "trrh_bm25_to_bytes": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_uint64)]),
     "trrh_bm25_from_bytes": (C.c_int, [C.c_char_p, C.c_uint64, C.c_int, vpp]),
+    "trrh_cli_index_from_json": (C.c_int, [C.c_char_p, C.c_uint64, vpp]),
+    "trrh_cli_index_free": (None, [vp]),
+    "trrh_cli_index_len": (C.c_uint64, [vp]),
+    "trrh_cli_index_n_embeddings": (C.c_uint64, [vp]),
+    "trrh_cli_index_dimension": (C.c_uint64, [vp]),
+    "trrh_cli_index_embedder_type": (C.c_char_p, [vp]),
+    "trrh_cli_index_model_name": (C.c_char_p, [vp]),
+    "trrh_cli_index_chunk": (C.c_int, [vp, C.c_uint64, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_char_p),
+                                       C.POINTER(C.c_char_p)]),
+    "trrh_cli_index_embedding": (C.c_int, [vp, C.c_uint64, C.POINTER(f32p), C.POINTER(C.c_uint64)]),
+    "trrh_cli_index_query": (C.c_int, [vp, f32p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), f32p,
+                                       C.POINTER(C.c_uint64)]),
     "trrh_fuse": (C.c_int, [C.c_int, C.c_float, idp, f32p, C.c_uint32, idp, f32p, C.c_uint32, idp, f32p, u32p]),
     "trrh_retriever_new": (C.c_int, [vp, vp, C.c_uint32, C.c_int, C.c_float, C.c_int, C.c_int, vpp]),
     "trrh_retriever_free": (None, [vp]),

@@ -611,6 +611,76 @@ class BM25Index:
 
 
 @dataclass
+class PersistedChunk:
+    """crates/trueno-rag-cli/src/main.rs:148-153"""
+    content: str
+    title: Optional[str] = None
+    source: Optional[str] = None
+
+
+class PersistedIndex:
+    """The CLI's `index.json` (crates/trueno-rag-cli/src/main.rs:133-146): parsed by the library (serde_json::from_str,
+    :437-439); `query` is `run_query`'s cosine scan + stable sort + truncate (:479-495) on the device."""
+
+    def __init__(self, _h):
+        self.L = _lib.load()
+        self.h = _h
+
+    @staticmethod
+    def from_json(text) -> "PersistedIndex":
+        raw = text.encode() if isinstance(text, str) else bytes(text)
+        h = C.c_void_p()
+        _hcheck(_lib.load().trrh_cli_index_from_json(raw, len(raw), C.byref(h)))
+        return PersistedIndex(h)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.trrh_cli_index_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self.L.trrh_cli_index_len(self.h))
+
+    @property
+    def n_embeddings(self) -> int:
+        return int(self.L.trrh_cli_index_n_embeddings(self.h))
+
+    @property
+    def dimension(self) -> int:
+        return int(self.L.trrh_cli_index_dimension(self.h))
+
+    @property
+    def embedder_type(self) -> str:
+        return self.L.trrh_cli_index_embedder_type(self.h).decode()
+
+    @property
+    def model_name(self) -> Optional[str]:
+        v = self.L.trrh_cli_index_model_name(self.h)
+        return None if v is None else v.decode()
+
+    def chunk(self, i: int) -> PersistedChunk:
+        content, n, title, source = C.c_void_p(), C.c_uint64(), C.c_char_p(), C.c_char_p()
+        _hcheck(self.L.trrh_cli_index_chunk(self.h, i, C.byref(content), C.byref(n), C.byref(title), C.byref(source)))
+        return PersistedChunk(C.string_at(content, n.value).decode(), None if title.value is None else title.value.decode(),
+                              None if source.value is None else source.value.decode())
+
+    def embedding(self, i: int) -> np.ndarray:
+        data, n = f32p(), C.c_uint64()
+        _hcheck(self.L.trrh_cli_index_embedding(self.h, i, C.byref(data), C.byref(n)))
+        return np.ctypeslib.as_array(data, shape=(n.value,)).copy() if n.value else np.zeros(0, np.float32)
+
+    def query(self, query_embedding, top_k: int) -> List[Tuple[int, float]]:
+        q = np.ascontiguousarray(query_embedding, dtype=np.float32)
+        cap = max(min(top_k, self.n_embeddings), 1)
+        idx, sc, n = (C.c_uint64 * cap)(), np.zeros(cap, np.float32), C.c_uint64()
+        _hcheck(self.L.trrh_cli_index_query(self.h, _p(q, f32p), q.size, top_k, idx, _p(sc, f32p), C.byref(n)))
+        return [(int(idx[i]), float(sc[i])) for i in range(n.value)]
+
+
+@dataclass
 class FusionStrategy:
     """Reference `FusionStrategy` (src/fusion.rs:9-63)."""
     kind: int = RRF

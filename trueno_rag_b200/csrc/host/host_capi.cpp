@@ -140,6 +140,42 @@ int trrh_bm25_from_bytes(const uint8_t* data, uint64_t n, int compression, trrh_
                                          : BM25Index::from_compressed_bytes(data, n, (Compression)compression)};
   });
 }
+struct trrh_cli_index { PersistedIndex v; };
+int trrh_cli_index_from_json(const char* text, uint64_t n, trrh_cli_index** out) {
+  return guarded([&] { *out = new trrh_cli_index{PersistedIndex::from_json(text, n)}; });
+}
+void trrh_cli_index_free(trrh_cli_index* h) { delete h; }
+uint64_t trrh_cli_index_len(trrh_cli_index* h) { return h->v.chunks.size(); }
+uint64_t trrh_cli_index_n_embeddings(trrh_cli_index* h) { return h->v.embeddings.size(); }
+uint64_t trrh_cli_index_dimension(trrh_cli_index* h) { return h->v.dimension; }
+const char* trrh_cli_index_embedder_type(trrh_cli_index* h) { return h->v.embedder_type.c_str(); }
+const char* trrh_cli_index_model_name(trrh_cli_index* h) { return h->v.model_name ? h->v.model_name->c_str() : nullptr; }
+int trrh_cli_index_chunk(trrh_cli_index* h, uint64_t i, const char** content, uint64_t* content_len, const char** title,
+                         const char** source) {
+  return guarded([&] {
+    if (i >= h->v.chunks.size()) throw Error(Error::Kind::InvalidConfig, "chunk index out of range");
+    const PersistedChunk& c = h->v.chunks[i];
+    *content = c.content.data();
+    *content_len = c.content.size();
+    *title = c.title ? c.title->c_str() : nullptr;
+    *source = c.source ? c.source->c_str() : nullptr;
+  });
+}
+int trrh_cli_index_embedding(trrh_cli_index* h, uint64_t i, const float** data, uint64_t* len) {
+  return guarded([&] {
+    if (i >= h->v.embeddings.size()) throw Error(Error::Kind::InvalidConfig, "embedding index out of range");
+    *data = h->v.embeddings[i].data();
+    *len = h->v.embeddings[i].size();
+  });
+}
+int trrh_cli_index_query(trrh_cli_index* h, const float* q, uint64_t q_len, uint64_t top_k, uint64_t* out_idx,
+                         float* out_score, uint64_t* out_n) {
+  return guarded([&] {
+    const auto r = h->v.query(std::vector<float>(q, q + q_len), top_k);
+    *out_n = r.size();
+    for (size_t i = 0; i < r.size(); ++i) { out_idx[i] = r[i].first; out_score[i] = r[i].second; }
+  });
+}
 int trrh_fuse(int kind, float param, const trrh_id* d_ids, const float* d_sc, uint32_t nd, const trrh_id* s_ids,
               const float* s_sc, uint32_t ns, trrh_id* out_ids, float* out_sc, uint32_t* out_n) {
   return guarded([&] {

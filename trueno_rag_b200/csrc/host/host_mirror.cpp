@@ -1,11 +1,13 @@
 // host_mirror.cpp — implementation of include/trueno_rag.hpp (host-side mirror of the reference API).
 // Only bookkeeping lives here (id maps, tokenizer, dictionary, CSR construction, idf via the platform logf);
 // every score, ranking and fusion is computed by the CUDA kernels through the C ABI.
+#include <errno.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <mutex>
 #include <random>
 
@@ -719,6 +721,263 @@ std::vector<uint8_t> BM25Index::to_compressed_bytes(Compression c) const {
 BM25Index BM25Index::from_compressed_bytes(const uint8_t* data, size_t n, Compression c) {
   const std::vector<uint8_t> b = decompress(c, data, n);
   return from_bytes(b.data(), b.size());
+}
+
+// ================================================================================================
+// PersistedIndex: the CLI's index.json (crates/trueno-rag-cli/src/main.rs:133-154, 437-439, 479-492)
+// ================================================================================================
+namespace {
+// a small recursive-descent JSON reader: exactly what serde_json::from_str needs for PersistedIndex
+struct Json {
+  const char* p;
+  const char* end;
+  [[noreturn]] void fail(const char* what) const { ser_fail(std::string("JSON deserialization failed: ") + what); }
+  void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p; }
+  bool peek(char c) { ws(); return p < end && *p == c; }
+  void expect(char c) { ws(); if (p >= end || *p != c) fail("unexpected character"); ++p; }
+  bool literal(const char* lit) {
+    ws();
+    const size_t l = strlen(lit);
+    if ((size_t)(end - p) >= l && memcmp(p, lit, l) == 0) { p += l; return true; }
+    return false;
+  }
+  static int hex(char c) { return c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : -1; }
+  uint32_t hex4() {
+    if (end - p < 4) fail("truncated \\u escape");
+    uint32_t v = 0;
+    for (int k = 0; k < 4; ++k) { const int h = hex(p[k]); if (h < 0) fail("bad \\u escape"); v = v * 16 + (uint32_t)h; }
+    p += 4;
+    return v;
+  }
+  std::string string() {
+    expect('"');
+    std::string out;
+    while (true) {
+      if (p >= end) fail("unterminated string");
+      const unsigned char c = (unsigned char)*p++;
+      if (c == '"') break;
+      if (c < 0x20) fail("control character in string");
+      if (c != '\\') { out.push_back((char)c); continue; }
+      if (p >= end) fail("unterminated escape");
+      const char e = *p++;
+      switch (e) {
+        case '"': out.push_back('"'); break;
+        case '\\': out.push_back('\\'); break;
+        case '/': out.push_back('/'); break;
+        case 'b': out.push_back('\b'); break;
+        case 'f': out.push_back('\f'); break;
+        case 'n': out.push_back('\n'); break;
+        case 'r': out.push_back('\r'); break;
+        case 't': out.push_back('\t'); break;
+        case 'u': {
+          uint32_t cp = hex4();
+          if (cp >= 0xD800 && cp <= 0xDBFF) {  // surrogate pair
+            if (end - p < 2 || p[0] != '\\' || p[1] != 'u') fail("lone surrogate");
+            p += 2;
+            const uint32_t lo = hex4();
+            if (lo < 0xDC00 || lo > 0xDFFF) fail("lone surrogate");
+            cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+          } else if (cp >= 0xDC00 && cp <= 0xDFFF) {
+            fail("lone surrogate");
+          }
+          encode_utf8(cp, out);
+          break;
+        }
+        default: fail("bad escape");
+      }
+    }
+    return out;
+  }
+  // the JSON number grammar; returns the token
+  std::string number_token() {
+    ws();
+    const char* s = p;
+    if (p < end && *p == '-') ++p;
+    if (p >= end || *p < '0' || *p > '9') fail("expected a number");
+    if (*p == '0') ++p; else while (p < end && *p >= '0' && *p <= '9') ++p;
+    if (p < end && *p == '.') {
+      ++p;
+      if (p >= end || *p < '0' || *p > '9') fail("digit expected after '.'");
+      while (p < end && *p >= '0' && *p <= '9') ++p;
+    }
+    if (p < end && (*p == 'e' || *p == 'E')) {
+      ++p;
+      if (p < end && (*p == '+' || *p == '-')) ++p;
+      if (p >= end || *p < '0' || *p > '9') fail("digit expected in exponent");
+      while (p < end && *p >= '0' && *p <= '9') ++p;
+    }
+    return std::string(s, p);
+  }
+  float f32() {  // serde_json: f64, then `as f32`
+    const std::string t = number_token();
+    const double d = strtod(t.c_str(), nullptr);
+    const float f = (float)d;
+    if (std::isinf(f) && !std::isinf(d)) return f;  // `as f32` saturates to infinity like the cast
+    return f;
+  }
+  size_t usize() {
+    const std::string t = number_token();
+    if (t.empty() || t[0] == '-' || t.find_first_of(".eE") != std::string::npos) fail("expected an unsigned integer");
+    errno = 0;
+    const unsigned long long v = strtoull(t.c_str(), nullptr, 10);
+    if (errno) fail("integer out of range");
+    return (size_t)v;
+  }
+  std::optional<std::string> opt_string() {
+    if (literal("null")) return std::nullopt;
+    return string();
+  }
+  void skip_value() {  // a value of a key the struct does not have
+    ws();
+    if (p >= end) fail("unexpected end of input");
+    if (*p == '"') { string(); return; }
+    if (*p == '{') {
+      ++p;
+      if (peek('}')) { ++p; return; }
+      while (true) { string(); expect(':'); skip_value(); if (peek(',')) { ++p; continue; } expect('}'); return; }
+    }
+    if (*p == '[') {
+      ++p;
+      if (peek(']')) { ++p; return; }
+      while (true) { skip_value(); if (peek(',')) { ++p; continue; } expect(']'); return; }
+    }
+    if (literal("true") || literal("false") || literal("null")) return;
+    number_token();
+  }
+  // calls body(key) for every member of an object
+  template <typename F>
+  void object(F&& body) {
+    expect('{');
+    if (peek('}')) { ++p; return; }
+    while (true) {
+      const std::string key = string();
+      expect(':');
+      body(key);
+      if (peek(',')) { ++p; continue; }
+      expect('}');
+      return;
+    }
+  }
+  template <typename F>
+  void array(F&& body) {
+    expect('[');
+    if (peek(']')) { ++p; return; }
+    while (true) {
+      body();
+      if (peek(',')) { ++p; continue; }
+      expect(']');
+      return;
+    }
+  }
+};
+}  // namespace
+
+PersistedIndex::PersistedIndex() = default;
+PersistedIndex::~PersistedIndex() = default;
+PersistedIndex::PersistedIndex(PersistedIndex&&) noexcept = default;
+PersistedIndex& PersistedIndex::operator=(PersistedIndex&&) noexcept = default;
+
+PersistedIndex PersistedIndex::from_json(const char* text, size_t n) {
+  Json j{text, text + n};
+  PersistedIndex out;
+  bool has_chunks = false, has_emb = false, has_dim = false, has_type = false, has_model = false;
+  auto once = [&](bool& seen, const char* name) {
+    if (seen) j.fail((std::string("duplicate field `") + name + "`").c_str());
+    seen = true;
+  };
+  j.object([&](const std::string& key) {
+    if (key == "chunks") {
+      once(has_chunks, "chunks");
+      j.array([&] {
+        PersistedChunk c;
+        bool has_content = false;
+        j.object([&](const std::string& k2) {
+          if (k2 == "content") { c.content = j.string(); has_content = true; }
+          else if (k2 == "title") c.title = j.opt_string();
+          else if (k2 == "source") c.source = j.opt_string();
+          else j.skip_value();
+        });
+        if (!has_content) j.fail("missing field `content`");
+        out.chunks.push_back(std::move(c));
+      });
+    } else if (key == "embeddings") {
+      once(has_emb, "embeddings");
+      j.array([&] {
+        std::vector<float> row;
+        if (!out.embeddings.empty()) row.reserve(out.embeddings.back().size());
+        j.array([&] { row.push_back(j.f32()); });
+        out.embeddings.push_back(std::move(row));
+      });
+    } else if (key == "dimension") {
+      once(has_dim, "dimension");
+      out.dimension = j.usize();
+    } else if (key == "embedder_type") {
+      once(has_type, "embedder_type");
+      out.embedder_type = j.string();
+    } else if (key == "model_name") {
+      once(has_model, "model_name");
+      out.model_name = j.opt_string();
+    } else {
+      j.skip_value();
+    }
+  });
+  j.ws();
+  if (j.p != j.end) j.fail("trailing characters");
+  if (!has_chunks) j.fail("missing field `chunks`");
+  if (!has_emb) j.fail("missing field `embeddings`");
+  if (!has_dim) j.fail("missing field `dimension`");
+  return out;
+}
+
+std::vector<std::pair<size_t, float>> PersistedIndex::query(const std::vector<float>& q, size_t top_k) const {
+  std::vector<std::pair<size_t, float>> out;
+  const size_t n = embeddings.size();
+  if (top_k == 0 || n == 0) return out;
+  const size_t len = q.size();
+  auto it = by_len_.find(len);
+  if (it == by_len_.end()) {
+    DeviceRows d;
+    std::vector<float> slab;
+    for (size_t i = 0; i < n; ++i) {
+      if (embeddings[i].size() != len) { d.n_other++; continue; }
+      d.index_of.push_back((uint32_t)i);
+      slab.insert(slab.end(), embeddings[i].begin(), embeddings[i].end());
+    }
+    if (!d.index_of.empty() && len > 0) {
+      d.dev = std::make_shared<detail::DeviceDense>();
+      check(trr_dense_create(default_context(), (uint32_t)len, TRR_METRIC_COSINE, TRR_DTYPE_F32, d.index_of.size(), &d.dev->h));
+      check(trr_dense_append(d.dev->h, slab.data(), d.index_of.size()));
+    }
+    it = by_len_.emplace(len, std::move(d)).first;
+  }
+  const DeviceRows& d = it->second;
+  const size_t k = std::min(top_k, n);
+  std::vector<uint32_t> ord(k);
+  std::vector<float> sc(k);
+  uint32_t got = 0;
+  if (d.dev) {
+    const uint32_t kk = (uint32_t)std::min(k, d.index_of.size());
+    check(trr_dense_search(d.dev->h, q.data(), 1, kk, ord.data(), sc.data(), &got));
+  }
+  // merge the device list (score desc, index asc) with the rows that score 0.0 by construction (other lengths, or every
+  // row when the query is empty), keeping the stable order of the reference's sort (:494-495)
+  std::vector<size_t> zeros;
+  if (d.n_other || !d.dev) {
+    for (size_t i = 0; i < n && zeros.size() < k; ++i)
+      if (!d.dev || embeddings[i].size() != len) zeros.push_back(i);
+  }
+  size_t a = 0, b = 0;
+  while (out.size() < k && (a < got || b < zeros.size())) {
+    bool take_dev;
+    if (a >= got) take_dev = false;
+    else if (b >= zeros.size()) take_dev = true;
+    else if (sc[a] > 0.0f) take_dev = true;
+    else if (sc[a] < 0.0f) take_dev = false;
+    else take_dev = d.index_of[ord[a]] < zeros[b];  // both 0.0 (or a NaN score, which partial_cmp treats as Equal)
+    if (take_dev) { out.emplace_back(d.index_of[ord[a]], sc[a]); ++a; }
+    else { out.emplace_back(zeros[b], 0.0f); ++b; }
+  }
+  return out;
 }
 
 // ================================================================================================
