@@ -207,7 +207,8 @@ class PersistedIndex {  // :133-146
   static PersistedIndex from_json(const char* text, size_t n);
   // run_query's scoring (:479-492): cosine of `query` against every stored embedding (an embedding of another length
   // scores 0.0, :529-531), stable sort by score descending (ties keep index order), first top_k.  The query embedding comes
-  // from the caller (the embedders are out of scope).  Pairs are (index into `chunks`, score).
+  // from the caller (the embedders are out of scope).  Pairs are (index into `chunks`, score).  top_k <= 1024 (the C ABI's
+  // per-query limit; larger values raise Error::Unsupported - the CLI's default is 5).
   std::vector<std::pair<size_t, float>> query(const std::vector<float>& query_embedding, size_t top_k) const;
 
   PersistedIndex();

@@ -137,7 +137,7 @@ def oracle_query(E, q, top_k):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,d,k", [(1, 8, 5), (50, 16, 5), (300, 384, 10), (2000, 64, 2000)])
+@pytest.mark.parametrize("n,d,k", [(1, 8, 5), (50, 16, 5), (300, 384, 10), (2000, 64, 1000)])
 def test_query_matches_reference_scan(n, d, k):
     rng = np.random.default_rng(n + d)
     E = rng.standard_normal((n, d)).astype(np.float32)
@@ -172,3 +172,12 @@ def test_query_with_rows_of_other_lengths_and_wrong_query_length():
     got = ix.query(q4, 3)
     assert got[0][0] == 2 and abs(got[0][1] - 1.0) < 1e-6 and [i for i, _ in got[1:]] == [0, 1]
     assert ix.query(q, 0) == []
+
+
+@pytest.mark.gpu
+def test_top_k_beyond_the_device_limit_is_reported():
+    E = np.random.default_rng(3).standard_normal((1500, 8)).astype(np.float32)
+    ix = api.PersistedIndex.from_json(make_json(E))
+    with pytest.raises(api.Error) as e:  # the C ABI serves k <= 1024 per query; no host-side scan is substituted
+        ix.query(E[0], 1500)
+    assert e.value.kind == "Unsupported"
