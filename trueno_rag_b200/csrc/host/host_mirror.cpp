@@ -459,6 +459,10 @@ std::vector<Scored> BM25Index::search(const std::string& query, size_t k) const 
 // ================================================================================================
 const char* compression_as_str(Compression c) { return c == Compression::Lz4 ? "lz4" : "zstd"; }
 
+// zstd_codec.cpp
+std::vector<uint8_t> zstd_decompress(const uint8_t* src, size_t n);
+std::vector<uint8_t> zstd_store(const uint8_t* src, size_t n);
+
 namespace {
 [[noreturn]] void ser_fail(const std::string& m) { throw Error(Error::Kind::Serialization, m); }
 
@@ -593,7 +597,7 @@ struct BinReader {
 
 std::vector<uint8_t> compress(Compression c, const uint8_t* data, size_t n) {
   if (n == 0) return {};  // :37-39
-  if (c == Compression::Zstd) throw Error(Error::Kind::Unsupported, "ZSTD compression is not built into this library (use LZ4, the reference's default)");
+  if (c == Compression::Zstd) return zstd_store(data, n);  // a valid frame of raw / RLE blocks (no entropy coding)
   if (n > 0xFFFFFFFFull) ser_fail("LZ4 compression failed: input larger than 4 GiB");
   std::vector<uint8_t> block = lz4_compress_block(data, n);
   std::vector<uint8_t> out(4);
@@ -605,7 +609,7 @@ std::vector<uint8_t> compress(Compression c, const uint8_t* data, size_t n) {
 
 std::vector<uint8_t> decompress(Compression c, const uint8_t* data, size_t n) {
   if (n == 0) return {};  // :54-56
-  if (c == Compression::Zstd) throw Error(Error::Kind::Unsupported, "ZSTD decompression is not built into this library (use LZ4, the reference's default)");
+  if (c == Compression::Zstd) return zstd_decompress(data, n);
   if (n < 4) ser_fail("LZ4 decompression failed: missing size prefix");
   return lz4_decompress_block(data + 4, n - 4, load32(data));
 }
