@@ -52,3 +52,14 @@ def test_product_never_references_the_oracle():
                 if re.search(r"(from|import)\s+oracle|libtrr_oracle|orc_\w+\s*\(", txt):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_rust_sys_crate_is_generated_from_the_header():
+    """integration/rust/trueno-rag-b200-sys/src/lib.rs is the mechanical translation of include/trueno_rag_b200.h: one
+    `pub fn` per TRR_API symbol, and regenerating it changes nothing"""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_rust_sys.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rs = open(os.path.join(ROOT, "integration", "rust", "trueno-rag-b200-sys", "src", "lib.rs")).read()
+    assert sorted(re.findall(r"pub fn (\w+)\(", rs)) == declared("trueno_rag_b200.h", "TRR_API")
