@@ -261,3 +261,4 @@ def test_remove_in_place_equals_rebuild_without_the_documents(api, ctx):
             assert np.array_equal(ords[b, :m], keep[eo[b, :m]] + 100), b
             assert np.array_equal(scores[b, :m], es[b, :m]), b
     dev.close()
+

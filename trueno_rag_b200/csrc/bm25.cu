@@ -539,6 +539,229 @@ bm25_search_kernel(Bm25SearchArgs a) {
   }
 }
 
+// =============================================================================================
+// V2 search kernel (opt-in, TRR_BM25_V2=1): warp-autonomous sub-ranges
+// =============================================================================================
+// A CTA (8 warps) still owns one (query, chunk) item with its candidate buffer and threshold in shared memory, but the
+// warps do not move in lockstep: each pulls 2048-document sub-ranges from a CTA-local counter, owns an 8 KB accumulator,
+// reads the posting bounds of all query terms with one lane-parallel look-up (fine skip table for frequent terms, the
+// coarse table + a document-range filter for the rest), loads the postings straight from global memory (four term slots
+// in flight) and harvests its own cells.  CTA-wide barriers happen only when the candidate buffer has to be compacted
+// and at the end of the item.  Sum order per document = query-term order, as in the V1 kernel.
+__global__ void bm25_fine_kernel(const uint2* __restrict__ post, const uint64_t* __restrict__ term_off,
+                                 const uint32_t* __restrict__ fine_terms, uint32_t n_fine, uint32_t* __restrict__ fine,
+                                 uint32_t fine_ld, uint32_t n_sub) {
+  const uint32_t f = blockIdx.x;
+  if (f >= n_fine) return;
+  const uint32_t t = fine_terms[f];
+  const uint64_t begin = term_off[t], end = term_off[t + 1];
+  uint32_t* row = fine + (uint64_t)f * fine_ld;
+  if (begin == end) {
+    for (uint32_t j = threadIdx.x; j <= n_sub; j += blockDim.x) row[j] = (uint32_t)begin;
+    return;
+  }
+  for (uint64_t p = begin + threadIdx.x; p < end; p += blockDim.x) {
+    const uint32_t cur = post[p].x >> TRR_BM25_SUB_SHIFT;
+    const int64_t prev = p == begin ? -1 : (int64_t)(post[p - 1].x >> TRR_BM25_SUB_SHIFT);
+    for (int64_t j = prev + 1; j <= (int64_t)cur; ++j) row[j] = (uint32_t)p;
+    if (p + 1 == end)
+      for (uint32_t j = cur + 1; j <= n_sub; ++j) row[j] = (uint32_t)end;
+  }
+}
+
+__global__ void __launch_bounds__(TRR_BM25_V2_WARPS * 32, 3)
+bm25_search_warp_kernel(Bm25SearchArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr uint32_t SUBN = 1u << TRR_BM25_SUB_SHIFT;
+  constexpr uint32_t NT = TRR_BM25_V2_WARPS * 32;
+  float* acc = reinterpret_cast<float*>(smem_raw);                                   // [warps][2048]
+  uint64_t* cand = reinterpret_cast<uint64_t*>(acc + TRR_BM25_V2_WARPS * SUBN);      // cand_cap
+  __shared__ uint32_t s_cnt, s_next, s_item, s_need;
+  __shared__ uint64_t s_thr;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* my = acc + warp * SUBN;
+  for (uint32_t i = tid; i < TRR_BM25_V2_WARPS * SUBN; i += NT) acc[i] = 0.0f;
+  const uint32_t compact_at = a.k + ((a.cand_cap - a.k) >> 1);
+  const uint32_t n_items = a.B * a.n_chunks;
+  const uint32_t coarse_shift = a.range_shift - TRR_BM25_SUB_SHIFT;
+
+  // candidate buffer -> sorted descending, s_cnt <= k, s_thr = k-th best; every thread of the CTA takes part
+  auto compact = [&]() {
+    const uint32_t cnt = min(s_cnt, a.cand_cap);
+    for (uint32_t i = cnt + tid; i < a.cand_cap; i += NT) cand[i] = TRR_KEY_EMPTY;
+    trr_bitonic_sort_desc(cand, a.cand_cap, tid, NT, BlockSync());
+    if (tid == 0) {
+      const uint32_t c2 = min(cnt, a.k);
+      s_cnt = c2;
+      if (c2 == a.k && a.k > 0) s_thr = cand[a.k - 1];
+      s_need = 0;
+    }
+    __syncthreads();
+  };
+
+  while (true) {
+    __syncthreads();  // the previous item is finished (outputs written, shared state free)
+    if (tid == 0) s_item = atomicAdd(a.queue, 1u);
+    __syncthreads();
+    const uint32_t item = s_item;
+    if (item >= n_items) break;
+    const uint32_t b = a.order[item / a.n_chunks], c = item % a.n_chunks;
+    const uint32_t sub0 = (uint32_t)(((uint64_t)c * a.n_sub) / a.n_chunks);
+    const uint32_t sub1 = (uint32_t)(((uint64_t)(c + 1) * a.n_sub) / a.n_chunks);
+    const uint64_t thr0 = a.thr0[b];
+    const uint32_t q0 = a.q_off[b];
+    const uint32_t T = a.q_off[b + 1] - q0;
+    const uint32_t G = (T + 31) >> 5;
+    if (tid == 0) { s_next = sub0; s_cnt = 0; s_thr = TRR_KEY_EMPTY; s_need = 0; }
+    __syncthreads();
+    // T <= 32 (the usual case): every lane resolves its term's skip row once per item; a sub-range then costs one
+    // dependent look-up instead of three (term id -> row id -> bounds)
+    const uint32_t* rowp = nullptr;
+    uint32_t rshift = 0;
+    if (G == 1 && lane < T) {
+      const uint32_t term = a.q_terms[q0 + lane];
+      if (term < a.n_terms) {
+        const uint32_t fr = a.fine_row[term];
+        if (fr != 0xFFFFFFFFu) { rowp = a.fine + (uint64_t)fr * a.fine_ld; }
+        else { rowp = a.skip + (uint64_t)term * a.skip_ld; rshift = coarse_shift; }
+      }
+    }
+
+    bool redo = false;       // the last harvest left candidates in the accumulator (buffer full): harvest again after the compaction
+    uint32_t redo_sub = 0;
+    while (true) {  // rounds, separated by compactions
+      bool exhausted = false;
+      while (true) {
+        uint32_t sub;
+        bool any = true;
+        if (redo) {
+          sub = redo_sub;
+        } else {
+          if (*reinterpret_cast<volatile uint32_t*>(&s_need)) break;
+          sub = 0;
+          if (lane == 0) sub = atomicAdd(&s_next, 1u);
+          sub = __shfl_sync(FULLM, sub, 0);
+          if (sub >= sub1) { exhausted = true; break; }
+          // ---- accumulate the sub-range, term slots in query order ----
+          any = false;
+          const uint32_t sub_base = sub << TRR_BM25_SUB_SHIFT;
+          for (uint32_t g = 0; g < G; ++g) {
+            const uint32_t ti = g * 32 + lane;
+            uint32_t s = 0, e = 0;
+            if (G == 1) {
+              if (rowp) { const uint32_t* r2 = rowp + (sub >> rshift); s = r2[0]; e = r2[1]; }
+            } else if (ti < T) {
+              const uint32_t term = a.q_terms[q0 + ti];
+              if (term < a.n_terms) {
+                const uint32_t fr = a.fine_row[term];
+                if (fr != 0xFFFFFFFFu) {
+                  const uint32_t* row = a.fine + (uint64_t)fr * a.fine_ld;
+                  s = row[sub];
+                  e = row[sub + 1];
+                } else {  // infrequent term: its postings of the whole coarse range, filtered by document below
+                  const uint32_t* row = a.skip + (uint64_t)term * a.skip_ld + (sub >> coarse_shift);
+                  s = row[0];
+                  e = row[1];
+                }
+              }
+            }
+            uint32_t m = __ballot_sync(FULLM, e > s);
+            while (m) {
+              uint32_t lo_[4], n_[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const bool valid = m != 0u;
+                const uint32_t l = valid ? __ffs(m) - 1 : 0u;
+                m &= m - 1;
+                lo_[u] = __shfl_sync(FULLM, s, l);
+                const uint32_t hi = __shfl_sync(FULLM, e, l);
+                n_[u] = valid ? hi - lo_[u] : 0u;
+              }
+              uint2 pe[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) pe[u] = lane < n_[u] ? a.post[lo_[u] + lane] : make_uint2(0xFFFFFFFFu, 0u);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (n_[u] == 0) continue;  // warp-uniform
+                uint32_t d = pe[u].x - sub_base;
+                if (lane < n_[u] && d < SUBN) { my[d] = my[d] + __uint_as_float(pe[u].y); any = true; }
+                for (uint32_t p = 32 + lane; p < n_[u]; p += 32) {  // a segment longer than one load (order inside a term is free)
+                  const uint2 x = a.post[lo_[u] + p];
+                  d = x.x - sub_base;
+                  if (d < SUBN) { my[d] = my[d] + __uint_as_float(x.y); any = true; }
+                }
+                __syncwarp();
+              }
+            }
+          }
+          any = __any_sync(FULLM, any);
+        }
+        // ---- harvest the warp's 2048 cells ----
+        redo = false;
+        if (any) {
+          const uint64_t thr = max(*reinterpret_cast<volatile uint64_t*>(&s_thr), thr0);
+          const float thr_f = thr == TRR_KEY_EMPTY ? -CUDART_INF_F : trr_key_score(thr);
+          const uint32_t ord0 = a.doc_base + (sub << TRR_BM25_SUB_SHIFT);
+          uint4* a4 = reinterpret_cast<uint4*>(my);
+          bool kept = false;
+          for (uint32_t i = lane; i < SUBN / 4; i += 32) {
+            const uint4 v = a4[i];
+            const bool nz = (v.x | v.y | v.z | v.w) != 0u;
+            const float mx = fmaxf(fmaxf(__uint_as_float(v.x), __uint_as_float(v.y)),
+                                   fmaxf(__uint_as_float(v.z), __uint_as_float(v.w)));
+            const bool hit = nz && mx >= thr_f;  // NaN compares false
+            if (nz && !hit) a4[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (hit) {
+#pragma unroll 1
+              for (int j = 0; j < 4; ++j) {
+                const float f = my[i * 4 + j];
+                bool keep = false;
+                if (f >= thr_f && f > 0.0f) {  // src/index.rs:236 keeps only score > 0.0
+                  const uint64_t key = trr_make_key(f, ord0 + i * 4 + j);
+                  if (key > thr) {
+                    const uint32_t pos = atomicAdd(&s_cnt, 1u);
+                    if (pos < a.cand_cap) cand[pos] = key;
+                    else keep = true;  // stays in the accumulator; harvested again after the compaction
+                  }
+                }
+                if (keep) kept = true; else my[i * 4 + j] = 0.0f;
+              }
+            }
+          }
+          __syncwarp();
+          redo = __any_sync(FULLM, kept);
+        }
+        if (redo) {
+          redo_sub = sub;
+          if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&s_need) = 1u;
+          break;
+        }
+        if (lane == 0 && *reinterpret_cast<volatile uint32_t*>(&s_cnt) >= compact_at)
+          *reinterpret_cast<volatile uint32_t*>(&s_need) = 1u;
+      }
+      // ---- end of a round: every warp is here (out of sub-ranges, or asked to stop for a compaction) ----
+      const int all_done = __syncthreads_and(exhausted && !redo);
+      compact();
+      if (all_done) break;
+    }
+    // ---- outputs of the item ----
+    const uint32_t n_out = s_cnt;
+    if (a.n_chunks == 1) {
+      for (uint32_t i = tid; i < a.k; i += NT) {
+        const bool ok = i < n_out;
+        const uint64_t key = ok ? cand[i] : TRR_KEY_EMPTY;
+        if (a.out_keys) a.out_keys[(uint64_t)b * a.k + i] = key;
+        if (a.out_ord) a.out_ord[(uint64_t)b * a.k + i] = ok ? trr_key_ord(key) : 0xFFFFFFFFu;
+        if (a.out_score) a.out_score[(uint64_t)b * a.k + i] = ok ? trr_key_score(key) : 0.0f;
+      }
+      if (tid == 0 && a.out_n) a.out_n[b] = n_out;
+    } else {
+      uint64_t* dst = a.partial + ((uint64_t)b * a.n_chunks + c) * a.k;
+      for (uint32_t i = tid; i < a.k; i += NT) dst[i] = i < n_out ? cand[i] : TRR_KEY_EMPTY;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
@@ -588,5 +811,25 @@ cudaError_t trr_launch_bm25_search(const Bm25SearchArgs& a, unsigned grid, cudaS
   if (e != cudaSuccess) return e;
   cudaFuncSetAttribute(bm25_search_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   bm25_search_kernel<<<grid, TRR_BM25_THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+size_t trr_bm25_search_warp_smem(uint32_t cand_cap) {
+  return (size_t)TRR_BM25_V2_WARPS * (4u << TRR_BM25_SUB_SHIFT) + (size_t)cand_cap * 8;
+}
+
+cudaError_t trr_launch_bm25_search_warp(const Bm25SearchArgs& a, unsigned grid, cudaStream_t st) {
+  const size_t smem = trr_bm25_search_warp_smem(a.cand_cap);
+  cudaError_t e = cudaFuncSetAttribute(bm25_search_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaFuncSetAttribute(bm25_search_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  bm25_search_warp_kernel<<<grid, TRR_BM25_V2_WARPS * 32, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t trr_launch_bm25_fine(const uint2* post, const uint64_t* term_off, const uint32_t* fine_terms, uint32_t n_fine,
+                                 uint32_t* fine, uint32_t fine_ld, uint32_t n_sub, cudaStream_t st) {
+  if (n_fine == 0) return cudaSuccess;
+  bm25_fine_kernel<<<n_fine, 256, 0, st>>>(post, term_off, fine_terms, n_fine, fine, fine_ld, n_sub);
   return cudaGetLastError();
 }

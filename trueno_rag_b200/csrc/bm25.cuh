@@ -60,7 +60,15 @@ struct Bm25SearchArgs {
   uint32_t* out_n;     // nullable
   uint32_t* dbg;       // nullable host-mapped word: site of a barrier timeout
   uint32_t debug_mode; // perf triage (TRR_BM25_DEBUG): 8 = CTA 0 records where its cycles go
+  // bm25_search_warp_kernel (TRR_BM25_V2=1) only: fine skip table of the frequent terms, 2048-document sub-ranges
+  const uint32_t* fine_row;  // [n_terms] row of the term in `fine`, 0xFFFFFFFF = not a frequent term
+  const uint32_t* fine;      // [n_fine][fine_ld]: first posting of the term with doc >= j * 2048
+  uint32_t fine_ld, n_sub;
 };
+
+constexpr uint32_t TRR_BM25_SUB_SHIFT = 11;   // documents per warp accumulator of the V2 kernel: 2048
+constexpr uint32_t TRR_BM25_V2_WARPS = 8;
+constexpr uint32_t TRR_BM25_FINE_MIN_DF = 2048;  // terms at least this frequent get a row in the fine skip table
 
 cudaError_t trr_launch_bm25_build(const Bm25BuildArgs& a, cudaStream_t st);
 cudaError_t trr_launch_bm25_merge(const Bm25MergeArgs& a, cudaStream_t st);
@@ -70,3 +78,9 @@ size_t trr_bm25_search_smem(uint32_t range_shift, uint32_t stage_cap, uint32_t c
 // plan_keys: scratch of max(pow2ceil(B), 1) u64
 cudaError_t trr_launch_bm25_plan(const Bm25SearchArgs& a, uint64_t* plan_keys, cudaStream_t st);
 cudaError_t trr_launch_bm25_search(const Bm25SearchArgs& a, unsigned grid, cudaStream_t st);
+// V2 (opt-in): warps of a CTA work on different 2048-document sub-ranges of one query without per-range barriers
+size_t trr_bm25_search_warp_smem(uint32_t cand_cap);
+cudaError_t trr_launch_bm25_search_warp(const Bm25SearchArgs& a, unsigned grid, cudaStream_t st);
+// fine skip table: fine[row][j] for the n_fine terms listed in fine_terms (term ids), j = 0..n_sub
+cudaError_t trr_launch_bm25_fine(const uint2* post, const uint64_t* term_off, const uint32_t* fine_terms, uint32_t n_fine,
+                                 uint32_t* fine, uint32_t fine_ld, uint32_t n_sub, cudaStream_t st);

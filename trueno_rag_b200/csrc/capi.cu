@@ -894,6 +894,11 @@ struct trr_bm25 {
   std::vector<uint64_t> h_term_off;
   uint64_t n_dead_postings = 0;    // postings of removed documents still in place (tf == 0)
   uint32_t range_shift = TRR_BM25_MAX_RANGE_SHIFT, n_ranges = 0, skip_ld = 0;
+  // V2 search kernel (TRR_BM25_V2=1): fine skip table of the frequent terms, built lazily after every index change
+  uint32_t* fine_row = nullptr;  // [n_terms]
+  uint32_t* fine = nullptr;      // [n_fine][fine_ld]
+  uint32_t fine_ld = 0, n_sub = 0;
+  bool fine_valid = false;
   trr_stats stats{};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -921,6 +926,7 @@ static uint32_t bm25_pick_shift(uint32_t n_docs) {
 static int bm25_weight_locked(trr_bm25* h, const uint32_t* d_post_doc, float avgdl, float k1, float b, const float* idf_host) {
   trr_ctx* ctx = h->ctx;
   cudaStream_t st = ctx->stream;
+  h->fine_valid = false;
   h->range_shift = bm25_pick_shift(h->n_docs);
   h->n_ranges = h->n_docs ? (uint32_t)(((uint64_t)h->n_docs + (1u << h->range_shift) - 1) >> h->range_shift) : 0;
   h->skip_ld = h->n_ranges + 1;
@@ -1099,6 +1105,8 @@ extern "C" int trr_bm25_destroy(trr_bm25* h) {
   if (h->d_term_off) cudaFree(h->d_term_off);
   if (h->tf) cudaFree(h->tf);
   if (h->doc_len) cudaFree(h->doc_len);
+  if (h->fine_row) cudaFree(h->fine_row);
+  if (h->fine) cudaFree(h->fine);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   delete h;
   return TRR_OK;
@@ -1118,6 +1126,40 @@ extern "C" int trr_bm25_copy_impacts(trr_bm25* h, float* out, uint64_t n) {
   std::vector<uint2> tmp(n);
   TRR_CUDA(cudaMemcpy(tmp.data(), h->post, n * sizeof(uint2), cudaMemcpyDeviceToHost));
   for (uint64_t i = 0; i < n; ++i) memcpy(&out[i], &tmp[i].y, 4);
+  return TRR_OK;
+}
+
+// V2 kernel: (re)builds the fine skip table (2048-document sub-ranges) of the terms with df >= TRR_BM25_FINE_MIN_DF
+static int bm25_ensure_fine(trr_bm25* h) {
+  if (h->fine_valid) return TRR_OK;
+  trr_ctx* c = h->ctx;
+  cudaStream_t st = c->stream;
+  if (h->h_term_off.size() != (size_t)h->n_terms + 1 || !h->d_term_off)
+    return trr_fail(TRR_ERR_UNSUPPORTED, "BM25 V2 kernel needs the raw index (term offsets) on the handle");
+  if (h->fine_row) { cudaFree(h->fine_row); h->fine_row = nullptr; }
+  if (h->fine) { cudaFree(h->fine); h->fine = nullptr; }
+  h->n_sub = (uint32_t)(((uint64_t)h->n_docs + (1u << TRR_BM25_SUB_SHIFT) - 1) >> TRR_BM25_SUB_SHIFT);
+  h->fine_ld = h->n_sub + 1;
+  std::vector<uint32_t> row(h->n_terms, 0xFFFFFFFFu), terms;
+  for (uint32_t t = 0; t < h->n_terms; ++t)
+    if (h->h_term_off[t + 1] - h->h_term_off[t] >= TRR_BM25_FINE_MIN_DF) { row[t] = (uint32_t)terms.size(); terms.push_back(t); }
+  TRR_CUDA(cudaMalloc(&h->fine_row, std::max<size_t>(h->n_terms, 1) * 4));
+  TRR_CUDA(cudaMalloc(&h->fine, std::max<size_t>((size_t)terms.size() * h->fine_ld, 1) * 4));
+  if (h->n_terms) TRR_CUDA(cudaMemcpyAsync(h->fine_row, row.data(), (size_t)h->n_terms * 4, cudaMemcpyHostToDevice, st));
+  uint32_t* d_terms = nullptr;
+  if (!terms.empty()) {
+    TRR_CUDA(cudaMalloc(&d_terms, terms.size() * 4));
+    cudaError_t e = cudaMemcpyAsync(d_terms, terms.data(), terms.size() * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+      e = trr_launch_bm25_fine(h->post, h->d_term_off, d_terms, (uint32_t)terms.size(), h->fine, h->fine_ld, h->n_sub, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_terms);
+    if (e != cudaSuccess) return trr_fail(TRR_ERR_CUDA, std::string("fine skip table: ") + cudaGetErrorString(e));
+    c->launches++;
+  } else {
+    TRR_CUDA(cudaStreamSynchronize(st));
+  }
+  h->fine_valid = true;
   return TRR_OK;
 }
 
@@ -1143,9 +1185,19 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   a.cand_cap = trr_pow2_ceil(k + 512);
   // stage buffers take what is left of the shared memory (two stages, 8 bytes per posting).  Ranges of <= 16K
   // documents leave room for two CTAs per SM.
+  // opt-in V2 kernel (warp-autonomous sub-ranges; see bm25.cu)
+  bool v2 = false;
+  if (const char* e = getenv("TRR_BM25_V2")) v2 = atoi(e) != 0;
+  if (v2 && trr_bm25_search_warp_smem(a.cand_cap) > c->smem_optin) v2 = false;
+  if (v2) {
+    TRR_CHECK(bm25_ensure_fine(h));
+    a.fine_row = h->fine_row; a.fine = h->fine; a.fine_ld = h->fine_ld; a.n_sub = h->n_sub;
+  }
   uint32_t ctas_per_sm = a.range_shift <= 14 ? 2u : 1u;
   if (const char* e = getenv("TRR_BM25_CTAS_PER_SM")) ctas_per_sm = std::min(2, std::max(1, atoi(e)));
-  {
+  if (v2) {
+    ctas_per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(3, ((size_t)228 * 1024) / (trr_bm25_search_warp_smem(a.cand_cap) + 2048)));
+  } else {
     const size_t fixed = trr_bm25_search_smem(a.range_shift, 0, a.cand_cap) + 64;
     size_t budget = c->smem_optin;
     if (ctas_per_sm == 2) budget = (228 * 1024) / 2 - 1024 - 1024;  // 228 KB per SM, 1 KB reserved per CTA, 1 KB slack
@@ -1158,8 +1210,9 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   // few queries: split every query into chunks of document ranges so that all SMs have work
   uint32_t n_chunks = 1;
   const uint32_t slots = (uint32_t)c->sm_count * ctas_per_sm;
-  if (B < 2u * slots) n_chunks = std::min<uint32_t>(h->n_ranges, (2u * slots + B - 1) / B);
-  if (const char* e = getenv("TRR_BM25_CHUNKS")) n_chunks = std::min<uint32_t>(h->n_ranges, std::max(1, atoi(e)));
+  const uint32_t max_chunks = v2 ? h->n_sub : h->n_ranges;
+  if (B < 2u * slots) n_chunks = std::min<uint32_t>(max_chunks, (2u * slots + B - 1) / B);
+  if (const char* e = getenv("TRR_BM25_CHUNKS")) n_chunks = std::min<uint32_t>(max_chunks, std::max(1, atoi(e)));
   n_chunks = std::max<uint32_t>(n_chunks, 1);
   a.n_chunks = n_chunks;
   const size_t need = scratch_off + WsCarver::need({(size_t)B * 4, (size_t)B * 8, 64, n_chunks > 1 ? (size_t)B * n_chunks * k * 8 : 8,
@@ -1178,7 +1231,8 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)B * n_chunks, (uint64_t)slots);
   TRR_CUDA(trr_launch_bm25_plan(a, plan_keys, st));
   TRR_CUDA(cudaEventRecord(h->ev[2], st));
-  TRR_CUDA(trr_launch_bm25_search(a, grid, st));
+  if (v2) TRR_CUDA(trr_launch_bm25_search_warp(a, grid, st));
+  else TRR_CUDA(trr_launch_bm25_search(a, grid, st));
   TRR_CUDA(cudaEventRecord(h->ev[3], st));
   const uint32_t plan_launches = (B > 1 && B <= 4096) ? 2u : 1u;
   c->launches += plan_launches + 1;
