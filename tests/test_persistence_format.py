@@ -571,3 +571,26 @@ def test_restored_index_keeps_accepting_adds_and_removes():
     r.remove(chunks[3].id)
     for q in ("w01 w02 w03", "w10 w10 w39", "w05"):
         assert _by_score_then_id(ix.search(q, 20)) == _by_score_then_id(r.search(q, 20))
+
+
+# ------------------------------------------------------------------------------------------------
+# committed fixtures (tests/golden/make_persistence_golden.py): a libzstd frame and an independently encoded LZ4 block
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,compression", [("bm25_index.zst", 1), ("bm25_index.lz4", 0)])
+def test_golden_index_files_load(name, compression):
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    want = json.load(open(os.path.join(here, "bm25_index.json")))
+    data = open(os.path.join(here, name), "rb").read()
+    raw = api.decompress(data, compression)
+    assert len(raw) == want["bincode_len"]
+    ix = api.BM25Index.from_compressed_bytes(data, compression)
+    got = read_bm25(ix.to_bytes())
+    assert len(ix) == want["count"] == got["count"]
+    assert struct.unpack("<I", struct.pack("<f", got["avg"]))[0] == want["avg_bits"]
+    assert struct.unpack("<I", struct.pack("<f", got["k1"]))[0] == want["k1_bits"] and got["b"] == want["b"]
+    assert got["lowercase"] == want["lowercase"] and sorted(got["stop"]) == want["stop"]
+    assert got["dfs"] == want["dfs"]
+    assert {c.hex: v for c, v in got["lens"].items()} == want["lens"]
+    assert {t: [[c.hex, tf] for c, tf in sorted(pl)] for t, pl in got["inv"].items()} == want["inv"]
