@@ -116,8 +116,9 @@ class VectorStore {  // src/index.rs:322-437
 // src/compressed.rs:13-66 — compression of serialised indexes, both formats restated here (no liblz4 / libzstd in the
 // build).  LZ4 = lz4_flex 0.11 `compress_prepend_size` / `decompress_size_prepended` (u32 little-endian length + one LZ4
 // block).  ZSTD = standard frames (RFC 8878): `decompress` is a complete frame decoder (Huffman literals, FSE sequences,
-// repeat offsets, checksums; no dictionaries), so anything the reference wrote loads; `compress` writes a valid frame of
-// raw / RLE blocks only - readable by the reference, but without entropy coding.  Empty input <-> empty output.
+// repeat offsets, checksums; no dictionaries), so anything the reference wrote loads; `compress` writes frames the
+// reference reads (LZ77 matches, FSE-coded sequences with the predefined distributions, raw literals - smaller than the
+// LZ4 output, larger than libzstd's own).  Empty input <-> empty output.
 enum class Compression { Lz4 = 0, Zstd = 1 };
 const char* compression_as_str(Compression c);                                  // :24-30
 std::vector<uint8_t> compress(Compression c, const uint8_t* data, size_t n);    // :36-47

@@ -44,7 +44,7 @@ TRRH_API float trrh_bm25_k1(trrh_bm25* s);
 TRRH_API float trrh_bm25_b(trrh_bm25* s);
 TRRH_API int trrh_bm25_contains_term(trrh_bm25* s, const char* term);
 /* Persistence in the reference's format (src/compressed.rs:13-108; bincode 1.3 of the struct at src/index.rs:30-51).
- * compression: -1 = plain bincode, 0 = LZ4 (lz4_flex size-prepended block), 1 = ZSTD (standard frames; the writer stores).
+ * compression: -1 = plain bincode, 0 = LZ4 (lz4_flex size-prepended block), 1 = ZSTD (standard frames).
  * Output buffers are owned by the library until trrh_bytes_free.  Status 7 = SerializationError. */
 TRRH_API int trrh_compress(int compression, const uint8_t* data, uint64_t n, uint8_t** out, uint64_t* out_n);
 TRRH_API int trrh_decompress(int compression, const uint8_t* data, uint64_t n, uint8_t** out, uint64_t* out_n);

@@ -499,11 +499,29 @@ def test_bm25_empty_index_compression():  # :236-244
     assert len(read_bm25(r.to_bytes())["stop"]) == DEFAULT_STOPWORDS
 
 
-def test_bm25_compression_reduces_size():  # :213-233 (LZ4 arm)
+def test_bm25_compression_reduces_size():  # :213-233
     ix = api.BM25Index()
     for i in range(100):
         ix.add(api.Chunk(f"document number {i} about machine learning and artificial intelligence"))
-    assert len(ix.to_compressed_bytes(api.Compression.Lz4)) < len(ix.to_bytes())
+    uncompressed = ix.to_bytes()
+    lz4 = ix.to_compressed_bytes(api.Compression.Lz4)
+    zstd = ix.to_compressed_bytes(api.Compression.Zstd)
+    assert len(lz4) < len(uncompressed) and len(zstd) < len(uncompressed)
+    assert len(zstd) <= len(lz4)                                   # "ZSTD typically achieves better compression than LZ4"
+    assert _real_zstd_decompress(zstd, len(uncompressed)) == uncompressed
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_zstd_compressor_output_is_read_by_libzstd(seed):
+    """the library's frames (LZ77 + predefined-FSE sequences, raw literals, RLE / stored blocks) through libzstd and through
+    the library's own decoder"""
+    for name, data in _corpus(seed).items():
+        c = api.compress(data, api.Compression.Zstd)
+        assert _real_zstd_decompress(c, len(data)) == data, name
+        assert api.decompress(c, api.Compression.Zstd) == data, name
+        if name in ("text", "runs", "skew", "period", "bincode", "mixed"):
+            assert len(c) < len(data), name
+            assert len(c) <= len(api.compress(data, api.Compression.Lz4)), name
 
 
 def test_removed_chunks_and_emptied_terms_are_not_written():

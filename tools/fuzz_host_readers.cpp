@@ -14,7 +14,10 @@
 
 #include "../include/trueno_rag.hpp"
 
-namespace trueno_rag { std::vector<uint8_t> zstd_decompress(const uint8_t*, size_t); }
+namespace trueno_rag {
+std::vector<uint8_t> zstd_decompress(const uint8_t*, size_t);
+std::vector<uint8_t> zstd_compress(const uint8_t*, size_t);
+}
 using namespace trueno_rag;
 
 static std::vector<uint8_t> load(const std::string& p) {
@@ -62,5 +65,25 @@ int main(int argc, char** argv) {
     }
     printf("%-8s accepted %ld rejected %ld\n", t.file, ok, err);
   }
+  // round trips of the two writers on generated data (runs, repeats of earlier content, noise)
+  long trips = 0;
+  for (int it = 0; it < 3000; ++it) {
+    std::vector<uint8_t> d;
+    const int parts = 1 + (int)(rnd() % 12);
+    for (int k = 0; k < parts; ++k) {
+      const int kind = (int)(rnd() % 4);
+      const size_t len = rnd() % (it % 50 == 0 ? 200000 : 3000);
+      if (kind == 0) for (size_t i = 0; i < len; ++i) d.push_back((uint8_t)rnd());
+      else if (kind == 1) d.insert(d.end(), len, (uint8_t)rnd());
+      else if (kind == 2 && !d.empty()) { const size_t from = rnd() % d.size(); for (size_t i = 0; i < len; ++i) d.push_back(d[from + i % (d.size() - from)]); }
+      else for (size_t i = 0; i < len; ++i) d.push_back((uint8_t)("abcab "[rnd() % 6]));
+    }
+    const auto z = zstd_compress(d.data(), d.size());
+    if (zstd_decompress(z.data(), z.size()) != d) { printf("zstd round trip mismatch at %d\n", it); return 1; }
+    const auto l = compress(Compression::Lz4, d.data(), d.size());
+    if (decompress(Compression::Lz4, l.data(), l.size()) != d) { printf("lz4 round trip mismatch at %d\n", it); return 1; }
+    trips++;
+  }
+  printf("round trips ok: %ld\n", trips);
   return 0;
 }

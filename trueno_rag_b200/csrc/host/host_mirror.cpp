@@ -462,6 +462,7 @@ const char* compression_as_str(Compression c) { return c == Compression::Lz4 ? "
 // zstd_codec.cpp
 std::vector<uint8_t> zstd_decompress(const uint8_t* src, size_t n);
 std::vector<uint8_t> zstd_store(const uint8_t* src, size_t n);
+std::vector<uint8_t> zstd_compress(const uint8_t* src, size_t n);
 
 namespace {
 [[noreturn]] void ser_fail(const std::string& m) { throw Error(Error::Kind::Serialization, m); }
@@ -597,7 +598,7 @@ struct BinReader {
 
 std::vector<uint8_t> compress(Compression c, const uint8_t* data, size_t n) {
   if (n == 0) return {};  // :37-39
-  if (c == Compression::Zstd) return zstd_store(data, n);  // a valid frame of raw / RLE blocks (no entropy coding)
+  if (c == Compression::Zstd) return zstd_compress(data, n);
   if (n > 0xFFFFFFFFull) ser_fail("LZ4 compression failed: input larger than 4 GiB");
   std::vector<uint8_t> block = lz4_compress_block(data, n);
   std::vector<uint8_t> out(4);

@@ -5,8 +5,10 @@
 //   * zstd_decompress: a complete frame decoder (raw / RLE / compressed blocks, Huffman literals with direct or
 //     FSE-compressed weights, treeless literals, FSE sequences in predefined / RLE / described / repeat mode, repeat
 //     offsets, multiple and skippable frames, content checksum verified with XXH64).  Dictionaries are not supported.
-//   * zstd_store: a frame WRITER that emits only raw and RLE blocks.  Every zstd decoder (the reference's included) reads
-//     what it writes, but it does not entropy-code: the reference's own files are smaller.
+//   * zstd_compress: a frame writer with real (if modest) compression: LZ77 matches whose sequences are FSE-coded with
+//     the predefined distributions, raw literals, RLE / stored blocks where coding does not pay.  Every zstd decoder (the
+//     reference's included) reads what it writes; libzstd's own files are smaller (no Huffman literals, no repeat offsets).
+//   * zstd_store: raw and RLE blocks only (kept as the trivially correct writer the tests compare against).
 // Host-side persistence only; nothing here is on the retrieval path.
 #include <stdint.h>
 #include <string.h>
@@ -555,6 +557,235 @@ std::vector<uint8_t> zstd_decompress(const uint8_t* src, size_t n) {
     any = true;
   }
   if (!any) zfail("no frame");
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// compressor: LZ77 matches + FSE-coded sequences with the PREDEFINED distributions, raw literals
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// forward bit writer (least-significant bit first); the decoder reads the finished stream backward from the end marker
+struct BitWriter {
+  std::vector<uint8_t> out;
+  uint64_t acc = 0;
+  int nacc = 0;
+  void add(uint64_t v, int nbits) {
+    while (nbits > 0) {  // keep the accumulator below 64 bits
+      const int take = std::min(nbits, 32);
+      acc |= (v & ((1ull << take) - 1)) << nacc;
+      nacc += take;
+      v >>= take;
+      nbits -= take;
+      while (nacc >= 8) { out.push_back((uint8_t)acc); acc >>= 8; nacc -= 8; }
+    }
+  }
+  void close() {  // the 1 marker above the payload, then zero padding
+    add(1, 1);
+    if (nacc) { out.push_back((uint8_t)acc); acc = 0; nacc = 0; }
+  }
+};
+
+// FSE encoding table of a normalised distribution (the mirror image of fse_build)
+struct FseEnc {
+  int log = 0;
+  std::vector<uint16_t> state_table;                     // [size]
+  std::vector<int32_t> delta_nb_bits, delta_find_state;  // [n_symbols]
+  void build(const int16_t* norm, int n_symbols, int accuracy_log) {
+    log = accuracy_log;
+    const uint32_t size = 1u << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
+    std::vector<uint8_t> symbol(size, 0);
+    std::vector<uint32_t> cumul(n_symbols + 1, 0);
+    uint32_t high = size - 1;
+    for (int s = 0; s < n_symbols; ++s) {
+      if (norm[s] == -1) { cumul[s + 1] = cumul[s] + 1; symbol[high--] = (uint8_t)s; }
+      else cumul[s + 1] = cumul[s] + (uint32_t)norm[s];
+    }
+    uint32_t pos = 0;
+    for (int s = 0; s < n_symbols; ++s)
+      for (int i = 0; i < norm[s]; ++i) {
+        symbol[pos] = (uint8_t)s;
+        do { pos = (pos + step) & mask; } while (pos > high);
+      }
+    state_table.assign(size, 0);
+    {
+      std::vector<uint32_t> c(cumul);
+      for (uint32_t u = 0; u < size; ++u) state_table[c[symbol[u]]++] = (uint16_t)(size + u);
+    }
+    delta_nb_bits.assign(n_symbols, 0);
+    delta_find_state.assign(n_symbols, 0);
+    int total = 0;
+    for (int s = 0; s < n_symbols; ++s) {
+      if (norm[s] == 0) {
+        delta_nb_bits[s] = ((log + 1) << 16) - (1 << log);
+      } else if (norm[s] == -1 || norm[s] == 1) {
+        delta_nb_bits[s] = (log << 16) - (1 << log);
+        delta_find_state[s] = total - 1;
+        total += 1;
+      } else {
+        const int max_bits_out = log - highest_set_bit((uint64_t)(norm[s] - 1));
+        const int min_state_plus = norm[s] << max_bits_out;
+        delta_nb_bits[s] = (max_bits_out << 16) - min_state_plus;
+        delta_find_state[s] = total - norm[s];
+        total += norm[s];
+      }
+    }
+  }
+  uint32_t init(int sym) const {
+    const int nb = (delta_nb_bits[sym] + (1 << 15)) >> 16;
+    const int value = (nb << 16) - delta_nb_bits[sym];
+    return state_table[(value >> nb) + delta_find_state[sym]];
+  }
+  void encode(BitWriter& w, uint32_t& state, int sym) const {
+    const int nb = (int)((state + (uint32_t)delta_nb_bits[sym]) >> 16);
+    w.add(state, nb);
+    state = state_table[(state >> nb) + delta_find_state[sym]];
+  }
+  void flush(BitWriter& w, uint32_t state) const { w.add(state, log); }
+};
+
+template <size_t N>
+int code_of(const uint32_t (&base)[N], uint32_t v) {  // the largest code whose baseline is <= v
+  int c = 0;
+  for (size_t i = 0; i < N; ++i) if (base[i] <= v) c = (int)i;
+  return c;
+}
+
+struct Seq { uint32_t lit_len, match_len, offset; };
+
+// encoding tables of the three predefined distributions (built once; C++11 static initialisation is thread-safe)
+struct SeqEnc {
+  FseEnc ll, of, ml;
+  SeqEnc() {
+    ll.build(LL_DEFAULT, 36, 6);
+    of.build(OF_DEFAULT, 29, 5);
+    ml.build(ML_DEFAULT, 53, 6);
+  }
+};
+const SeqEnc& seq_enc() {
+  static const SeqEnc e;
+  return e;
+}
+
+// one block of at most 128 KB: returns false when coding it does not pay (the caller then stores it)
+bool compress_block(const uint8_t* base, size_t bs, size_t be, std::vector<int64_t>& table, std::vector<uint8_t>& out) {
+  const size_t n = be - bs;
+  std::vector<Seq> seqs;
+  std::vector<uint8_t> lits;
+  lits.reserve(n);
+  size_t anchor = bs, i = bs;
+  if (n >= 16) {
+    const size_t limit = be - 8;
+    while (i < limit) {
+      const uint32_t v = rd32(base + i);
+      const uint32_t h = (v * 2654435761u) >> 15;  // 17 bits
+      const int64_t cand = table[h];
+      table[h] = (int64_t)i;
+      if (cand >= 0 && i - (size_t)cand < ((size_t)1 << 27) && rd32(base + cand) == v) {
+        size_t ml = 4;
+        while (i + ml < be && base[(size_t)cand + ml] == base[i + ml]) ++ml;
+        seqs.push_back(Seq{(uint32_t)(i - anchor), (uint32_t)ml, (uint32_t)(i - (size_t)cand)});
+        lits.insert(lits.end(), base + anchor, base + i);
+        // index a few positions inside the match so that later data finds it
+        for (size_t k = i + 1; k + 4 <= be && k < i + ml; k += 3) table[(rd32(base + k) * 2654435761u) >> 15] = (int64_t)k;
+        i += ml;
+        anchor = i;
+      } else {
+        ++i;
+      }
+    }
+  }
+  if (seqs.empty()) return false;
+  lits.insert(lits.end(), base + anchor, base + be);
+
+  const FseEnc &ll_enc = seq_enc().ll, &of_enc = seq_enc().of, &ml_enc = seq_enc().ml;
+  std::vector<uint8_t> blk;
+  // literals section: raw
+  const size_t L = lits.size();
+  if (L < 32) blk.push_back((uint8_t)(L << 3));
+  else if (L < 4096) { blk.push_back((uint8_t)((L << 4) | 4)); blk.push_back((uint8_t)(L >> 4)); }
+  else { blk.push_back((uint8_t)((L << 4) | 12)); blk.push_back((uint8_t)(L >> 4)); blk.push_back((uint8_t)(L >> 12)); }
+  blk.insert(blk.end(), lits.begin(), lits.end());
+  // sequences section: count, modes (all predefined), bitstream written last sequence first
+  const size_t ns = seqs.size();
+  if (ns < 128) blk.push_back((uint8_t)ns);
+  else if (ns < 0x7F00) { blk.push_back((uint8_t)((ns >> 8) + 128)); blk.push_back((uint8_t)ns); }
+  else { blk.push_back(255); blk.push_back((uint8_t)(ns - 0x7F00)); blk.push_back((uint8_t)((ns - 0x7F00) >> 8)); }
+  blk.push_back(0);
+  BitWriter w;
+  auto codes = [&](const Seq& q, int& llc, int& mlc, int& ofc, uint32_t& ofv) {
+    llc = code_of(LL_BASE, q.lit_len);
+    mlc = code_of(ML_BASE, q.match_len);
+    ofv = q.offset + 3;  // never a repeat-offset code
+    ofc = highest_set_bit(ofv);
+  };
+  int llc, mlc, ofc;
+  uint32_t ofv;
+  codes(seqs[ns - 1], llc, mlc, ofc, ofv);
+  uint32_t ml_state = ml_enc.init(mlc), of_state = of_enc.init(ofc), ll_state = ll_enc.init(llc);
+  w.add(seqs[ns - 1].lit_len - LL_BASE[llc], LL_EXTRA[llc]);
+  w.add(seqs[ns - 1].match_len - ML_BASE[mlc], ML_EXTRA[mlc]);
+  w.add(ofv - (1u << ofc), ofc);
+  for (size_t k = ns - 1; k-- > 0;) {
+    codes(seqs[k], llc, mlc, ofc, ofv);
+    of_enc.encode(w, of_state, ofc);
+    ml_enc.encode(w, ml_state, mlc);
+    ll_enc.encode(w, ll_state, llc);
+    w.add(seqs[k].lit_len - LL_BASE[llc], LL_EXTRA[llc]);
+    w.add(seqs[k].match_len - ML_BASE[mlc], ML_EXTRA[mlc]);
+    w.add(ofv - (1u << ofc), ofc);
+  }
+  ml_enc.flush(w, ml_state);
+  of_enc.flush(w, of_state);
+  ll_enc.flush(w, ll_state);
+  w.close();
+  blk.insert(blk.end(), w.out.begin(), w.out.end());
+  if (blk.size() >= n) return false;
+  out.swap(blk);
+  return true;
+}
+
+}  // namespace
+
+// zstd::encode_all: one frame (single segment, content size declared, no checksum); blocks are compressed (LZ77 matches,
+// sequences FSE-coded with the predefined distributions, raw literals), RLE, or stored when coding does not pay
+std::vector<uint8_t> zstd_compress(const uint8_t* src, size_t n) {
+  std::vector<uint8_t> out;
+  out.reserve(n / 2 + 64);
+  const uint32_t magic = 0xFD2FB528u;
+  out.insert(out.end(), reinterpret_cast<const uint8_t*>(&magic), reinterpret_cast<const uint8_t*>(&magic) + 4);
+  int fcs_flag, fsz;
+  uint64_t field = n;
+  if (n < 256) { fcs_flag = 0; fsz = 1; }
+  else if (n < 65536 + 256) { fcs_flag = 1; fsz = 2; field = n - 256; }
+  else if (n < ((uint64_t)1 << 32)) { fcs_flag = 2; fsz = 4; }
+  else { fcs_flag = 3; fsz = 8; }
+  out.push_back((uint8_t)((fcs_flag << 6) | (1 << 5)));
+  for (int i = 0; i < fsz; ++i) out.push_back((uint8_t)(field >> (8 * i)));
+  auto header = [&](int type, size_t size, bool last) {
+    const uint32_t h = (uint32_t)(last ? 1 : 0) | ((uint32_t)type << 1) | ((uint32_t)size << 3);
+    out.push_back((uint8_t)h); out.push_back((uint8_t)(h >> 8)); out.push_back((uint8_t)(h >> 16));
+  };
+  if (n == 0) { header(0, 0, true); return out; }
+  const size_t BLOCK = 128u << 10;
+  std::vector<int64_t> table((size_t)1 << 17, -1);
+  std::vector<uint8_t> blk;
+  for (size_t bs = 0; bs < n; bs += BLOCK) {
+    const size_t be = std::min(n, bs + BLOCK), len = be - bs;
+    const bool last = be == n;
+    bool same = true;
+    for (size_t k = bs + 1; k < be && same; ++k) same = src[k] == src[bs];
+    if (same && len > 1) {
+      header(1, len, last);
+      out.push_back(src[bs]);
+    } else if (compress_block(src, bs, be, table, blk)) {
+      header(2, blk.size(), last);
+      out.insert(out.end(), blk.begin(), blk.end());
+    } else {
+      header(0, len, last);
+      out.insert(out.end(), src + bs, src + be);
+    }
+  }
   return out;
 }
 
