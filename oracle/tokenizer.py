@@ -1,8 +1,22 @@
 """Oracle-side restatement of BM25Index::tokenize (reference src/index.rs:93-124).  TEST INFRASTRUCTURE ONLY.
 
 split on `!char::is_alphanumeric`, drop empties, lowercase, drop the 90 stopwords, drop tokens whose UTF-8 byte
-length is < 2.  Python's str.isalnum()/lower() agree with Rust's char::is_alphanumeric/to_lowercase on ASCII and on
-the Latin/Greek/Cyrillic letters used in the tests; exotic code points may differ (documented in DESIGN.md)."""
+length is < 2.  Rust's `char::is_alphanumeric` is `Alphabetic || Nd || Nl || No`, taken here from the `regex` package's
+UCD properties; `str::to_lowercase` (full mapping + Final_Sigma) is what CPython's `str.lower()` implements.  The product's
+tokenizer uses its own generated tables and its own Final_Sigma code, so the comparison is between two implementations.
+Without the `regex` package the split falls back to `str.isalnum()` (letters and digits only: exact on ASCII/Latin/Greek/
+Cyrillic text, not on marks and letter-like symbols)."""
+import unicodedata as _ud
+
+try:
+    import regex as _regex
+    _ALNUM = _regex.compile(r"[\p{Alphabetic}\p{N}]")
+
+    def _is_alnum(ch):  # one Unicode version: only code points CPython's UCD (the source of str.lower) assigns
+        return _ud.category(ch) != "Cn" and _ALNUM.fullmatch(ch) is not None
+except ImportError:  # pragma: no cover
+    def _is_alnum(ch):
+        return ch.isalnum()
 
 STOPWORDS = frozenset("""a an the is are was were be been being have has had do does did will would could should may
 might must shall can need dare ought used to of in for on with at by from as into through during before after above
@@ -23,7 +37,7 @@ def tokenize(text: str, stopwords=STOPWORDS, lowercase=True):
             cur.clear()
 
     for ch in text:
-        if ch.isalnum():
+        if ch < "\x80" and ch.isalnum() or ch >= "\x80" and _is_alnum(ch):
             cur.append(ch)
         else:
             emit()

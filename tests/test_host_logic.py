@@ -168,3 +168,80 @@ def test_host_synth_generators_match_oracle(built_lib):
     assert L.trr_synth_bm25_fill(seed, cdf.ctypes.data_as(u64p), V, lo, hi, s_off.ctypes.data_as(u64p),
                                  pd.ctypes.data_as(u32p), ptf.ctypes.data_as(u32p)) == 0
     assert np.array_equal(pd, post_doc[keep] - lo) and np.array_equal(ptf, post_tf[keep])
+
+
+@pytest.mark.parametrize("text", [
+    "ΟΔΥΣΣΕΥΣ ΣΟΦΟΣ Σ ΑΣ ΑΣ́ ΑΣ́Β Σ́Α",                 # Final_Sigma: word-final, lone, with case-ignorable marks around
+    "İstanbul IŞIK ǅungla ǈ ǋ ẞ STRASSE straße",        # multi-code-point and title-case mappings
+    "日本語のテキスト 漢字 ｶﾀｶﾅ ㈱ ㊙",                    # CJK letters, half-width kana, enclosed ideographs (No / So)
+    "٣٤٥ ۴۵۶ ①②③ Ⅻ ⅻ ½ x² ৳৭",                        # Nd / Nl / No digits of several scripts
+    "x̀y áb क्षत्रिय ไทย ภาษา",                            # combining marks: Mn that are / are not Alphabetic
+    "ˆˇ ˂˃ ʰʱ ªº µ ·",                                   # modifier letters vs modifier symbols
+    "😀emoji😀 𝒜𝓁𝓅𝒽𝒶 𝟘𝟙𝟚 𐐀𐐨 🄰",                        # astral: symbols, math alphanumerics, Deseret case pair
+    "ᾈ ᾘ ᾨ ᾼ ῌ ῼ Ω K Å",                                # Greek titlecase with iota, Ohm / Kelvin / Angstrom signs
+])
+def test_tokenizer_unicode_semantics_match_oracle(api, text):
+    assert api.BM25Index().tokenize(text) == oracle_tokenize(text)
+
+
+def test_tokenizer_random_unicode_matches_oracle(api):
+    """the product's generated tables + Final_Sigma code against the oracle (regex UCD properties + CPython str.lower)"""
+    import random
+    rng = random.Random(20261018)
+    blocks = [(0x20, 0x7E), (0xA0, 0x24F), (0x250, 0x36F), (0x370, 0x3FF), (0x400, 0x52F), (0x530, 0x6FF), (0x900, 0xDFF),
+              (0xE00, 0x10FF), (0x1D00, 0x1FFF), (0x2000, 0x2BFF), (0x2C00, 0x2DFF), (0x3000, 0x30FF), (0x4E00, 0x4E80),
+              (0xA640, 0xA7FF), (0xFB00, 0xFB4F), (0xFF00, 0xFFEF), (0x10400, 0x1044F), (0x1D400, 0x1D7FF), (0x1E900, 0x1E95F),
+              (0x1F100, 0x1F1FF), (0x1F600, 0x1F64F)]
+    ix = api.BM25Index()
+    for _ in range(400):
+        chars = []
+        for _ in range(rng.randint(1, 60)):
+            r = rng.random()
+            if r < 0.15:
+                chars.append(rng.choice(" Σσςİ.-'"))
+            elif r < 0.25:
+                cp = rng.randrange(1, 0x110000)  # (U+0000 cannot cross the C-string API of the test binding)
+                chars.append(chr(cp) if not 0xD800 <= cp <= 0xDFFF else " ")
+            else:
+                lo, hi = rng.choice(blocks)
+                chars.append(chr(rng.randint(lo, hi)))
+        text = "".join(chars)
+        assert ix.tokenize(text) == oracle_tokenize(text), [hex(ord(c)) for c in text]
+
+
+def test_every_code_point_is_classified_like_the_oracle(api):
+    """exhaustive over all planes: a code point either joins its neighbours into one token or splits them"""
+    import unicodedata
+    import regex
+    alnum_re = regex.compile(r"[\p{Alphabetic}\p{N}]")
+
+    class alnum:  # the oracle's definition (oracle/tokenizer.py)
+        @staticmethod
+        def fullmatch(ch):
+            return unicodedata.category(ch) != "Cn" and alnum_re.fullmatch(ch)
+    ix = api.BM25Index()
+    step = 4096
+    for base in range(0, 0x110000, step):
+        cps = [cp for cp in range(max(base, 1), min(base + step, 0x110000)) if not 0xD800 <= cp <= 0xDFFF]
+        if not cps:
+            continue
+        text = " ".join("qq" + chr(cp) + "zz" for cp in cps)
+        toks = ix.tokenize(text)
+        i = 0
+        for cp in cps:
+            if alnum.fullmatch(chr(cp)):
+                assert toks[i] == ("qq" + chr(cp) + "zz").lower(), hex(cp)
+                i += 1
+            else:
+                assert toks[i] == "qq" and toks[i + 1] == "zz", hex(cp)
+                i += 2
+        assert i == len(toks)
+
+
+def test_unicode_tables_are_generated():
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_unicode_tables.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr

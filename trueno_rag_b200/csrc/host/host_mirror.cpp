@@ -206,8 +206,8 @@ BM25Index::BM25Index(BM25Index&&) noexcept = default;
 BM25Index& BM25Index::operator=(BM25Index&&) noexcept = default;
 
 // --- tokenizer: split on !char::is_alphanumeric, lowercase, drop stopwords, drop tokens with byte length < 2 ---
-// ASCII is exact.  Outside ASCII, Unicode `Alphabetic || Numeric` and `to_lowercase` are approximated by range
-// tables that cover Latin-1, Latin Extended-A, Greek, Cyrillic and the common punctuation / symbol blocks.
+// Unicode semantics come from generated UCD tables (unicode_tables.inc, tools/gen_unicode_tables.py): Alphabetic || N* for
+// the split, the full lowercase mapping plus the Final_Sigma rule for the case fold.
 static void decode_utf8(const std::string& s, size_t& i, uint32_t& cp) {
   const unsigned char c = (unsigned char)s[i];
   const int n = c < 0x80 ? 0 : (c >> 5) == 0x6 ? 1 : (c >> 4) == 0xE ? 2 : (c >> 3) == 0x1E ? 3 : -1;
@@ -231,50 +231,73 @@ static void encode_utf8(uint32_t cp, std::string& out) {
     out.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out.push_back((char)(0x80 | (cp & 0x3F)));
   }
 }
+#include "unicode_tables.inc"
+
+template <size_t N>
+static bool in_ranges(const uint32_t (&r)[N][2], uint32_t c) {
+  size_t lo = 0, hi = N;  // first range whose end is >= c
+  while (lo < hi) {
+    const size_t mid = (lo + hi) >> 1;
+    if (r[mid][1] < c) lo = mid + 1; else hi = mid;
+  }
+  return lo < N && r[lo][0] <= c;
+}
+// char::is_alphanumeric = Alphabetic || Nd || Nl || No
 static bool is_alphanumeric(uint32_t c) {
   if (c < 0x80) return (c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z');
-  if (c < 0xC0) return c == 0xAA || c == 0xB5 || c == 0xBA || c == 0xB2 || c == 0xB3 || c == 0xB9 || (c >= 0xBC && c <= 0xBE);
-  if (c == 0xD7 || c == 0xF7) return false;
-  if (c >= 0x2000 && c <= 0x206F) return false;   // general punctuation
-  if (c >= 0x20A0 && c <= 0x20CF) return false;   // currency
-  if (c >= 0x2190 && c <= 0x245F) return false;   // arrows, math, technical
-  if (c >= 0x2500 && c <= 0x27BF) return false;   // box drawing, shapes, dingbats
-  if (c >= 0x3000 && c <= 0x3004) return false;   // CJK punctuation
-  if (c >= 0x3008 && c <= 0x3020) return false;
-  if (c >= 0xFF00 && c <= 0xFF0F) return false;   // full-width punctuation
-  if (c >= 0xFF1A && c <= 0xFF20) return false;
-  if (c >= 0xE000 && c <= 0xF8FF) return false;   // private use
-  if (c == 0xFFFD) return false;
-  return true;
+  return in_ranges(TRR_UC_ALNUM, c);
 }
-static uint32_t to_lower(uint32_t c) {
-  if (c >= 'A' && c <= 'Z') return c + 32;
-  if (c < 0x80) return c;
-  if (c >= 0xC0 && c <= 0xDE && c != 0xD7) return c + 32;
-  if (c >= 0x100 && c <= 0x17F) {
-    if ((c >= 0x139 && c <= 0x148) || (c >= 0x179 && c <= 0x17E)) return (c & 1) ? c + 1 : c;
-    if (c == 0x130 || c == 0x178) return c == 0x178 ? 0xFF : c;
-    return (c & 1) ? c : c + 1;
+static const TrrLowerEntry* lower_entry(uint32_t c) {
+  size_t lo = 0, hi = sizeof(TRR_UC_LOWER) / sizeof(TRR_UC_LOWER[0]);
+  while (lo < hi) {
+    const size_t mid = (lo + hi) >> 1;
+    if (TRR_UC_LOWER[mid].cp < c) lo = mid + 1; else hi = mid;
   }
-  if (c >= 0x391 && c <= 0x3A9 && c != 0x3A2) return c + 32;
-  if (c >= 0x410 && c <= 0x42F) return c + 32;
-  if (c >= 0x400 && c <= 0x40F) return c + 80;
-  return c;
+  return lo < sizeof(TRR_UC_LOWER) / sizeof(TRR_UC_LOWER[0]) && TRR_UC_LOWER[lo].cp == c ? &TRR_UC_LOWER[lo] : nullptr;
+}
+// str::to_lowercase of one token (code points): full mapping, and U+03A3 becomes the final sigma when it is preceded by
+// a cased letter and not followed by one, case-ignorable characters skipped (Final_Sigma, as library/alloc/src/str.rs)
+static void lowercase_token(const std::vector<uint32_t>& tok, std::string& out) {
+  auto ignorable_then_cased = [&](long from, long step) {
+    for (long k = from; k >= 0 && k < (long)tok.size(); k += step) {
+      if (in_ranges(TRR_UC_CASE_IGNORABLE, tok[(size_t)k])) continue;
+      return in_ranges(TRR_UC_CASED, tok[(size_t)k]);
+    }
+    return false;
+  };
+  for (size_t i = 0; i < tok.size(); ++i) {
+    const uint32_t c = tok[i];
+    if (c < 0x80) { out.push_back((char)((c >= 'A' && c <= 'Z') ? c + 32 : c)); continue; }
+    if (c == 0x3A3) {
+      const bool final_sigma = ignorable_then_cased((long)i - 1, -1) && !ignorable_then_cased((long)i + 1, 1);
+      encode_utf8(final_sigma ? 0x3C2 : 0x3C3, out);
+      continue;
+    }
+    if (const TrrLowerEntry* e = lower_entry(c)) {
+      for (uint32_t k = 0; k < e->n; ++k) encode_utf8(e->to[k], out);
+    } else {
+      encode_utf8(c, out);
+    }
+  }
 }
 
 std::vector<std::string> BM25Index::tokenize(const std::string& text) const {
   std::vector<std::string> out;
-  std::string cur;
+  std::vector<uint32_t> cur;
+  std::string tok;
   auto emit = [&]() {
     if (cur.empty()) return;
-    if (!stopwords_.count(cur) && cur.size() >= 2) out.push_back(cur);  // :121-122
+    tok.clear();
+    if (lowercase_) lowercase_token(cur, tok);
+    else for (uint32_t c : cur) encode_utf8(c, tok);
+    if (!stopwords_.count(tok) && tok.size() >= 2) out.push_back(tok);  // :121-122 (byte length)
     cur.clear();
   };
   size_t i = 0;
   while (i < text.size()) {
     uint32_t cp;
     decode_utf8(text, i, cp);
-    if (is_alphanumeric(cp)) encode_utf8(lowercase_ ? to_lower(cp) : cp, cur);
+    if (is_alphanumeric(cp)) cur.push_back(cp);
     else emit();
   }
   emit();
