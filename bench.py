@@ -392,6 +392,36 @@ def run_ours(a):
     launches = torch.tensor([launches1.value - launches0.value], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(launches)
+    # device time of the merge + fusion kernel (K4), one un-pipelined step at a time on the compute stream.
+    # Informational and single-GPU only: an extra collective here could hang a sharded run if one rank failed, and the
+    # sharded runs overlap the all-gather with the next batch anyway (profiles/r01_scale.txt compares both schedules).
+    exchange = None
+    try:
+        if world != 1:
+            raise RuntimeError("measured on single-GPU runs only")
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t_gather = t_merge = 0.0
+        reps = 5
+        barrier()
+        for _ in range(reps):
+            api._check(L.trr_hybrid_local_device(dense.h, bm.h, C.c_void_p(d_q.data_ptr()), C.c_void_p(d_terms.data_ptr()),
+                                                 C.c_void_p(d_off.data_ptr()), q_off.ctypes.data_as(u32p), B, Cn, 1, 1,
+                                                 C.c_void_p(d_rec.data_ptr())))
+            evs[0].record()
+            g = gather()
+            evs[1].record()
+            api._check(L.trr_hybrid_merge_device(ctx.h, C.c_void_p(g.data_ptr()), world, B, Cn, api.RRF, 60.0, K,
+                                                 *[C.c_void_p(t.data_ptr()) for t in d_out]))
+            evs[2].record()
+            torch.cuda.synchronize()
+            t_gather += evs[0].elapsed_time(evs[1])
+            t_merge += evs[1].elapsed_time(evs[2])
+        exchange = {"all_gather_us": round(1e3 * t_gather / reps, 1), "merge_fuse_us": round(1e3 * t_merge / reps, 1),
+                    "bytes_per_rank": int(d_rec.numel() * d_rec.element_size()),
+                    "note": "un-pipelined, CUDA events on the compute stream; the timed steps overlap both with the next batch"}
+        barrier()
+    except Exception as ex:  # noqa: BLE001
+        exchange = {"skipped": str(ex)[:120]}
 
     # ---- correctness spot check against the oracle (outside every timed region)
     verify = None
@@ -437,7 +467,7 @@ def run_ours(a):
                                      "how": "same bytes per step with asynchronous copies from / to pinned memory around the device-resident step (copies overlap neighbouring steps); results verified against the blocking calls"},
                     "h2d_bytes_per_step": int(B * D * 4 + nt * 4 + (B + 1) * 4), "d2h_bytes_per_step": int(B * K * 16 + B * 4)},
             "gpu_launches": int(launches.item()),
-            "roofline": {"kernel": ("dense_gemm_topk_kernel (tcgen05 bf16 GEMM + fused top-k), rank 0 shard" if os.environ.get("TRR_GEMM_PAIR") == "0" or args.batch <= 128 else "dense_gemm_topk_pair_kernel (tcgen05 cta_group::2 bf16 GEMM + fused top-k), rank 0 shard"),
+            "roofline": {"kernel": ("dense_gemm_topk_kernel (tcgen05 bf16 GEMM + fused top-k), rank 0 shard" if os.environ.get("TRR_GEMM_PAIR") == "0" or a.batch <= 128 else "dense_gemm_topk_pair_kernel (tcgen05 cta_group::2 bf16 GEMM + fused top-k), rank 0 shard"),
                          "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
                          "traffic": ncu_traffic("gemm", a), "traffic_source": "profiles/r*_gemm_ncu.txt (ncu --set full, same command)",
                          "peak_source": peak_src,
@@ -446,7 +476,7 @@ def run_ours(a):
                         "gemm_ms_mean_of_extra_steps": float(np.mean(gemm_ms)), "bm25_ms_mean_of_extra_steps": float(np.mean(bm25_ms)),
                         "bm25": {"bound": "hbm", "achieved": bm_gbs, "peak": peak_hbm, "unit": "GB/s", "frac": bm_gbs / peak_hbm,
                                  "algorithmic": f"8 B x {postings_per_batch_local} postings per launch"},
-                        "guard_fallbacks_per_batch": float(np.mean(fallbacks))},
+                        "guard_fallbacks_per_batch": float(np.mean(fallbacks)), "exchange": exchange},
             "clocks": clocks, "verify": verify,
         }
         if world == 1 and not a.no_cpu_baseline:
