@@ -8,21 +8,24 @@
 // order come from the exact rescoring + candidate proof in dense_scan.cu (rescore_select_kernel), which
 // reproduces the reference arithmetic bit for bit.
 //
-// Kernel shape (sm_100a, cta_group::1):
-//   grid  = n_slices x n_qblocks persistent CTAs (<= one per SM); a CTA owns 128 queries (rows of A) and a
-//           contiguous range of 256-document tiles (rows of B), so its per-query candidate lists live in
-//           shared memory for the whole kernel.
-//   warp 0   TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) of Q [128 x 64] and docs [256 x 64]
-//            into a 3-stage ring, completion on mbarriers.
-//   warp 1   TMEM allocator + MMA issuer: 4 x tcgen05.mma (M128 N256 K16, bf16 -> f32) per k-block, commits
+// Kernel shape (sm_100a; dense_gemm_topk_kernel = cta_group::1, dense_gemm_topk_pair_kernel = cta_group::2, the default
+// for two or more query blocks - see the comment above the 2-CTA kernel):
+//   grid  = n_slices x n_qblocks persistent CTAs of 320 threads (<= one per SM); a CTA owns 128 queries (rows of A) and
+//           a contiguous range of 256-document tiles (rows of B), so its per-query candidate lists live in shared
+//           memory for the whole kernel.
+//   warp 0   TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) of Q [128 x 64] and docs [256 x 64] (2-CTA:
+//            each CTA of the pair loads half of the document tile) into a 3-stage (2-CTA: 4-stage) ring, completion on
+//            mbarriers; the scale/bias of a tile's documents arrive by a 2 KB bulk copy.
+//   warp 1   TMEM allocator + MMA issuer: 4 x tcgen05.mma (M128 / M256, N256, K16, bf16 -> f32) per k-block, commits
 //            release the smem stage and, after the last k-block, publish the accumulator stage.
-//   warps 2-5 epilogue: tcgen05.ld of the accumulator (lane == query row), fused scale/bias, threshold test
-//            against the minimum of the row's candidate list (8 / 16 / 32 / 64 entries per slice, chosen by the host),
-//            lane-private replace-min insertion with a compare-tree rescan.
+//   warps 2-9 epilogue: the two warps that share a TMEM lane quarter split the 256 columns of a tile; tcgen05.ld of the
+//            accumulator (lane == query row), fused scale/bias from shared memory, one 3-input max tree + compare per
+//            32-column chunk against the row's threshold, lane-private replace-min insertion into the (row, half) list
+//            (8 / 16 / 32 entries, chosen by the host) with a compare-tree rescan in the rare chunks that have a hit.
 //            Two accumulator stages (2 x 256 TMEM columns) overlap epilogue(t) with MMA(t+1).
 //   CTAs working on different document slices of the same queries share their thresholds through a global
-//   atomicMax table.  Measured (10M x 768 bf16, B = 1024): 12.9 ms = 1223 TFLOP/s; the bare TMA -> MMA pipeline without
-//   epilogue reads runs at 1346 TFLOP/s, i.e. the fused top-k costs about 9 % on top of the GEMM.
+//   atomicMax table.  Measured (10M x 768 bf16, B = 1024, inside the bench step): 11.9-12.2 ms = 1293-1317 TFLOP/s,
+//   93-95 % of the measured sustained bf16 peak; the part runs this kernel against its power cap.
 #include <cuda.h>
 #include <math_constants.h>
 
