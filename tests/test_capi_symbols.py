@@ -63,3 +63,47 @@ def test_rust_sys_crate_is_generated_from_the_header():
     assert r.returncode == 0, r.stdout + r.stderr
     rs = open(os.path.join(ROOT, "integration", "rust", "trueno-rag-b200-sys", "src", "lib.rs")).read()
     assert sorted(re.findall(r"pub fn (\w+)\(", rs)) == declared("trueno_rag_b200.h", "TRR_API")
+
+
+def _top_level_args(src, i):
+    """src[i] is the '(' of a call: returns the number of top-level arguments and the index after the closing ')'"""
+    depth, n, seen = 0, 0, False
+    j = i
+    while j < len(src):
+        c = src[j]
+        if c in "([{":
+            depth += 1
+        elif c in ")]}":
+            depth -= 1
+            if depth == 0:
+                return (n + 1 if seen else 0), j + 1
+        elif c == "," and depth == 1:
+            n += 1
+            seen_after = src[j + 1:].lstrip()
+            if seen_after.startswith(")"):  # trailing comma
+                n -= 1
+        elif not c.isspace() and depth >= 1:
+            seen = True
+        j += 1
+    raise AssertionError("unbalanced call")
+
+
+def test_rust_wrapper_calls_match_the_generated_signatures():
+    """the safe wrapper crate cannot be compiled here (no rustc): at least every `sys::trr_*` call in it must name a
+    function of the generated -sys crate and pass as many arguments as the C declaration has"""
+    rs = open(os.path.join(ROOT, "integration", "rust", "trueno-rag-b200-sys", "src", "lib.rs")).read()
+    arity = {}
+    for m in re.finditer(r"pub fn (\w+)\(", rs):
+        n, _ = _top_level_args(rs, m.end() - 1)
+        arity[m.group(1)] = n
+    shim = open(os.path.join(ROOT, "integration", "rust", "trueno-rag-b200", "src", "lib.rs")).read()
+    shim = re.sub(r"//[^\n]*", "", shim)
+    calls = list(re.finditer(r"sys::(trr_\w+)\(", shim))
+    assert len(calls) >= 12
+    for m in calls:
+        name = m.group(1)
+        assert name in arity, f"{name} is not in the -sys crate"
+        n, _ = _top_level_args(shim, m.end() - 1)
+        assert n == arity[name], f"{name}: the wrapper passes {n} arguments, the C ABI takes {arity[name]}"
+    for const in set(re.findall(r"sys::(TRR_\w+)", shim)):
+        assert re.search(rf"pub const {const}: c_int", rs), const
