@@ -577,7 +577,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
       return trr_fail(TRR_ERR_UNSUPPORTED, "GEMM mode supports cosine/dot metrics with k <= 100");
     use_gemm = false;
   }
-  if (use_gemm && k > 50) {
+  if (use_gemm && (k > 50 || getenv("TRR_GEMM_CP128"))) {
     // re-scoring width 128 needs at least four half-slice lists of 32 entries
     const uint32_t n_qb = (B + TRR_GEMM_TILE_M - 1) / TRR_GEMM_TILE_M;
     const uint64_t tiles = (h->n + TRR_GEMM_TILE_N - 1) / TRR_GEMM_TILE_N;
@@ -625,7 +625,9 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     if (n_slices == 0) n_slices = 1;
     const uint32_t B_pad = n_qblocks * TRR_GEMM_TILE_M;
     // exact re-scoring width per query: k plus a margin of ranks for the candidate proof
-    const uint32_t CP = k <= 50 ? TRR_GEMM_CP : 2 * TRR_GEMM_CP;
+    // (TRR_GEMM_CP128=1 forces the wide width for every k: to be measured - with f32 queries the quantisation term of the
+    // proof is worth about 10 ranks of score spacing, so k = 50 of 64 often falls through to the second pass)
+    const uint32_t CP = (k <= 50 && !getenv("TRR_GEMM_CP128")) ? TRR_GEMM_CP : 2 * TRR_GEMM_CP;
     // list length per (query, slice): the global top-CP by fast score is spread over the slices (about CP / n_slices
     // per slice), so short lists suffice when there are many slices (Poisson tail < 1e-6 for the choices below); the
     // candidate proof (rescore_select_kernel) catches the data sets where they do not
