@@ -208,6 +208,10 @@ class PersistedIndex {  // :133-146
   // serde_json::from_str::<PersistedIndex>: unknown keys ignored, `chunks` / `embeddings` / `dimension` required, numbers
   // parsed as f64 and narrowed to f32 like serde_json does; malformed input -> Error::Serialization
   static PersistedIndex from_json(const char* text, size_t n);
+  // serde_json::to_string_pretty(&persisted) (:423): two-space indentation, struct field order, every f32 printed with the
+  // fewest digits that parse back to the same value (what serde_json's ryu does; the exponent style may differ, the value
+  // never), non-finite numbers as `null` (which, as in the reference, cannot be read back), non-ASCII text unescaped
+  std::string to_json() const;
   // run_query's scoring (:479-492): cosine of `query` against every stored embedding (an embedding of another length
   // scores 0.0, :529-531), stable sort by score descending (ties keep index order), first top_k.  The query embedding comes
   // from the caller (the embedders are out of scope).  Pairs are (index into `chunks`, score).  top_k <= 1024 (the C ABI's

@@ -56,6 +56,11 @@ TRRH_API int trrh_bm25_from_bytes(const uint8_t* data, uint64_t n, int compressi
  * scan (:479-492) on the device.  Strings are owned by the handle; NULL = None. */
 typedef struct trrh_cli_index trrh_cli_index;
 TRRH_API int trrh_cli_index_from_json(const char* text, uint64_t n, trrh_cli_index** out);
+/* building and writing one (:407-424): an empty index, chunks with their embeddings, serde_json::to_string_pretty */
+TRRH_API int trrh_cli_index_new(uint64_t dimension, const char* embedder_type, const char* model_name, trrh_cli_index** out);
+TRRH_API int trrh_cli_index_push(trrh_cli_index* h, const char* content, const char* title, const char* source,
+                                 const float* embedding, uint64_t len);
+TRRH_API int trrh_cli_index_to_json(trrh_cli_index* h, uint8_t** out, uint64_t* out_n);
 TRRH_API void trrh_cli_index_free(trrh_cli_index* h);
 TRRH_API uint64_t trrh_cli_index_len(trrh_cli_index* h);
 TRRH_API uint64_t trrh_cli_index_n_embeddings(trrh_cli_index* h);

@@ -181,3 +181,62 @@ def test_top_k_beyond_the_device_limit_is_reported():
     with pytest.raises(api.Error) as e:  # the C ABI serves k <= 1024 per query; no host-side scan is substituted
         ix.query(E[0], 1500)
     assert e.value.kind == "Unsupported"
+
+
+# ------------------------------------------------------------------------------------------------
+# writing index.json (run_index, :407-424)
+# ------------------------------------------------------------------------------------------------
+def _build(E, chunks):
+    ix = api.PersistedIndex.new(len(E[0]) if len(E) else 0, "tfidf", None)
+    for c, e in zip(chunks, E):
+        ix.push(api.PersistedChunk(c["content"], c["title"], c["source"]), e)
+    return ix
+
+
+def test_to_json_round_trips_and_matches_pretty_layout():
+    rng = np.random.default_rng(9)
+    E = rng.standard_normal((7, 12)).astype(np.float32)
+    E[0, :6] = [0.0, -0.0, 1.0, 1e21, np.float32(1e-45), np.float32(3.4028235e38)]
+    chunks = [{"content": f'c{i} "q" \\ / \n\t\r\b\f \x01 é ☃ 😀', "title": None if i % 2 else f"T{i}", "source": f"s{i}.md"} for i in range(7)]
+    text = _build(E, chunks).to_json()
+    doc = json.loads(text)
+    assert doc["chunks"] == chunks and doc["dimension"] == 12 and doc["embedder_type"] == "tfidf" and doc["model_name"] is None
+    assert list(doc) == ["chunks", "embeddings", "dimension", "embedder_type", "model_name"]   # struct field order
+    with np.errstate(over="ignore"):
+        assert np.array(doc["embeddings"], np.float64).astype(np.float32).tobytes() == E.tobytes()
+    # the layout of serde_json's PrettyFormatter is the layout of json.dumps(indent=2); only number spelling may differ
+    skeleton = lambda s: __import__("re").sub(r"-?\d[0-9.eE+-]*", "#", s)  # noqa: E731
+    assert skeleton(text) == skeleton(json.dumps(doc, indent=2, ensure_ascii=False))
+    again = api.PersistedIndex.from_json(text)
+    assert again.to_json() == text
+    for i in range(7):
+        assert again.embedding(i).tobytes() == E[i].tobytes()
+        assert again.chunk(i).content == chunks[i]["content"]
+
+
+def test_to_json_prints_the_shortest_round_tripping_digits():
+    rng = np.random.default_rng(10)
+    vals = np.concatenate([rng.standard_normal(2000).astype(np.float32), (rng.standard_normal(500) * 1e-20).astype(np.float32),
+                           (rng.standard_normal(500) * 1e20).astype(np.float32),
+                           np.array([0.1, 0.2, 0.3, 1 / 3, 16777216.0, 1e-38, 123456.79, 5e-324], np.float32)])
+    ix = api.PersistedIndex.new(len(vals))
+    ix.push(api.PersistedChunk("x"), vals)
+    toks = [t.strip().rstrip(",") for t in ix.to_json().split('"embeddings": [')[1].split("]")[0].split("\n") if t.strip() not in ("", "[")]
+    assert len(toks) == len(vals)
+    for t, v in zip(toks, vals):
+        assert np.float32(float(t)).tobytes() == np.float32(v).tobytes(), (t, v)
+        digits = lambda s: len(s.lower().split("e")[0].replace("-", "").replace(".", "").strip("0")) or 1  # noqa: E731
+        want = np.format_float_scientific(v, unique=True, trim="-")
+        assert digits(t) <= digits(want), (t, want)          # never more digits than the shortest representation
+        assert "." in t or "e" in t                            # always spelled as a float
+
+
+def test_to_json_empty_and_non_finite():
+    assert json.loads(api.PersistedIndex.new(384, "semantic", "BAAI/bge-small-en-v1.5").to_json()) == {
+        "chunks": [], "embeddings": [], "dimension": 384, "embedder_type": "semantic", "model_name": "BAAI/bge-small-en-v1.5"}
+    ix = api.PersistedIndex.new(2)
+    ix.push(api.PersistedChunk("x"), np.array([np.nan, np.inf], np.float32))
+    text = ix.to_json()
+    assert json.loads(text)["embeddings"] == [[None, None]]        # serde_json writes null for NaN / infinity ...
+    with pytest.raises(api.Error):
+        api.PersistedIndex.from_json(text)                          # ... and cannot read it back (neither can the reference)

@@ -123,6 +123,9 @@ TRRH_PROTOS = {
     "trrh_bm25_from_bytes": (C.c_int, [C.c_char_p, C.c_uint64, C.c_int, vpp]),
     "trrh_cli_index_from_json": (C.c_int, [C.c_char_p, C.c_uint64, vpp]),
     "trrh_cli_index_free": (None, [vp]),
+    "trrh_cli_index_new": (C.c_int, [C.c_uint64, C.c_char_p, C.c_char_p, vpp]),
+    "trrh_cli_index_push": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_char_p, f32p, C.c_uint64]),
+    "trrh_cli_index_to_json": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]),
     "trrh_cli_index_len": (C.c_uint64, [vp]),
     "trrh_cli_index_n_embeddings": (C.c_uint64, [vp]),
     "trrh_cli_index_dimension": (C.c_uint64, [vp]),

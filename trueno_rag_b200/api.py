@@ -627,6 +627,25 @@ class PersistedIndex:
         self.h = _h
 
     @staticmethod
+    def new(dimension: int, embedder_type: str = "", model_name: Optional[str] = None) -> "PersistedIndex":
+        h = C.c_void_p()
+        _hcheck(_lib.load().trrh_cli_index_new(dimension, embedder_type.encode(),
+                                               None if model_name is None else model_name.encode(), C.byref(h)))
+        return PersistedIndex(h)
+
+    def push(self, chunk: "PersistedChunk", embedding) -> None:
+        """one chunk and its embedding (`run_index`, crates/trueno-rag-cli/src/main.rs:380-414)"""
+        e = np.ascontiguousarray(embedding, dtype=np.float32)
+        _hcheck(self.L.trrh_cli_index_push(self.h, chunk.content.encode(), None if chunk.title is None else chunk.title.encode(),
+                                           None if chunk.source is None else chunk.source.encode(), _p(e, f32p), e.size))
+
+    def to_json(self) -> str:
+        """`serde_json::to_string_pretty(&persisted)` (:423)"""
+        out, n = C.c_void_p(), C.c_uint64()
+        _hcheck(self.L.trrh_cli_index_to_json(self.h, C.byref(out), C.byref(n)))
+        return _take_bytes(self.L, out, n).decode()
+
+    @staticmethod
     def from_json(text) -> "PersistedIndex":
         raw = text.encode() if isinstance(text, str) else bytes(text)
         h = C.c_void_p()

@@ -145,6 +145,32 @@ int trrh_cli_index_from_json(const char* text, uint64_t n, trrh_cli_index** out)
   return guarded([&] { *out = new trrh_cli_index{PersistedIndex::from_json(text, n)}; });
 }
 void trrh_cli_index_free(trrh_cli_index* h) { delete h; }
+int trrh_cli_index_new(uint64_t dimension, const char* embedder_type, const char* model_name, trrh_cli_index** out) {
+  return guarded([&] {
+    PersistedIndex p;
+    p.dimension = dimension;
+    p.embedder_type = embedder_type ? embedder_type : "";
+    if (model_name) p.model_name = std::string(model_name);
+    *out = new trrh_cli_index{std::move(p)};
+  });
+}
+int trrh_cli_index_push(trrh_cli_index* h, const char* content, const char* title, const char* source,
+                        const float* embedding, uint64_t len) {
+  return guarded([&] {
+    PersistedChunk c;
+    c.content = content ? content : "";
+    if (title) c.title = std::string(title);
+    if (source) c.source = std::string(source);
+    h->v.chunks.push_back(std::move(c));
+    h->v.embeddings.emplace_back(embedding, embedding + len);
+  });
+}
+int trrh_cli_index_to_json(trrh_cli_index* h, uint8_t** out, uint64_t* out_n) {
+  return guarded([&] {
+    const std::string j = h->v.to_json();
+    bytes_out(std::vector<uint8_t>(j.begin(), j.end()), out, out_n);
+  });
+}
 uint64_t trrh_cli_index_len(trrh_cli_index* h) { return h->v.chunks.size(); }
 uint64_t trrh_cli_index_n_embeddings(trrh_cli_index* h) { return h->v.embeddings.size(); }
 uint64_t trrh_cli_index_dimension(trrh_cli_index* h) { return h->v.dimension; }

@@ -3,6 +3,7 @@
 // every score, ranking and fusion is computed by the CUDA kernels through the C ABI.
 #include <errno.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -955,6 +956,78 @@ PersistedIndex PersistedIndex::from_json(const char* text, size_t n) {
   if (!has_emb) j.fail("missing field `embeddings`");
   if (!has_dim) j.fail("missing field `dimension`");
   return out;
+}
+
+namespace {
+void json_string(const std::string& v, std::string& o) {
+  o.push_back('"');
+  for (const char ch : v) {
+    const unsigned char c = (unsigned char)ch;
+    switch (c) {
+      case '"': o += "\\\""; break;
+      case '\\': o += "\\\\"; break;
+      case '\b': o += "\\b"; break;
+      case '\f': o += "\\f"; break;
+      case '\n': o += "\\n"; break;
+      case '\r': o += "\\r"; break;
+      case '\t': o += "\\t"; break;
+      default:
+        if (c < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04x", c); o += b; }
+        else o.push_back(ch);
+    }
+  }
+  o.push_back('"');
+}
+void json_f32(float v, std::string& o) {
+  if (!std::isfinite(v)) { o += "null"; return; }
+  char b[40];
+  for (int prec = 1; prec <= 9; ++prec) {  // fewest significant digits that round-trip (9 always do for f32)
+    snprintf(b, sizeof b, "%.*g", prec, (double)v);
+    if ((float)strtod(b, nullptr) == v && (v != 0.0f || std::signbit((float)strtod(b, nullptr)) == std::signbit(v))) break;
+  }
+  std::string t(b);
+  if (t.find_first_of(".eEn") == std::string::npos) t += ".0";           // keep it a float token, like serde_json
+  const size_t e = t.find("e+");
+  if (e != std::string::npos) t.erase(e + 1, 1);                          // 1e+21 -> 1e21
+  for (size_t k = t.find('e'); k != std::string::npos;) {                 // e-07 -> e-7
+    size_t d = k + 1 + (t[k + 1] == '-' ? 1 : 0);
+    while (d + 1 < t.size() && t[d] == '0') t.erase(d, 1);
+    break;
+  }
+  o += t;
+}
+void json_opt(const std::optional<std::string>& v, std::string& o) {
+  if (v) json_string(*v, o); else o += "null";
+}
+}  // namespace
+
+std::string PersistedIndex::to_json() const {
+  std::string o;
+  o.reserve(64 + embeddings.size() * (dimension * 14 + 32));
+  o += "{\n  \"chunks\": [";
+  for (size_t i = 0; i < chunks.size(); ++i) {
+    o += i ? ",\n    {\n" : "\n    {\n";
+    o += "      \"content\": "; json_string(chunks[i].content, o);
+    o += ",\n      \"title\": "; json_opt(chunks[i].title, o);
+    o += ",\n      \"source\": "; json_opt(chunks[i].source, o);
+    o += "\n    }";
+  }
+  o += chunks.empty() ? "],\n" : "\n  ],\n";
+  o += "  \"embeddings\": [";
+  for (size_t i = 0; i < embeddings.size(); ++i) {
+    o += i ? ",\n    [" : "\n    [";
+    for (size_t j = 0; j < embeddings[i].size(); ++j) {
+      o += j ? ",\n      " : "\n      ";
+      json_f32(embeddings[i][j], o);
+    }
+    o += embeddings[i].empty() ? "]" : "\n    ]";
+  }
+  o += embeddings.empty() ? "],\n" : "\n  ],\n";
+  o += "  \"dimension\": " + std::to_string(dimension) + ",\n";
+  o += "  \"embedder_type\": "; json_string(embedder_type, o);
+  o += ",\n  \"model_name\": "; json_opt(model_name, o);
+  o += "\n}";
+  return o;
 }
 
 std::vector<std::pair<size_t, float>> PersistedIndex::query(const std::vector<float>& q, size_t top_k) const {
