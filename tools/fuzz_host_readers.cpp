@@ -56,7 +56,14 @@ int main(int argc, char** argv) {
           case 0: { auto o = zstd_decompress(m.data(), m.size()); if (o.size() > (64u << 20)) { printf("runaway output\n"); return 1; } break; }
           case 1: { auto x = BM25Index::from_bytes(m.data(), m.size()); auto b = x.to_bytes(); break; }
           case 2: { auto x = decompress(Compression::Lz4, m.data(), m.size()); break; }
-          default: { auto x = PersistedIndex::from_json(reinterpret_cast<const char*>(m.data()), m.size()); break; }
+          default: {
+            auto x = PersistedIndex::from_json(reinterpret_cast<const char*>(m.data()), m.size());
+            const std::string j = x.to_json();
+            bool finite = true;  // (a non-finite number is written as null, which - as in the reference - does not parse back)
+            for (const auto& row : x.embeddings) for (float v : row) finite = finite && v == v && v - v == 0.0f;
+            if (finite && PersistedIndex::from_json(j.data(), j.size()).to_json() != j) { printf("json writer not idempotent\n"); return 1; }
+            break;
+          }
         }
         ok++;
       } catch (const Error&) {
