@@ -569,6 +569,11 @@ __global__ void bm25_fine_kernel(const uint2* __restrict__ post, const uint64_t*
   }
 }
 
+// VARIANT 1 is the kernel measured in round 1.  VARIANT 2 (TRR_BM25_V2=2) applies the next steps listed in DESIGN.md
+// section 7 - slot bounds compacted into shared memory instead of two shuffles + ffs per slot, posting loads of the next
+// eight slots issued before the read-modify-writes of the current eight, four-fold unrolled branch-light harvest - and
+// HAS NOT RUN ON HARDWARE YET (the round's GPU budget was spent); no test selects it.
+template <int VARIANT>
 __global__ void __launch_bounds__(TRR_BM25_V2_WARPS * 32, 3)
 bm25_search_warp_kernel(Bm25SearchArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -576,6 +581,7 @@ bm25_search_warp_kernel(Bm25SearchArgs a) {
   constexpr uint32_t NT = TRR_BM25_V2_WARPS * 32;
   float* acc = reinterpret_cast<float*>(smem_raw);                                   // [warps][2048]
   uint64_t* cand = reinterpret_cast<uint64_t*>(acc + TRR_BM25_V2_WARPS * SUBN);      // cand_cap
+  uint32_t* slot_tab = reinterpret_cast<uint32_t*>(cand + a.cand_cap);               // VARIANT 2: [warps][2][32] compacted slot bounds
   __shared__ uint32_t s_cnt, s_next, s_item, s_need;
   __shared__ uint64_t s_thr;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -665,33 +671,83 @@ bm25_search_warp_kernel(Bm25SearchArgs a) {
                 }
               }
             }
-            uint32_t m = __ballot_sync(FULLM, e > s);
-            while (m) {
-              uint32_t lo_[4], n_[4];
+            if constexpr (VARIANT == 1) {
+              uint32_t m = __ballot_sync(FULLM, e > s);
+              while (m) {
+                uint32_t lo_[4], n_[4];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const bool valid = m != 0u;
-                const uint32_t l = valid ? __ffs(m) - 1 : 0u;
-                m &= m - 1;
-                lo_[u] = __shfl_sync(FULLM, s, l);
-                const uint32_t hi = __shfl_sync(FULLM, e, l);
-                n_[u] = valid ? hi - lo_[u] : 0u;
-              }
-              uint2 pe[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) pe[u] = lane < n_[u] ? a.post[lo_[u] + lane] : make_uint2(0xFFFFFFFFu, 0u);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                if (n_[u] == 0) continue;  // warp-uniform
-                uint32_t d = pe[u].x - sub_base;
-                if (lane < n_[u] && d < SUBN) { my[d] = my[d] + __uint_as_float(pe[u].y); any = true; }
-                for (uint32_t p = 32 + lane; p < n_[u]; p += 32) {  // a segment longer than one load (order inside a term is free)
-                  const uint2 x = a.post[lo_[u] + p];
-                  d = x.x - sub_base;
-                  if (d < SUBN) { my[d] = my[d] + __uint_as_float(x.y); any = true; }
+                for (int u = 0; u < 4; ++u) {
+                  const bool valid = m != 0u;
+                  const uint32_t l = valid ? __ffs(m) - 1 : 0u;
+                  m &= m - 1;
+                  lo_[u] = __shfl_sync(FULLM, s, l);
+                  const uint32_t hi = __shfl_sync(FULLM, e, l);
+                  n_[u] = valid ? hi - lo_[u] : 0u;
                 }
-                __syncwarp();
+                uint2 pe[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pe[u] = lane < n_[u] ? a.post[lo_[u] + lane] : make_uint2(0xFFFFFFFFu, 0u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  if (n_[u] == 0) continue;  // warp-uniform
+                  uint32_t d = pe[u].x - sub_base;
+                  if (lane < n_[u] && d < SUBN) { my[d] = my[d] + __uint_as_float(pe[u].y); any = true; }
+                  for (uint32_t p = 32 + lane; p < n_[u]; p += 32) {  // a segment longer than one load (order inside a term is free)
+                    const uint2 x = a.post[lo_[u] + p];
+                    d = x.x - sub_base;
+                    if (d < SUBN) { my[d] = my[d] + __uint_as_float(x.y); any = true; }
+                  }
+                  __syncwarp();
+                }
               }
+            } else {
+              // compacted (first posting, count) of the non-empty slots, in slot order
+              uint32_t* w_lo = slot_tab + warp * 64;
+              uint32_t* w_n = w_lo + 32;
+              const uint32_t ne = __ballot_sync(FULLM, e > s);
+              const uint32_t n_ne = (uint32_t)__popc(ne);
+              if (e > s) {
+                const uint32_t r = (uint32_t)__popc(ne & ((1u << lane) - 1u));
+                w_lo[r] = s;
+                w_n[r] = e - s;
+              }
+              __syncwarp();
+              uint2 nxt[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                nxt[u] = make_uint2(0xFFFFFFFFu, 0u);
+                if ((uint32_t)u < n_ne && lane < w_n[u]) nxt[u] = a.post[w_lo[u] + lane];
+              }
+              for (uint32_t base = 0; base < n_ne; base += 8) {
+                uint2 cur[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {  // the next eight slots' postings are in flight while these eight are added
+                  const uint32_t slot = base + 8 + (uint32_t)u;
+                  nxt[u] = make_uint2(0xFFFFFFFFu, 0u);
+                  if (slot < n_ne && lane < w_n[slot]) nxt[u] = a.post[w_lo[slot] + lane];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  const uint32_t slot = base + (uint32_t)u;
+                  if (slot < n_ne) {  // warp-uniform
+                    const uint32_t n = w_n[slot];
+                    uint32_t d = cur[u].x - sub_base;
+                    if (lane < n && d < SUBN) { my[d] = my[d] + __uint_as_float(cur[u].y); any = true; }
+                    if (n > 32) {
+                      const uint32_t lo = w_lo[slot];
+                      for (uint32_t p = 32 + lane; p < n; p += 32) {
+                        const uint2 x = a.post[lo + p];
+                        d = x.x - sub_base;
+                        if (d < SUBN) { my[d] = my[d] + __uint_as_float(x.y); any = true; }
+                      }
+                    }
+                    __syncwarp();
+                  }
+                }
+              }
+              __syncwarp();  // the table is rewritten by the next group of terms
             }
           }
           any = __any_sync(FULLM, any);
@@ -704,27 +760,49 @@ bm25_search_warp_kernel(Bm25SearchArgs a) {
           const uint32_t ord0 = a.doc_base + (sub << TRR_BM25_SUB_SHIFT);
           uint4* a4 = reinterpret_cast<uint4*>(my);
           bool kept = false;
-          for (uint32_t i = lane; i < SUBN / 4; i += 32) {
-            const uint4 v = a4[i];
-            const bool nz = (v.x | v.y | v.z | v.w) != 0u;
-            const float mx = fmaxf(fmaxf(__uint_as_float(v.x), __uint_as_float(v.y)),
-                                   fmaxf(__uint_as_float(v.z), __uint_as_float(v.w)));
-            const bool hit = nz && mx >= thr_f;  // NaN compares false
-            if (nz && !hit) a4[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (hit) {
+          auto cells4 = [&](uint32_t i) {  // per-element pass over one 128-bit group that holds a candidate
 #pragma unroll 1
-              for (int j = 0; j < 4; ++j) {
-                const float f = my[i * 4 + j];
-                bool keep = false;
-                if (f >= thr_f && f > 0.0f) {  // src/index.rs:236 keeps only score > 0.0
-                  const uint64_t key = trr_make_key(f, ord0 + i * 4 + j);
-                  if (key > thr) {
-                    const uint32_t pos = atomicAdd(&s_cnt, 1u);
-                    if (pos < a.cand_cap) cand[pos] = key;
-                    else keep = true;  // stays in the accumulator; harvested again after the compaction
-                  }
+            for (int j = 0; j < 4; ++j) {
+              const float f = my[i * 4 + j];
+              bool keep = false;
+              if (f >= thr_f && f > 0.0f) {  // src/index.rs:236 keeps only score > 0.0
+                const uint64_t key = trr_make_key(f, ord0 + i * 4 + j);
+                if (key > thr) {
+                  const uint32_t pos = atomicAdd(&s_cnt, 1u);
+                  if (pos < a.cand_cap) cand[pos] = key;
+                  else keep = true;  // stays in the accumulator; harvested again after the compaction
                 }
-                if (keep) kept = true; else my[i * 4 + j] = 0.0f;
+              }
+              if (keep) kept = true; else my[i * 4 + j] = 0.0f;
+            }
+          };
+          if constexpr (VARIANT == 1) {
+            for (uint32_t i = lane; i < SUBN / 4; i += 32) {
+              const uint4 v = a4[i];
+              const bool nz = (v.x | v.y | v.z | v.w) != 0u;
+              const float mx = fmaxf(fmaxf(__uint_as_float(v.x), __uint_as_float(v.y)),
+                                     fmaxf(__uint_as_float(v.z), __uint_as_float(v.w)));
+              const bool hit = nz && mx >= thr_f;  // NaN compares false
+              if (nz && !hit) a4[i] = make_uint4(0u, 0u, 0u, 0u);
+              if (hit) cells4(i);
+            }
+          } else {
+            auto pre4 = [&](uint32_t i, const uint4& v) -> bool {
+              const bool nz = (v.x | v.y | v.z | v.w) != 0u;
+              const float mx = fmaxf(fmaxf(__uint_as_float(v.x), __uint_as_float(v.y)),
+                                     fmaxf(__uint_as_float(v.z), __uint_as_float(v.w)));
+              const bool hit = nz && mx >= thr_f;
+              if (nz && !hit) a4[i] = make_uint4(0u, 0u, 0u, 0u);
+              return hit;
+            };
+            for (uint32_t i = lane; i < SUBN / 4; i += 128) {  // SUBN / 4 is a multiple of 128
+              const uint4 v0 = a4[i], v1 = a4[i + 32], v2 = a4[i + 64], v3 = a4[i + 96];
+              const bool h0 = pre4(i, v0), h1 = pre4(i + 32, v1), h2 = pre4(i + 64, v2), h3 = pre4(i + 96, v3);
+              if (__any_sync(FULLM, h0 | h1 | h2 | h3)) {
+                if (h0) cells4(i);
+                if (h1) cells4(i + 32);
+                if (h2) cells4(i + 64);
+                if (h3) cells4(i + 96);
               }
             }
           }
@@ -815,15 +893,16 @@ cudaError_t trr_launch_bm25_search(const Bm25SearchArgs& a, unsigned grid, cudaS
 }
 
 size_t trr_bm25_search_warp_smem(uint32_t cand_cap) {
-  return (size_t)TRR_BM25_V2_WARPS * (4u << TRR_BM25_SUB_SHIFT) + (size_t)cand_cap * 8;
+  return (size_t)TRR_BM25_V2_WARPS * (4u << TRR_BM25_SUB_SHIFT) + (size_t)cand_cap * 8 + (size_t)TRR_BM25_V2_WARPS * 64 * 4;
 }
 
-cudaError_t trr_launch_bm25_search_warp(const Bm25SearchArgs& a, unsigned grid, cudaStream_t st) {
+cudaError_t trr_launch_bm25_search_warp(const Bm25SearchArgs& a, unsigned grid, int variant, cudaStream_t st) {
   const size_t smem = trr_bm25_search_warp_smem(a.cand_cap);
-  cudaError_t e = cudaFuncSetAttribute(bm25_search_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kernel = variant == 2 ? bm25_search_warp_kernel<2> : bm25_search_warp_kernel<1>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  cudaFuncSetAttribute(bm25_search_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  bm25_search_warp_kernel<<<grid, TRR_BM25_V2_WARPS * 32, smem, st>>>(a);
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  kernel<<<grid, TRR_BM25_V2_WARPS * 32, smem, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -80,7 +80,7 @@ cudaError_t trr_launch_bm25_plan(const Bm25SearchArgs& a, uint64_t* plan_keys, c
 cudaError_t trr_launch_bm25_search(const Bm25SearchArgs& a, unsigned grid, cudaStream_t st);
 // V2 (opt-in): warps of a CTA work on different 2048-document sub-ranges of one query without per-range barriers
 size_t trr_bm25_search_warp_smem(uint32_t cand_cap);
-cudaError_t trr_launch_bm25_search_warp(const Bm25SearchArgs& a, unsigned grid, cudaStream_t st);
+cudaError_t trr_launch_bm25_search_warp(const Bm25SearchArgs& a, unsigned grid, int variant, cudaStream_t st);
 // fine skip table: fine[row][j] for the n_fine terms listed in fine_terms (term ids), j = 0..n_sub
 cudaError_t trr_launch_bm25_fine(const uint2* post, const uint64_t* term_off, const uint32_t* fine_terms, uint32_t n_fine,
                                  uint32_t* fine, uint32_t fine_ld, uint32_t n_sub, cudaStream_t st);

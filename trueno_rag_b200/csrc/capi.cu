@@ -1189,7 +1189,8 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   // documents leave room for two CTAs per SM.
   // opt-in V2 kernel (warp-autonomous sub-ranges; see bm25.cu)
   bool v2 = false;
-  if (const char* e = getenv("TRR_BM25_V2")) v2 = atoi(e) != 0;
+  int v2_variant = 1;  // 2 = the not yet measured variant (see bm25.cu)
+  if (const char* e = getenv("TRR_BM25_V2")) { v2 = atoi(e) != 0; v2_variant = atoi(e) == 2 ? 2 : 1; }
   if (v2 && trr_bm25_search_warp_smem(a.cand_cap) > c->smem_optin) v2 = false;
   if (v2) {
     TRR_CHECK(bm25_ensure_fine(h));
@@ -1233,7 +1234,7 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)B * n_chunks, (uint64_t)slots);
   TRR_CUDA(trr_launch_bm25_plan(a, plan_keys, st));
   TRR_CUDA(cudaEventRecord(h->ev[2], st));
-  if (v2) TRR_CUDA(trr_launch_bm25_search_warp(a, grid, st));
+  if (v2) TRR_CUDA(trr_launch_bm25_search_warp(a, grid, v2_variant, st));
   else TRR_CUDA(trr_launch_bm25_search(a, grid, st));
   TRR_CUDA(cudaEventRecord(h->ev[3], st));
   const uint32_t plan_launches = (B > 1 && B <= 4096) ? 2u : 1u;
