@@ -67,12 +67,14 @@ typedef struct trr_bm25 trr_bm25;
 typedef struct {
   uint32_t mode_used;        /* trr_dense_mode actually run */
   uint32_t n_queries;
-  uint32_t n_guard_fallbacks;/* GEMM path: queries whose candidate proof failed and were re-run through SCAN */
+  uint32_t n_guard_fallbacks;/* queries whose candidate proof failed: GEMM path -> re-run through SCAN; BM25 -> re-run with 32-bit cells */
   uint32_t n_kernel_launches;/* kernels of this library launched by the call */
   float ms_total;            /* device time of the call (CUDA events on the context stream) */
   float ms_main_kernel;      /* device time of the dominant kernel (scan / gemm / bm25) */
   float max_fast_exact_gap;  /* GEMM path: max |fast score - exact score| over rescored candidates */
   float eps_bound;           /* GEMM path: the a-priori bound used by the candidate proof */
+  uint32_t n_exact_fallbacks;/* BM25: queries whose 32-bit proof failed too and were re-run by the exact kernel */
+  uint32_t reserved;
 } trr_stats;
 
 TRR_API const char* trr_last_error(void);

@@ -88,6 +88,25 @@ def test_duplicate_terms_and_massive_ties(api, ctx):
     q_terms = np.array([x for q in qs for x in q], np.uint32)
     for k in (1, 50, 1000):
         compare(dev, oix, q_terms, q_off, k)
+    # thousands of documents tie exactly at the k-th score: neither integer fast pass can prove its selection, so these
+    # queries must have gone through both fallback levels (32-bit cells, then the exact kernel)
+    compare(dev, oix, q_terms, q_off, 50)
+    st = dev.stats()
+    assert st.n_guard_fallbacks >= 1 and st.n_exact_fallbacks >= 1, (st.n_guard_fallbacks, st.n_exact_fallbacks)
+    dev.close()
+
+
+def test_fast_pass_proves_ordinary_queries(api, ctx):
+    # on a Zipfian corpus the 16-bit fast pass + exact re-scoring must settle (nearly) every query without a fallback
+    n_docs, n_terms = 120000, 30000
+    cdf = O.zipf_cdf(n_terms)
+    doc_off, toks = O.synth_doc_tokens(SEED + 7, cdf, 0, n_docs)
+    oix = O.BM25(n_terms=n_terms, doc_off=doc_off, tokens=toks)
+    dev = build(api, ctx, oix, n_docs)
+    q_off, q_terms = O.synth_query_terms(SEED + 7, cdf, 0, 300)
+    compare(dev, oix, q_terms, q_off, 50)
+    st = dev.stats()
+    assert st.mode_used == 2 and st.n_exact_fallbacks == 0 and st.n_guard_fallbacks <= 30, (st.mode_used, st.n_guard_fallbacks, st.n_exact_fallbacks)
     dev.close()
 
 

@@ -260,7 +260,7 @@ def step_perf_bm25_big():
         got = dev.search(q_terms, q_off, K)
         st = dev.stats()
         print(f"K3 {N} docs B={B} k={K}: main {st.ms_main_kernel:.3f} ms  postings/query {vol/B:.0f}  {8*vol/st.ms_main_kernel/1e6:.0f} GB/s "
-              f"{B/st.ms_main_kernel*1e3:.0f} q/s", flush=True)
+              f"{B/st.ms_main_kernel*1e3:.0f} q/s  fallbacks {st.n_guard_fallbacks}/{st.n_exact_fallbacks} launches {st.n_kernel_launches}", flush=True)
     print("checksum", int(got[0].astype(np.uint64).sum()), float(got[1].astype(np.float64).sum()), int(got[2].sum()))
     dev.close()
 

@@ -64,7 +64,8 @@ __global__ void bm25_build_kernel(Bm25BuildArgs a) {
     a.post[p] = make_uint2(doc, __float_as_uint(impact));
     if (!dead) {
       atomicMin(&a.term_min[t], trr_f32_orderable(impact));
-      if (!(impact > 0.0f)) a.flags[0] = 1u;
+      atomicMax(&a.term_max[t], trr_f32_orderable(impact));
+      if (!(impact > 0.0f && impact < CUDART_INF_F)) a.flags[0] = 1u;  // NaN compares false
     }
     // skip table
     const uint64_t t_begin = a.term_off[t], t_end = a.term_off[t + 1];
@@ -127,7 +128,7 @@ __global__ void bm25_skip_empty_kernel(Bm25BuildArgs a) {
 __global__ void __launch_bounds__(256)
 bm25_cost_kernel(Bm25SearchArgs a, uint64_t* __restrict__ keys, uint32_t cap2) {
   const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (blockIdx.x == 0 && threadIdx.x == 0) { a.queue[0] = 0; a.queue[1] = 0; }
+  if (blockIdx.x == 0 && threadIdx.x < 8) a.queue[threadIdx.x] = 0;  // work queues and flagged-query counters of the search
   const uint32_t n_loop = cap2 ? cap2 : a.B;
   if (b >= n_loop) return;
   if (b >= a.B) {  // padding entries of the sort
@@ -141,22 +142,57 @@ bm25_cost_kernel(Bm25SearchArgs a, uint64_t* __restrict__ keys, uint32_t cap2) {
   const bool boot = a.n_chunks == 1 && a.flags[0] == 0u;
   uint64_t cost = 0;  // postings the query touches in this shard
   uint32_t best = 0;  // largest min-impact among its terms with >= k postings
-  for (uint32_t i = a.q_off[b] + lane; i < a.q_off[b + 1]; i += 32) {
+  float smax = 0.0f;  // sum over the term slots of the term's largest impact: bounds every document's score
+  float mmax = 0.0f;  // largest single impact
+  const uint32_t q0 = a.q_off[b], T = a.q_off[b + 1] - q0;
+  for (uint32_t i = q0 + lane; i < q0 + T; i += 32) {
     const uint32_t t = a.q_terms[i];
     if (t < a.n_terms) {
       const uint32_t* row = a.skip + (uint64_t)t * a.skip_ld;
       const uint32_t cnt = row[a.n_ranges] - row[0];
       cost += cnt;
       if (boot && cnt >= a.k) best = max(best, a.term_min[t]);
+      const uint32_t mx = a.term_max[t];
+      if (mx) { const float m = trr_orderable_f32(mx); smax += m; mmax = fmaxf(mmax, m); }
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o);
     best = max(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+    smax += __shfl_xor_sync(0xFFFFFFFFu, smax, o);
+    mmax = fmaxf(mmax, __shfl_xor_sync(0xFFFFFFFFu, mmax, o));
+  }
+  // Fixed-point scales of the integer fast pass: every posting adds ceil(impact * scale) to a cell.  A cell never exceeds
+  // scale * smax + T, which has to fit the cell (2^16 - 1 / 2^31), and a single term stays below 2^22 (the FFMA trick).
+  float scale16 = 1.0f, scale32 = 1.0f;
+  if (smax > 0.0f) {
+    // (0.9999: smax is a float tree sum; 1e30: a denormal-sized smax must not turn the scale into infinity)
+    scale16 = fminf((65535.0f - (float)T) / smax * 0.9999f, 1e30f);
+    scale32 = fminf(fminf(4194304.0f / mmax, 2147483000.0f / smax) * 0.9999f, 1e30f);
+  }
+  uint32_t bestf16 = 0, bestf32 = 0;
+  if (a.thr0f16 && boot) {  // the same bootstrap in the fixed-point domains, for the kf candidates of the fast pass
+    for (uint32_t i = q0 + lane; i < q0 + T; i += 32) {
+      const uint32_t t = a.q_terms[i];
+      if (t < a.n_terms) {
+        const uint32_t* row = a.skip + (uint64_t)t * a.skip_ld;
+        if (row[a.n_ranges] - row[0] >= a.kf) {
+          const float mn = trr_orderable_f32(a.term_min[t]);
+          bestf16 = max(bestf16, __float_as_uint(__fmaf_ru(mn, scale16, 8388608.0f)) & 0x7FFFFFu);
+          bestf32 = max(bestf32, __float_as_uint(__fmaf_ru(mn, scale32, 8388608.0f)) & 0x7FFFFFu);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      bestf16 = max(bestf16, __shfl_xor_sync(0xFFFFFFFFu, bestf16, o));
+      bestf32 = max(bestf32, __shfl_xor_sync(0xFFFFFFFFu, bestf32, o));
+    }
   }
   if (lane == 0) {
     a.thr0[b] = best ? (((uint64_t)best << 32) - 1ull) : TRR_KEY_EMPTY;
+    if (a.thr0f16) { a.qscale16[b] = scale16; a.thr0f16[b] = bestf16; a.qscale32[b] = scale32; a.thr0f32[b] = bestf32; }
     if (cost > 0xFFFFFFFFull) cost = 0xFFFFFFFFull;
     if (cap2) keys[b] = ((cost + 1) << 32) | (uint64_t)(0xFFFFFFFFu - b);  // never TRR_KEY_EMPTY; ties: smaller b first
     else a.order[b] = b;
@@ -257,10 +293,6 @@ bm25_search_kernel(Bm25SearchArgs a) {
   if (warp < CW) for (uint32_t i = tid; i < R; i += CT) acc[i] = 0.0f;
   __syncthreads();
 
-  // perf triage (TRR_BM25_DEBUG=8): where CTA 0 spends its cycles
-  const bool timed = (a.debug_mode & 8u) && blockIdx.x == 0 && a.dbg != nullptr;
-  long long w_prod = 0, w_full = 0, w_bnd = 0, w_acc = 0, w_harv = 0;
-  const long long t_begin = timed ? clock64() : 0;
   if (warp == CW) {
     // ============================ producer warp ============================
     uint32_t stage = 0, phase = 0;
@@ -268,9 +300,7 @@ bm25_search_kernel(Bm25SearchArgs a) {
     uint64_t item_thr0 = TRR_KEY_EMPTY;
     auto emit = [&](uint32_t flags, uint32_t range_base, uint32_t item, uint32_t off, uint32_t src_al, uint32_t al,
                     uint32_t begin, uint32_t end, uint32_t total_al) {
-      const long long tw = timed ? clock64() : 0;
       mbar_wait_or_trap(&empty_bar[stage], phase ^ 1, 1, a.dbg);
-      if (timed) w_prod += clock64() - tw;
       PassDesc& d = desc[stage];
       d.seg_begin[lane] = begin;
       d.seg_end[lane] = end;
@@ -287,14 +317,14 @@ bm25_search_kernel(Bm25SearchArgs a) {
       if (al) trr_bulk_g2s(stage_buf + (size_t)stage * a.stage_cap + off, a.post + src_al, al * 8u, &full_bar[stage]);
       if (++stage == 2) { stage = 0; phase ^= 1; }
     };
-    const uint32_t n_items = a.B * a.n_chunks;
+    const uint32_t n_items = (a.n_sel_ptr ? *a.n_sel_ptr : a.B) * a.n_chunks;
     while (true) {
       uint32_t item = 0;
       if (lane == 0) item = atomicAdd(a.queue, 1u);
       item = __shfl_sync(FULLM, item, 0);
       if (item >= n_items) { emit(F_QUIT, 0, item, 0, 0, 0, 0, 0, 0); break; }
       const uint32_t b = a.order[item / a.n_chunks], c = item % a.n_chunks;
-      item_thr0 = a.thr0[b];
+      item_thr0 = a.n_chunks == 1 ? a.thr0[b] : TRR_KEY_EMPTY;  // (the bootstrap counts the postings of the whole shard)
       const uint32_t r0 = (uint32_t)(((uint64_t)c * a.n_ranges) / a.n_chunks);
       const uint32_t r1 = (uint32_t)(((uint64_t)(c + 1) * a.n_ranges) / a.n_chunks);
       const uint32_t q0 = a.q_off[b];
@@ -370,7 +400,6 @@ bm25_search_kernel(Bm25SearchArgs a) {
       }
       emit(F_END_ITEM, 0, item, 0, 0, 0, 0, 0, 0);
     }
-    if (timed && lane == 0) a.dbg[9] = (uint32_t)(w_prod >> 4);
   } else {
     // ============================ consumer warps ============================
     uint32_t stage = 0, phase = 0;
@@ -393,9 +422,7 @@ bm25_search_kernel(Bm25SearchArgs a) {
       consumer_bar();
     };
     while (true) {
-      long long tc = timed ? clock64() : 0;
       mbar_wait_or_trap(&full_bar[stage], phase, 2, a.dbg);
-      if (timed) { const long long t = clock64(); w_full += t - tc; tc = t; }
       const PassDesc& d = desc[stage];
       const uint32_t flags = d.flags, range_base = d.range_base, item = d.item;
       const uint64_t thr0 = d.thr0;
@@ -421,7 +448,6 @@ bm25_search_kernel(Bm25SearchArgs a) {
         }
         uint32_t lo = 0, hi = 0;
         if (flags & F_HAS_POSTINGS) { lo = bnd[lane * 17 + warp]; hi = bnd[lane * 17 + warp + 1]; }
-        if (timed) { const long long t = clock64(); w_bnd += t - tc; tc = t; }
         // Measured and dropped (4M documents, 1024 queries; this loop: 4.0 ms): a flattened walk (all slots of the warp as
         // one sequence, 32 postings per step, match.any for documents that occur in two slots of a step) 6.7 ms, and 4.1 ms
         // even without the conflict handling; four slots per round with the posting loads in flight together 4.7 ms.
@@ -441,7 +467,6 @@ bm25_search_kernel(Bm25SearchArgs a) {
         }
       }
       __syncwarp();
-      if (timed) { const long long t = clock64(); w_acc += t - tc; tc = t; }
       if (lane == 0) trr_mbar_arrive(&empty_bar[stage]);  // stage and descriptor are free again
       if (++stage == 2) { stage = 0; phase ^= 1; }
 
@@ -508,7 +533,6 @@ bm25_search_kernel(Bm25SearchArgs a) {
         }
         touched = false;
       }
-      if (timed) { const long long t = clock64(); w_harv += t - tc; tc = t; }
       if (flags & F_END_ITEM) {
         compact();
         const uint32_t n_out = s_cnt;
@@ -523,7 +547,7 @@ bm25_search_kernel(Bm25SearchArgs a) {
           }
           if (tid == 0 && a.out_n) a.out_n[b] = n_out;
         } else {
-          uint64_t* dst = a.partial + ((uint64_t)b * a.n_chunks + c) * a.k;
+          uint64_t* dst = a.partial + (uint64_t)item * a.k;  // indexed by position in `order` (x n_chunks + chunk)
           for (uint32_t i = tid; i < a.k; i += CT) dst[i] = i < n_out ? cand[i] : TRR_KEY_EMPTY;
         }
         consumer_bar();
@@ -531,312 +555,470 @@ bm25_search_kernel(Bm25SearchArgs a) {
         consumer_bar();
       }
     }
-    if (timed && tid == 0) {
-      a.dbg[8] = (uint32_t)((clock64() - t_begin) >> 4);
-      a.dbg[10] = (uint32_t)(w_full >> 4); a.dbg[11] = (uint32_t)(w_bnd >> 4);
-      a.dbg[12] = (uint32_t)(w_acc >> 4); a.dbg[13] = (uint32_t)(w_harv >> 4);
-    }
   }
 }
 
 // =============================================================================================
-// V2 search kernel (opt-in, TRR_BM25_V2=1): warp-autonomous sub-ranges
+// integer fast pass (the default search path): order-free accumulation, then exact re-scoring of the survivors
 // =============================================================================================
-// A CTA (8 warps) still owns one (query, chunk) item with its candidate buffer and threshold in shared memory, but the
-// warps do not move in lockstep: each pulls 2048-document sub-ranges from a CTA-local counter, owns an 8 KB accumulator,
-// reads the posting bounds of all query terms with one lane-parallel look-up (fine skip table for frequent terms, the
-// coarse table + a document-range filter for the rest), loads the postings straight from global memory (four term slots
-// in flight) and harvests its own cells.  CTA-wide barriers happen only when the candidate buffer has to be compacted
-// and at the end of the item.  Sum order per document = query-term order, as in the V1 kernel.
-__global__ void bm25_fine_kernel(const uint2* __restrict__ post, const uint64_t* __restrict__ term_off,
-                                 const uint32_t* __restrict__ fine_terms, uint32_t n_fine, uint32_t* __restrict__ fine,
-                                 uint32_t fine_ld, uint32_t n_sub) {
-  const uint32_t f = blockIdx.x;
-  if (f >= n_fine) return;
-  const uint32_t t = fine_terms[f];
-  const uint64_t begin = term_off[t], end = term_off[t + 1];
-  uint32_t* row = fine + (uint64_t)f * fine_ld;
-  if (begin == end) {
-    for (uint32_t j = threadIdx.x; j <= n_sub; j += blockDim.x) row[j] = (uint32_t)begin;
-    return;
-  }
-  for (uint64_t p = begin + threadIdx.x; p < end; p += blockDim.x) {
-    const uint32_t cur = post[p].x >> TRR_BM25_SUB_SHIFT;
-    const int64_t prev = p == begin ? -1 : (int64_t)(post[p - 1].x >> TRR_BM25_SUB_SHIFT);
-    for (int64_t j = prev + 1; j <= (int64_t)cur; ++j) row[j] = (uint32_t)p;
-    if (p + 1 == end)
-      for (uint32_t j = cur + 1; j <= n_sub; ++j) row[j] = (uint32_t)end;
-  }
-}
+// The exact kernel above pays for the reference's summation order: every consumer warp owns a sub-range and walks its
+// slice of every term segment on its own (a dozen postings per slice), and the f32 cells force plain read-modify-write.
+// The fast pass only SELECTS.  Every posting adds ceil(impact * scale) to an integer cell with one native shared-memory
+// atomic (ATOMS.ADD: measured 6.3 cycles per 32 random cells against 10.4 for a plain LDS/FADD/STS chain and 16.4 for
+// the CAS loop an f32 atomic compiles to; tools/ubench/smem_atom.cu), so the order inside a pass is free and all 512
+// consumer threads walk the staged postings FLAT - no sub-range ownership, no boundary searches, no per-segment shuffles.
+// ceil(impact * scale) is one FFMA with round-up onto 2^23 (the integer appears in the mantissa; F2I runs at a fraction of
+// the FMA rate).  Integer sums are exact and never below scale * (real-number sum of the impacts), which bounds the
+// reference's f32 score of every document from above:  score_f32(d) <= F(d) / scale * (1 + T * 2^-23)  (T term slots,
+// each f32 add rounds by at most 2^-24 relative).  The kernel keeps the kf best documents per query by (F, ordinal);
+// bm25_rescore_kernel recomputes their scores in the reference's order and proves that nothing that was dropped can reach
+// the k-th exact score.
+// Two cell widths (template BITS): 16-bit cells, two per word, halve the per-range scan of the accumulator - the largest
+// shared-memory cost of the pass - and leave room for 48 KB stages; their scale (65535 / sum of the query terms' largest
+// impacts) makes the bound a few hundredths wide, far below the score gap between rank k and rank kf on ordinary data.
+// A query whose 16-bit proof fails is re-run with 32-bit cells (bound ~1e-5 relative), and only if that proof fails too
+// (dozens of documents within rounding distance of the k-th score, e.g. exact duplicates) by the exact kernel.  Both
+// fallbacks are device-driven: they read the number of flagged queries from device memory and leave at once when it is 0.
+//
+// Producer warp and staging are those of the exact kernel (one cp.async.bulk per term segment into a shared-memory
+// ring, here three stages), with one difference: a flat walk cannot mask the alignment padding of a copy by segment
+// bounds.  Padding postings of the SAME term fall outside the document range and are dropped by the range check; the only
+// paddings that could fall inside are the last posting of the previous term / the first of the next one, i.e. when an
+// odd-aligned segment starts (ends) exactly at its term's first (last) posting.  Those segments are copied without that
+// posting, which travels in the pass descriptor instead (FastDesc::single).
+#ifdef TRR_TRIAGE  // cycle counters of CTA 0 (tools/gpu_probe.py): where the producer and consumer warp 0 spend their time
+#define TRI(...) __VA_ARGS__
+#else
+#define TRI(...)
+#endif
 
-// VARIANT 1 is the kernel measured in round 1.  VARIANT 2 (TRR_BM25_V2=2) applies the next steps listed in DESIGN.md
-// section 7 - slot bounds compacted into shared memory instead of two shuffles + ffs per slot, posting loads of the next
-// eight slots issued before the read-modify-writes of the current eight, four-fold unrolled branch-light harvest - and
-// HAS NOT RUN ON HARDWARE YET (the round's GPU budget was spent); no test selects it.
-template <int VARIANT>
-__global__ void __launch_bounds__(TRR_BM25_V2_WARPS * 32, 3)
-bm25_search_warp_kernel(Bm25SearchArgs a) {
+namespace {
+
+constexpr uint32_t NS = TRR_BM25_FAST_STAGES;
+constexpr uint32_t NONE32 = 0xFFFFFFFFu;
+
+struct FastDesc {
+  uint32_t flags;
+  uint32_t range_base;  // local id of the first document of the range
+  uint32_t item;
+  uint32_t total;       // staged postings (alignment padding included)
+  uint32_t thr0f;       // the item's bootstrap threshold in fixed point (0 = none)
+  float scale;          // 2^e of the item's query
+  uint32_t pad0, pad1;
+  uint2 single[64];     // [slot] first / [32 + slot] last posting of a term, when the aligned copy had to leave it out
+};
+
+}  // namespace
+
+template <int BITS>  // width of an accumulator cell: 16 (two cells per word) or 32
+__global__ void __launch_bounds__(TRR_BM25_THREADS, 1)
+bm25_fast_kernel(Bm25SearchArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  constexpr uint32_t SUBN = 1u << TRR_BM25_SUB_SHIFT;
-  constexpr uint32_t NT = TRR_BM25_V2_WARPS * 32;
-  float* acc = reinterpret_cast<float*>(smem_raw);                                   // [warps][2048]
-  uint64_t* cand = reinterpret_cast<uint64_t*>(acc + TRR_BM25_V2_WARPS * SUBN);      // cand_cap
-  uint32_t* slot_tab = reinterpret_cast<uint32_t*>(cand + a.cand_cap);               // VARIANT 2: [warps][2][32] compacted slot bounds
-  __shared__ uint32_t s_cnt, s_next, s_item, s_need;
+  const uint32_t R = 1u << a.range_shift;
+  const uint32_t W = BITS == 16 ? R >> 1 : R;                                             // accumulator words
+  uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                                  // R fixed-point cells
+  uint2* stage_buf = reinterpret_cast<uint2*>(acc + W);                                   // NS x stage_cap
+  uint64_t* cand = reinterpret_cast<uint64_t*>(stage_buf + (size_t)NS * a.stage_cap);     // cand_cap
+  FastDesc* desc = reinterpret_cast<FastDesc*>(cand + a.cand_cap);                        // NS
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(desc + NS);                            // NS
+  uint64_t* empty_bar = full_bar + NS;                                                    // NS
+  __shared__ uint32_t s_cnt, s_overflow, s_ovf_latched;
   __shared__ uint64_t s_thr;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* my = acc + warp * SUBN;
-  for (uint32_t i = tid; i < TRR_BM25_V2_WARPS * SUBN; i += NT) acc[i] = 0.0f;
-  const uint32_t compact_at = a.k + ((a.cand_cap - a.k) >> 1);
-  const uint32_t n_items = a.B * a.n_chunks;
-  const uint32_t coarse_shift = a.range_shift - TRR_BM25_SUB_SHIFT;
 
-  // candidate buffer -> sorted descending, s_cnt <= k, s_thr = k-th best; every thread of the CTA takes part
-  auto compact = [&]() {
-    const uint32_t cnt = min(s_cnt, a.cand_cap);
-    for (uint32_t i = cnt + tid; i < a.cand_cap; i += NT) cand[i] = TRR_KEY_EMPTY;
-    trr_bitonic_sort_desc(cand, a.cand_cap, tid, NT, BlockSync());
-    if (tid == 0) {
-      const uint32_t c2 = min(cnt, a.k);
-      s_cnt = c2;
-      if (c2 == a.k && a.k > 0) s_thr = cand[a.k - 1];
-      s_need = 0;
-    }
-    __syncthreads();
-  };
+  if (tid == 0) {
+    for (uint32_t s = 0; s < NS; ++s) { trr_mbar_init(&full_bar[s], 1); trr_mbar_init(&empty_bar[s], CW); }
+    trr_fence_mbar_init();
+    s_cnt = 0; s_overflow = 0; s_thr = TRR_KEY_EMPTY;
+  }
+  if (warp < CW) for (uint32_t i = tid; i < W; i += CT) acc[i] = 0u;
+  __syncthreads();
 
-  while (true) {
-    __syncthreads();  // the previous item is finished (outputs written, shared state free)
-    if (tid == 0) s_item = atomicAdd(a.queue, 1u);
-    __syncthreads();
-    const uint32_t item = s_item;
-    if (item >= n_items) break;
-    const uint32_t b = a.order[item / a.n_chunks], c = item % a.n_chunks;
-    const uint32_t sub0 = (uint32_t)(((uint64_t)c * a.n_sub) / a.n_chunks);
-    const uint32_t sub1 = (uint32_t)(((uint64_t)(c + 1) * a.n_sub) / a.n_chunks);
-    const uint64_t thr0 = a.thr0[b];
-    const uint32_t q0 = a.q_off[b];
-    const uint32_t T = a.q_off[b + 1] - q0;
-    const uint32_t G = (T + 31) >> 5;
-    if (tid == 0) { s_next = sub0; s_cnt = 0; s_thr = TRR_KEY_EMPTY; s_need = 0; }
-    __syncthreads();
-    // T <= 32 (the usual case): every lane resolves its term's skip row once per item; a sub-range then costs one
-    // dependent look-up instead of three (term id -> row id -> bounds)
-    const uint32_t* rowp = nullptr;
-    uint32_t rshift = 0;
-    if (G == 1 && lane < T) {
-      const uint32_t term = a.q_terms[q0 + lane];
-      if (term < a.n_terms) {
-        const uint32_t fr = a.fine_row[term];
-        if (fr != 0xFFFFFFFFu) { rowp = a.fine + (uint64_t)fr * a.fine_ld; }
-        else { rowp = a.skip + (uint64_t)term * a.skip_ld; rshift = coarse_shift; }
+  TRI(long long w_prod = 0, w_full = 0, w_acc = 0, w_harv = 0, w_end = 0; uint32_t n_pass = 0, n_compact = 0;)
+  TRI(const long long t_begin = clock64();)
+  if (warp == CW) {
+    // ============================ producer warp ============================
+    uint32_t stage = 0, phase = 0;
+    uint32_t item_thr0f = 0;
+    float item_scale = 1.0f;
+    const uint2 none2 = make_uint2(NONE32, 0u);
+    // publishes one pass: descriptor + bulk copies.  Every lane passes its own slot (al == 0: no copy for the slot).
+    auto emit = [&](uint32_t flags, uint32_t range_base, uint32_t item, uint32_t off, uint32_t src_al, uint32_t al,
+                    uint32_t total_al, uint2 sf, uint2 sb) {
+      TRI(const long long tw = clock64();)
+      mbar_wait_or_trap(&empty_bar[stage], phase ^ 1, 1, a.dbg);
+      TRI(w_prod += clock64() - tw; ++n_pass;)
+      FastDesc& d = desc[stage];
+      d.single[lane] = sf;
+      d.single[32 + lane] = sb;
+      if (lane == 0) {
+        d.flags = flags; d.range_base = range_base; d.item = item; d.total = total_al;
+        d.thr0f = item_thr0f; d.scale = item_scale;
       }
-    }
-
-    bool redo = false;       // the last harvest left candidates in the accumulator (buffer full): harvest again after the compaction
-    uint32_t redo_sub = 0;
-    while (true) {  // rounds, separated by compactions
-      bool exhausted = false;
-      while (true) {
-        uint32_t sub;
-        bool any = true;
-        if (redo) {
-          sub = redo_sub;
-        } else {
-          if (*reinterpret_cast<volatile uint32_t*>(&s_need)) break;
-          sub = 0;
-          if (lane == 0) sub = atomicAdd(&s_next, 1u);
-          sub = __shfl_sync(FULLM, sub, 0);
-          if (sub >= sub1) { exhausted = true; break; }
-          // ---- accumulate the sub-range, term slots in query order ----
-          any = false;
-          const uint32_t sub_base = sub << TRR_BM25_SUB_SHIFT;
-          for (uint32_t g = 0; g < G; ++g) {
+      __syncwarp();
+      if (lane == 0) {
+        if (total_al) trr_mbar_expect_tx(&full_bar[stage], total_al * 8u);
+        else trr_mbar_arrive(&full_bar[stage]);
+      }
+      __syncwarp();
+      if (al) trr_bulk_g2s(stage_buf + (size_t)stage * a.stage_cap + off, a.post + src_al, al * 8u, &full_bar[stage]);
+      if (++stage == NS) { stage = 0; phase ^= 1; }
+    };
+    const uint32_t n_items = (a.n_sel_ptr ? *a.n_sel_ptr : a.B) * a.n_chunks;
+    while (true) {
+      uint32_t item = 0;
+      if (lane == 0) item = atomicAdd(a.queue, 1u);
+      item = __shfl_sync(FULLM, item, 0);
+      if (item >= n_items) { emit(F_QUIT, 0, item, 0, 0, 0, 0, none2, none2); break; }
+      const uint32_t b = a.order[item / a.n_chunks], c = item % a.n_chunks;
+      item_thr0f = a.n_chunks == 1 ? a.thr0f[b] : 0u;  // (the bootstrap counts the postings of the whole shard)
+      item_scale = a.qscale[b];
+      const uint32_t r0 = (uint32_t)(((uint64_t)c * a.n_ranges) / a.n_chunks);
+      const uint32_t r1 = (uint32_t)(((uint64_t)(c + 1) * a.n_ranges) / a.n_chunks);
+      const uint32_t q0 = a.q_off[b];
+      const uint32_t T = a.q_off[b + 1] - q0;
+      const uint32_t G = (T + 31) >> 5;
+      // G == 1: every lane keeps a cursor through the skip row of its term, fetched one range ahead, and knows the term's
+      // first / last posting (the ones an aligned copy may have to leave out)
+      const uint32_t* row1 = nullptr;
+      uint32_t c_s = 0, c_e = 0, c_n = 0, ts1 = 0, te1 = 0;
+      uint2 fp1 = none2, lp1 = none2;
+      if (G == 1 && lane < T) {
+        const uint32_t term = a.q_terms[q0 + lane];
+        if (term < a.n_terms) {
+          row1 = a.skip + (uint64_t)term * a.skip_ld;
+          c_s = row1[r0];
+          c_e = r0 < r1 ? row1[r0 + 1] : c_s;
+          c_n = r0 + 2 <= a.n_ranges ? row1[r0 + 2] : c_e;
+          ts1 = row1[0];
+          te1 = row1[a.n_ranges];
+          if (te1 > ts1) {
+            if (ts1 & 1u) fp1 = a.post[ts1];
+            if (te1 & 1u) lp1 = a.post[te1 - 1];
+          }
+        }
+      }
+      for (uint32_t r = r0; r < r1; ++r) {
+        const uint32_t range_base = r << a.range_shift;
+        bool pending_harvest = false;  // a pass of this range was emitted without the harvest flag
+        for (uint32_t g = 0; g < G; ++g) {
+          uint32_t s = 0, e = 0, ts = 0, te = 0;
+          if (G == 1) {
+            s = c_s; e = c_e; ts = ts1; te = te1;
+            c_s = c_e; c_e = c_n;
+            if (row1 && r + 3 <= a.n_ranges) c_n = row1[r + 3];
+          } else {
             const uint32_t ti = g * 32 + lane;
-            uint32_t s = 0, e = 0;
-            if (G == 1) {
-              if (rowp) { const uint32_t* r2 = rowp + (sub >> rshift); s = r2[0]; e = r2[1]; }
-            } else if (ti < T) {
+            if (ti < T) {
               const uint32_t term = a.q_terms[q0 + ti];
               if (term < a.n_terms) {
-                const uint32_t fr = a.fine_row[term];
-                if (fr != 0xFFFFFFFFu) {
-                  const uint32_t* row = a.fine + (uint64_t)fr * a.fine_ld;
-                  s = row[sub];
-                  e = row[sub + 1];
-                } else {  // infrequent term: its postings of the whole coarse range, filtered by document below
-                  const uint32_t* row = a.skip + (uint64_t)term * a.skip_ld + (sub >> coarse_shift);
-                  s = row[0];
-                  e = row[1];
-                }
+                const uint32_t* row = a.skip + (uint64_t)term * a.skip_ld;
+                s = row[r]; e = row[r + 1]; ts = row[0]; te = row[a.n_ranges];
               }
-            }
-            if constexpr (VARIANT == 1) {
-              uint32_t m = __ballot_sync(FULLM, e > s);
-              while (m) {
-                uint32_t lo_[4], n_[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const bool valid = m != 0u;
-                  const uint32_t l = valid ? __ffs(m) - 1 : 0u;
-                  m &= m - 1;
-                  lo_[u] = __shfl_sync(FULLM, s, l);
-                  const uint32_t hi = __shfl_sync(FULLM, e, l);
-                  n_[u] = valid ? hi - lo_[u] : 0u;
-                }
-                uint2 pe[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) pe[u] = lane < n_[u] ? a.post[lo_[u] + lane] : make_uint2(0xFFFFFFFFu, 0u);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  if (n_[u] == 0) continue;  // warp-uniform
-                  uint32_t d = pe[u].x - sub_base;
-                  if (lane < n_[u] && d < SUBN) { my[d] = my[d] + __uint_as_float(pe[u].y); any = true; }
-                  for (uint32_t p = 32 + lane; p < n_[u]; p += 32) {  // a segment longer than one load (order inside a term is free)
-                    const uint2 x = a.post[lo_[u] + p];
-                    d = x.x - sub_base;
-                    if (d < SUBN) { my[d] = my[d] + __uint_as_float(x.y); any = true; }
-                  }
-                  __syncwarp();
-                }
-              }
-            } else {
-              // compacted (first posting, count) of the non-empty slots, in slot order
-              uint32_t* w_lo = slot_tab + warp * 64;
-              uint32_t* w_n = w_lo + 32;
-              const uint32_t ne = __ballot_sync(FULLM, e > s);
-              const uint32_t n_ne = (uint32_t)__popc(ne);
-              if (e > s) {
-                const uint32_t r = (uint32_t)__popc(ne & ((1u << lane) - 1u));
-                w_lo[r] = s;
-                w_n[r] = e - s;
-              }
-              __syncwarp();
-              uint2 nxt[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                nxt[u] = make_uint2(0xFFFFFFFFu, 0u);
-                if ((uint32_t)u < n_ne && lane < w_n[u]) nxt[u] = a.post[w_lo[u] + lane];
-              }
-              for (uint32_t base = 0; base < n_ne; base += 8) {
-                uint2 cur[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {  // the next eight slots' postings are in flight while these eight are added
-                  const uint32_t slot = base + 8 + (uint32_t)u;
-                  nxt[u] = make_uint2(0xFFFFFFFFu, 0u);
-                  if (slot < n_ne && lane < w_n[slot]) nxt[u] = a.post[w_lo[slot] + lane];
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                  const uint32_t slot = base + (uint32_t)u;
-                  if (slot < n_ne) {  // warp-uniform
-                    const uint32_t n = w_n[slot];
-                    uint32_t d = cur[u].x - sub_base;
-                    if (lane < n && d < SUBN) { my[d] = my[d] + __uint_as_float(cur[u].y); any = true; }
-                    if (n > 32) {
-                      const uint32_t lo = w_lo[slot];
-                      for (uint32_t p = 32 + lane; p < n; p += 32) {
-                        const uint2 x = a.post[lo + p];
-                        d = x.x - sub_base;
-                        if (d < SUBN) { my[d] = my[d] + __uint_as_float(x.y); any = true; }
-                      }
-                    }
-                    __syncwarp();
-                  }
-                }
-              }
-              __syncwarp();  // the table is rewritten by the next group of terms
             }
           }
-          any = __any_sync(FULLM, any);
-        }
-        // ---- harvest the warp's 2048 cells ----
-        redo = false;
-        if (any) {
-          const uint64_t thr = max(*reinterpret_cast<volatile uint64_t*>(&s_thr), thr0);
-          const float thr_f = thr == TRR_KEY_EMPTY ? -CUDART_INF_F : trr_key_score(thr);
-          const uint32_t ord0 = a.doc_base + (sub << TRR_BM25_SUB_SHIFT);
-          uint4* a4 = reinterpret_cast<uint4*>(my);
-          bool kept = false;
-          auto cells4 = [&](uint32_t i) {  // per-element pass over one 128-bit group that holds a candidate
-#pragma unroll 1
-            for (int j = 0; j < 4; ++j) {
-              const float f = my[i * 4 + j];
-              bool keep = false;
-              if (f >= thr_f && f > 0.0f) {  // src/index.rs:236 keeps only score > 0.0
-                const uint64_t key = trr_make_key(f, ord0 + i * 4 + j);
-                if (key > thr) {
-                  const uint32_t pos = atomicAdd(&s_cnt, 1u);
-                  if (pos < a.cand_cap) cand[pos] = key;
-                  else keep = true;  // stays in the accumulator; harvested again after the compaction
-                }
+          // the first / last posting of the term, when it sits on an odd index, leaves the copy and rides in the descriptor
+          uint2 sf = none2, sb = none2;
+          if (e > s && (s & 1u) && s == ts) { sf = G == 1 ? fp1 : a.post[s]; ++s; }
+          if (e > s && (e & 1u) && e == te) { sb = G == 1 ? lp1 : a.post[e - 1]; --e; }
+          bool singles = __any_sync(FULLM, sf.x != NONE32 || sb.x != NONE32);
+          uint32_t first = 0;  // slots below `first` are done
+          while (true) {
+            const uint32_t len = lane >= first ? e - s : 0u;
+            const uint32_t al = len ? (((s & 1u) + len + 1u) & ~1u) : 0u;  // postings copied: 16-byte aligned both ends
+            uint32_t incl = al;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const uint32_t v = __shfl_up_sync(FULLM, incl, o);
+              if ((int)lane >= o) incl += v;
+            }
+            const uint32_t total = __shfl_sync(FULLM, incl, 31);
+            if (total == 0) {
+              if (singles) {  // nothing to copy, but some slot's only postings ride in the descriptor
+                emit(0u, range_base, item, 0, 0, 0, 0, sf, sb);
+                pending_harvest = true;
               }
-              if (keep) kept = true; else my[i * 4 + j] = 0.0f;
+              break;
+            }
+            const uint32_t fits = __ballot_sync(FULLM, incl <= a.stage_cap);
+            const uint32_t n_fit = fits == FULLM ? 32u : (uint32_t)(__ffs(~fits) - 1);  // slots [first, n_fit) fit
+            if (n_fit == first) {
+              // slot `first` alone exceeds the stage: stream it in stage-sized pieces that end on even indices, so that no
+              // piece carries a padding posting of the same range
+              const bool me = lane == first;
+              const uint32_t s_al = s & ~1u;
+              emit(0u, range_base, item, 0, me ? s_al : 0u, me ? a.stage_cap : 0u, a.stage_cap, singles ? sf : none2,
+                   singles ? sb : none2);
+              if (me) s = s_al + a.stage_cap;  // < e, because the slot did not fit
+              pending_harvest = true;
+            } else {
+              const bool me = lane >= first && lane < n_fit;
+              const uint32_t taken = __shfl_sync(FULLM, incl, n_fit - 1);
+              const bool last = (G == 1) && (taken == total);
+              emit(last ? F_HARVEST : 0u, range_base, item, me ? incl - al : 0u, me ? (s & ~1u) : 0u, me ? al : 0u, taken,
+                   singles ? sf : none2, singles ? sb : none2);
+              pending_harvest = !last;
+              first = n_fit;
+            }
+            singles = false;
+            sf = none2; sb = none2;
+          }
+        }
+        if (pending_harvest) emit(F_HARVEST, range_base, item, 0, 0, 0, 0, none2, none2);
+      }
+      emit(F_END_ITEM, 0, item, 0, 0, 0, 0, none2, none2);
+    }
+    TRI(if (blockIdx.x == 0 && lane == 0 && a.dbg) { a.dbg[9] = (uint32_t)(w_prod >> 4); a.dbg[14] = n_pass; })
+  } else {
+    // ============================ consumer warps ============================
+    uint32_t stage = 0, phase = 0;
+    const uint32_t compact_at = a.kf + ((a.cand_cap - a.kf) >> 1);
+    // block-wide (consumer warps) compaction: afterwards cand[0..s_cnt) is sorted descending and s_thr is the kf-th best
+    auto compact = [&]() {
+      consumer_bar();
+      const uint32_t cnt = min(s_cnt, a.cand_cap);
+      for (uint32_t i = cnt + tid; i < a.cand_cap; i += CT) cand[i] = TRR_KEY_EMPTY;
+      trr_bitonic_sort_desc(cand, a.cand_cap, tid, CT, ConsumerSync());
+      if (tid == 0) {
+        const uint32_t c2 = min(cnt, a.kf);
+        s_cnt = c2;
+        s_ovf_latched = s_overflow;
+        s_overflow = 0;
+        if (c2 == a.kf) s_thr = cand[a.kf - 1];
+      }
+      consumer_bar();
+    };
+    while (true) {
+      TRI(long long tc = clock64();)
+      mbar_wait_or_trap(&full_bar[stage], phase, 2, a.dbg);
+      TRI({ const long long t = clock64(); w_full += t - tc; tc = t; })
+      const FastDesc& d = desc[stage];
+      const uint32_t flags = d.flags, range_base = d.range_base, item = d.item, total = d.total, thr0f = d.thr0f;
+      const float scale = d.scale;
+      if (flags & F_QUIT) break;
+      const uint2* st = stage_buf + (size_t)stage * a.stage_cap;
+      {
+        // flat walk: posting p of the stage belongs to thread p mod 512; padding and foreign ranges fail the range check
+        const uint32_t acc_s = trr_smem_u32(acc);
+        auto add1 = [&](const uint2 e) {
+          const uint32_t dd = e.x - range_base;
+          // ceil(impact * scale) in the low mantissa bits of RU(impact * scale + 2^23)  (impact * scale < 2^22)
+          uint32_t q = __float_as_uint(__fmaf_ru(__uint_as_float(e.y), scale, 8388608.0f)) & 0x7FFFFFu;
+#ifdef TRR_TRIAGE
+          if (a.triage & 1u) { if (dd < R && q == 0x12345u) acc[dd & (W - 1)] = 1u; return; }
+#endif
+          uint32_t addr;
+          if (BITS == 16) { addr = acc_s + ((dd >> 1) << 2); q <<= (dd & 1u) << 4; }
+          else addr = acc_s + (dd << 2);
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, %1;\n\t@p red.shared.add.u32 [%2], %3;\n\t}"
+                       ::"r"(dd), "r"(R), "r"(addr), "r"(q) : "memory");
+        };
+        uint32_t p = tid;
+        for (; p + 3 * CT < total; p += 4 * CT) {
+          const uint2 e0 = st[p], e1 = st[p + CT], e2 = st[p + 2 * CT], e3 = st[p + 3 * CT];
+          add1(e0); add1(e1); add1(e2); add1(e3);
+        }
+#pragma unroll 1
+        for (; p < total; p += CT) add1(st[p]);
+        if (tid < 64) {
+          const uint2 e = d.single[tid];
+          if (e.x != NONE32) add1(e);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) trr_mbar_arrive(&empty_bar[stage]);  // stage and descriptor are free again
+      if (++stage == NS) { stage = 0; phase ^= 1; }
+      TRI({ const long long t = clock64(); w_acc += t - tc; tc = t; })
+
+      if (flags & F_HARVEST) {
+        consumer_bar();  // every add of the range has landed
+        while (true) {
+          bool need_compact = false;
+          const uint64_t thr = *reinterpret_cast<volatile uint64_t*>(&s_thr);
+          const uint32_t thr_hi = max(max((uint32_t)(thr >> 32), thr0f), 1u);
+          uint4* a4 = reinterpret_cast<uint4*>(acc);
+          const uint32_t ord0 = a.doc_base + range_base;
+          auto push = [&](uint32_t f, uint32_t cell) -> bool {  // true: the cell has to stay (candidate buffer full)
+            if (f < thr_hi) return false;
+            const uint64_t key = ((uint64_t)f << 32) | (uint64_t)(0xFFFFFFFFu - (ord0 + cell));
+            if (key <= thr) return false;
+            const uint32_t pos = atomicAdd(&s_cnt, 1u);
+            if (pos + 1u >= compact_at) need_compact = true;
+            if (pos < a.cand_cap) { cand[pos] = key; return false; }
+            s_overflow = 1u;  // stays in the accumulator; retried after the compaction
+            return true;
+          };
+          auto harvest4 = [&](uint32_t i) {  // per-cell pass over a 128-bit group that holds a candidate
+#pragma unroll 1
+            for (uint32_t j = 0; j < 4; ++j) {
+              const uint32_t wv = acc[i * 4 + j];
+              uint32_t nw = 0;
+              if (BITS == 16) {
+                const uint32_t lo = wv & 0xFFFFu, hi = wv >> 16;
+                if (push(lo, (i * 4 + j) * 2)) nw |= lo;
+                if (push(hi, (i * 4 + j) * 2 + 1)) nw |= hi << 16;
+              } else {
+                if (push(wv, i * 4 + j)) nw = wv;
+              }
+              acc[i * 4 + j] = nw;
             }
           };
-          if constexpr (VARIANT == 1) {
-            for (uint32_t i = lane; i < SUBN / 4; i += 32) {
-              const uint4 v = a4[i];
-              const bool nz = (v.x | v.y | v.z | v.w) != 0u;
-              const float mx = fmaxf(fmaxf(__uint_as_float(v.x), __uint_as_float(v.y)),
-                                     fmaxf(__uint_as_float(v.z), __uint_as_float(v.w)));
-              const bool hit = nz && mx >= thr_f;  // NaN compares false
-              if (nz && !hit) a4[i] = make_uint4(0u, 0u, 0u, 0u);
-              if (hit) cells4(i);
+          auto pre4 = [&](uint32_t i, const uint4& v) -> bool {
+            uint32_t mx;
+            if (BITS == 16) {
+              const uint32_t m2 = __vmaxu2(__vmaxu2(v.x, v.y), __vmaxu2(v.z, v.w));
+              mx = max(m2 & 0xFFFFu, m2 >> 16);
+            } else {
+              mx = max(max(v.x, v.y), max(v.z, v.w));
             }
-          } else {
-            auto pre4 = [&](uint32_t i, const uint4& v) -> bool {
-              const bool nz = (v.x | v.y | v.z | v.w) != 0u;
-              const float mx = fmaxf(fmaxf(__uint_as_float(v.x), __uint_as_float(v.y)),
-                                     fmaxf(__uint_as_float(v.z), __uint_as_float(v.w)));
-              const bool hit = nz && mx >= thr_f;
-              if (nz && !hit) a4[i] = make_uint4(0u, 0u, 0u, 0u);
-              return hit;
-            };
-            for (uint32_t i = lane; i < SUBN / 4; i += 128) {  // SUBN / 4 is a multiple of 128
-              const uint4 v0 = a4[i], v1 = a4[i + 32], v2 = a4[i + 64], v3 = a4[i + 96];
-              const bool h0 = pre4(i, v0), h1 = pre4(i + 32, v1), h2 = pre4(i + 64, v2), h3 = pre4(i + 96, v3);
-              if (__any_sync(FULLM, h0 | h1 | h2 | h3)) {
-                if (h0) cells4(i);
-                if (h1) cells4(i + 32);
-                if (h2) cells4(i + 64);
-                if (h3) cells4(i + 96);
-              }
-            }
+            const bool hit = mx >= thr_hi;
+            if (mx != 0u && !hit) a4[i] = make_uint4(0u, 0u, 0u, 0u);
+            return hit;
+          };
+          const uint32_t n4 = W >> 2;
+          uint32_t i = tid;
+          TRI(if (a.triage & 4u) i = n4;)
+          for (; i + 3 * CT < n4; i += 4 * CT) {
+            const uint4 v0 = a4[i], v1 = a4[i + CT], v2 = a4[i + 2 * CT], v3 = a4[i + 3 * CT];
+            const bool h0 = pre4(i, v0), h1 = pre4(i + CT, v1), h2 = pre4(i + 2 * CT, v2), h3 = pre4(i + 3 * CT, v3);
+            if (h0) harvest4(i);
+            if (h1) harvest4(i + CT);
+            if (h2) harvest4(i + 2 * CT);
+            if (h3) harvest4(i + 3 * CT);
           }
-          __syncwarp();
-          redo = __any_sync(FULLM, kept);
+          for (; i < n4; i += CT) {
+            const uint4 v = a4[i];
+            if (pre4(i, v)) harvest4(i);
+          }
+          // one barrier per harvest: it also tells every thread whether some push reached the compaction mark (or overflowed)
+          if (!consumer_bar_or(need_compact)) break;
+          TRI(++n_compact;)
+          compact();
+          if (!s_ovf_latched) break;  // (stable until the next compaction, which is behind further barriers)
         }
-        if (redo) {
-          redo_sub = sub;
-          if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&s_need) = 1u;
-          break;
+        TRI({ const long long t = clock64(); w_harv += t - tc; tc = t; })
+      }
+      if (flags & F_END_ITEM) {
+        compact();
+        const uint32_t n_out = s_cnt;
+        uint64_t* dst = a.fast_keys + (uint64_t)item * a.kf;  // indexed by position in `order` (x n_chunks + chunk)
+        for (uint32_t i = tid; i < a.kf; i += CT) dst[i] = i < n_out ? cand[i] : TRR_KEY_EMPTY;
+        consumer_bar();
+        if (tid == 0) { s_cnt = 0; s_thr = TRR_KEY_EMPTY; }
+        consumer_bar();
+        TRI({ const long long t = clock64(); w_end += t - tc; tc = t; })
+      }
+    }
+    TRI(if (blockIdx.x == 0 && tid == 0 && a.dbg) {
+      a.dbg[8] = (uint32_t)((clock64() - t_begin) >> 4); a.dbg[10] = (uint32_t)(w_full >> 4); a.dbg[11] = (uint32_t)(w_acc >> 4);
+      a.dbg[12] = (uint32_t)(w_harv >> 4); a.dbg[13] = (uint32_t)(w_end >> 4); a.dbg[15] = n_compact;
+    })
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact re-scoring of the fast pass's candidates + proof.  One CTA per query.
+//   1. impact of every (candidate, term slot) pair by binary search in the term's postings of the candidate's range
+//      (32 slots at a time through shared memory);
+//   2. per candidate the reference's sum: slots in query order, f32, sequential (src/index.rs:228-233; a slot whose term
+//      does not contain the document adds +0.0, which leaves a non-negative partial sum unchanged);
+//   3. canonical sort, top k;
+//   4. proof: a document the fast pass dropped has F <= F_kf (the last kept fixed-point score), hence an f32 score
+//      <= F_kf * 2^-e * (1 + T * 2^-23); if that is below the k-th exact score nothing dropped can enter or tie the
+//      top k.  A list that is not full dropped nothing with a positive score.
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr uint32_t RS_THREADS = 256;
+constexpr uint32_t RS_CB = 64;   // candidates per block
+constexpr uint32_t RS_TB = 32;   // term slots per block
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+bm25_rescore_kernel(Bm25RescoreArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);            // cap2
+  float* sums = reinterpret_cast<float*>(keys + a.cap2);             // kf
+  float* w = sums + a.kf;                                            // RS_CB x (RS_TB + 1)
+  __shared__ uint32_t s_n;
+  const uint32_t tid = threadIdx.x;
+  if (blockIdx.x >= (a.sel_n ? *a.sel_n : a.B)) return;
+  const uint32_t b = a.sel[blockIdx.x];
+  const uint64_t* fk = a.fast_keys + (uint64_t)blockIdx.x * a.kf;
+  const uint32_t q0 = a.q_off[b], T = a.q_off[b + 1] - q0;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  {
+    uint32_t local = 0;
+    for (uint32_t i = tid; i < a.kf; i += RS_THREADS) { sums[i] = 0.0f; local += fk[i] != TRR_KEY_EMPTY; }
+    if (local) atomicAdd(&s_n, local);
+  }
+  __syncthreads();
+  const uint32_t n = s_n;  // candidates (the list is sorted: entries [0, n) are the non-empty ones)
+  for (uint32_t c0 = 0; c0 < n; c0 += RS_CB) {
+    const uint32_t nc = min(RS_CB, n - c0);
+    for (uint32_t t0 = 0; t0 < T; t0 += RS_TB) {
+      const uint32_t nt = min(RS_TB, T - t0);
+      for (uint32_t pi = tid; pi < nc * nt; pi += RS_THREADS) {
+        const uint32_t ci = pi / nt, ti = pi - ci * nt;
+        const uint32_t doc = trr_key_ord(fk[c0 + ci]) - a.doc_base;
+        const uint32_t term = a.q_terms[q0 + t0 + ti];
+        float v = 0.0f;
+        if (term < a.n_terms) {
+          const uint32_t* row = a.skip + (uint64_t)term * a.skip_ld + (doc >> a.range_shift);
+          uint32_t lo = row[0];
+          const uint32_t end = row[1];
+          uint32_t hi = end;
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (a.post[mid].x < doc) lo = mid + 1; else hi = mid;
+          }
+          if (lo < end) {
+            const uint2 e = a.post[lo];
+            if (e.x == doc) v = __uint_as_float(e.y);
+          }
         }
-        if (lane == 0 && *reinterpret_cast<volatile uint32_t*>(&s_cnt) >= compact_at)
-          *reinterpret_cast<volatile uint32_t*>(&s_need) = 1u;
+        w[ci * (RS_TB + 1) + ti] = v;
       }
-      // ---- end of a round: every warp is here (out of sub-ranges, or asked to stop for a compaction) ----
-      const int all_done = __syncthreads_and(exhausted && !redo);
-      compact();
-      if (all_done) break;
-    }
-    // ---- outputs of the item ----
-    const uint32_t n_out = s_cnt;
-    if (a.n_chunks == 1) {
-      for (uint32_t i = tid; i < a.k; i += NT) {
-        const bool ok = i < n_out;
-        const uint64_t key = ok ? cand[i] : TRR_KEY_EMPTY;
-        if (a.out_keys) a.out_keys[(uint64_t)b * a.k + i] = key;
-        if (a.out_ord) a.out_ord[(uint64_t)b * a.k + i] = ok ? trr_key_ord(key) : 0xFFFFFFFFu;
-        if (a.out_score) a.out_score[(uint64_t)b * a.k + i] = ok ? trr_key_score(key) : 0.0f;
+      __syncthreads();
+      if (tid < nc) {
+        float s = sums[c0 + tid];
+        for (uint32_t ti = 0; ti < nt; ++ti) s = s + w[tid * (RS_TB + 1) + ti];
+        sums[c0 + tid] = s;
       }
-      if (tid == 0 && a.out_n) a.out_n[b] = n_out;
-    } else {
-      uint64_t* dst = a.partial + ((uint64_t)b * a.n_chunks + c) * a.k;
-      for (uint32_t i = tid; i < a.k; i += NT) dst[i] = i < n_out ? cand[i] : TRR_KEY_EMPTY;
+      __syncthreads();
     }
+  }
+  for (uint32_t i = tid; i < a.cap2; i += RS_THREADS) {
+    uint64_t key = TRR_KEY_EMPTY;
+    if (i < n) {
+      const float s = sums[i];
+      if (s > 0.0f) key = trr_make_key(s, trr_key_ord(fk[i]));  // src/index.rs:236 keeps only score > 0.0
+    }
+    keys[i] = key;
+  }
+  trr_bitonic_sort_desc(keys, a.cap2, tid, RS_THREADS, BlockSync());
+  uint32_t local = 0;
+  for (uint32_t i = tid; i < a.k; i += RS_THREADS) {
+    const uint64_t key = i < a.cap2 ? keys[i] : TRR_KEY_EMPTY;
+    const bool ok = key != TRR_KEY_EMPTY;
+    local += ok;
+    a.out_ord[(uint64_t)b * a.k + i] = ok ? trr_key_ord(key) : 0xFFFFFFFFu;
+    a.out_score[(uint64_t)b * a.k + i] = ok ? trr_key_score(key) : 0.0f;
+  }
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  if (local) atomicAdd(&s_n, local);
+  __syncthreads();
+  if (tid == 0) {
+    a.out_n[b] = s_n;
+    bool proven = true;
+    if (n == a.kf) {  // the list is full: documents were dropped
+      const uint32_t f_excl = (uint32_t)(fk[a.kf - 1] >> 32) + a.margin_f;
+      const double bound = (double)f_excl / (double)a.qscale[b] * (1.0 + (double)T * 1.1920928955078125e-07);
+      const uint64_t kth = keys[a.k - 1];
+      proven = kth != TRR_KEY_EMPTY && bound < (double)trr_key_score(kth);
+    }
+    if (!proven) a.flagged[atomicAdd(a.n_flagged, 1u)] = b;
   }
 }
 
@@ -892,23 +1074,28 @@ cudaError_t trr_launch_bm25_search(const Bm25SearchArgs& a, unsigned grid, cudaS
   return cudaGetLastError();
 }
 
-size_t trr_bm25_search_warp_smem(uint32_t cand_cap) {
-  return (size_t)TRR_BM25_V2_WARPS * (4u << TRR_BM25_SUB_SHIFT) + (size_t)cand_cap * 8 + (size_t)TRR_BM25_V2_WARPS * 64 * 4;
+
+size_t trr_bm25_fast_smem(int bits, uint32_t range_shift, uint32_t stage_cap, uint32_t cand_cap) {
+  return ((size_t)(bits == 16 ? 2 : 4) << range_shift) + (size_t)NS * stage_cap * 8 + (size_t)cand_cap * 8 + NS * sizeof(FastDesc) +
+         2 * NS * 8;
 }
 
-cudaError_t trr_launch_bm25_search_warp(const Bm25SearchArgs& a, unsigned grid, int variant, cudaStream_t st) {
-  const size_t smem = trr_bm25_search_warp_smem(a.cand_cap);
-  auto kernel = variant == 2 ? bm25_search_warp_kernel<2> : bm25_search_warp_kernel<1>;
+cudaError_t trr_launch_bm25_fast(const Bm25SearchArgs& a, int bits, unsigned grid, cudaStream_t st) {
+  if (a.B == 0 || grid == 0) return cudaSuccess;
+  const size_t smem = trr_bm25_fast_smem(bits, a.range_shift, a.stage_cap, a.cand_cap);
+  auto kernel = bits == 16 ? bm25_fast_kernel<16> : bm25_fast_kernel<32>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  kernel<<<grid, TRR_BM25_V2_WARPS * 32, smem, st>>>(a);
+  kernel<<<grid, TRR_BM25_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
 
-cudaError_t trr_launch_bm25_fine(const uint2* post, const uint64_t* term_off, const uint32_t* fine_terms, uint32_t n_fine,
-                                 uint32_t* fine, uint32_t fine_ld, uint32_t n_sub, cudaStream_t st) {
-  if (n_fine == 0) return cudaSuccess;
-  bm25_fine_kernel<<<n_fine, 256, 0, st>>>(post, term_off, fine_terms, n_fine, fine, fine_ld, n_sub);
+cudaError_t trr_launch_bm25_rescore(const Bm25RescoreArgs& a, cudaStream_t st) {
+  if (a.B == 0) return cudaSuccess;
+  const size_t smem = (size_t)a.cap2 * 8 + (size_t)a.kf * 4 + (size_t)RS_CB * (RS_TB + 1) * 4;
+  cudaError_t e = cudaFuncSetAttribute(bm25_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  bm25_rescore_kernel<<<a.B, RS_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }

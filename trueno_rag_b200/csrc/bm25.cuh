@@ -21,7 +21,9 @@ struct Bm25BuildArgs {
   uint2* post;     // out: {doc, impact bits}
   uint32_t* skip;  // out: [n_terms][skip_ld]
   uint32_t* term_min;  // out: [n_terms] smallest impact of the term (order-preserving u32 image), pre-set to 0xFFFFFFFF
-  uint32_t* flags;     // out: [0] = 1 when some impact is not > 0 (disables the threshold bootstrap), pre-set to 0
+  uint32_t* term_max;  // out: [n_terms] largest impact of the term (order-preserving u32 image), pre-set to 0
+  uint32_t* flags;     // out: [0] bit 0 = some live impact is not a finite value > 0 (disables the threshold bootstrap and the
+                       //      integer fast pass), pre-set to 0; the host ORs bit 1 in when dead postings exist (no bootstrap)
 };
 
 struct Bm25MergeArgs {  // trr_bm25_append: old CSR + CSR of the appended documents -> new CSR (doc ids and tf only)
@@ -49,26 +51,50 @@ struct Bm25SearchArgs {
   uint32_t cand_cap;   // candidate buffer capacity: power of two > k
   uint32_t n_chunks;   // work items per query (contiguous chunks of document ranges)
   const uint32_t* term_min;  // [n_terms] smallest impact per term (orderable image)
-  const uint32_t* flags;     // [0] != 0: impacts are not all positive, no bootstrap
-  uint64_t* thr0;      // [B] initial threshold key per query (written by the plan kernel; 0 = none)
-  uint32_t* order;     // [B] queries by decreasing posting volume (written by the plan kernel)
-  uint32_t* queue;     // [2] dynamic work queue (reset by the plan kernel)
-  uint64_t* partial;   // n_chunks > 1: [B][n_chunks][k] keys, merged by topk_merge_kernel
+  const uint32_t* term_max;  // [n_terms] largest impact per term (orderable image)
+  const uint32_t* flags;     // [0] != 0: no threshold bootstrap (see Bm25BuildArgs::flags)
+  uint64_t* thr0;      // [B] initial threshold key per query for the exact kernel (written by the plan kernel; 0 = none)
+  uint32_t* order;     // [B] queries by decreasing posting volume (written by the plan kernel); the exact kernel run as the
+                       //     fallback of the fast pass gets the list of flagged queries here
+  const uint32_t* n_sel_ptr;  // nullable: DEVICE count of entries of `order` to process (else B)
+  uint32_t* queue;     // [1] dynamic work queue (reset by the plan kernel)
+  uint64_t* partial;   // n_chunks > 1: [position in `order`][n_chunks][k] keys, merged by topk_merge_kernel
   uint64_t* out_keys;  // n_chunks == 1: nullable [B][k]
   uint32_t* out_ord;   // nullable [B][k]
   float* out_score;    // nullable
   uint32_t* out_n;     // nullable
   uint32_t* dbg;       // nullable host-mapped word: site of a barrier timeout
-  uint32_t debug_mode; // perf triage (TRR_BM25_DEBUG): 8 = CTA 0 records where its cycles go
-  // bm25_search_warp_kernel (TRR_BM25_V2=1) only: fine skip table of the frequent terms, 2048-document sub-ranges
-  const uint32_t* fine_row;  // [n_terms] row of the term in `fine`, 0xFFFFFFFF = not a frequent term
-  const uint32_t* fine;      // [n_fine][fine_ld]: first posting of the term with doc >= j * 2048
-  uint32_t fine_ld, n_sub;
+  // integer fast pass (bm25_fast_kernel): k = kf candidates per query by fast score
+  uint32_t kf;         // candidates kept per query by the fast pass (> the k of the search)
+  const float* qscale;     // [B] scale of the query's fixed-point scores for the cell width of this launch
+  const uint32_t* thr0f;   // [B] initial fixed-point threshold for the cell width of this launch (0 = none)
+  float* qscale16;         // plan kernel outputs: [B] scale / bootstrap threshold for 16-bit cells ...
+  uint32_t* thr0f16;
+  float* qscale32;         // ... and for 32-bit cells
+  uint32_t* thr0f32;
+  uint64_t* fast_keys; // [position in `order`][n_chunks][kf] keys (fixed-point score << 32 | ~ordinal), descending, 0 = empty
+  uint32_t triage;     // -DTRR_TRIAGE builds only (timing experiments that break the results); 0 otherwise
 };
 
-constexpr uint32_t TRR_BM25_SUB_SHIFT = 11;   // documents per warp accumulator of the V2 kernel: 2048
-constexpr uint32_t TRR_BM25_V2_WARPS = 8;
-constexpr uint32_t TRR_BM25_FINE_MIN_DF = 2048;  // terms at least this frequent get a row in the fine skip table
+// exact re-scoring of the fast pass's candidates + proof (bm25_rescore_kernel)
+struct Bm25RescoreArgs {
+  const uint2* post;
+  const uint32_t* skip;
+  uint32_t skip_ld, n_terms, range_shift, doc_base;
+  const uint32_t* q_terms;
+  const uint32_t* q_off;
+  uint32_t B, k, kf, cap2;     // cap2 = power of two >= kf
+  const uint32_t* sel;         // CTA i handles query sel[i] ...
+  const uint32_t* sel_n;       // ... for i < *sel_n (nullable: B)
+  const uint64_t* fast_keys;   // [position i][kf]
+  const float* qscale;         // [B] scale of the fast pass that produced the keys
+  uint32_t* out_ord;           // [B][k]
+  float* out_score;
+  uint32_t* out_n;
+  uint32_t* flagged;           // [B] queries whose proof failed
+  uint32_t* n_flagged;         // device counter (zeroed by the plan kernel)
+  uint32_t margin_f;           // fixed-point units added to the bound (0; tests use it to force the fallbacks)
+};
 
 cudaError_t trr_launch_bm25_build(const Bm25BuildArgs& a, cudaStream_t st);
 cudaError_t trr_launch_bm25_merge(const Bm25MergeArgs& a, cudaStream_t st);
@@ -78,9 +104,8 @@ size_t trr_bm25_search_smem(uint32_t range_shift, uint32_t stage_cap, uint32_t c
 // plan_keys: scratch of max(pow2ceil(B), 1) u64
 cudaError_t trr_launch_bm25_plan(const Bm25SearchArgs& a, uint64_t* plan_keys, cudaStream_t st);
 cudaError_t trr_launch_bm25_search(const Bm25SearchArgs& a, unsigned grid, cudaStream_t st);
-// V2 (opt-in): warps of a CTA work on different 2048-document sub-ranges of one query without per-range barriers
-size_t trr_bm25_search_warp_smem(uint32_t cand_cap);
-cudaError_t trr_launch_bm25_search_warp(const Bm25SearchArgs& a, unsigned grid, int variant, cudaStream_t st);
-// fine skip table: fine[row][j] for the n_fine terms listed in fine_terms (term ids), j = 0..n_sub
-cudaError_t trr_launch_bm25_fine(const uint2* post, const uint64_t* term_off, const uint32_t* fine_terms, uint32_t n_fine,
-                                 uint32_t* fine, uint32_t fine_ld, uint32_t n_sub, cudaStream_t st);
+// integer fast pass + exact re-scoring (the default BM25 search path)
+size_t trr_bm25_fast_smem(int bits, uint32_t range_shift, uint32_t stage_cap, uint32_t cand_cap);
+cudaError_t trr_launch_bm25_fast(const Bm25SearchArgs& a, int bits, unsigned grid, cudaStream_t st);
+cudaError_t trr_launch_bm25_rescore(const Bm25RescoreArgs& a, cudaStream_t st);
+constexpr uint32_t TRR_BM25_FAST_STAGES = 3;

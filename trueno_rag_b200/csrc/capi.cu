@@ -441,13 +441,13 @@ static int plan_scan(trr_dense* h, uint32_t k, ScanPlan* p, uint32_t n_queries =
   const size_t optin = h->ctx->smem_optin;
   p->tma = false; p->n_slots = 0;
   p->bulk = (h->row_bytes % 16 == 0) && h->n >= 4096;
-  if (p->bulk && !getenv("TRR_SCAN_NO_TMA")) {
+  if (p->bulk && !TRR_KNOB("TRR_SCAN_NO_TMA")) {
     // 16 warps per CTA hide the per-box serial overheads (measured 6.44 TB/s vs 5.70 TB/s with 4 warps on 1M x 384 f32);
     // ring slots per warp come from what is left of the shared memory (4 KB per slot, at least 3)
     uint32_t nw_first = 16;
-    if (const char* e = getenv("TRR_SCAN_WARPS")) nw_first = (uint32_t)std::min(16, std::max(1, atoi(e)));
+    if (const char* e = TRR_KNOB("TRR_SCAN_WARPS")) nw_first = (uint32_t)std::min(16, std::max(1, atoi(e)));
     // several queries on the exact path share each pass over the slab four at a time (if the buffers fit with >= 8 warps)
-    uint32_t nq = (n_queries >= 2 && !getenv("TRR_SCAN_NQ1")) ? 4u : 1u;
+    uint32_t nq = (n_queries >= 2 && !TRR_KNOB("TRR_SCAN_NQ1")) ? 4u : 1u;
     if (nq == 4 && trr_scan_tma_smem(h->dim, p->cap, 3, 8, 4) > optin) nq = 1;
     p->nq = nq;
     for (uint32_t nw = nw_first; nw >= 1; nw >>= 1) {
@@ -455,7 +455,7 @@ static int plan_scan(trr_dense* h, uint32_t k, ScanPlan* p, uint32_t n_queries =
       if (fixed + (size_t)nw * 3 * 4104 > optin) continue;
       uint32_t slots = (uint32_t)((optin - fixed) / ((size_t)nw * (4096 + 8)));
       if (slots > 12) slots = 12;
-      if (const char* e = getenv("TRR_SCAN_SLOTS")) slots = std::min<uint32_t>(slots, (uint32_t)std::max(3, atoi(e)));
+      if (const char* e = TRR_KNOB("TRR_SCAN_SLOTS")) slots = std::min<uint32_t>(slots, (uint32_t)std::max(3, atoi(e)));
       p->tma = true; p->bulk = false; p->n_slots = slots; p->warps = nw;
       p->grid = (unsigned)h->ctx->sm_count;
       p->ch_bytes = 0; p->n_chunks = 0;
@@ -577,7 +577,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
       return trr_fail(TRR_ERR_UNSUPPORTED, "GEMM mode supports cosine/dot metrics with k <= 100");
     use_gemm = false;
   }
-  if (use_gemm && (k > 50 || getenv("TRR_GEMM_CP128"))) {
+  if (use_gemm && (k > 50 || TRR_KNOB("TRR_GEMM_CP128"))) {
     // re-scoring width 128 needs at least four half-slice lists of 32 entries
     const uint32_t n_qb = (B + TRR_GEMM_TILE_M - 1) / TRR_GEMM_TILE_M;
     const uint64_t tiles = (h->n + TRR_GEMM_TILE_N - 1) / TRR_GEMM_TILE_N;
@@ -616,7 +616,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     // the saving is time: 12.9 ms vs 14.1 ms at 10M x 768, B = 1024 under back-to-back launches.  It needs an even number
     // of query blocks; an odd count is padded only when the padding costs less than the gain (TRR_GEMM_PAIR=0/1 overrides).
     int pair_mode = n_qblocks >= 2 && (n_qblocks % 2 == 0 || n_qblocks >= 9) ? 1 : 0;
-    if (const char* e = getenv("TRR_GEMM_PAIR")) pair_mode = atoi(e) ? 1 : 0;
+    if (const char* e = TRR_KNOB("TRR_GEMM_PAIR")) pair_mode = atoi(e) ? 1 : 0;
     if (pair_mode) n_qblocks = (n_qblocks + 1) & ~1u;
     if (n_qblocks > (uint32_t)c->sm_count)
       return trr_fail(TRR_ERR_UNSUPPORTED, "batch larger than 128 x SM count; split the batch");
@@ -627,7 +627,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     // exact re-scoring width per query: k plus a margin of ranks for the candidate proof
     // (TRR_GEMM_CP128=1 forces the wide width for every k: to be measured - with f32 queries the quantisation term of the
     // proof is worth about 10 ranks of score spacing, so k = 50 of 64 often falls through to the second pass)
-    const uint32_t CP = (k <= 50 && !getenv("TRR_GEMM_CP128")) ? TRR_GEMM_CP : 2 * TRR_GEMM_CP;
+    const uint32_t CP = (k <= 50 && !TRR_KNOB("TRR_GEMM_CP128")) ? TRR_GEMM_CP : 2 * TRR_GEMM_CP;
     // list length per (query, slice): the global top-CP by fast score is spread over the slices (about CP / n_slices
     // per slice), so short lists suffice when there are many slices (Poisson tail < 1e-6 for the choices below); the
     // candidate proof (rescore_select_kernel) catches the data sets where they do not
@@ -637,7 +637,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     const uint32_t cps_max = TRR_GEMM_CPS_MAX;
     const float per_slice = (float)CP / (float)vslices;
     uint32_t cps = per_slice <= 1.0f ? 8u : (per_slice <= 4.0f ? 16u : 32u);
-    if (const char* e = getenv("TRR_GEMM_CPS")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) cps = (uint32_t)v; }
+    if (const char* e = TRR_KNOB("TRR_GEMM_CPS")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) cps = (uint32_t)v; }
     if ((uint64_t)vslices * cps < CP) cps = cps_max;  // (vslices * cps_max >= CP is checked before taking this path)
     const size_t n_cand = (size_t)vslices * n_qblocks * TRR_GEMM_TILE_M * cps;
     const uint32_t cap2 = std::max<uint32_t>(trr_pow2_ceil(vslices * cps), 2 * CP);
@@ -648,7 +648,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     // queries whose candidate proof fails are re-run through the exact scan.  Normally the fallback is DEVICE-DRIVEN (the
     // scan and merge kernels read the number of flagged queries from device memory and return at once when it is zero), so
     // the whole search is enqueued without a host round trip; very large B x k falls back to a host-read count and chunks.
-    const bool dev_fallback = (size_t)B * lists * k * 8 <= ((size_t)256 << 20) && !getenv("TRR_GEMM_HOST_FALLBACK");
+    const bool dev_fallback = (size_t)B * lists * k * 8 <= ((size_t)256 << 20) && !TRR_KNOB("TRR_GEMM_HOST_FALLBACK");
     const uint32_t fb_chunk = dev_fallback ? B : 64;  // fallback queries per scan launch
     const size_t need = WsCarver::need({(size_t)B * 4, (size_t)B * 4, n_cand * 4, n_cand * 4, (size_t)B_pad * 4,
                                         (size_t)B * 4, (size_t)B * 4, (size_t)B * 4, 256, (size_t)B_pad * h->dim_pad * 2,
@@ -681,8 +681,8 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     ga.cand_score = cand_score; ga.cand_ord = cand_ord; ga.gthr = gthr; ga.share_thresholds = 1;
     ga.pair_mode = pair_mode; ga.cps = cps;
     ga.dbg = extra(c)->dbg_dev;
-    if (const char* e = getenv("TRR_GEMM_DEBUG")) ga.debug_mode = atoi(e);      // perf triage only; results are wrong
-    if (const char* e = getenv("TRR_GEMM_NOSHARE")) ga.share_thresholds = atoi(e) ? 0 : 1;
+    if (const char* e = TRR_KNOB("TRR_GEMM_DEBUG")) ga.debug_mode = atoi(e);      // perf triage only; results are wrong
+    if (const char* e = TRR_KNOB("TRR_GEMM_NOSHARE")) ga.share_thresholds = atoi(e) ? 0 : 1;
     TRR_CUDA(cudaEventRecord(h->ev[2], st));
     TRR_CUDA(trr_launch_gemm_topk(ga, map_q, pair_mode ? h->map_d_half : h->map_d, n_slices * n_qblocks, st));
     TRR_CUDA(cudaEventRecord(h->ev[3], st));
@@ -696,8 +696,8 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     ra.B = B; ra.k = k; ra.metric = h->metric;
     // candidate rows are staged in shared memory in chunks (28 KB per CTA keeps six CTAs per SM)
     uint32_t stage_budget = 28u << 10;
-    if (const char* e = getenv("TRR_RESCORE_STAGE_KB")) stage_budget = (uint32_t)std::max(1, atoi(e)) << 10;
-    ra.stage_chunk = (h->row_bytes % 16 == 0 && !getenv("TRR_RESCORE_NO_STAGE"))
+    if (const char* e = TRR_KNOB("TRR_RESCORE_STAGE_KB")) stage_budget = (uint32_t)std::max(1, atoi(e)) << 10;
+    ra.stage_chunk = (h->row_bytes % 16 == 0 && !TRR_KNOB("TRR_RESCORE_NO_STAGE"))
                          ? std::min<uint32_t>(h->row_bytes, (uint32_t)((stage_budget / CP - 16) & ~15u)) : 0u;
     if (ra.stage_chunk < 64) ra.stage_chunk = 0;
     // |fast - exact| <= eps_rel * |q||d|: products of bf16 values are exact in f32; the tensor-core sum and the
@@ -718,7 +718,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     const uint32_t cp_wide = trr_pow2_ceil(vslices * cps);
     uint32_t* flagged_final = flagged;
     uint32_t* counters_final = counters;
-    if (cp_wide > CP && cp_wide <= 2048 && !getenv("TRR_GEMM_NO_WIDE")) {
+    if (cp_wide > CP && cp_wide <= 2048 && !TRR_KNOB("TRR_GEMM_NO_WIDE")) {
       RescoreArgs rw = ra;
       rw.cp = cp_wide; rw.cap2 = std::max(cap2, cp_wide); rw.stage_chunk = 0;
       rw.sel = flagged; rw.sel_n = counters;
@@ -770,7 +770,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     cudaEventElapsedTime(&h->stats.ms_total, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&h->stats.ms_main_kernel, h->ev[2], h->ev[3]);
     dense_resolve_stats(h);
-    if (getenv("TRR_GEMM_DEBUG") && (atoi(getenv("TRR_GEMM_DEBUG")) & 8) && extra(c)->dbg_host)
+    if (TRR_KNOB("TRR_GEMM_DEBUG") && (atoi(TRR_KNOB("TRR_GEMM_DEBUG")) & 8) && extra(c)->dbg_host)
       fprintf(stderr, "[trr] K2 CTA 0: %u cycles in %u ns = %.0f MHz; MMA warp waited %u on operands, %u on the epilogue; "
                       "producer(s) waited %u / %u on free stages\n", extra(c)->dbg_host[8], extra(c)->dbg_host[9],
               1000.0 * extra(c)->dbg_host[8] / std::max(1u, extra(c)->dbg_host[9]), extra(c)->dbg_host[10],
@@ -841,7 +841,7 @@ extern "C" TRR_API int trr_debug_gemm_scores(trr_dense* h, const float* q, uint3
   TRR_CHECK(dense_prepare_gemm(h));
   uint32_t n_qblocks = (B + 127) / 128;
   int pair_mode = 0;
-  if (const char* e = getenv("TRR_GEMM_PAIR")) pair_mode = atoi(e) ? 1 : 0;
+  if (const char* e = TRR_KNOB("TRR_GEMM_PAIR")) pair_mode = atoi(e) ? 1 : 0;
   if (pair_mode) n_qblocks = (n_qblocks + 1) & ~1u;
   const uint32_t B_pad = n_qblocks * 128;
   const uint64_t n_pad = h->n_tiles * TRR_GEMM_TILE_N;
@@ -889,6 +889,10 @@ struct trr_bm25 {
   uint2* post = nullptr;
   uint32_t* skip = nullptr;
   uint32_t* term_min = nullptr;  // [n_terms + 1]: per-term minimum impact, then one flag word
+  uint32_t* term_max = nullptr;  // [n_terms]: per-term maximum impact (scale of the integer fast pass)
+  bool impacts_ok = true;        // every live impact is a finite value > 0 (the integer fast pass relies on it)
+  uint32_t* stat_dev = nullptr;  // device copy of the number of queries the last search sent to the exact fallback
+  bool stat_pending = false;
   // raw index kept for trr_bm25_append (every impact depends on the global N / df / avgdl, so an append re-weights all)
   uint64_t* d_term_off = nullptr;  // [n_terms + 1]
   uint32_t* tf = nullptr;          // [n_postings] term frequencies
@@ -896,11 +900,6 @@ struct trr_bm25 {
   std::vector<uint64_t> h_term_off;
   uint64_t n_dead_postings = 0;    // postings of removed documents still in place (tf == 0)
   uint32_t range_shift = TRR_BM25_MAX_RANGE_SHIFT, n_ranges = 0, skip_ld = 0;
-  // V2 search kernel (TRR_BM25_V2=1): fine skip table of the frequent terms, built lazily after every index change
-  uint32_t* fine_row = nullptr;  // [n_terms]
-  uint32_t* fine = nullptr;      // [n_fine][fine_ld]
-  uint32_t fine_ld = 0, n_sub = 0;
-  bool fine_valid = false;
   trr_stats stats{};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -908,7 +907,7 @@ struct trr_bm25 {
 static uint32_t bm25_pick_shift(uint32_t n_docs) {
   // documents per range: 32768 (128 KB of f32 accumulators in shared memory, one CTA per SM), fewer for small indexes
   uint32_t shift = TRR_BM25_MAX_RANGE_SHIFT;
-  if (const char* e = getenv("TRR_BM25_RANGE_SHIFT")) shift = (uint32_t)atoi(e);
+  if (const char* e = TRR_KNOB("TRR_BM25_RANGE_SHIFT")) shift = (uint32_t)atoi(e);
   shift = std::min(std::max(shift, TRR_BM25_MIN_RANGE_SHIFT), TRR_BM25_MAX_RANGE_SHIFT);
   while (shift > TRR_BM25_MIN_RANGE_SHIFT && (1u << (shift - 1)) >= std::max<uint32_t>(n_docs, 1)) --shift;
   return shift;
@@ -928,16 +927,18 @@ static uint32_t bm25_pick_shift(uint32_t n_docs) {
 static int bm25_weight_locked(trr_bm25* h, const uint32_t* d_post_doc, float avgdl, float k1, float b, const float* idf_host) {
   trr_ctx* ctx = h->ctx;
   cudaStream_t st = ctx->stream;
-  h->fine_valid = false;
   h->range_shift = bm25_pick_shift(h->n_docs);
   h->n_ranges = h->n_docs ? (uint32_t)(((uint64_t)h->n_docs + (1u << h->range_shift) - 1) >> h->range_shift) : 0;
   h->skip_ld = h->n_ranges + 1;
   if (h->skip) { cudaFree(h->skip); h->skip = nullptr; }
   if (h->term_min) { cudaFree(h->term_min); h->term_min = nullptr; }
+  if (h->term_max) { cudaFree(h->term_max); h->term_max = nullptr; }
   BM_TRY(cudaMalloc(&h->skip, std::max<uint64_t>((uint64_t)h->n_terms * h->skip_ld, 1) * 4));
   BM_TRY(cudaMalloc(&h->term_min, ((uint64_t)h->n_terms + 1) * 4));
+  BM_TRY(cudaMalloc(&h->term_max, std::max<uint64_t>(h->n_terms, 1) * 4));
   BM_TRY(cudaMemsetAsync(h->term_min, 0xFF, (uint64_t)h->n_terms * 4, st));
   BM_TRY(cudaMemsetAsync(h->term_min + h->n_terms, 0, 4, st));
+  BM_TRY(cudaMemsetAsync(h->term_max, 0, std::max<uint64_t>(h->n_terms, 1) * 4, st));
   float* d_idf = nullptr;
   BM_TRY(cudaMalloc(&d_idf, std::max<uint64_t>(h->n_terms, 1) * 4));
   if (h->n_terms && idf_host) BM_TRY(cudaMemcpyAsync(d_idf, idf_host, (uint64_t)h->n_terms * 4, cudaMemcpyHostToDevice, st));
@@ -945,12 +946,18 @@ static int bm25_weight_locked(trr_bm25* h, const uint32_t* d_post_doc, float avg
   a.n_postings = h->n_postings; a.n_terms = h->n_terms; a.n_docs = h->n_docs; a.term_off = h->d_term_off;
   a.post_doc = d_post_doc; a.post_tf = h->tf; a.doc_len = h->doc_len; a.idf = d_idf; a.avgdl = avgdl; a.k1 = k1; a.b = b;
   a.range_shift = h->range_shift; a.n_ranges = h->n_ranges; a.skip_ld = h->skip_ld; a.post = h->post; a.skip = h->skip;
-  a.term_min = h->term_min; a.flags = h->term_min + h->n_terms;
+  a.term_min = h->term_min; a.term_max = h->term_max; a.flags = h->term_min + h->n_terms;
   cudaError_t e = trr_launch_bm25_build(a, st);
   ctx->launches += 2;
-  // dead postings make the posting count of a term an over-estimate of its live documents: no threshold bootstrap then
-  if (e == cudaSuccess && h->n_dead_postings) e = cudaMemsetAsync(h->term_min + h->n_terms, 1, 4, st);
+  uint32_t flag_word = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&flag_word, h->term_min + h->n_terms, 4, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  h->impacts_ok = flag_word == 0;
+  // dead postings make the posting count of a term an over-estimate of its live documents: no threshold bootstrap then
+  if (e == cudaSuccess && h->n_dead_postings) {
+    flag_word |= 2u;
+    e = cudaMemcpy(h->term_min + h->n_terms, &flag_word, 4, cudaMemcpyHostToDevice);
+  }
   cudaFree(d_idf);
   BM_TRY(e);
   return TRR_OK;
@@ -1104,11 +1111,11 @@ extern "C" int trr_bm25_destroy(trr_bm25* h) {
   if (h->post) cudaFree(h->post);
   if (h->skip) cudaFree(h->skip);
   if (h->term_min) cudaFree(h->term_min);
+  if (h->term_max) cudaFree(h->term_max);
+  if (h->stat_dev) cudaFree(h->stat_dev);
   if (h->d_term_off) cudaFree(h->d_term_off);
   if (h->tf) cudaFree(h->tf);
   if (h->doc_len) cudaFree(h->doc_len);
-  if (h->fine_row) cudaFree(h->fine_row);
-  if (h->fine) cudaFree(h->fine);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   delete h;
   return TRR_OK;
@@ -1131,37 +1138,16 @@ extern "C" int trr_bm25_copy_impacts(trr_bm25* h, float* out, uint64_t n) {
   return TRR_OK;
 }
 
-// V2 kernel: (re)builds the fine skip table (2048-document sub-ranges) of the terms with df >= TRR_BM25_FINE_MIN_DF
-static int bm25_ensure_fine(trr_bm25* h) {
-  if (h->fine_valid) return TRR_OK;
-  trr_ctx* c = h->ctx;
-  cudaStream_t st = c->stream;
-  if (h->h_term_off.size() != (size_t)h->n_terms + 1 || !h->d_term_off)
-    return trr_fail(TRR_ERR_UNSUPPORTED, "BM25 V2 kernel needs the raw index (term offsets) on the handle");
-  if (h->fine_row) { cudaFree(h->fine_row); h->fine_row = nullptr; }
-  if (h->fine) { cudaFree(h->fine); h->fine = nullptr; }
-  h->n_sub = (uint32_t)(((uint64_t)h->n_docs + (1u << TRR_BM25_SUB_SHIFT) - 1) >> TRR_BM25_SUB_SHIFT);
-  h->fine_ld = h->n_sub + 1;
-  std::vector<uint32_t> row(h->n_terms, 0xFFFFFFFFu), terms;
-  for (uint32_t t = 0; t < h->n_terms; ++t)
-    if (h->h_term_off[t + 1] - h->h_term_off[t] >= TRR_BM25_FINE_MIN_DF) { row[t] = (uint32_t)terms.size(); terms.push_back(t); }
-  TRR_CUDA(cudaMalloc(&h->fine_row, std::max<size_t>(h->n_terms, 1) * 4));
-  TRR_CUDA(cudaMalloc(&h->fine, std::max<size_t>((size_t)terms.size() * h->fine_ld, 1) * 4));
-  if (h->n_terms) TRR_CUDA(cudaMemcpyAsync(h->fine_row, row.data(), (size_t)h->n_terms * 4, cudaMemcpyHostToDevice, st));
-  uint32_t* d_terms = nullptr;
-  if (!terms.empty()) {
-    TRR_CUDA(cudaMalloc(&d_terms, terms.size() * 4));
-    cudaError_t e = cudaMemcpyAsync(d_terms, terms.data(), terms.size() * 4, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess)
-      e = trr_launch_bm25_fine(h->post, h->d_term_off, d_terms, (uint32_t)terms.size(), h->fine, h->fine_ld, h->n_sub, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_terms);
-    if (e != cudaSuccess) return trr_fail(TRR_ERR_CUDA, std::string("fine skip table: ") + cudaGetErrorString(e));
-    c->launches++;
-  } else {
-    TRR_CUDA(cudaStreamSynchronize(st));
-  }
-  h->fine_valid = true;
+// stage capacity (postings) of a BM25 search kernel: what is left of the shared memory after the fixed part, split over
+// n_stages buffers of 8 bytes per posting; ranges of <= 16K documents leave room for two CTAs per SM
+static int bm25_stage_cap(trr_ctx* c, size_t fixed, uint32_t n_stages, uint32_t* ctas_per_sm, uint32_t* stage_cap) {
+  size_t budget = c->smem_optin;
+  if (*ctas_per_sm == 2) budget = (228 * 1024) / 2 - 1024 - 1024;  // 228 KB per SM, 1 KB reserved per CTA, 1 KB slack
+  if (fixed + (size_t)n_stages * 8 * 256 > budget) { *ctas_per_sm = 1; budget = c->smem_optin; }
+  if (fixed + (size_t)n_stages * 8 * 256 > budget) return trr_fail(TRR_ERR_UNSUPPORTED, "BM25 kernel does not fit shared memory");
+  size_t cap = (budget - fixed) / ((size_t)8 * n_stages);
+  cap = std::min<size_t>(cap, n_stages == 2 ? 8192 : 4096) & ~size_t(1);
+  *stage_cap = (uint32_t)cap;
   return TRR_OK;
 }
 
@@ -1180,76 +1166,128 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   for (uint32_t b = 0; b < B; ++b)
     if (h_q_off[b + 1] - h_q_off[b] > TRR_BM25_MAX_QUERY_TERMS)
       return trr_fail(TRR_ERR_UNSUPPORTED, "more than 512 terms in one query");
+  // Default path: integer fast pass with 16-bit cells (selection) + exact re-scoring with a proof; queries whose proof fails
+  // repeat both with 32-bit cells, and what still fails goes to the exact kernel.  The fallback levels are device-driven and
+  // split every flagged query into chunks of document ranges, so that a single failure does not serialise on one CTA.
+  // The exact kernel alone serves indexes whose impacts are not all finite and positive (the fast pass's bounds rely on it).
+  const bool fast = h->impacts_ok && !TRR_KNOB("TRR_BM25_EXACT");
+  const uint32_t kf = k + std::max<uint32_t>(64, k / 2);  // candidates kept by the fast pass: k plus a margin for the proof
   Bm25SearchArgs a{};
   a.post = h->post; a.skip = h->skip; a.skip_ld = h->skip_ld; a.n_terms = h->n_terms; a.n_docs = h->n_docs;
   a.n_ranges = h->n_ranges; a.range_shift = h->range_shift; a.doc_base = h->doc_base;
-  a.q_terms = d_q_terms; a.q_off = d_q_off; a.B = B; a.k = k;
-  a.cand_cap = trr_pow2_ceil(k + 512);
-  // stage buffers take what is left of the shared memory (two stages, 8 bytes per posting).  Ranges of <= 16K
-  // documents leave room for two CTAs per SM.
-  // opt-in V2 kernel (warp-autonomous sub-ranges; see bm25.cu)
-  bool v2 = false;
-  int v2_variant = 1;  // 2 = the not yet measured variant (see bm25.cu)
-  if (const char* e = getenv("TRR_BM25_V2")) { v2 = atoi(e) != 0; v2_variant = atoi(e) == 2 ? 2 : 1; }
-  if (v2 && trr_bm25_search_warp_smem(a.cand_cap) > c->smem_optin) v2 = false;
-  if (v2) {
-    TRR_CHECK(bm25_ensure_fine(h));
-    a.fine_row = h->fine_row; a.fine = h->fine; a.fine_ld = h->fine_ld; a.n_sub = h->n_sub;
-  }
-  uint32_t ctas_per_sm = a.range_shift <= 14 ? 2u : 1u;
-  if (const char* e = getenv("TRR_BM25_CTAS_PER_SM")) ctas_per_sm = std::min(2, std::max(1, atoi(e)));
-  if (v2) {
-    ctas_per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(3, ((size_t)228 * 1024) / (trr_bm25_search_warp_smem(a.cand_cap) + 2048)));
-  } else {
-    const size_t fixed = trr_bm25_search_smem(a.range_shift, 0, a.cand_cap) + 64;
-    size_t budget = c->smem_optin;
-    if (ctas_per_sm == 2) budget = (228 * 1024) / 2 - 1024 - 1024;  // 228 KB per SM, 1 KB reserved per CTA, 1 KB slack
-    if (fixed + 2 * 8 * 256 > budget) { ctas_per_sm = 1; budget = c->smem_optin; }
-    if (fixed + 2 * 8 * 256 > budget) return trr_fail(TRR_ERR_UNSUPPORTED, "BM25 kernel does not fit shared memory");
-    size_t cap = (budget - fixed) / 16;
-    cap = std::min<size_t>(cap, 8192) & ~size_t(1);
-    a.stage_cap = (uint32_t)cap;
+  a.q_terms = d_q_terms; a.q_off = d_q_off; a.B = B; a.k = k; a.kf = kf;
+  const uint32_t cand_exact = trr_pow2_ceil(k + 512), cand_fast = trr_pow2_ceil(kf + 512);
+  uint32_t ctas_exact = a.range_shift <= 14 ? 2u : 1u, ctas16 = a.range_shift <= 15 ? 2u : 1u, ctas32 = ctas_exact;
+  if (a.range_shift == 15) ctas16 = 1;  // 64 KB of cells + three large stages: one CTA per SM
+  if (const char* e = TRR_KNOB("TRR_BM25_CTAS_PER_SM")) ctas_exact = ctas16 = ctas32 = std::min(2, std::max(1, atoi(e)));
+  uint32_t stage_exact = 0, stage16 = 0, stage32 = 0;
+  TRR_CHECK(bm25_stage_cap(c, trr_bm25_search_smem(a.range_shift, 0, cand_exact) + 64, 2, &ctas_exact, &stage_exact));
+  if (fast) {
+    TRR_CHECK(bm25_stage_cap(c, trr_bm25_fast_smem(16, a.range_shift, 0, cand_fast) + 64, TRR_BM25_FAST_STAGES, &ctas16, &stage16));
+    TRR_CHECK(bm25_stage_cap(c, trr_bm25_fast_smem(32, a.range_shift, 0, cand_fast) + 64, TRR_BM25_FAST_STAGES, &ctas32, &stage32));
   }
   // few queries: split every query into chunks of document ranges so that all SMs have work
+  const uint32_t slots = (uint32_t)c->sm_count * (fast ? ctas16 : ctas_exact);
   uint32_t n_chunks = 1;
-  const uint32_t slots = (uint32_t)c->sm_count * ctas_per_sm;
-  const uint32_t max_chunks = v2 ? h->n_sub : h->n_ranges;
-  if (B < 2u * slots) n_chunks = std::min<uint32_t>(max_chunks, (2u * slots + B - 1) / B);
-  if (const char* e = getenv("TRR_BM25_CHUNKS")) n_chunks = std::min<uint32_t>(max_chunks, std::max(1, atoi(e)));
+  if (B < 2u * slots) n_chunks = std::min<uint32_t>(h->n_ranges, (2u * slots + B - 1) / B);
+  if (const char* e = TRR_KNOB("TRR_BM25_CHUNKS")) n_chunks = std::min<uint32_t>(h->n_ranges, std::max(1, atoi(e)));
   n_chunks = std::max<uint32_t>(n_chunks, 1);
   a.n_chunks = n_chunks;
-  const size_t need = scratch_off + WsCarver::need({(size_t)B * 4, (size_t)B * 8, 64, n_chunks > 1 ? (size_t)B * n_chunks * k * 8 : 8,
-                                                    (size_t)trr_pow2_ceil(B) * 8});
+  const uint32_t nc_fb = std::max<uint32_t>(n_chunks, std::min<uint32_t>(h->n_ranges, 32));  // chunks per query of the fallback levels
+  const size_t k_list = fast ? kf : k;
+  const size_t list_items = (size_t)B * std::max(n_chunks, fast ? nc_fb : 1u);
+  const size_t need = scratch_off + WsCarver::need({(size_t)B * 4, (size_t)B * 8, 64, list_items * k_list * 8 + 8,
+                                                    (size_t)trr_pow2_ceil(B) * 8, (size_t)B * 16, (size_t)B * kf * 8 + 8,
+                                                    (size_t)B * 8});
   TRR_CHECK(extra(c)->scratch.reserve(need));
   WsCarver ws(static_cast<char*>(extra(c)->scratch.p) + scratch_off);
-  a.term_min = h->term_min; a.flags = h->term_min + h->n_terms;
+  a.term_min = h->term_min; a.term_max = h->term_max; a.flags = h->term_min + h->n_terms;
   a.order = ws.take<uint32_t>(B);
   a.thr0 = ws.take<uint64_t>(B);
-  a.queue = ws.take<uint32_t>(16);
-  a.partial = ws.take<uint64_t>(n_chunks > 1 ? (size_t)B * n_chunks * k : 1);
+  a.queue = ws.take<uint32_t>(16);  // [0..2] work queues of the three levels, [3] / [4] queries flagged by the 16- / 32-bit proof
+  uint64_t* lists = ws.take<uint64_t>(list_items * k_list + 1);  // per-chunk lists of the level that is running
   uint64_t* plan_keys = ws.take<uint64_t>(trr_pow2_ceil(B));
-  a.out_keys = nullptr; a.out_ord = d_ord; a.out_score = d_score; a.out_n = d_n;
+  uint32_t* per_query = ws.take<uint32_t>((size_t)B * 4);
+  uint64_t* merged = ws.take<uint64_t>((size_t)B * kf + 1);
+  uint32_t* flagged1 = ws.take<uint32_t>((size_t)B * 2);
+  uint32_t* flagged2 = flagged1 + B;
   a.dbg = extra(c)->dbg_dev;
-  if (const char* e = getenv("TRR_BM25_DEBUG")) a.debug_mode = (uint32_t)atoi(e);
-  const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)B * n_chunks, (uint64_t)slots);
-  TRR_CUDA(trr_launch_bm25_plan(a, plan_keys, st));
-  TRR_CUDA(cudaEventRecord(h->ev[2], st));
-  if (v2) TRR_CUDA(trr_launch_bm25_search_warp(a, grid, v2_variant, st));
-  else TRR_CUDA(trr_launch_bm25_search(a, grid, st));
-  TRR_CUDA(cudaEventRecord(h->ev[3], st));
-  const uint32_t plan_launches = (B > 1 && B <= 4096) ? 2u : 1u;
-  c->launches += plan_launches + 1;
-  h->stats.n_kernel_launches = plan_launches + 1;
-  if (n_chunks > 1) {
+  if (const char* e = TRR_KNOB("TRR_BM25_TRIAGE")) a.triage = (uint32_t)atoi(e);
+  uint32_t launches = (B > 1 && B <= 4096) ? 2u : 1u;  // plan
+  auto merge = [&](const uint64_t* src, uint32_t n_lists, uint32_t stride, uint32_t kk, const uint32_t* n_rows_ptr,
+                   const uint32_t* row_map, uint64_t* out_keys, bool outputs) -> int {
     TopkMergeArgs m{};
-    m.lists = a.partial; m.list_n = nullptr; m.n_lists = n_chunks; m.list_stride = k;
-    m.n_rows = B; m.n_rows_ptr = nullptr; m.row_map = nullptr; m.k = k; m.k2 = trr_pow2_ceil(k);
-    m.out_keys = nullptr; m.out_ord = d_ord; m.out_score = d_score; m.out_n = d_n;
-    TRR_CUDA(trr_launch_topk_merge(m, B, st));
-    c->launches++;
-    h->stats.n_kernel_launches++;
+    m.lists = src; m.list_n = nullptr; m.n_lists = n_lists; m.list_stride = stride;
+    m.n_rows = B; m.n_rows_ptr = n_rows_ptr; m.row_map = row_map; m.k = kk; m.k2 = trr_pow2_ceil(kk);
+    m.out_keys = out_keys;
+    if (outputs) { m.out_ord = d_ord; m.out_score = d_score; m.out_n = d_n; }
+    TRR_CUDA(trr_launch_topk_merge(m, n_rows_ptr ? std::min<uint32_t>(B, 4u * (uint32_t)c->sm_count) : B, st));
+    ++launches;
+    return TRR_OK;
+  };
+  // the exact kernel over the queries listed in sel (count on the device, or all B in plan order)
+  auto run_exact = [&](const uint32_t* sel, const uint32_t* n_sel_ptr, uint32_t* queue, uint32_t nc) -> int {
+    Bm25SearchArgs x = a;
+    if (sel) x.order = const_cast<uint32_t*>(sel);
+    x.n_sel_ptr = n_sel_ptr; x.queue = queue; x.n_chunks = nc;
+    x.stage_cap = stage_exact; x.cand_cap = cand_exact; x.partial = lists;
+    x.out_keys = nullptr; x.out_ord = d_ord; x.out_score = d_score; x.out_n = d_n;
+    const unsigned grid_x = (unsigned)std::min<uint64_t>((uint64_t)B * nc, (uint64_t)c->sm_count * ctas_exact);
+    TRR_CUDA(trr_launch_bm25_search(x, grid_x, st));
+    ++launches;
+    if (nc > 1) TRR_CHECK(merge(lists, nc, k, k, n_sel_ptr, x.order, nullptr, true));
+    return TRR_OK;
+  };
+  if (!fast) {
+    TRR_CUDA(trr_launch_bm25_plan(a, plan_keys, st));
+    TRR_CUDA(cudaEventRecord(h->ev[2], st));
+    TRR_CHECK(run_exact(nullptr, nullptr, a.queue, n_chunks));
+    TRR_CUDA(cudaEventRecord(h->ev[3], st));
+    h->stats.mode_used = 1;
+  } else {
+    a.qscale16 = reinterpret_cast<float*>(per_query); a.thr0f16 = per_query + B;
+    a.qscale32 = reinterpret_cast<float*>(per_query + 2 * (size_t)B); a.thr0f32 = per_query + 3 * (size_t)B;
+    TRR_CUDA(trr_launch_bm25_plan(a, plan_keys, st));
+    TRR_CUDA(cudaEventRecord(h->ev[2], st));
+    uint32_t margin = 0;
+    if (const char* e = TRR_KNOB("TRR_BM25_PROOF_MARGIN")) margin = (uint32_t)atoi(e);  // tests: force the fallback levels
+    // one level of the fast pass: fast kernel -> (merge of the chunk lists) -> exact re-scoring + proof
+    auto level = [&](int bits, const uint32_t* sel, const uint32_t* n_sel_ptr, uint32_t* queue, uint32_t nc, uint32_t ctas,
+                     uint32_t stage_cap, uint32_t* flagged, uint32_t* n_flagged, uint32_t margin_f) -> int {
+      Bm25SearchArgs x = a;
+      if (sel) x.order = const_cast<uint32_t*>(sel);
+      x.n_sel_ptr = n_sel_ptr; x.queue = queue; x.n_chunks = nc;
+      x.qscale = bits == 16 ? a.qscale16 : a.qscale32; x.thr0f = bits == 16 ? a.thr0f16 : a.thr0f32;
+      x.fast_keys = lists; x.stage_cap = stage_cap; x.cand_cap = cand_fast;
+      const unsigned grid_x = (unsigned)std::min<uint64_t>((uint64_t)B * nc, (uint64_t)c->sm_count * ctas);
+      TRR_CUDA(trr_launch_bm25_fast(x, bits, grid_x, st));
+      ++launches;
+      const uint64_t* fast_keys = lists;
+      if (nc > 1) {
+        TRR_CHECK(merge(lists, nc, kf, kf, n_sel_ptr, nullptr, merged, false));
+        fast_keys = merged;
+      }
+      Bm25RescoreArgs r{};
+      r.post = h->post; r.skip = h->skip; r.skip_ld = h->skip_ld; r.n_terms = h->n_terms; r.range_shift = h->range_shift;
+      r.doc_base = h->doc_base; r.q_terms = d_q_terms; r.q_off = d_q_off; r.B = B; r.k = k; r.kf = kf;
+      r.cap2 = trr_pow2_ceil(kf); r.sel = x.order; r.sel_n = n_sel_ptr; r.fast_keys = fast_keys; r.qscale = x.qscale;
+      r.out_ord = d_ord; r.out_score = d_score; r.out_n = d_n; r.flagged = flagged; r.n_flagged = n_flagged;
+      r.margin_f = margin_f;
+      TRR_CUDA(trr_launch_bm25_rescore(r, st));
+      ++launches;
+      return TRR_OK;
+    };
+    TRR_CHECK(level(16, nullptr, nullptr, a.queue, n_chunks, ctas16, stage16, flagged1, a.queue + 3, margin));
+    TRR_CHECK(level(32, flagged1, a.queue + 3, a.queue + 1, nc_fb, ctas32, stage32, flagged2, a.queue + 4, margin > 1 ? margin : 0));
+    TRR_CHECK(run_exact(flagged2, a.queue + 4, a.queue + 2, nc_fb));
+    TRR_CUDA(cudaEventRecord(h->ev[3], st));
+    if (!h->stat_dev) TRR_CUDA(cudaMalloc(&h->stat_dev, 64));
+    TRR_CUDA(cudaMemcpyAsync(h->stat_dev, a.queue + 3, 8, cudaMemcpyDeviceToDevice, st));
+    h->stat_pending = true;
+    h->stats.mode_used = 2;
   }
-  h->stats.mode_used = 1;
+  c->launches += launches;
+  h->stats.n_kernel_launches = launches;
   return TRR_OK;
 }
 
@@ -1308,12 +1346,22 @@ extern "C" int trr_bm25_last_stats(trr_bm25* h, trr_stats* out) {
   if (h->stats.mode_used) {
     cudaEventElapsedTime(&h->stats.ms_main_kernel, h->ev[2], h->ev[3]);
     cudaGetLastError();
-    const char* e = getenv("TRR_BM25_DEBUG");
-    if (e && (atoi(e) & 8) && extra(h->ctx)->dbg_host) {
-      const uint32_t* w = extra(h->ctx)->dbg_host;
-      fprintf(stderr, "[trr] K3 CTA 0 (x16 cycles): total %u; producer waited %u for a free stage; consumer warp 0: %u waiting "
-                      "for postings, %u boundaries, %u accumulate, %u harvest\n", w[8], w[9], w[10], w[11], w[12], w[13]);
+  }
+#ifdef TRR_TRIAGE
+  if (h->stats.mode_used == 2 && extra(h->ctx)->dbg_host) {
+    const uint32_t* w = extra(h->ctx)->dbg_host;
+    fprintf(stderr, "[trr] K3 fast, CTA 0 (x16 cycles): total %u; producer: %u passes, waited %u for a free stage; consumer warp 0: "
+                    "%u waiting for postings, %u accumulate, %u harvest (%u compactions), %u end of item\n", w[8], w[14], w[9], w[10],
+            w[11], w[12], w[15], w[13]);
+  }
+#endif
+  if (h->stat_pending && h->stat_dev) {
+    uint32_t nf[2] = {0, 0};  // queries re-run with 32-bit cells / by the exact kernel
+    if (cudaMemcpy(nf, h->stat_dev, 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      h->stats.n_guard_fallbacks = nf[0];
+      h->stats.n_exact_fallbacks = nf[1];
     }
+    h->stat_pending = false;
   }
   *out = h->stats;
   return TRR_OK;
@@ -1353,9 +1401,11 @@ struct DenseSnapHeader {
   uint64_t n, n_dead;
 };
 struct Bm25SnapHeader {
-  char magic[8];  // "TRRBM252"
+  char magic[8];  // "TRRBM253"
   uint32_t n_docs, n_terms, doc_base, range_shift, n_ranges, skip_ld;
   uint64_t n_postings;
+  uint64_t n_dead_postings;  // postings of removed documents still in place (tf == 0)
+  uint32_t impacts_ok, reserved;
 };
 }  // namespace
 
@@ -1414,13 +1464,15 @@ extern "C" int trr_bm25_save(trr_bm25* h, const char* path) {
   FileCloser fc{fopen(path, "wb")};
   if (!fc.f) return trr_fail(TRR_ERR_INVALID_ARG, std::string("trr_bm25_save: cannot open ") + path);
   Bm25SnapHeader hd{};
-  memcpy(hd.magic, "TRRBM252", 8);
+  memcpy(hd.magic, "TRRBM253", 8);
   hd.n_docs = h->n_docs; hd.n_terms = h->n_terms; hd.doc_base = h->doc_base; hd.range_shift = h->range_shift;
   hd.n_ranges = h->n_ranges; hd.skip_ld = h->skip_ld; hd.n_postings = h->n_postings;
+  hd.n_dead_postings = h->n_dead_postings; hd.impacts_ok = h->impacts_ok ? 1u : 0u;
   if (fwrite(&hd, sizeof(hd), 1, fc.f) != 1) return trr_fail(TRR_ERR_INVALID_ARG, "snapshot: short write");
   TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->post, (h->n_postings + 2) * sizeof(uint2)));
   TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->skip, (uint64_t)h->n_terms * h->skip_ld * 4));
   TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->term_min, ((uint64_t)h->n_terms + 1) * 4));
+  TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->term_max, (uint64_t)h->n_terms * 4));
   TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->d_term_off, ((uint64_t)h->n_terms + 1) * 8));
   TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->tf, h->n_postings * 4));
   TRR_CHECK(snap_write_dev(h->ctx, fc.f, h->doc_len, (uint64_t)h->n_docs * 4));
@@ -1433,10 +1485,10 @@ extern "C" int trr_bm25_load(trr_ctx* ctx, const char* path, trr_bm25** out) {
   FileCloser fc{fopen(path, "rb")};
   if (!fc.f) return trr_fail(TRR_ERR_INVALID_ARG, std::string("trr_bm25_load: cannot open ") + path);
   Bm25SnapHeader hd{};
-  if (fread(&hd, sizeof(hd), 1, fc.f) != 1 || memcmp(hd.magic, "TRRBM252", 8) != 0)
+  if (fread(&hd, sizeof(hd), 1, fc.f) != 1 || memcmp(hd.magic, "TRRBM253", 8) != 0)
     return trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_load: not a BM25 snapshot");
   if (hd.range_shift < TRR_BM25_MIN_RANGE_SHIFT || hd.range_shift > TRR_BM25_MAX_RANGE_SHIFT || hd.skip_ld != hd.n_ranges + 1 ||
-      hd.n_postings >= 0xFFFFFFFFull ||
+      hd.n_postings >= 0xFFFFFFFFull || hd.n_dead_postings > hd.n_postings ||
       hd.n_ranges != (hd.n_docs ? (uint32_t)(((uint64_t)hd.n_docs + (1u << hd.range_shift) - 1) >> hd.range_shift) : 0u))
     return trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_load: corrupt header");
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1444,11 +1496,13 @@ extern "C" int trr_bm25_load(trr_ctx* ctx, const char* path, trr_bm25** out) {
   trr_bm25* h = new trr_bm25();
   h->ctx = ctx; h->n_docs = hd.n_docs; h->n_terms = hd.n_terms; h->doc_base = hd.doc_base; h->n_postings = hd.n_postings;
   h->range_shift = hd.range_shift; h->n_ranges = hd.n_ranges; h->skip_ld = hd.skip_ld;
+  h->n_dead_postings = hd.n_dead_postings; h->impacts_ok = hd.impacts_ok != 0;
   for (auto& e : h->ev) cudaEventCreate(&e);
   auto fail = [&](int s) { trr_bm25_destroy(h); return s; };
   if (cudaMalloc(&h->post, (hd.n_postings + 2) * sizeof(uint2)) != cudaSuccess ||
       cudaMalloc(&h->skip, std::max<uint64_t>((uint64_t)hd.n_terms * hd.skip_ld, 1) * 4) != cudaSuccess ||
       cudaMalloc(&h->term_min, ((uint64_t)hd.n_terms + 1) * 4) != cudaSuccess ||
+      cudaMalloc(&h->term_max, std::max<uint64_t>(hd.n_terms, 1) * 4) != cudaSuccess ||
       cudaMalloc(&h->d_term_off, ((uint64_t)hd.n_terms + 1) * 8) != cudaSuccess ||
       cudaMalloc(&h->tf, std::max<uint64_t>(hd.n_postings, 1) * 4) != cudaSuccess ||
       cudaMalloc(&h->doc_len, std::max<uint64_t>(hd.n_docs, 1) * 4) != cudaSuccess) {
@@ -1459,6 +1513,7 @@ extern "C" int trr_bm25_load(trr_ctx* ctx, const char* path, trr_bm25** out) {
   int s = snap_read_dev(ctx, fc.f, h->post, (hd.n_postings + 2) * sizeof(uint2));
   if (s == TRR_OK) s = snap_read_dev(ctx, fc.f, h->skip, (uint64_t)hd.n_terms * hd.skip_ld * 4);
   if (s == TRR_OK) s = snap_read_dev(ctx, fc.f, h->term_min, ((uint64_t)hd.n_terms + 1) * 4);
+  if (s == TRR_OK) s = snap_read_dev(ctx, fc.f, h->term_max, (uint64_t)hd.n_terms * 4);
   if (s == TRR_OK) s = snap_read_dev(ctx, fc.f, h->d_term_off, ((uint64_t)hd.n_terms + 1) * 8);
   if (s == TRR_OK) s = snap_read_dev(ctx, fc.f, h->tf, hd.n_postings * 4);
   if (s == TRR_OK) s = snap_read_dev(ctx, fc.f, h->doc_len, (uint64_t)hd.n_docs * 4);

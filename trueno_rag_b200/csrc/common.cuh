@@ -31,6 +31,15 @@ int trr_fail(int status, const std::string& msg);
     if (_s != TRR_OK) return _s; \
   } while (0)
 
+// Triage knobs (environment variables read by the orchestration) exist only in -DTRR_TRIAGE builds, which
+// tools/gpu_probe.py uses; the default build ignores the environment, so a stray variable cannot change a result.
+#ifdef TRR_TRIAGE
+#include <stdlib.h>
+#define TRR_KNOB(name) getenv(name)
+#else
+#define TRR_KNOB(name) (static_cast<const char*>(nullptr))
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // context: one GPU, one stream, a reusable workspace, launch counters
 // ------------------------------------------------------------------------------------------------
