@@ -15,13 +15,35 @@ __device__ __forceinline__ bool cbar_or(bool pred) {
   return r != 0;
 }
 // MODE bit0: F2I path; bit1: barrier.red.or at the end (else bar.sync); bit2: skip scan; bit3: skip atomics
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 template <int MODE>
-__global__ void __launch_bounds__(CT + 32, 1) k(const uint2* __restrict__ post, uint32_t n_post, uint32_t* out, long long* cyc, float scale) {
+__global__ void __launch_bounds__(CT + 32, 1) k(const uint2* __restrict__ post, uint32_t n_post, uint32_t* out, long long* cyc, float scale, const uint8_t* src, uint32_t K, uint32_t S) {
+  __shared__ uint64_t tbar[3];
+  __shared__ volatile uint32_t s_iter;
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem);
   uint2* st = reinterpret_cast<uint2*>(smem + CELLS * 4);
   const uint32_t tid = threadIdx.x;
-  if (tid >= CT) return;
+  if (tid == 0) { for (int j = 0; j < 3; ++j) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(&tbar[j])), "r"(1)); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); s_iter = 0; }
+  __syncthreads();
+  if (tid >= CT) {
+    // side warp: per consumer iteration, K bulk copies of S bytes into a ring nobody reads (3 in flight)
+    if (K == 0) return;
+    const uint32_t lane = tid & 31;
+    uint8_t* ring = smem + CELLS * 4 + 8192 * 8;
+    size_t off = (size_t)blockIdx.x * 33554432u;
+    for (int it = 0; it < ITEMS; ++it) {
+      const int st3 = it % 3;
+      if (it >= 3) { uint32_t ok = 0; const uint32_t par = ((it / 3) - 1) & 1; while (!ok) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(s32(&tbar[st3])), "r"(par) : "memory"); }
+      while ((int)s_iter < it - 2) __nanosleep(50);
+      if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(&tbar[st3])), "r"(K * S) : "memory");
+      __syncwarp();
+      if (lane < K) asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(s32(ring + st3 * 32768 + lane * S)), "l"(src + ((off + (size_t)lane * 1048576u) & 0xFFFFFFF0ull) % ((size_t)3 << 30)), "r"(S), "r"(s32(&tbar[st3])) : "memory");
+      off += 65536 + K * S;
+    }
+    return;
+  }
   for (uint32_t i = tid; i < CELLS; i += CT) acc[i] = 0;
   for (uint32_t i = tid; i < n_post; i += CT) st[i] = post[(size_t)blockIdx.x * 8192 + i];
   cbar();
@@ -29,6 +51,7 @@ __global__ void __launch_bounds__(CT + 32, 1) k(const uint2* __restrict__ post, 
   uint32_t sink = 0;
   const uint32_t range_base = 7, R = CELLS, thr_hi = 0x7fffff00u;
   for (int it = 0; it < ITEMS; ++it) {
+    if (tid == 0) s_iter = it;
     if (!(MODE & 8)) {
       auto add1 = [&](const uint2 e) {
         const uint32_t dd = e.x - range_base;
@@ -69,15 +92,15 @@ __global__ void __launch_bounds__(CT + 32, 1) k(const uint2* __restrict__ post, 
   if (s2 == 0x12345678u) out[0] = s2;
 }
 template <int MODE>
-void run(const char* name, const uint2* post, uint32_t n_post, uint32_t* out, long long* cyc) {
-  const size_t smem = (size_t)CELLS * 4 + 8192 * 8;
+void run(const char* name, const uint2* post, uint32_t n_post, uint32_t* out, long long* cyc, const uint8_t* src = nullptr, uint32_t K = 0, uint32_t S = 0) {
+  const size_t smem = (size_t)CELLS * 4 + 8192 * 8 + (K ? 3 * 32768 : 0);
   cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k<MODE><<<148, CT + 32, smem>>>(post, n_post, out, cyc, 1024.0f);
-  k<MODE><<<148, CT + 32, smem>>>(post, n_post, out, cyc, 1024.0f);
+  k<MODE><<<148, CT + 32, smem>>>(post, n_post, out, cyc, 1024.0f, src, K, S);
+  k<MODE><<<148, CT + 32, smem>>>(post, n_post, out, cyc, 1024.0f, src, K, S);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[148]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
   double avg = 0; for (int i = 0; i < 148; ++i) avg += (double)h[i]; avg /= 148;
-  printf("%-64s n=%5u %8.0f cyc/item (%s)\n", name, n_post, avg / ITEMS, cudaGetErrorString(e));
+  printf("%-64s n=%5u K=%2u S=%5u %8.0f cyc/item (%s)\n", name, n_post, K, S, avg / ITEMS, cudaGetErrorString(e));
 }
 int main() {
   uint2* hp = new uint2[(size_t)148 * 8192];
@@ -86,7 +109,13 @@ int main() {
   uint2* post; uint32_t* out; long long* cyc;
   cudaMalloc(&post, (size_t)148 * 8192 * 8); cudaMalloc(&out, 8); cudaMalloc(&cyc, 148 * 8);
   cudaMemcpy(post, hp, (size_t)148 * 8192 * 8, cudaMemcpyHostToDevice);
-  for (uint32_t n : {4096u, 2048u}) {
+  uint8_t* src; cudaMalloc(&src, ((size_t)3 << 30) + (64 << 20)); cudaMemset(src, 1, ((size_t)3 << 30) + (64 << 20));
+  run<3>("RED(F2I) + bar + scan + bar.red.or", post, 4096, out, cyc);
+  run<3>("same + side warp: TMA 16 x 2 KB per iteration", post, 4096, out, cyc, src, 16, 2048);
+  run<3>("same + side warp: TMA 16 x 16 B per iteration", post, 4096, out, cyc, src, 16, 16);
+  run<3>("same + side warp: TMA 2 x 16 KB per iteration", post, 4096, out, cyc, src, 2, 16384);
+  run<3>("same + side warp: TMA 32 x 1 KB per iteration", post, 4096, out, cyc, src, 32, 1024);
+  for (uint32_t n : {4096u}) {
     run<0>("RED + bar + scan + bar", post, n, out, cyc);
     run<1>("RED(F2I) + bar + scan + bar", post, n, out, cyc);
     run<3>("RED(F2I) + bar + scan + bar.red.or", post, n, out, cyc);

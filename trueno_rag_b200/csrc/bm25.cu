@@ -229,10 +229,12 @@ struct PassDesc {
   uint32_t seg_end[32];
 };
 
+template <bool BACKOFF = false>  // BACKOFF: a waiting producer warp sleeps between polls instead of taking issue slots
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity, uint32_t site, uint32_t* dbg) {
   if (trr_mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!trr_mbar_try_wait(bar, parity)) {
+    if (BACKOFF) __nanosleep(100);
     if (clock64() - t0 > 4000000000LL) {  // ~2 s: a protocol bug must surface as an error, never as a hung GPU
       if (dbg) { *dbg = 0x40000000u | (site << 16) | (blockIdx.x & 0xFFFFu); __threadfence_system(); }
       __trap();
@@ -596,6 +598,34 @@ namespace {
 
 constexpr uint32_t NS = TRR_BM25_FAST_STAGES;
 constexpr uint32_t NONE32 = 0xFFFFFFFFu;
+// A cp.async.bulk costs the issuing warp ~50 cycles whatever its size (tools/ubench/tma_small.cu: 16 copies from one warp
+// take 1300 cycles per stage, from four warps 800), and a range needs one copy per query term with postings in it (~16).
+// Four producer warps run the same plan in lockstep; each issues the copies of every fourth slot, warp 0 also publishes
+// the descriptor.
+constexpr uint32_t PW = 4;
+// (28 consumer warps - the 1024-thread limit - measured no faster than 16: 5.84 vs 5.60 ms at cfg4)
+#ifndef TRR_BM25_FAST_CONSUMER_WARPS
+#define TRR_BM25_FAST_CONSUMER_WARPS 16
+#endif
+constexpr uint32_t FCW = TRR_BM25_FAST_CONSUMER_WARPS;
+constexpr uint32_t FCT = FCW * 32;
+constexpr uint32_t FAST_THREADS = (FCW + PW) * 32;
+constexpr int FU = (4096 + FCT - 1) / FCT;  // loads per thread and round trip: one round covers 4096 postings / 128-bit groups
+__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 2, %0;" ::"n"(PW * 32) : "memory"); }
+__device__ __forceinline__ void fast_bar() { asm volatile("bar.sync 1, %0;" ::"n"(FCT) : "memory"); }
+struct FastSync { __device__ __forceinline__ void operator()() const { fast_bar(); } };
+__device__ __forceinline__ bool fast_bar_or(bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 p, %1, 0;\n\t"
+      "barrier.red.or.pred q, 1, %2, p;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t}"
+      : "=r"(r)
+      : "r"((uint32_t)pred), "n"(FCT)
+      : "memory");
+  return r != 0;
+}
 
 struct FastDesc {
   uint32_t flags;
@@ -611,7 +641,7 @@ struct FastDesc {
 }  // namespace
 
 template <int BITS>  // width of an accumulator cell: 16 (two cells per word) or 32
-__global__ void __launch_bounds__(TRR_BM25_THREADS, 1)
+__global__ void __launch_bounds__(FAST_THREADS, 1)
 bm25_fast_kernel(Bm25SearchArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t R = 1u << a.range_shift;
@@ -622,22 +652,23 @@ bm25_fast_kernel(Bm25SearchArgs a) {
   FastDesc* desc = reinterpret_cast<FastDesc*>(cand + a.cand_cap);                        // NS
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(desc + NS);                            // NS
   uint64_t* empty_bar = full_bar + NS;                                                    // NS
-  __shared__ uint32_t s_cnt, s_overflow, s_ovf_latched;
+  __shared__ uint32_t s_cnt, s_overflow, s_ovf_latched, s_item;
   __shared__ uint64_t s_thr;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) {
-    for (uint32_t s = 0; s < NS; ++s) { trr_mbar_init(&full_bar[s], 1); trr_mbar_init(&empty_bar[s], CW); }
+    for (uint32_t s = 0; s < NS; ++s) { trr_mbar_init(&full_bar[s], 1); trr_mbar_init(&empty_bar[s], FCW); }
     trr_fence_mbar_init();
     s_cnt = 0; s_overflow = 0; s_thr = TRR_KEY_EMPTY;
   }
-  if (warp < CW) for (uint32_t i = tid; i < W; i += CT) acc[i] = 0u;
+  if (warp < FCW) for (uint32_t i = tid; i < W; i += FCT) acc[i] = 0u;
   __syncthreads();
 
-  TRI(long long w_prod = 0, w_full = 0, w_acc = 0, w_harv = 0, w_end = 0; uint32_t n_pass = 0, n_compact = 0;)
+  TRI(long long w_prod = 0, w_full = 0, w_acc = 0, w_harv = 0, w_end = 0, w_b1 = 0, w_scan = 0, w_arr = 0, w_bar = 0; uint32_t n_pass = 0, n_compact = 0;)
   TRI(const long long t_begin = clock64();)
-  if (warp == CW) {
-    // ============================ producer warp ============================
+  if (warp >= FCW) {
+    // ============================ producer warps ============================
+    const uint32_t pw = warp - FCW;
     uint32_t stage = 0, phase = 0;
     uint32_t item_thr0f = 0;
     float item_scale = 1.0f;
@@ -646,29 +677,33 @@ bm25_fast_kernel(Bm25SearchArgs a) {
     auto emit = [&](uint32_t flags, uint32_t range_base, uint32_t item, uint32_t off, uint32_t src_al, uint32_t al,
                     uint32_t total_al, uint2 sf, uint2 sb) {
       TRI(const long long tw = clock64();)
-      mbar_wait_or_trap(&empty_bar[stage], phase ^ 1, 1, a.dbg);
+      mbar_wait_or_trap<true>(&empty_bar[stage], phase ^ 1, 1, a.dbg);
       TRI(w_prod += clock64() - tw; ++n_pass;)
-      FastDesc& d = desc[stage];
-      d.single[lane] = sf;
-      d.single[32 + lane] = sb;
-      if (lane == 0) {
-        d.flags = flags; d.range_base = range_base; d.item = item; d.total = total_al;
-        d.thr0f = item_thr0f; d.scale = item_scale;
+      if (pw == 0) {
+        FastDesc& d = desc[stage];
+        d.single[lane] = sf;
+        d.single[32 + lane] = sb;
+        if (lane == 0) {
+          d.flags = flags; d.range_base = range_base; d.item = item; d.total = total_al;
+          d.thr0f = item_thr0f; d.scale = item_scale;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          if (total_al) trr_mbar_expect_tx(&full_bar[stage], total_al * 8u);
+          else trr_mbar_arrive(&full_bar[stage]);
+        }
       }
-      __syncwarp();
-      if (lane == 0) {
-        if (total_al) trr_mbar_expect_tx(&full_bar[stage], total_al * 8u);
-        else trr_mbar_arrive(&full_bar[stage]);
-      }
-      __syncwarp();
-      if (al) trr_bulk_g2s(stage_buf + (size_t)stage * a.stage_cap + off, a.post + src_al, al * 8u, &full_bar[stage]);
+      // (a copy may complete its bytes before warp 0 has announced them: the phase cannot end before warp 0's arrival)
+      if (al && (lane & (PW - 1)) == pw)
+        trr_bulk_g2s(stage_buf + (size_t)stage * a.stage_cap + off, a.post + src_al, al * 8u, &full_bar[stage]);
       if (++stage == NS) { stage = 0; phase ^= 1; }
     };
     const uint32_t n_items = (a.n_sel_ptr ? *a.n_sel_ptr : a.B) * a.n_chunks;
     while (true) {
-      uint32_t item = 0;
-      if (lane == 0) item = atomicAdd(a.queue, 1u);
-      item = __shfl_sync(FULLM, item, 0);
+      producer_bar();  // every producer warp has read the previous item id
+      if (pw == 0 && lane == 0) s_item = atomicAdd(a.queue, 1u);
+      producer_bar();
+      const uint32_t item = s_item;
       if (item >= n_items) { emit(F_QUIT, 0, item, 0, 0, 0, 0, none2, none2); break; }
       const uint32_t b = a.order[item / a.n_chunks], c = item % a.n_chunks;
       item_thr0f = a.n_chunks == 1 ? a.thr0f[b] : 0u;  // (the bootstrap counts the postings of the whole shard)
@@ -768,17 +803,17 @@ bm25_fast_kernel(Bm25SearchArgs a) {
       }
       emit(F_END_ITEM, 0, item, 0, 0, 0, 0, none2, none2);
     }
-    TRI(if (blockIdx.x == 0 && lane == 0 && a.dbg) { a.dbg[9] = (uint32_t)(w_prod >> 4); a.dbg[14] = n_pass; })
+    TRI(if (blockIdx.x == 0 && pw == 0 && lane == 0 && a.dbg && n_pass > 8) { a.dbg[9] = (uint32_t)(w_prod >> 4); a.dbg[14] = n_pass; })
   } else {
     // ============================ consumer warps ============================
     uint32_t stage = 0, phase = 0;
     const uint32_t compact_at = a.kf + ((a.cand_cap - a.kf) >> 1);
     // block-wide (consumer warps) compaction: afterwards cand[0..s_cnt) is sorted descending and s_thr is the kf-th best
     auto compact = [&]() {
-      consumer_bar();
+      fast_bar();
       const uint32_t cnt = min(s_cnt, a.cand_cap);
-      for (uint32_t i = cnt + tid; i < a.cand_cap; i += CT) cand[i] = TRR_KEY_EMPTY;
-      trr_bitonic_sort_desc(cand, a.cand_cap, tid, CT, ConsumerSync());
+      for (uint32_t i = cnt + tid; i < a.cand_cap; i += FCT) cand[i] = TRR_KEY_EMPTY;
+      trr_bitonic_sort_desc(cand, a.cand_cap, tid, FCT, FastSync());
       if (tid == 0) {
         const uint32_t c2 = min(cnt, a.kf);
         s_cnt = c2;
@@ -786,26 +821,117 @@ bm25_fast_kernel(Bm25SearchArgs a) {
         s_overflow = 0;
         if (c2 == a.kf) s_thr = cand[a.kf - 1];
       }
-      consumer_bar();
+      fast_bar();
     };
+    // Scan of one accumulator (all of its adds have landed): cells that beat the query's running kf-th best key go to the
+    // candidate buffer, everything is re-zeroed.  Returns true when a push reached the compaction mark (or overflowed).
+    auto scan = [&](uint32_t* accx, uint32_t range_base, uint32_t thr0f) -> bool {
+      bool need_compact = false;
+      const uint64_t thr = *reinterpret_cast<volatile uint64_t*>(&s_thr);
+      const uint32_t thr_hi = max(max((uint32_t)(thr >> 32), thr0f), 1u);
+      uint4* a4 = reinterpret_cast<uint4*>(accx);
+      const uint32_t ord0 = a.doc_base + range_base;
+      // a 128-bit group with a candidate, processed from the registers of the scan: one atomic reserves the slots of all
+      // its qualifying cells (a single shared-memory round trip - the warp that finds a candidate delays the barrier)
+      auto harvest4 = [&](uint32_t i, const uint4& v) {
+        constexpr int NC = BITS == 16 ? 8 : 4;
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t f[NC];
+        uint32_t qual = 0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          f[c] = BITS == 16 ? ((w[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu) : w[c];
+          const uint64_t key = ((uint64_t)f[c] << 32) | (uint64_t)(0xFFFFFFFFu - (ord0 + i * NC + c));
+          if (f[c] >= thr_hi && key > thr) qual |= 1u << c;
+        }
+        uint32_t nw[4] = {0u, 0u, 0u, 0u};
+        if (qual) {
+          const uint32_t n = __popc(qual);
+          uint32_t pos = atomicAdd(&s_cnt, n);
+          if (pos + n >= compact_at) need_compact = true;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            if ((qual >> c) & 1u) {
+              if (pos < a.cand_cap) {
+                cand[pos] = ((uint64_t)f[c] << 32) | (uint64_t)(0xFFFFFFFFu - (ord0 + i * NC + c));
+              } else {  // candidate buffer full: the cell stays in the accumulator and is retried after the compaction
+                s_overflow = 1u;
+                nw[BITS == 16 ? (c >> 1) : c] |= BITS == 16 ? f[c] << ((c & 1) * 16) : f[c];
+              }
+              ++pos;
+            }
+          }
+        }
+        a4[i] = make_uint4(nw[0], nw[1], nw[2], nw[3]);
+      };
+      auto pre4 = [&](uint32_t i, const uint4& v) -> bool {
+        uint32_t mx;
+        if (BITS == 16) {
+          const uint32_t m2 = __vmaxu2(__vmaxu2(v.x, v.y), __vmaxu2(v.z, v.w));
+          mx = max(m2 & 0xFFFFu, m2 >> 16);
+        } else {
+          mx = max(max(v.x, v.y), max(v.z, v.w));
+        }
+        const bool hit = mx >= thr_hi;
+        if (mx != 0u && !hit) a4[i] = make_uint4(0u, 0u, 0u, 0u);
+        return hit;
+      };
+      const uint32_t n4 = W >> 2;
+      uint32_t i = tid;
+      TRI(if (a.triage & 4u) i = n4;)
+      for (; i + (FU - 1) * FCT < n4; i += FU * FCT) {  // FU 128-bit groups per round trip (see the accumulate walk)
+        uint4 v[FU];
+#pragma unroll
+        for (int u = 0; u < FU; ++u) v[u] = a4[i + u * FCT];
+        uint32_t hits = 0;
+#pragma unroll
+        for (int u = 0; u < FU; ++u) hits |= pre4(i + u * FCT, v[u]) ? 1u << u : 0u;
+        if (hits) {
+#pragma unroll
+          for (int u = 0; u < FU; ++u)
+            if ((hits >> u) & 1u) harvest4(i + u * FCT, v[u]);
+        }
+      }
+      for (; i < n4; i += FCT) {
+        const uint4 v = a4[i];
+        if (pre4(i, v)) harvest4(i, v);
+      }
+      return need_compact;
+    };
+    // Closes a scan: ONE barrier, which also tells every thread whether some push reached the compaction mark; when the
+    // candidate buffer overflowed, the cells that stayed behind are scanned again after the compaction.
+    auto settle = [&](uint32_t* accx, uint32_t range_base, uint32_t thr0f, bool need) {
+      while (fast_bar_or(need)) {
+        TRI(++n_compact;)
+        compact();
+        if (!s_ovf_latched) break;  // (stable until the next compaction, which is behind further barriers)
+        need = scan(accx, range_base, thr0f);
+      }
+    };
+    // (Measured and dropped: two accumulators for the 16-bit cells, so that the scan of range i shares a barrier interval
+    // with the accumulation of range i + 1 - one barrier per range instead of two - ran 6.0 ms against 5.6 ms at cfg4: the
+    // time inside the barriers is not waiting for a slow warp, every warp spends it there while the shared-memory pipe
+    // drains the atomics and the zeroing stores queued by the phase, and the second accumulator costs a third of the stage.)
     while (true) {
       TRI(long long tc = clock64();)
       mbar_wait_or_trap(&full_bar[stage], phase, 2, a.dbg);
       TRI({ const long long t = clock64(); w_full += t - tc; tc = t; })
+      TRI(const long long t_pass = tc;)
       const FastDesc& d = desc[stage];
       const uint32_t flags = d.flags, range_base = d.range_base, item = d.item, total = d.total, thr0f = d.thr0f;
       const float scale = d.scale;
       if (flags & F_QUIT) break;
       const uint2* st = stage_buf + (size_t)stage * a.stage_cap;
+      uint32_t* acc_cur = acc;
       {
         // flat walk: posting p of the stage belongs to thread p mod 512; padding and foreign ranges fail the range check
-        const uint32_t acc_s = trr_smem_u32(acc);
+        const uint32_t acc_s = trr_smem_u32(acc_cur);
         auto add1 = [&](const uint2 e) {
           const uint32_t dd = e.x - range_base;
           // ceil(impact * scale) in the low mantissa bits of RU(impact * scale + 2^23)  (impact * scale < 2^22)
           uint32_t q = __float_as_uint(__fmaf_ru(__uint_as_float(e.y), scale, 8388608.0f)) & 0x7FFFFFu;
 #ifdef TRR_TRIAGE
-          if (a.triage & 1u) { if (dd < R && q == 0x12345u) acc[dd & (W - 1)] = 1u; return; }
+          if (a.triage & 1u) { if (dd < R && q == 0x12345u) acc_cur[dd & (W - 1)] = 1u; return; }
 #endif
           uint32_t addr;
           if (BITS == 16) { addr = acc_s + ((dd >> 1) << 2); q <<= (dd & 1u) << 4; }
@@ -813,105 +939,49 @@ bm25_fast_kernel(Bm25SearchArgs a) {
           asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, %1;\n\t@p red.shared.add.u32 [%2], %3;\n\t}"
                        ::"r"(dd), "r"(R), "r"(addr), "r"(q) : "memory");
         };
-        uint32_t p = tid;
-        for (; p + 3 * CT < total; p += 4 * CT) {
-          const uint2 e0 = st[p], e1 = st[p + CT], e2 = st[p + 2 * CT], e3 = st[p + 3 * CT];
-          add1(e0); add1(e1); add1(e2); add1(e3);
+        // Every load of a round is issued before the first atomic: under load a shared-memory round trip takes hundreds of
+        // cycles (the atomics of 16 warps queue in the same pipe), so the walk is bound by the number of dependent rounds.
+        // Stage positions past `total` hold stale postings; they are read (in bounds) and replaced by a no-op.
+        const uint2 nop = make_uint2(NONE32, 0u);
+        const uint2 sg = tid < 64 ? d.single[tid] : nop;
+        for (uint32_t p = tid; p < total; p += FU * FCT) {
+          uint2 e[FU];
+#pragma unroll
+          for (int u = 0; u < FU; ++u) { const uint32_t pu = p + u * FCT; e[u] = st[min(pu, a.stage_cap - 1)]; if (pu >= total) e[u] = nop; }
+#pragma unroll
+          for (int u = 0; u < FU; ++u) add1(e[u]);
         }
-#pragma unroll 1
-        for (; p < total; p += CT) add1(st[p]);
-        if (tid < 64) {
-          const uint2 e = d.single[tid];
-          if (e.x != NONE32) add1(e);
-        }
+        add1(sg);
       }
       __syncwarp();
       if (lane == 0) trr_mbar_arrive(&empty_bar[stage]);  // stage and descriptor are free again
       if (++stage == NS) { stage = 0; phase ^= 1; }
       TRI({ const long long t = clock64(); w_acc += t - tc; tc = t; })
-
-      if (flags & F_HARVEST) {
-        consumer_bar();  // every add of the range has landed
-        while (true) {
-          bool need_compact = false;
-          const uint64_t thr = *reinterpret_cast<volatile uint64_t*>(&s_thr);
-          const uint32_t thr_hi = max(max((uint32_t)(thr >> 32), thr0f), 1u);
-          uint4* a4 = reinterpret_cast<uint4*>(acc);
-          const uint32_t ord0 = a.doc_base + range_base;
-          auto push = [&](uint32_t f, uint32_t cell) -> bool {  // true: the cell has to stay (candidate buffer full)
-            if (f < thr_hi) return false;
-            const uint64_t key = ((uint64_t)f << 32) | (uint64_t)(0xFFFFFFFFu - (ord0 + cell));
-            if (key <= thr) return false;
-            const uint32_t pos = atomicAdd(&s_cnt, 1u);
-            if (pos + 1u >= compact_at) need_compact = true;
-            if (pos < a.cand_cap) { cand[pos] = key; return false; }
-            s_overflow = 1u;  // stays in the accumulator; retried after the compaction
-            return true;
-          };
-          auto harvest4 = [&](uint32_t i) {  // per-cell pass over a 128-bit group that holds a candidate
-#pragma unroll 1
-            for (uint32_t j = 0; j < 4; ++j) {
-              const uint32_t wv = acc[i * 4 + j];
-              uint32_t nw = 0;
-              if (BITS == 16) {
-                const uint32_t lo = wv & 0xFFFFu, hi = wv >> 16;
-                if (push(lo, (i * 4 + j) * 2)) nw |= lo;
-                if (push(hi, (i * 4 + j) * 2 + 1)) nw |= hi << 16;
-              } else {
-                if (push(wv, i * 4 + j)) nw = wv;
-              }
-              acc[i * 4 + j] = nw;
-            }
-          };
-          auto pre4 = [&](uint32_t i, const uint4& v) -> bool {
-            uint32_t mx;
-            if (BITS == 16) {
-              const uint32_t m2 = __vmaxu2(__vmaxu2(v.x, v.y), __vmaxu2(v.z, v.w));
-              mx = max(m2 & 0xFFFFu, m2 >> 16);
-            } else {
-              mx = max(max(v.x, v.y), max(v.z, v.w));
-            }
-            const bool hit = mx >= thr_hi;
-            if (mx != 0u && !hit) a4[i] = make_uint4(0u, 0u, 0u, 0u);
-            return hit;
-          };
-          const uint32_t n4 = W >> 2;
-          uint32_t i = tid;
-          TRI(if (a.triage & 4u) i = n4;)
-          for (; i + 3 * CT < n4; i += 4 * CT) {
-            const uint4 v0 = a4[i], v1 = a4[i + CT], v2 = a4[i + 2 * CT], v3 = a4[i + 3 * CT];
-            const bool h0 = pre4(i, v0), h1 = pre4(i + CT, v1), h2 = pre4(i + 2 * CT, v2), h3 = pre4(i + 3 * CT, v3);
-            if (h0) harvest4(i);
-            if (h1) harvest4(i + CT);
-            if (h2) harvest4(i + 2 * CT);
-            if (h3) harvest4(i + 3 * CT);
-          }
-          for (; i < n4; i += CT) {
-            const uint4 v = a4[i];
-            if (pre4(i, v)) harvest4(i);
-          }
-          // one barrier per harvest: it also tells every thread whether some push reached the compaction mark (or overflowed)
-          if (!consumer_bar_or(need_compact)) break;
-          TRI(++n_compact;)
-          compact();
-          if (!s_ovf_latched) break;  // (stable until the next compaction, which is behind further barriers)
-        }
+      if (flags & F_HARVEST) {  // last pass of the range
+        TRI(const long long tb0 = clock64(); w_arr += tb0 - t_pass;)
+        fast_bar();  // every add of the range has landed
+        TRI({ const long long t = clock64(); w_b1 += t - tc; tc = t; w_bar += t - tb0; })
+        const bool need = scan(acc_cur, range_base, thr0f);
+        TRI({ const long long t = clock64(); w_scan += t - tc; tc = t; })
+        settle(acc_cur, range_base, thr0f, need);
         TRI({ const long long t = clock64(); w_harv += t - tc; tc = t; })
       }
       if (flags & F_END_ITEM) {
         compact();
         const uint32_t n_out = s_cnt;
         uint64_t* dst = a.fast_keys + (uint64_t)item * a.kf;  // indexed by position in `order` (x n_chunks + chunk)
-        for (uint32_t i = tid; i < a.kf; i += CT) dst[i] = i < n_out ? cand[i] : TRR_KEY_EMPTY;
-        consumer_bar();
+        for (uint32_t i = tid; i < a.kf; i += FCT) dst[i] = i < n_out ? cand[i] : TRR_KEY_EMPTY;
+        fast_bar();
         if (tid == 0) { s_cnt = 0; s_thr = TRR_KEY_EMPTY; }
-        consumer_bar();
+        fast_bar();
         TRI({ const long long t = clock64(); w_end += t - tc; tc = t; })
       }
     }
-    TRI(if (blockIdx.x == 0 && tid == 0 && a.dbg) {
+    TRI(if (blockIdx.x == 0 && lane == 0 && a.triage_out && w_acc > 100000) { a.triage_out[warp * 2] = (uint32_t)(w_arr >> 4); a.triage_out[warp * 2 + 1] = (uint32_t)(w_bar >> 4); })
+    TRI(if (blockIdx.x == 0 && tid == 0 && a.dbg && w_acc > 100000) {
       a.dbg[8] = (uint32_t)((clock64() - t_begin) >> 4); a.dbg[10] = (uint32_t)(w_full >> 4); a.dbg[11] = (uint32_t)(w_acc >> 4);
       a.dbg[12] = (uint32_t)(w_harv >> 4); a.dbg[13] = (uint32_t)(w_end >> 4); a.dbg[15] = n_compact;
+      a.dbg[6] = (uint32_t)(w_b1 >> 4); a.dbg[7] = (uint32_t)(w_scan >> 4);
     })
   }
 }
@@ -1087,7 +1157,7 @@ cudaError_t trr_launch_bm25_fast(const Bm25SearchArgs& a, int bits, unsigned gri
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  kernel<<<grid, TRR_BM25_THREADS, smem, st>>>(a);
+  kernel<<<grid, FAST_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -74,6 +74,7 @@ struct Bm25SearchArgs {
   uint32_t* thr0f32;
   uint64_t* fast_keys; // [position in `order`][n_chunks][kf] keys (fixed-point score << 32 | ~ordinal), descending, 0 = empty
   uint32_t triage;     // -DTRR_TRIAGE builds only (timing experiments that break the results); 0 otherwise
+  uint32_t* triage_out; // -DTRR_TRIAGE builds only: per-warp counters
 };
 
 // exact re-scoring of the fast pass's candidates + proof (bm25_rescore_kernel)

@@ -1140,13 +1140,16 @@ extern "C" int trr_bm25_copy_impacts(trr_bm25* h, float* out, uint64_t n) {
 
 // stage capacity (postings) of a BM25 search kernel: what is left of the shared memory after the fixed part, split over
 // n_stages buffers of 8 bytes per posting; ranges of <= 16K documents leave room for two CTAs per SM
+#ifdef TRR_TRIAGE
+static uint32_t* g_triage_out = nullptr;
+#endif
 static int bm25_stage_cap(trr_ctx* c, size_t fixed, uint32_t n_stages, uint32_t* ctas_per_sm, uint32_t* stage_cap) {
   size_t budget = c->smem_optin;
   if (*ctas_per_sm == 2) budget = (228 * 1024) / 2 - 1024 - 1024;  // 228 KB per SM, 1 KB reserved per CTA, 1 KB slack
   if (fixed + (size_t)n_stages * 8 * 256 > budget) { *ctas_per_sm = 1; budget = c->smem_optin; }
   if (fixed + (size_t)n_stages * 8 * 256 > budget) return trr_fail(TRR_ERR_UNSUPPORTED, "BM25 kernel does not fit shared memory");
   size_t cap = (budget - fixed) / ((size_t)8 * n_stages);
-  cap = std::min<size_t>(cap, n_stages == 2 ? 8192 : 4096) & ~size_t(1);
+  cap = std::min<size_t>(cap, 8192) & ~size_t(1);
   *stage_cap = (uint32_t)cap;
   return TRR_OK;
 }
@@ -1213,6 +1216,11 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   uint32_t* flagged2 = flagged1 + B;
   a.dbg = extra(c)->dbg_dev;
   if (const char* e = TRR_KNOB("TRR_BM25_TRIAGE")) a.triage = (uint32_t)atoi(e);
+#ifdef TRR_TRIAGE
+  if (!g_triage_out) { cudaMalloc(&g_triage_out, 256); }
+  cudaMemsetAsync(g_triage_out, 0, 256, st);
+  a.triage_out = g_triage_out;
+#endif
   uint32_t launches = (B > 1 && B <= 4096) ? 2u : 1u;  // plan
   auto merge = [&](const uint64_t* src, uint32_t n_lists, uint32_t stride, uint32_t kk, const uint32_t* n_rows_ptr,
                    const uint32_t* row_map, uint64_t* out_keys, bool outputs) -> int {
@@ -1348,11 +1356,18 @@ extern "C" int trr_bm25_last_stats(trr_bm25* h, trr_stats* out) {
     cudaGetLastError();
   }
 #ifdef TRR_TRIAGE
+  if (h->stats.mode_used == 2 && g_triage_out) {
+    uint32_t pw[64] = {0};
+    cudaMemcpy(pw, g_triage_out, 256, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[trr] K3 fast, CTA 0, per consumer warp (x16 cycles) pass start -> range barrier / in the barrier:");
+    for (int w = 0; w < 16; ++w) fprintf(stderr, " %u/%u", pw[2 * w], pw[2 * w + 1]);
+    fprintf(stderr, "\n");
+  }
   if (h->stats.mode_used == 2 && extra(h->ctx)->dbg_host) {
     const uint32_t* w = extra(h->ctx)->dbg_host;
     fprintf(stderr, "[trr] K3 fast, CTA 0 (x16 cycles): total %u; producer: %u passes, waited %u for a free stage; consumer warp 0: "
-                    "%u waiting for postings, %u accumulate, %u harvest (%u compactions), %u end of item\n", w[8], w[14], w[9], w[10],
-            w[11], w[12], w[15], w[13]);
+                    "%u waiting for postings, %u accumulate, %u harvest (%u compactions; remainder after: first barrier %u, scan %u), %u end of item\n", w[8], w[14], w[9], w[10],
+            w[11], w[12], w[15], w[6], w[7], w[13]);
   }
 #endif
   if (h->stat_pending && h->stat_dev) {
