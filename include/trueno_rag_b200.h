@@ -210,6 +210,47 @@ TRR_API int trr_hybrid_merge_device(trr_ctx* ctx, const void* d_gathered, uint32
                                     float param, uint32_t k, uint32_t* d_out_ord, float* d_out_fused, float* d_out_dense,
                                     float* d_out_sparse, uint32_t* d_out_n);
 
+/* ---- sharded search: one process per GPU, the exchange inside the call ------------------- */
+/* HybridRetriever::retrieve (reference src/retrieve.rs:175-220) over a corpus sharded by document across the GPUs of one
+ * node, one process (rank) per GPU: ONE call = shard-local dense + BM25 top-C -> cross-GPU exchange -> merge of the G
+ * sorted lists per source + fusion + top-k on every rank.  The group owns the communicator (NCCL, resolved with dlopen
+ * at run time) and the exchange buffers; the host language only carries the 128-byte rendezvous id from rank 0 to the
+ * other ranks.  Two exchanges: NCCL all-gather, or peer memory - every rank stores its record straight into the gather
+ * buffers of all peers over NVLink (CUDA IPC mappings set up once) and publishes a flag, so a step has no collective
+ * launch; the peer exchange falls back to NCCL when IPC is not available. */
+typedef struct trr_group trr_group;
+enum trr_exchange { TRR_EXCHANGE_NCCL = 0, TRR_EXCHANGE_PEER = 1 };
+TRR_API int trr_group_unique_id(void* out_id128);                 /* rank 0: ncclGetUniqueId */
+/* collective over the ranks.  max_record_bytes: the largest trr_exchange_bytes(B, C) the peer exchange has to serve
+ * (larger batches use NCCL); ignored for TRR_EXCHANGE_NCCL.  world == 1 needs no id and no NCCL. */
+TRR_API int trr_group_create(trr_ctx* ctx, const void* id128, int rank, int world, int exchange, size_t max_record_bytes,
+                             trr_group** out);
+TRR_API int trr_group_destroy(trr_group* g);
+TRR_API int trr_group_info(trr_group* g, int* out_rank, int* out_world, int* out_exchange /* trr_exchange in use */);
+/* waits for everything enqueued by the *_device call below (both streams) */
+TRR_API int trr_group_sync(trr_group* g);
+/* element-wise sum (op_max = 0) or max (1) over the ranks of n u64 values in HOST memory: the global BM25 statistics
+ * (df, total document length; reference src/index.rs:157-164) every shard's impacts have to be computed from */
+TRR_API int trr_group_allreduce_u64(trr_group* g, uint64_t* inout, size_t n, int op_max);
+/* HOST buffers, blocking; arguments as trr_hybrid_search; every rank passes the same queries and receives the same result */
+TRR_API int trr_hybrid_search_sharded(trr_group* g, trr_dense* dense, trr_bm25* bm25, const float* q, const uint32_t* q_terms,
+                                      const uint32_t* q_off, uint32_t B, uint32_t C, int strategy, float param, uint32_t k,
+                                      int use_dense, int use_sparse, uint32_t* out_ord, float* out_fused, float* out_dense,
+                                      float* out_sparse, uint32_t* out_n);
+/* The same call without the final wait: the host buffers must stay valid (and should be page-locked) until
+ * trr_group_sync; consecutive calls overlap their input / result copies with each other's kernels. */
+TRR_API int trr_hybrid_search_sharded_async(trr_group* g, trr_dense* dense, trr_bm25* bm25, const float* q,
+                                            const uint32_t* q_terms, const uint32_t* q_off, uint32_t B, uint32_t C, int strategy,
+                                            float param, uint32_t k, int use_dense, int use_sparse, uint32_t* out_ord,
+                                            float* out_fused, float* out_dense, float* out_sparse, uint32_t* out_n);
+/* DEVICE buffers; enqueues and returns.  The exchange + merge of a call run on the group's second stream and overlap the
+ * shard-local kernels of the next call; outputs are valid after trr_group_sync (h_q_off: host copy of q_off). */
+TRR_API int trr_hybrid_search_sharded_device(trr_group* g, trr_dense* dense, trr_bm25* bm25, const float* d_q,
+                                             const uint32_t* d_q_terms, const uint32_t* d_q_off, const uint32_t* h_q_off,
+                                             uint32_t B, uint32_t C, int strategy, float param, uint32_t k, int use_dense,
+                                             int use_sparse, uint32_t* d_out_ord, float* d_out_fused, float* d_out_dense,
+                                             float* d_out_sparse, uint32_t* d_out_n);
+
 /* ---- persistence -> device load --------------------------------------------- */
 /* The reference can serialise only BM25Index (bincode + LZ4/ZSTD, src/compressed.rs:71-108); VectorStore is not
  * serialisable (src/compressed.rs:9-10) and the CLI dumps embeddings as JSON (crates/trueno-rag-cli/src/main.rs:135-146).

@@ -64,6 +64,8 @@ def _proto(L):
     L.orc_bm25_from_csr.argtypes = [C.c_uint32, C.c_uint32, u64p, u32p, u32p, u32p, u32p, C.c_float, C.c_float, C.c_float]
     L.orc_bm25_free.restype = None
     L.orc_bm25_free.argtypes = [C.c_void_p]
+    L.orc_bm25_set_stat_docs.restype = None
+    L.orc_bm25_set_stat_docs.argtypes = [C.c_void_p, C.c_uint32]
     L.orc_bm25_n_postings.restype = C.c_uint64
     L.orc_bm25_n_postings.argtypes = [C.c_void_p]
     L.orc_bm25_avgdl.restype = C.c_float
@@ -205,6 +207,10 @@ class BM25:
         self.h = lib().orc_bm25_from_csr(self.n_docs, self.n_terms, _p(t, u64p), _p(pd, u32p), _p(ptf, u32p), _p(dl, u32p),
                                          _p(dfa, u32p), C.c_float(avgdl), C.c_float(k1), C.c_float(b))
         return self
+
+    def set_stat_docs(self, n_docs_global: int):
+        """This index is one shard: N of the idf formula is the global document count (df / avgdl already are global)."""
+        lib().orc_bm25_set_stat_docs(self.h, int(n_docs_global))
 
     def __del__(self):
         try:

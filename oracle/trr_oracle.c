@@ -216,6 +216,8 @@ ORC_API uint32_t orc_dense_search_par(int metric, const void* rows, int is_bf16,
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
   uint32_t n_docs, n_terms;
+  uint32_t n_stat;     /* N of the idf formula: n_docs, or the GLOBAL document count when this index is one shard of a
+                          corpus scored with global statistics */
   uint64_t* term_off;  /* n_terms + 1 */
   uint32_t* post_doc;  /* postings sorted by doc within a term (insertion order, :193-196) */
   uint32_t* post_tf;
@@ -236,7 +238,7 @@ static int orc_u32_cmp(const void* a, const void* b) {
 ORC_API orc_bm25* orc_bm25_build(const uint64_t* doc_off, const uint32_t* tokens, uint32_t n_docs,
                                  uint32_t n_terms, float k1, float b) {
   orc_bm25* ix = (orc_bm25*)calloc(1, sizeof(orc_bm25));
-  ix->n_docs = n_docs; ix->n_terms = n_terms; ix->k1 = k1; ix->b = b;
+  ix->n_docs = n_docs; ix->n_stat = n_docs; ix->n_terms = n_terms; ix->k1 = k1; ix->b = b;
   ix->term_off = (uint64_t*)calloc((size_t)n_terms + 1, sizeof(uint64_t));
   ix->doc_len = (uint32_t*)calloc(n_docs ? n_docs : 1, sizeof(uint32_t));
   ix->df = (uint32_t*)calloc(n_terms ? n_terms : 1, sizeof(uint32_t));
@@ -293,7 +295,7 @@ ORC_API orc_bm25* orc_bm25_build(const uint64_t* doc_off, const uint32_t* tokens
 ORC_API orc_bm25* orc_bm25_from_csr(uint32_t n_docs, uint32_t n_terms, uint64_t* term_off, uint32_t* post_doc,
                                     uint32_t* post_tf, uint32_t* doc_len, uint32_t* df, float avgdl, float k1, float b) {
   orc_bm25* ix = (orc_bm25*)calloc(1, sizeof(orc_bm25));
-  ix->n_docs = n_docs; ix->n_terms = n_terms; ix->k1 = k1; ix->b = b; ix->avgdl = avgdl;
+  ix->n_docs = n_docs; ix->n_stat = n_docs; ix->n_terms = n_terms; ix->k1 = k1; ix->b = b; ix->avgdl = avgdl;
   ix->term_off = term_off; ix->post_doc = post_doc; ix->post_tf = post_tf; ix->doc_len = doc_len; ix->df = df;
   ix->borrowed = 1;
   return ix;
@@ -305,6 +307,8 @@ ORC_API void orc_bm25_free(orc_bm25* ix) {
   free(ix->term_off); free(ix->post_doc); free(ix->post_tf); free(ix->doc_len); free(ix->df); free(ix);
 }
 
+/* a shard of a larger corpus: N of the idf formula (df and avgdl are passed as global values to orc_bm25_from_csr) */
+ORC_API void orc_bm25_set_stat_docs(orc_bm25* ix, uint32_t n_stat) { ix->n_stat = n_stat; }
 ORC_API uint64_t orc_bm25_n_postings(const orc_bm25* ix) { return ix->term_off[ix->n_terms]; }
 ORC_API float orc_bm25_avgdl(const orc_bm25* ix) { return ix->avgdl; }
 ORC_API const uint64_t* orc_bm25_term_off(const orc_bm25* ix) { return ix->term_off; }
@@ -359,7 +363,7 @@ ORC_API uint32_t orc_bm25_search_literal(const orc_bm25* ix, const uint32_t* q_t
       uint32_t term = q_terms[t];
       uint32_t tf = orc_bm25_term_frequency(ix, term, doc);
       uint32_t df = term < ix->n_terms ? ix->df[term] : 0;
-      score = score + orc_bm25_score_term(tf, df, ix->n_docs, ix->doc_len[doc], ix->avgdl, ix->k1, ix->b);
+      score = score + orc_bm25_score_term(tf, df, ix->n_stat, ix->doc_len[doc], ix->avgdl, ix->k1, ix->b);
     }
     if (score > 0.0f) { all[m].score = score; all[m].ord = doc; ++m; }
   }
@@ -383,7 +387,7 @@ ORC_API uint32_t orc_bm25_search(const orc_bm25* ix, const uint32_t* q_terms, ui
     uint32_t df = ix->df[term];
     for (uint64_t p = ix->term_off[term]; p < ix->term_off[term + 1]; ++p) {
       uint32_t doc = ix->post_doc[p];
-      acc[doc] = acc[doc] + orc_bm25_score_term(ix->post_tf[p], df, ix->n_docs, ix->doc_len[doc], ix->avgdl, ix->k1, ix->b);
+      acc[doc] = acc[doc] + orc_bm25_score_term(ix->post_tf[p], df, ix->n_stat, ix->doc_len[doc], ix->avgdl, ix->k1, ix->b);
     }
   }
   orc_hit* top = (orc_hit*)malloc(sizeof(orc_hit) * (k ? k : 1));

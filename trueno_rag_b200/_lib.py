@@ -90,6 +90,18 @@ TRR_PROTOS = {
     "trr_hybrid_local": (C.c_int, [vp, vp, f32p, u32p, u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, vp]),
     "trr_hybrid_merge": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.c_uint32, u32p,
                                    f32p, f32p, f32p, u32p]),
+    "trr_group_unique_id": (C.c_int, [vp]),
+    "trr_group_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, vpp]),
+    "trr_group_destroy": (C.c_int, [vp]),
+    "trr_group_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "trr_group_sync": (C.c_int, [vp]),
+    "trr_group_allreduce_u64": (C.c_int, [vp, u64p, C.c_size_t, C.c_int]),
+    "trr_hybrid_search_sharded": (C.c_int, [vp, vp, vp, f32p, u32p, u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_float,
+                                            C.c_uint32, C.c_int, C.c_int, u32p, f32p, f32p, f32p, u32p]),
+    "trr_hybrid_search_sharded_async": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_float,
+                                                  C.c_uint32, C.c_int, C.c_int, vp, vp, vp, vp, vp]),
+    "trr_hybrid_search_sharded_device": (C.c_int, [vp, vp, vp, vp, vp, vp, u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_float,
+                                                   C.c_uint32, C.c_int, C.c_int, vp, vp, vp, vp, vp]),
 }
 
 idp = C.POINTER(HostId)

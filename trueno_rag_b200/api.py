@@ -353,6 +353,81 @@ def hybrid_merge(ctx: Context, d_gathered: int, G: int, B: int, C_: int, strateg
     return o_ord, o_f, o_d, o_s, o_n
 
 
+# ---------------------------------------------------------------------------------------------------
+# sharded search: one process per GPU, the exchange inside the call
+# ---------------------------------------------------------------------------------------------------
+EXCHANGE_NCCL, EXCHANGE_PEER = 0, 1
+
+
+def group_unique_id() -> bytes:
+    """Rank 0: the 128-byte rendezvous id the other ranks need for Group(...)."""
+    buf = C.create_string_buffer(128)
+    _check(_lib.load().trr_group_unique_id(buf))
+    return buf.raw
+
+
+class Group:
+    """The ranks (one process per GPU) that hold the shards of one corpus.  Owns the communicator and the exchange
+    buffers; `search` is HybridRetriever::retrieve over the whole corpus in ONE call per rank
+    (reference src/retrieve.rs:175-220)."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, unique_id: Optional[bytes] = None, exchange: int = EXCHANGE_NCCL,
+                 max_record_bytes: int = 0):
+        self.L, self.ctx, self.rank, self.world = ctx.L, ctx, rank, world
+        self.h = C.c_void_p()
+        idbuf = C.create_string_buffer(unique_id, 128) if unique_id else None
+        _check(self.L.trr_group_create(ctx.h, idbuf, rank, world, exchange, max_record_bytes, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.L.trr_group_destroy(self.h)
+            self.h = C.c_void_p()
+
+    @property
+    def exchange(self) -> int:
+        e = C.c_int()
+        _check(self.L.trr_group_info(self.h, None, None, C.byref(e)))
+        return e.value
+
+    def sync(self):
+        _check(self.L.trr_group_sync(self.h))
+
+    def allreduce_u64(self, values: np.ndarray, op_max: bool = False) -> np.ndarray:
+        v = np.ascontiguousarray(values, dtype=np.uint64).copy()
+        _check(self.L.trr_group_allreduce_u64(self.h, _p(v, u64p), v.size, int(op_max)))
+        return v
+
+    def search(self, dense, bm25, q, q_terms, q_off, C_: int, strategy: int, param: float, k: int, use_dense=True,
+               use_sparse=True):
+        q = np.ascontiguousarray(q, dtype=np.float32) if q is not None else None
+        q_off = np.ascontiguousarray(q_off, dtype=np.uint32) if q_off is not None else None
+        q_terms = np.ascontiguousarray(q_terms, dtype=np.uint32) if q_terms is not None else None
+        B = q.shape[0] if q is not None else len(q_off) - 1
+        o_ord, o_f, o_d, o_s, o_n = _hybrid_outputs(B, k)
+        qt = q_terms if (q_terms is not None and q_terms.size) else np.zeros(1, np.uint32)
+        _check(self.L.trr_hybrid_search_sharded(self.h, dense.h if dense else None, bm25.h if bm25 else None, _p(q, f32p),
+                                                _p(qt, u32p), _p(q_off, u32p), B, C_, strategy, param, k, int(use_dense),
+                                                int(use_sparse), _p(o_ord, u32p), _p(o_f, f32p), _p(o_d, f32p), _p(o_s, f32p),
+                                                _p(o_n, u32p)))
+        return o_ord, o_f, o_d, o_s, o_n
+
+    def search_async(self, dense, bm25, q_ptr: int, terms_ptr: int, off_ptr: int, B: int, C_: int, strategy: int, param: float,
+                     k: int, out_ptrs, use_dense=True, use_sparse=True):
+        """The host-buffer call without the final wait: raw addresses of (page-locked) host buffers, valid until sync()."""
+        _check(self.L.trr_hybrid_search_sharded_async(self.h, dense.h if dense else None, bm25.h if bm25 else None,
+                                                      C.c_void_p(q_ptr), C.c_void_p(terms_ptr), C.c_void_p(off_ptr), B, C_,
+                                                      strategy, param, k, int(use_dense), int(use_sparse),
+                                                      *[C.c_void_p(p) for p in out_ptrs]))
+
+    def step_device(self, dense, bm25, d_q: int, d_terms: int, d_off: int, h_q_off: np.ndarray, B: int, C_: int,
+                    strategy: int, param: float, k: int, d_out, use_dense=True, use_sparse=True):
+        """Enqueues one sharded step on device buffers (d_out: five device pointers ord, fused, dense, sparse, n)."""
+        _check(self.L.trr_hybrid_search_sharded_device(self.h, dense.h if dense else None, bm25.h if bm25 else None,
+                                                       C.c_void_p(d_q), C.c_void_p(d_terms), C.c_void_p(d_off),
+                                                       _p(h_q_off, u32p), B, C_, strategy, param, k, int(use_dense),
+                                                       int(use_sparse), *[C.c_void_p(p) for p in d_out]))
+
+
 # =====================================================================================================
 # host mirror (reference names)
 # =====================================================================================================

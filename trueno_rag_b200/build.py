@@ -25,7 +25,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
           "--extended-lambda"]
 STRICT = ["-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]
 
-CU_STRICT = ["dense_scan.cu", "bm25.cu", "fusion.cu", "synth.cu"]
+CU_STRICT = ["dense_scan.cu", "bm25.cu", "fusion.cu", "synth.cu", "exchange.cu"]
 CU_FAST = ["dense_gemm.cu", "capi.cu"]
 CPP = ["host/host_mirror.cpp", "host/host_capi.cpp", "host/synth_host.cpp", "host/zstd_codec.cpp"]
 

@@ -1564,7 +1564,8 @@ static ExchangeView exchange_view(void* rec, uint32_t B, uint32_t C) {
 
 static int fuse_locked(trr_ctx* c, const ExchangeView& v, uint64_t shard_stride, uint32_t G, uint32_t B, uint32_t C,
                        int strategy, float param, uint32_t k, bool have_dense, bool have_sparse, uint32_t* d_out_ord,
-                       float* d_out_fused, float* d_out_dense, float* d_out_sparse, uint32_t* d_out_n) {
+                       float* d_out_fused, float* d_out_dense, float* d_out_sparse, uint32_t* d_out_n,
+                       cudaStream_t st_override = nullptr) {
   if (strategy < 0 || strategy > 5) return trr_fail(TRR_ERR_INVALID_ARG, "bad fusion strategy");
   if (C == 0 || C > 1024) return trr_fail(TRR_ERR_UNSUPPORTED, "candidates per source must be in 1..1024");
   if ((uint64_t)G * C > 8192) return trr_fail(TRR_ERR_UNSUPPORTED, "shards x candidates > 8192");
@@ -1577,7 +1578,7 @@ static int fuse_locked(trr_ctx* c, const ExchangeView& v, uint64_t shard_stride,
   a.out_ord = d_out_ord; a.out_fused = d_out_fused; a.out_dense = d_out_dense; a.out_sparse = d_out_sparse;
   a.out_n = d_out_n;
   if (trr_fuse_smem(a) > c->smem_optin) return trr_fail(TRR_ERR_UNSUPPORTED, "fusion lists exceed shared memory");
-  TRR_CUDA(trr_launch_fuse(a, c->stream));
+  TRR_CUDA(trr_launch_fuse(a, st_override ? st_override : c->stream));
   c->launches++;
   return TRR_OK;
 }
@@ -1762,4 +1763,379 @@ extern "C" int trr_hybrid_search(trr_dense* dense, trr_bm25* bm25, const float* 
   TRR_CHECK(hybrid_local_locked(dense, bm25, c, q, q_terms, q_off, B, C, use_dense != 0, use_sparse != 0, extra(c)->hy.p));
   return hybrid_merge_locked(c, extra(c)->hy.p, 1, B, C, strategy, param, k, out_ord, out_fused, out_dense, out_sparse,
                              out_n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sharded search: one process per GPU, the cross-GPU exchange inside the call
+// ------------------------------------------------------------------------------------------------
+// NCCL is resolved at run time (dlopen of libnccl.so.2, the library torch.distributed already maps into a Python host and
+// a Rust host links): the library itself has no link-time dependency on it, and a single-GPU host never needs it.
+#include <dlfcn.h>
+
+namespace {
+struct NcclId { char internal[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+int nccl_load() {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.lib) return TRR_OK;
+  void* lib = nullptr;
+  for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+    lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) return trr_fail(TRR_ERR_UNSUPPORTED, std::string("sharded search needs NCCL (libnccl.so.2 on the library path): ") + dlerror());
+  NcclApi n;
+  n.lib = lib;
+  n.GetUniqueId = reinterpret_cast<decltype(n.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+  n.CommInitRank = reinterpret_cast<decltype(n.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+  n.CommDestroy = reinterpret_cast<decltype(n.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+  n.AllGather = reinterpret_cast<decltype(n.AllGather)>(dlsym(lib, "ncclAllGather"));
+  n.AllReduce = reinterpret_cast<decltype(n.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+  n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+  if (!n.GetUniqueId || !n.CommInitRank || !n.CommDestroy || !n.AllGather || !n.AllReduce || !n.GetErrorString)
+    return trr_fail(TRR_ERR_UNSUPPORTED, "libnccl lacks a required symbol");
+  g_nccl = n;
+  return TRR_OK;
+}
+constexpr int NCCL_U8 = 1, NCCL_U64 = 5, NCCL_SUM = 0, NCCL_MAX = 2;
+}  // namespace
+
+#define TRR_NCCL(expr)                                                                                     \
+  do {                                                                                                     \
+    int _r = (expr);                                                                                       \
+    if (_r != 0) return trr_fail(TRR_ERR_CUDA, std::string(#expr) + ": " + g_nccl.GetErrorString(_r));    \
+  } while (0)
+
+struct trr_group {
+  trr_ctx* ctx = nullptr;
+  int rank = 0, world = 1;
+  void* comm = nullptr;
+  int exchange = TRR_EXCHANGE_NCCL;   // what the calls use
+  cudaStream_t xs = nullptr;          // exchange + merge stream (overlaps the shard-local kernels of the next call)
+  cudaStream_t cs = nullptr;          // host-buffer calls: input copies (overlap the kernels of the previous call)
+  cudaEvent_t ev_local[2] = {nullptr, nullptr}, ev_rec_free[2] = {nullptr, nullptr};
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  size_t io_set = 0;                  // bytes of one staging set of the host-buffer calls
+  uint64_t calls = 0;
+  DevBuf rec[2];                      // this rank's exchange record, by parity of the call
+  DevBuf gath[2];                     // NCCL exchange: gathered records
+  DevBuf stage;                       // all-reduce / handle staging
+  DevBuf io;                          // device copies of the host-buffer entry point
+  // peer exchange
+  size_t max_rec = 0;                 // record slot size of the shared gather buffers
+  uint8_t* shared = nullptr;          // own block: gather[2][world][max_rec] | flags[2][world]
+  size_t flags_off = 0;
+  uint8_t* peer_base[TRR_MAX_GROUP] = {};
+  uint32_t* block_counter = nullptr;
+};
+
+extern "C" int trr_group_unique_id(void* out_id128) {
+  if (!out_id128) return trr_fail(TRR_ERR_INVALID_ARG, "trr_group_unique_id: NULL argument");
+  TRR_CHECK(nccl_load());
+  NcclId id;
+  TRR_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(out_id128, &id, sizeof(id));
+  return TRR_OK;
+}
+
+extern "C" int trr_group_destroy(trr_group* g) {
+  if (!g) return TRR_OK;
+  DeviceGuard dg(g->ctx->device);
+  cudaStreamSynchronize(g->ctx->stream);
+  if (g->xs) cudaStreamSynchronize(g->xs);
+  if (g->cs) cudaStreamSynchronize(g->cs);
+  for (int p = 0; p < g->world && p < (int)TRR_MAX_GROUP; ++p)
+    if (p != g->rank && g->peer_base[p]) cudaIpcCloseMemHandle(g->peer_base[p]);
+  if (g->comm) g_nccl.CommDestroy(g->comm);
+  if (g->shared) cudaFree(g->shared);
+  if (g->block_counter) cudaFree(g->block_counter);
+  for (auto& b : g->rec) b.release();
+  for (auto& b : g->gath) b.release();
+  g->stage.release(); g->io.release();
+  for (auto& e : g->ev_local) if (e) cudaEventDestroy(e);
+  for (auto& e : g->ev_rec_free) if (e) cudaEventDestroy(e);
+  for (auto& e : g->ev_in) if (e) cudaEventDestroy(e);
+  for (auto& e : g->ev_out) if (e) cudaEventDestroy(e);
+  if (g->xs) cudaStreamDestroy(g->xs);
+  if (g->cs) cudaStreamDestroy(g->cs);
+  cudaGetLastError();
+  delete g;
+  return TRR_OK;
+}
+
+extern "C" int trr_group_create(trr_ctx* ctx, const void* id128, int rank, int world, int exchange, size_t max_record_bytes,
+                                trr_group** out) {
+  if (!ctx || !out || (world > 1 && !id128)) return trr_fail(TRR_ERR_INVALID_ARG, "trr_group_create: NULL argument");
+  *out = nullptr;
+  if (world < 1 || world > (int)TRR_MAX_GROUP || rank < 0 || rank >= world)
+    return trr_fail(TRR_ERR_INVALID_ARG, "trr_group_create: rank / world out of range (at most 16 ranks)");
+  if (exchange != TRR_EXCHANGE_NCCL && exchange != TRR_EXCHANGE_PEER) return trr_fail(TRR_ERR_INVALID_ARG, "bad exchange kind");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard dg(ctx->device);
+  trr_group* g = new trr_group();
+  g->ctx = ctx; g->rank = rank; g->world = world;
+  auto fail = [&](int s) { trr_group_destroy(g); return s; };
+  if (cudaStreamCreateWithFlags(&g->xs, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&g->cs, cudaStreamNonBlocking) != cudaSuccess)
+    return fail(trr_fail(TRR_ERR_CUDA, "stream creation failed"));
+  for (int p = 0; p < 2; ++p) {
+    cudaEventCreateWithFlags(&g->ev_local[p], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&g->ev_rec_free[p], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&g->ev_in[p], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&g->ev_out[p], cudaEventDisableTiming);
+  }
+  if (world > 1) {
+    int s = nccl_load();
+    if (s != TRR_OK) return fail(s);
+    NcclId id;
+    memcpy(&id, id128, sizeof(id));
+    int r = g_nccl.CommInitRank(&g->comm, world, id, rank);
+    if (r != 0) return fail(trr_fail(TRR_ERR_CUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)));
+  }
+  g->exchange = TRR_EXCHANGE_NCCL;
+  if (exchange == TRR_EXCHANGE_PEER && world > 1 && max_record_bytes) {
+    // one IPC-shared block per rank; the handles travel through an NCCL all-gather; any failure falls back to NCCL exchange
+    g->max_rec = (max_record_bytes + 255) & ~size_t(255);
+    g->flags_off = (size_t)2 * world * g->max_rec;
+    const size_t total = g->flags_off + 4096;
+    bool ok = cudaMalloc(&g->shared, total) == cudaSuccess && cudaMemset(g->shared, 0, total) == cudaSuccess &&
+              cudaMalloc(&g->block_counter, 256) == cudaSuccess && cudaMemset(g->block_counter, 0, 256) == cudaSuccess;
+    cudaIpcMemHandle_t mine;
+    ok = ok && cudaIpcGetMemHandle(&mine, g->shared) == cudaSuccess;
+    // every rank takes part in the all-gather (a rank whose allocation failed sends zeros and the group agrees on NCCL)
+    uint64_t okflag = ok ? 1 : 0;
+    if (g->stage.reserve((size_t)(world + 1) * 128) != TRR_OK) return fail(TRR_ERR_OOM);
+    uint8_t sendbuf[128] = {0};
+    if (ok) memcpy(sendbuf, &mine, sizeof(mine));
+    memcpy(sendbuf + 64, &okflag, 8);
+    uint8_t* d_send = static_cast<uint8_t*>(g->stage.p);
+    uint8_t* d_recv = d_send + 128;
+    cudaMemcpy(d_send, sendbuf, 128, cudaMemcpyHostToDevice);
+    int r = g_nccl.AllGather(d_send, d_recv, 128, NCCL_U8, g->comm, g->xs);
+    if (r != 0 || cudaStreamSynchronize(g->xs) != cudaSuccess) return fail(trr_fail(TRR_ERR_CUDA, "handle all-gather failed"));
+    std::vector<uint8_t> all((size_t)world * 128);
+    cudaMemcpy(all.data(), d_recv, all.size(), cudaMemcpyDeviceToHost);
+    bool all_ok = true;
+    for (int p = 0; p < world; ++p) { uint64_t f; memcpy(&f, &all[(size_t)p * 128 + 64], 8); all_ok = all_ok && f == 1; }
+    if (all_ok) {
+      for (int p = 0; p < world && all_ok; ++p) {
+        if (p == rank) { g->peer_base[p] = g->shared; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, &all[(size_t)p * 128], sizeof(h));
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); all_ok = false; }
+        g->peer_base[p] = static_cast<uint8_t*>(ptr);
+      }
+    }
+    // second agreement round: a rank that could not open a peer's block must take everyone back to NCCL
+    uint64_t v = all_ok ? 0 : 1;
+    cudaMemcpy(d_send, &v, 8, cudaMemcpyHostToDevice);
+    r = g_nccl.AllReduce(d_send, d_send, 1, NCCL_U64, NCCL_SUM, g->comm, g->xs);
+    if (r != 0 || cudaStreamSynchronize(g->xs) != cudaSuccess) return fail(trr_fail(TRR_ERR_CUDA, "agreement all-reduce failed"));
+    cudaMemcpy(&v, d_send, 8, cudaMemcpyDeviceToHost);
+    if (v == 0) g->exchange = TRR_EXCHANGE_PEER;
+    cudaGetLastError();
+  }
+  *out = g;
+  return TRR_OK;
+}
+
+extern "C" int trr_group_info(trr_group* g, int* out_rank, int* out_world, int* out_exchange) {
+  if (!g) return trr_fail(TRR_ERR_INVALID_ARG, "group is NULL");
+  if (out_rank) *out_rank = g->rank;
+  if (out_world) *out_world = g->world;
+  if (out_exchange) *out_exchange = g->exchange;
+  return TRR_OK;
+}
+
+extern "C" int trr_group_sync(trr_group* g) {
+  if (!g) return trr_fail(TRR_ERR_INVALID_ARG, "group is NULL");
+  DeviceGuard dg(g->ctx->device);
+  TRR_CUDA(cudaStreamSynchronize(g->ctx->stream));
+  TRR_CUDA(cudaStreamSynchronize(g->xs));
+  TRR_CUDA(cudaStreamSynchronize(g->cs));
+  return TRR_OK;
+}
+
+// element-wise sum / max over the ranks of n u64 values held in HOST memory (global BM25 statistics: df, total length;
+// max-over-ranks timings).  Blocking.
+extern "C" int trr_group_allreduce_u64(trr_group* g, uint64_t* inout, size_t n, int op_max) {
+  if (!g || (n && !inout)) return trr_fail(TRR_ERR_INVALID_ARG, "trr_group_allreduce_u64: NULL argument");
+  if (g->world == 1 || n == 0) return TRR_OK;
+  std::lock_guard<std::mutex> lk(g->ctx->mu);
+  DeviceGuard dg(g->ctx->device);
+  TRR_CHECK(g->stage.reserve(n * 8));
+  TRR_CUDA(cudaMemcpyAsync(g->stage.p, inout, n * 8, cudaMemcpyHostToDevice, g->xs));
+  TRR_NCCL(g_nccl.AllReduce(g->stage.p, g->stage.p, n, NCCL_U64, op_max ? NCCL_MAX : NCCL_SUM, g->comm, g->xs));
+  TRR_CUDA(cudaMemcpyAsync(inout, g->stage.p, n * 8, cudaMemcpyDeviceToHost, g->xs));
+  TRR_CUDA(cudaStreamSynchronize(g->xs));
+  return TRR_OK;
+}
+
+// One sharded hybrid step with DEVICE buffers.  The shard-local kernels are enqueued on the context stream; the exchange
+// and the merge + fusion kernel on the group's second stream, behind an event, so that they overlap the shard-local
+// kernels of the NEXT call (records and gather buffers alternate by the parity of the call).  Nothing waits on the host.
+static int group_step_locked(trr_group* g, trr_dense* dense, trr_bm25* bm25, const float* d_q, const uint32_t* d_q_terms,
+                             const uint32_t* d_q_off, const uint32_t* h_q_off, uint32_t B, uint32_t C, int strategy,
+                             float param, uint32_t k, bool use_dense, bool use_sparse, uint32_t* d_out_ord, float* d_out_fused,
+                             float* d_out_dense, float* d_out_sparse, uint32_t* d_out_n) {
+  trr_ctx* c = g->ctx;
+  cudaStream_t st = c->stream;
+  const uint32_t G = (uint32_t)g->world;
+  const size_t rec_bytes = trr_exchange_bytes(B, C);
+  const int p = (int)(g->calls & 1);
+  const uint64_t seq = ++g->calls;
+  TRR_CHECK(g->rec[p].reserve(rec_bytes));
+  const bool peer = g->exchange == TRR_EXCHANGE_PEER && rec_bytes <= g->max_rec && (rec_bytes % 16) == 0;
+  if (!peer && G > 1) TRR_CHECK(g->gath[p].reserve((size_t)G * rec_bytes));
+  // the exchange of call seq-2 has consumed rec[p]
+  TRR_CUDA(cudaStreamWaitEvent(st, g->ev_rec_free[p], 0));
+  ExchangeView v = exchange_view(g->rec[p].p, B, C);
+  if (use_dense) TRR_CHECK(dense_search_locked(dense, d_q, B, C, v.ord[0], v.score[0], v.n[0], false));
+  else TRR_CUDA(cudaMemsetAsync(v.n[0], 0, (size_t)B * 4, st));
+  if (use_sparse) TRR_CHECK(bm25_search_locked(bm25, d_q_terms, d_q_off, h_q_off, B, C, v.ord[1], v.score[1], v.n[1], 0));
+  else TRR_CUDA(cudaMemsetAsync(v.n[1], 0, (size_t)B * 4, st));
+  TRR_CUDA(cudaEventRecord(g->ev_local[p], st));
+  TRR_CUDA(cudaStreamWaitEvent(g->xs, g->ev_local[p], 0));
+  const void* gathered = g->rec[p].p;
+  uint64_t stride_words = rec_bytes / 4;
+  if (G > 1) {
+    if (peer) {
+      ExchangeScatterArgs a{};
+      a.record = static_cast<const uint8_t*>(g->rec[p].p); a.record_bytes = rec_bytes;
+      for (uint32_t r = 0; r < G; ++r) {
+        a.peer_gath[r] = g->peer_base[r];
+        a.peer_flags[r] = reinterpret_cast<uint32_t*>(g->peer_base[r] + g->flags_off);
+      }
+      a.slot_off = ((size_t)p * G + (size_t)g->rank) * g->max_rec;
+      a.flag_index = (uint32_t)p * G + (uint32_t)g->rank;
+      a.seq = (uint32_t)seq; a.block_counter = g->block_counter;
+      TRR_CUDA(trr_launch_exchange_scatter(a, G, g->xs));
+      TRR_CUDA(cudaEventRecord(g->ev_rec_free[p], g->xs));
+      TRR_CUDA(trr_launch_exchange_wait(reinterpret_cast<const uint32_t*>(g->shared + g->flags_off) + (size_t)p * G, G, (uint32_t)seq,
+                                        extra(c)->dbg_dev, g->xs));
+      c->launches += 2;
+      gathered = g->shared + (size_t)p * G * g->max_rec;
+      stride_words = g->max_rec / 4;
+    } else {
+      TRR_NCCL(g_nccl.AllGather(g->rec[p].p, g->gath[p].p, rec_bytes, NCCL_U8, g->comm, g->xs));
+      TRR_CUDA(cudaEventRecord(g->ev_rec_free[p], g->xs));
+      gathered = g->gath[p].p;
+    }
+  }
+  ExchangeView gv = exchange_view(const_cast<void*>(gathered), B, C);
+  TRR_CHECK(fuse_locked(c, gv, stride_words, G, B, C, strategy, param, k, true, true, d_out_ord, d_out_fused, d_out_dense,
+                        d_out_sparse, d_out_n, g->xs));
+  if (G == 1) TRR_CUDA(cudaEventRecord(g->ev_rec_free[p], g->xs));  // (the merge reads the record itself)
+  return TRR_OK;
+}
+
+extern "C" int trr_hybrid_search_sharded_device(trr_group* g, trr_dense* dense, trr_bm25* bm25, const float* d_q,
+                                                const uint32_t* d_q_terms, const uint32_t* d_q_off, const uint32_t* h_q_off,
+                                                uint32_t B, uint32_t C, int strategy, float param, uint32_t k, int use_dense,
+                                                int use_sparse, uint32_t* d_out_ord, float* d_out_fused, float* d_out_dense,
+                                                float* d_out_sparse, uint32_t* d_out_n) {
+  if (!g) return trr_fail(TRR_ERR_INVALID_ARG, "group is NULL");
+  trr_ctx* c = nullptr;
+  TRR_CHECK(hybrid_check(dense, bm25, d_q, h_q_off, B, C, use_dense, use_sparse, &c));
+  if (c != g->ctx) return trr_fail(TRR_ERR_INVALID_ARG, "sharded search: the indexes live on another context than the group");
+  if (B && (!d_out_ord || !d_out_fused || !d_out_n || (use_sparse && !d_q_off))) return trr_fail(TRR_ERR_INVALID_ARG, "sharded search: NULL device buffer");
+  if (B == 0) return TRR_OK;
+  if (k == 0) return trr_fail(TRR_ERR_INVALID_ARG, "hybrid: k must be >= 1");
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard dg(c->device);
+  return group_step_locked(g, dense, bm25, d_q, d_q_terms, d_q_off, h_q_off, B, C, strategy, param, k, use_dense != 0,
+                           use_sparse != 0, d_out_ord, d_out_fused, d_out_dense, d_out_sparse, d_out_n);
+}
+
+// HybridRetriever::retrieve over a corpus sharded by document across the ranks of the group: ONE call = shard-local
+// dense + BM25 top-C -> exchange -> merge, fusion, top-k; every rank receives the full result.  HOST buffers.
+// The inputs of a call travel on a copy stream into one of two device staging sets (by the parity of the call) and the
+// results leave behind the merge kernel on the exchange stream, so consecutive asynchronous calls overlap their copies
+// with each other's kernels; the blocking form is the asynchronous one followed by a wait.
+static int group_search_host(trr_group* g, trr_dense* dense, trr_bm25* bm25, const float* q, const uint32_t* q_terms,
+                             const uint32_t* q_off, uint32_t B, uint32_t C, int strategy, float param, uint32_t k,
+                             int use_dense, int use_sparse, uint32_t* out_ord, float* out_fused, float* out_dense,
+                             float* out_sparse, uint32_t* out_n, bool blocking) {
+  if (!g) return trr_fail(TRR_ERR_INVALID_ARG, "group is NULL");
+  trr_ctx* c = nullptr;
+  TRR_CHECK(hybrid_check(dense, bm25, q, q_off, B, C, use_dense, use_sparse, &c));
+  if (c != g->ctx) return trr_fail(TRR_ERR_INVALID_ARG, "sharded search: the indexes live on another context than the group");
+  if (B && (!out_ord || !out_fused || !out_n)) return trr_fail(TRR_ERR_INVALID_ARG, "hybrid: NULL output");
+  if (B == 0) return TRR_OK;
+  if (k == 0) return trr_fail(TRR_ERR_INVALID_ARG, "hybrid: k must be >= 1");
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard dg(c->device);
+  cudaStream_t st = c->stream;
+  const uint32_t dim = dense ? dense->dim : 0;
+  const size_t nt = (use_sparse && q_off) ? q_off[B] : 0;
+  const size_t bk = (size_t)B * k;
+  const int p = (int)(g->calls & 1);  // parity of the call that group_step_locked is about to run
+  const size_t set_bytes = WsCarver::need({(size_t)B * dim * 4, std::max<size_t>(nt, 1) * 4, (size_t)(B + 1) * 4, bk * 4, bk * 4,
+                                           bk * 4, bk * 4, (size_t)B * 4});
+  if (g->io.bytes < 2 * set_bytes) {
+    // (re)allocation: nothing may still be using the old buffers
+    TRR_CUDA(cudaStreamSynchronize(st)); TRR_CUDA(cudaStreamSynchronize(g->xs)); TRR_CUDA(cudaStreamSynchronize(g->cs));
+    TRR_CHECK(g->io.reserve(2 * set_bytes));
+    g->io_set = set_bytes;
+  }
+  WsCarver io(static_cast<char*>(g->io.p) + (size_t)p * g->io_set);
+  float* d_q = io.take<float>((size_t)B * dim);
+  uint32_t* d_terms = io.take<uint32_t>(std::max<size_t>(nt, 1));
+  uint32_t* d_off = io.take<uint32_t>(B + 1);
+  uint32_t* o_ord = io.take<uint32_t>(bk);
+  float* o_f = io.take<float>(bk);
+  float* o_d = io.take<float>(bk);
+  float* o_s = io.take<float>(bk);
+  uint32_t* o_n = io.take<uint32_t>(B);
+  // the call two steps back used this staging set: its kernels have read the inputs, its results have left
+  cudaStream_t cs = g->cs;
+  TRR_CUDA(cudaStreamWaitEvent(cs, g->ev_local[p], 0));
+  TRR_CUDA(cudaStreamWaitEvent(cs, g->ev_out[p], 0));
+  if (use_dense) TRR_CUDA(cudaMemcpyAsync(d_q, q, (size_t)B * dim * 4, cudaMemcpyHostToDevice, cs));
+  if (use_sparse) {
+    if (nt) TRR_CUDA(cudaMemcpyAsync(d_terms, q_terms, nt * 4, cudaMemcpyHostToDevice, cs));
+    TRR_CUDA(cudaMemcpyAsync(d_off, q_off, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, cs));
+  }
+  TRR_CUDA(cudaEventRecord(g->ev_in[p], cs));
+  TRR_CUDA(cudaStreamWaitEvent(st, g->ev_in[p], 0));
+  TRR_CHECK(group_step_locked(g, dense, bm25, d_q, d_terms, d_off, q_off, B, C, strategy, param, k, use_dense != 0,
+                              use_sparse != 0, o_ord, o_f, o_d, o_s, o_n));
+  cudaStream_t xs = g->xs;
+  TRR_CUDA(cudaMemcpyAsync(out_ord, o_ord, bk * 4, cudaMemcpyDeviceToHost, xs));
+  TRR_CUDA(cudaMemcpyAsync(out_fused, o_f, bk * 4, cudaMemcpyDeviceToHost, xs));
+  if (out_dense) TRR_CUDA(cudaMemcpyAsync(out_dense, o_d, bk * 4, cudaMemcpyDeviceToHost, xs));
+  if (out_sparse) TRR_CUDA(cudaMemcpyAsync(out_sparse, o_s, bk * 4, cudaMemcpyDeviceToHost, xs));
+  TRR_CUDA(cudaMemcpyAsync(out_n, o_n, (size_t)B * 4, cudaMemcpyDeviceToHost, xs));
+  TRR_CUDA(cudaEventRecord(g->ev_out[p], xs));
+  if (blocking) TRR_CUDA(cudaStreamSynchronize(xs));
+  return TRR_OK;
+}
+
+extern "C" int trr_hybrid_search_sharded(trr_group* g, trr_dense* dense, trr_bm25* bm25, const float* q,
+                                         const uint32_t* q_terms, const uint32_t* q_off, uint32_t B, uint32_t C, int strategy,
+                                         float param, uint32_t k, int use_dense, int use_sparse, uint32_t* out_ord,
+                                         float* out_fused, float* out_dense, float* out_sparse, uint32_t* out_n) {
+  return group_search_host(g, dense, bm25, q, q_terms, q_off, B, C, strategy, param, k, use_dense, use_sparse, out_ord,
+                           out_fused, out_dense, out_sparse, out_n, true);
+}
+
+extern "C" int trr_hybrid_search_sharded_async(trr_group* g, trr_dense* dense, trr_bm25* bm25, const float* q,
+                                               const uint32_t* q_terms, const uint32_t* q_off, uint32_t B, uint32_t C,
+                                               int strategy, float param, uint32_t k, int use_dense, int use_sparse,
+                                               uint32_t* out_ord, float* out_fused, float* out_dense, float* out_sparse,
+                                               uint32_t* out_n) {
+  return group_search_host(g, dense, bm25, q, q_terms, q_off, B, C, strategy, param, k, use_dense, use_sparse, out_ord,
+                           out_fused, out_dense, out_sparse, out_n, false);
 }

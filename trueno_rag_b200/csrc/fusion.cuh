@@ -25,3 +25,18 @@ struct FuseArgs {
 
 size_t trr_fuse_smem(const FuseArgs& a);
 cudaError_t trr_launch_fuse(const FuseArgs& a, cudaStream_t st);
+
+// peer-memory exchange (exchange.cu)
+constexpr uint32_t TRR_MAX_GROUP = 16;
+struct ExchangeScatterArgs {
+  const uint8_t* record;                 // this rank's exchange record (record_bytes, multiple of 16)
+  uint64_t record_bytes;
+  uint8_t* peer_gath[TRR_MAX_GROUP];     // base of every rank's gather buffer (own buffer for g == rank)
+  uint32_t* peer_flags[TRR_MAX_GROUP];   // base of every rank's flag array
+  uint64_t slot_off;                     // byte offset of (parity, this rank's slot) inside a gather buffer
+  uint32_t flag_index;                   // parity * world + rank
+  uint32_t seq;                          // sequence number of the call (> 0)
+  uint32_t* block_counter;               // [world] zero-initialised device scratch
+};
+cudaError_t trr_launch_exchange_scatter(const ExchangeScatterArgs& a, uint32_t world, cudaStream_t st);
+cudaError_t trr_launch_exchange_wait(const uint32_t* flags, uint32_t world, uint32_t seq, uint32_t* dbg, cudaStream_t st);
