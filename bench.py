@@ -428,7 +428,7 @@ def run_ours(a):
                                  "unit": "GB/s", "frac": bm_gbs / peak_hbm,
                                  "algorithmic": f"8 B x {postings_per_batch_local} postings per batch",
                                  "fallbacks_32bit": int(sb_t.n_guard_fallbacks), "fallbacks_exact": int(sb_t.n_exact_fallbacks)},
-                        "dense_guard_fallbacks": int(sd_t.n_guard_fallbacks)},
+                        "dense_guard_fallbacks": int(sd_t.n_guard_fallbacks), "dense_rescore_width": int(sd_t.rescore_width)},
             "clocks": clocks, "verify": verify,
         }
         if extra_cfgs is not None:

@@ -74,7 +74,7 @@ typedef struct {
   float max_fast_exact_gap;  /* GEMM path: max |fast score - exact score| over rescored candidates */
   float eps_bound;           /* GEMM path: the a-priori bound used by the candidate proof */
   uint32_t n_exact_fallbacks;/* BM25: queries whose 32-bit proof failed too and were re-run by the exact kernel */
-  uint32_t reserved;
+  uint32_t rescore_width;    /* GEMM path: candidates re-scored exactly per query in the first pass (adapts to the data) */
 } trr_stats;
 
 TRR_API const char* trr_last_error(void);

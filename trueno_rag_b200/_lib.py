@@ -23,7 +23,7 @@ class Stats(C.Structure):
     _fields_ = [("mode_used", C.c_uint32), ("n_queries", C.c_uint32), ("n_guard_fallbacks", C.c_uint32),
                 ("n_kernel_launches", C.c_uint32), ("ms_total", C.c_float), ("ms_main_kernel", C.c_float),
                 ("max_fast_exact_gap", C.c_float), ("eps_bound", C.c_float), ("n_exact_fallbacks", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("rescore_width", C.c_uint32)]
 
 
 class HostId(C.Structure):

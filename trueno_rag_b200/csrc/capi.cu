@@ -195,6 +195,14 @@ struct trr_dense {
   const void* map_scan_base = nullptr;
   uint32_t* stat_dev = nullptr;         // [2] device copy of {n_flagged, max_gap bits} of the last GEMM search
   bool stat_pending = false;
+  // Width of the first exact re-scoring pass, adapted to the data: the candidate proof needs (width - k) ranks of score
+  // spacing to exceed the a-priori error bound, and the spacing depends on the corpus (dimension, size, distribution).
+  // After every GEMM search the number of queries that failed the first proof lands in page-locked host memory
+  // (asynchronous copy); the next search doubles the width while more than 1/64 of the batch failed.  Results are exact at
+  // every width - only the time moves.
+  uint32_t cp_level = 0;
+  uint32_t* feedback_host = nullptr;    // [2] {queries of the last search, queries that failed the first proof}
+  uint32_t feedback_B = 0;
   int mode = TRR_DENSE_AUTO;
   trr_stats stats{};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // [0,1] whole call, [2,3] dominant kernel
@@ -251,6 +259,7 @@ extern "C" int trr_dense_destroy(trr_dense* h) {
   if (h->norms) cudaFree(h->norms);
   if (h->dead) cudaFree(h->dead);
   if (h->stat_dev) cudaFree(h->stat_dev);
+  if (h->feedback_host) cudaFreeHost(h->feedback_host);
   h->shadow.release(); h->scale_bias.release(); h->max_norm.release(); h->qbuf.release();
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   delete h;
@@ -577,13 +586,23 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
       return trr_fail(TRR_ERR_UNSUPPORTED, "GEMM mode supports cosine/dot metrics with k <= 100");
     use_gemm = false;
   }
-  if (use_gemm && (k > 50 || TRR_KNOB("TRR_GEMM_CP128"))) {
-    // re-scoring width 128 needs at least four half-slice lists of 32 entries
+  // feedback of the previous GEMM search on this store (see trr_dense::cp_level)
+  if (h->feedback_host && h->feedback_B) {
+    const uint32_t failed = *reinterpret_cast<volatile uint32_t*>(h->feedback_host + 1);
+    if (failed != 0xFFFFFFFFu) {
+      if (failed * 64u > h->feedback_B && h->cp_level < 4) ++h->cp_level;  // (a failed query costs a wide pass; one exact scan costs a pass over the slab)
+      h->feedback_host[1] = 0xFFFFFFFFu;  // consumed
+    }
+  }
+  uint32_t CP = (k <= 50 ? TRR_GEMM_CP : 2 * TRR_GEMM_CP) << h->cp_level;
+  if (use_gemm) {
+    // the width cannot exceed what the half-slice lists of the tensor-core pass hold (2 * slices * 32 entries)
     const uint32_t n_qb = (B + TRR_GEMM_TILE_M - 1) / TRR_GEMM_TILE_M;
     const uint64_t tiles = (h->n + TRR_GEMM_TILE_N - 1) / TRR_GEMM_TILE_N;
     const uint64_t n_sl = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->sm_count / std::max(n_qb, 1u), tiles));
-    if (2 * n_sl * TRR_GEMM_CPS_MAX < 2 * TRR_GEMM_CP) {
-      if (h->mode == TRR_DENSE_GEMM) return trr_fail(TRR_ERR_UNSUPPORTED, "GEMM mode: batch too large for k > 50");
+    while (CP > TRR_GEMM_CP && 2 * n_sl * TRR_GEMM_CPS_MAX < CP) CP >>= 1;
+    if (2 * n_sl * TRR_GEMM_CPS_MAX < CP || CP < k) {
+      if (h->mode == TRR_DENSE_GEMM) return trr_fail(TRR_ERR_UNSUPPORTED, "GEMM mode: batch too large for this k");
       use_gemm = false;
     }
   }
@@ -627,7 +646,6 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     // exact re-scoring width per query: k plus a margin of ranks for the candidate proof
     // (TRR_GEMM_CP128=1 forces the wide width for every k: to be measured - with f32 queries the quantisation term of the
     // proof is worth about 10 ranks of score spacing, so k = 50 of 64 often falls through to the second pass)
-    const uint32_t CP = (k <= 50 && !TRR_KNOB("TRR_GEMM_CP128")) ? TRR_GEMM_CP : 2 * TRR_GEMM_CP;
     // list length per (query, slice): the global top-CP by fast score is spread over the slices (about CP / n_slices
     // per slice), so short lists suffice when there are many slices (Poisson tail < 1e-6 for the choices below); the
     // candidate proof (rescore_select_kernel) catches the data sets where they do not
@@ -636,6 +654,9 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     const uint32_t vslices = 2 * n_slices;
     const uint32_t cps_max = TRR_GEMM_CPS_MAX;
     const float per_slice = (float)CP / (float)vslices;
+    // (measured at cfg5, width 256 = 7 per half slice: lists of 16 make the tensor-core pass 2 ms faster than lists of 32, but
+    // a few queries per batch then fail even the wide proof - a full list bounds what it dropped by its own minimum - and
+    // one exact scan of the 20 GB shard costs 5 ms)
     uint32_t cps = per_slice <= 1.0f ? 8u : (per_slice <= 4.0f ? 16u : 32u);
     if (const char* e = TRR_KNOB("TRR_GEMM_CPS")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) cps = (uint32_t)v; }
     if ((uint64_t)vslices * cps < CP) cps = cps_max;  // (vslices * cps_max >= CP is checked before taking this path)
@@ -697,9 +718,9 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     // candidate rows are staged in shared memory in chunks (28 KB per CTA keeps six CTAs per SM)
     uint32_t stage_budget = 28u << 10;
     if (const char* e = TRR_KNOB("TRR_RESCORE_STAGE_KB")) stage_budget = (uint32_t)std::max(1, atoi(e)) << 10;
-    ra.stage_chunk = (h->row_bytes % 16 == 0 && !TRR_KNOB("TRR_RESCORE_NO_STAGE"))
-                         ? std::min<uint32_t>(h->row_bytes, (uint32_t)((stage_budget / CP - 16) & ~15u)) : 0u;
-    if (ra.stage_chunk < 64) ra.stage_chunk = 0;
+    const int per_cand = (int)(stage_budget / CP) - 16;  // bytes of a candidate row that fit the staging budget
+    ra.stage_chunk = (h->row_bytes % 16 == 0 && per_cand >= 64 && !TRR_KNOB("TRR_RESCORE_NO_STAGE"))
+                         ? std::min<uint32_t>(h->row_bytes, (uint32_t)per_cand & ~15u) : 0u;
     // |fast - exact| <= eps_rel * |q||d|: products of bf16 values are exact in f32; the tensor-core sum and the
     // reference's sequential sum each carry at most D roundings of relative size 2^-23 on partial sums bounded by
     // sum|q_i d_i| <= |q||d|; the scale multiply, the division and the norm product add a few more ulps.
@@ -711,6 +732,12 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     ra.flags = flags; ra.flagged = flagged; ra.n_flagged = counters; ra.max_gap = reinterpret_cast<float*>(counters + 1);
     TRR_CUDA(trr_launch_rescore(ra, h->dtype == TRR_DTYPE_BF16, st));
     c->launches++;
+    if (!h->feedback_host) {
+      TRR_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->feedback_host), 64));
+      h->feedback_host[0] = 0; h->feedback_host[1] = 0xFFFFFFFFu;
+    }
+    h->feedback_B = B;
+    TRR_CUDA(cudaMemcpyAsync(h->feedback_host + 1, counters, 4, cudaMemcpyDeviceToHost, st));
     // Second level: a query whose proof failed (rank spacing tighter than the a-priori error bound: large dimensions, large
     // k) is re-scored over EVERYTHING the slices kept (n_slices x cps candidates instead of the best CP), so that the only
     // documents left out are the ones the slices dropped, which sit far further down the ranking.  Only the queries that
@@ -730,6 +757,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
       counters_final = counters + 4;
     }
     h->stats.eps_bound = eps_rel;
+    h->stats.rescore_width = CP;
     if (dev_fallback) {
       if (!h->stat_dev) TRR_CUDA(cudaMalloc(&h->stat_dev, 64));
       TRR_CUDA(cudaMemcpyAsync(h->stat_dev, counters_final, 4, cudaMemcpyDeviceToDevice, st));
