@@ -196,11 +196,12 @@ def test_batches_above_4096_queries_are_served_in_pieces(api, ctx):
     check(api, ctx, b, Q, 7, 0, 1, mode=0)
 
 
-def test_gemm_two_cta_variant_matches_oracle(api, ctx, monkeypatch):
-    """The cta_group::2 kernel (two SMs of a TPC share one 256 x 256 tile; opt-in, slower than the 1-CTA kernel on this
-    shape) must return the same bit-exact results."""
-    monkeypatch.setenv("TRR_GEMM_PAIR", "1")
-    n, d, B = 40000, 768, 300
+@pytest.mark.parametrize("B", [300, 256, 512])
+def test_gemm_one_and_two_cta_kernels_match_oracle(api, ctx, B):
+    """Both tensor-core kernels must return the same bit-exact results: an even number of 128-query blocks (B = 256, 512)
+    takes the cta_group::2 kernel (two SMs of a TPC share one 256 x 256 tile, the default at bench size), an odd number
+    below nine (B = 300: three blocks) the cta_group::1 kernel."""
+    n, d = 40000, 768
     f, b = O.synth_corpus(SEED + 4, 0, n, d, bf16=True, dups=True)
     Q = bf16_round(O.synth_queries(SEED + 4, 0, B, d, n, corpus_bf16=True, dups=True))
     st = check(api, ctx, b, Q, 50, 0, 1, mode=2, expect_mode=2)

@@ -148,3 +148,66 @@ def test_cfg5_shape_linear_top100_eight_shards(api, ctx):
     assert_hybrid(got, oracle_hybrid(c, O.LINEAR, np.float32(0.7), C_, k))
     for h in handles:
         h.close()
+
+
+def test_concurrent_searches_on_one_handle(api, ctx):
+    """The header promises that search entry points are re-entrant on one handle (the reference's query methods take &self
+    and SparseIndex is Send + Sync, src/index.rs:8): four host threads hammer trr_hybrid_search / trr_dense_search /
+    trr_bm25_search on the same handles and every result must equal the oracle's."""
+    import threading
+    n, d, n_terms, B, Cn, K = 30000, 128, 4000, 24, 20, 7
+    f, bf = O.synth_corpus(SEED + 21, 0, n, d, bf16=True)
+    rows = (bf.astype(np.uint32) << 16).view(np.float32)
+    cdf = O.zipf_cdf(n_terms)
+    doc_off, toks = O.synth_doc_tokens(SEED + 21, cdf, 0, n)
+    oix = O.BM25(n_terms=n_terms, doc_off=doc_off, tokens=toks)
+    term_off, post_doc, post_tf, doc_len, df = oix.csr()
+    dense = api.DenseIndex(ctx, d, api.COSINE, api.BF16)
+    dense.append(bf)
+    bm = api.Bm25Device(ctx, n, term_off, post_doc, post_tf, doc_len, oix.avgdl, api.bm25_idf_host(n, df))
+    errors = []
+
+    def worker(tid):
+        try:
+            for it in range(6):
+                q = O.synth_queries(SEED + 100 * tid + it, 0, B, d, n, corpus_bf16=True)
+                q_off, q_terms = O.synth_query_terms(SEED + 100 * tid + it, cdf, 0, B)
+                d_exp = O.dense_search_batch(rows, q, Cn)
+                s_exp = oix.search_batch(q_terms, q_off, Cn)
+                o_ord, o_f, o_d, o_s, o_n = api.hybrid_search(dense, bm, q, q_terms, q_off, Cn, api.RRF, 60.0, K)
+                for b in range(B):
+                    i, fsc, dd, ss = O.hybrid_assemble(O.RRF, 60.0, (d_exp[0][b, :d_exp[2][b]], d_exp[1][b, :d_exp[2][b]]),
+                                                       (s_exp[0][b, :s_exp[2][b]], s_exp[1][b, :s_exp[2][b]]), K)
+                    m = int(o_n[b])
+                    assert m == len(i) and np.array_equal(o_ord[b, :m], i) and np.array_equal(o_f[b, :m], fsc)
+                g = dense.search(q, Cn)
+                assert np.array_equal(g[2], d_exp[2]) and np.array_equal(g[0], d_exp[0]) and np.array_equal(g[1], d_exp[1])
+                s = bm.search(q_terms, q_off, Cn)
+                assert np.array_equal(s[2], s_exp[2])
+                for b in range(B):
+                    m = int(s_exp[2][b])
+                    assert np.array_equal(s[0][b, :m], s_exp[0][b, :m]) and np.array_equal(s[1][b, :m], s_exp[1][b, :m])
+        except Exception as ex:  # noqa: BLE001
+            errors.append((tid, repr(ex)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    dense.close(); bm.close()
+    assert not errors, errors
+
+
+def test_hybrid_input_validation(api, ctx):
+    """A query of the wrong width raises DimensionMismatch (VectorStore::search, src/index.rs:387-392) instead of reading
+    past the buffer; a 1-D query is one query; q_off must have B + 1 entries."""
+    from trueno_rag_b200 import _lib
+    dense = api.DenseIndex(ctx, 32)
+    dense.append(np.random.default_rng(0).standard_normal((100, 32)).astype(np.float32))
+    with pytest.raises(api.TrrError) as e:
+        api.hybrid_search(dense, None, np.zeros((3, 31), np.float32), None, None, 5, api.RRF, 60.0, 3, use_sparse=False)
+    assert e.value.status == _lib.TRR_ERR_DIM_MISMATCH
+    out = api.hybrid_search(dense, None, np.ones(32, np.float32), None, None, 5, api.RRF, 60.0, 3, use_sparse=False)
+    assert out[0].shape == (1, 3) and out[4][0] == 3
+    dense.close()

@@ -77,6 +77,60 @@ def test_bm25_snapshot_round_trip(api, ctx, tmp_path):
     dev2.close()
 
 
+def test_bm25_remove_save_load_append_keeps_dead_postings_accounted(api, ctx, tmp_path):
+    """remove -> save -> load -> append: the snapshot carries the number of tombstoned postings; without it the threshold
+    bootstrap after the append takes a term's posting count (dead ones included) for its live document count and drops valid
+    hits.  The restored index must keep returning exactly what an index built from the surviving + appended documents returns."""
+    V, n0, n1 = 800, 30000, 4000
+    cdf = O.zipf_cdf(V)
+    doc_off, toks = O.synth_doc_tokens(SEED + 41, cdf, 0, n0 + n1)
+    first = O.BM25(n_terms=V, doc_off=doc_off[:n0 + 1], tokens=toks[:int(doc_off[n0])])
+    t_off, pd, ptf, dl, df = first.csr()
+    dev = api.Bm25Device(ctx, n0, t_off, pd, ptf, dl, first.avgdl, api.bm25_idf_host(n0, df))
+    # remove nearly every document that contains term t_star: afterwards its live df (3) is far below k while its posting
+    # count (dead postings included) stays far above
+    t_star = int(np.argmin(np.abs(df.astype(np.int64) - 400)))
+    holders = pd[int(t_off[t_star]):int(t_off[t_star + 1])]
+    assert len(holders) > 150
+    gone = np.unique(holders[3:])
+    keep = np.setdiff1d(np.arange(n0, dtype=np.uint32), gone)
+    lens = np.diff(doc_off).astype(np.int64)
+
+    def oracle_over(ids):
+        off = np.zeros(len(ids) + 1, np.uint64)
+        np.cumsum(lens[ids], out=off[1:])
+        tk = np.concatenate([toks[int(doc_off[d]):int(doc_off[d + 1])] for d in ids])
+        return O.BM25(n_terms=V, doc_off=off, tokens=tk)
+
+    kept = oracle_over(keep)
+    df_kept = kept.csr()[4]
+    assert dev.remove(gone, kept.avgdl, api.bm25_idf_host(len(keep), df_kept)) > 0
+    path = os.path.join(tmp_path, "bm25_dead.trr")
+    dev.save(path)
+    dev.close()
+    dev2 = api.Bm25Device.load(ctx, path)
+    # append the documents n0 .. n0 + n1 with the statistics of (survivors + appended)
+    ids_all = np.concatenate([keep, np.arange(n0, n0 + n1, dtype=np.uint32)])
+    allo = oracle_over(ids_all)
+    df_all = allo.csr()[4]
+    sub_off = (doc_off[n0:n0 + n1 + 1] - doc_off[n0]).astype(np.uint64)
+    delta = O.BM25(n_terms=V, doc_off=sub_off, tokens=toks[int(doc_off[n0]):int(doc_off[n0 + n1])])
+    d_off, d_pd, d_ptf, d_dl, _ = delta.csr()
+    dev2.append(n1, d_off, d_pd, d_ptf, d_dl, allo.avgdl, api.bm25_idf_host(len(ids_all), df_all))
+    qs = [[t_star], [t_star, 5], [t_star, t_star, 7, 9], [11, 12, 13]]
+    q_off = np.cumsum([0] + [len(q) for q in qs]).astype(np.uint32)
+    q_terms = np.array([x for q in qs for x in q], np.uint32)
+    for k in (5, 50):
+        ords, scores, cnt = dev2.search(q_terms, q_off, k)
+        eo, es, en = allo.search_batch(q_terms, q_off, k)
+        assert np.array_equal(cnt, en), (cnt, en)
+        for b in range(len(qs)):
+            m = int(en[b])
+            assert np.array_equal(ords[b, :m], ids_all[eo[b, :m]]), (k, b)
+            assert np.array_equal(scores[b, :m], es[b, :m]), (k, b)
+    dev2.close()
+
+
 def test_snapshot_rejects_foreign_and_truncated_files(api, ctx, tmp_path):
     bad = os.path.join(tmp_path, "bad.trr")
     open(bad, "wb").write(b"not a snapshot at all, just some bytes" * 4)

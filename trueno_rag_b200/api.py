@@ -310,6 +310,26 @@ def fuse(ctx: Context, strategy: int, param: float, dense_lists, sparse_lists, k
             for b in range(B)]
 
 
+def _hybrid_inputs(dense, q, q_terms, q_off, use_dense, use_sparse):
+    """Shapes of a hybrid batch as the C ABI expects them; the dimension check of VectorStore::search
+    (reference src/index.rs:387-392) lives in this host layer, as in DenseIndex.search."""
+    q = np.ascontiguousarray(q, dtype=np.float32) if q is not None else None
+    if q is not None and q.ndim == 1:
+        q = q[None, :]
+    if q is not None and use_dense and dense is not None and q.shape[1] != dense.dim:
+        raise TrrError(_lib.TRR_ERR_DIM_MISMATCH, f"expected {dense.dim}, got {q.shape[1]}")
+    q_off = np.ascontiguousarray(q_off, dtype=np.uint32) if q_off is not None else None
+    q_terms = np.ascontiguousarray(q_terms, dtype=np.uint32) if q_terms is not None else None
+    B = q.shape[0] if q is not None else len(q_off) - 1
+    if q_off is not None and use_sparse:
+        if len(q_off) != B + 1:
+            raise TrrError(_lib.TRR_ERR_INVALID_ARG, f"q_off must have B + 1 = {B + 1} entries, got {len(q_off)}")
+        if int(q_off[-1]) > (q_terms.size if q_terms is not None else 0):
+            raise TrrError(_lib.TRR_ERR_INVALID_ARG, "q_off points past the end of q_terms")
+    qt = q_terms if (q_terms is not None and q_terms.size) else np.zeros(1, np.uint32)
+    return q, qt, q_off, B
+
+
 def _hybrid_outputs(B, k):
     return (np.full((B, k), 0xFFFFFFFF, np.uint32), np.zeros((B, k), np.float32), np.zeros((B, k), np.float32),
             np.zeros((B, k), np.float32), np.zeros(B, np.uint32))
@@ -319,12 +339,8 @@ def hybrid_search(dense: Optional[DenseIndex], bm25: Optional[Bm25Device], q, q_
                   param: float, k: int, use_dense: bool = True, use_sparse: bool = True):
     """HybridRetriever::retrieve for B queries (reference src/retrieve.rs:175-220) in one C-ABI call."""
     L = (dense or bm25).L
-    q = np.ascontiguousarray(q, dtype=np.float32) if q is not None else None
-    q_off = np.ascontiguousarray(q_off, dtype=np.uint32) if q_off is not None else None
-    q_terms = np.ascontiguousarray(q_terms, dtype=np.uint32) if q_terms is not None else None
-    B = q.shape[0] if q is not None else len(q_off) - 1
+    q, qt, q_off, B = _hybrid_inputs(dense, q, q_terms, q_off, use_dense, use_sparse)
     o_ord, o_f, o_d, o_s, o_n = _hybrid_outputs(B, k)
-    qt = q_terms if (q_terms is not None and q_terms.size) else np.zeros(1, np.uint32)
     _check(L.trr_hybrid_search(dense.h if dense else None, bm25.h if bm25 else None, _p(q, f32p), _p(qt, u32p),
                                _p(q_off, u32p), B, C_, strategy, param, k, int(use_dense), int(use_sparse),
                                _p(o_ord, u32p), _p(o_f, f32p), _p(o_d, f32p), _p(o_s, f32p), _p(o_n, u32p)))
@@ -337,11 +353,7 @@ def exchange_bytes(B: int, C_: int) -> int:
 
 def hybrid_local(dense, bm25, q, q_terms, q_off, C_: int, d_exchange: int, use_dense=True, use_sparse=True):
     L = (dense or bm25).L
-    q = np.ascontiguousarray(q, dtype=np.float32) if q is not None else None
-    q_off = np.ascontiguousarray(q_off, dtype=np.uint32) if q_off is not None else None
-    q_terms = np.ascontiguousarray(q_terms, dtype=np.uint32) if q_terms is not None else None
-    B = q.shape[0] if q is not None else len(q_off) - 1
-    qt = q_terms if (q_terms is not None and q_terms.size) else np.zeros(1, np.uint32)
+    q, qt, q_off, B = _hybrid_inputs(dense, q, q_terms, q_off, use_dense, use_sparse)
     _check(L.trr_hybrid_local(dense.h if dense else None, bm25.h if bm25 else None, _p(q, f32p), _p(qt, u32p),
                               _p(q_off, u32p), B, C_, int(use_dense), int(use_sparse), C.c_void_p(d_exchange)))
 
@@ -399,12 +411,8 @@ class Group:
 
     def search(self, dense, bm25, q, q_terms, q_off, C_: int, strategy: int, param: float, k: int, use_dense=True,
                use_sparse=True):
-        q = np.ascontiguousarray(q, dtype=np.float32) if q is not None else None
-        q_off = np.ascontiguousarray(q_off, dtype=np.uint32) if q_off is not None else None
-        q_terms = np.ascontiguousarray(q_terms, dtype=np.uint32) if q_terms is not None else None
-        B = q.shape[0] if q is not None else len(q_off) - 1
+        q, qt, q_off, B = _hybrid_inputs(dense, q, q_terms, q_off, use_dense, use_sparse)
         o_ord, o_f, o_d, o_s, o_n = _hybrid_outputs(B, k)
-        qt = q_terms if (q_terms is not None and q_terms.size) else np.zeros(1, np.uint32)
         _check(self.L.trr_hybrid_search_sharded(self.h, dense.h if dense else None, bm25.h if bm25 else None, _p(q, f32p),
                                                 _p(qt, u32p), _p(q_off, u32p), B, C_, strategy, param, k, int(use_dense),
                                                 int(use_sparse), _p(o_ord, u32p), _p(o_f, f32p), _p(o_d, f32p), _p(o_s, f32p),

@@ -1028,26 +1028,63 @@ bm25_rescore_kernel(Bm25RescoreArgs a) {
     const uint32_t nc = min(RS_CB, n - c0);
     for (uint32_t t0 = 0; t0 < T; t0 += RS_TB) {
       const uint32_t nt = min(RS_TB, T - t0);
-      for (uint32_t pi = tid; pi < nc * nt; pi += RS_THREADS) {
-        const uint32_t ci = pi / nt, ti = pi - ci * nt;
-        const uint32_t doc = trr_key_ord(fk[c0 + ci]) - a.doc_base;
-        const uint32_t term = a.q_terms[q0 + t0 + ti];
-        float v = 0.0f;
-        if (term < a.n_terms) {
-          const uint32_t* row = a.skip + (uint64_t)term * a.skip_ld + (doc >> a.range_shift);
-          uint32_t lo = row[0];
-          const uint32_t end = row[1];
-          uint32_t hi = end;
-          while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (a.post[mid].x < doc) lo = mid + 1; else hi = mid;
-          }
-          if (lo < end) {
-            const uint2 e = a.post[lo];
-            if (e.x == doc) v = __uint_as_float(e.y);
+      // every thread resolves its (candidate, slot) pairs TOGETHER: the look-ups are chains of dependent loads that miss
+      // the L2 (the postings of a 10M-document index do not fit), so what matters is how many chains are in flight
+      constexpr uint32_t NP = (RS_CB * RS_TB + RS_THREADS - 1) / RS_THREADS;  // 8 pairs per thread at most
+      uint32_t lo[NP], hi[NP], end[NP], dc[NP];
+#pragma unroll
+      for (uint32_t j = 0; j < NP; ++j) {
+        const uint32_t pi = tid + j * RS_THREADS;
+        lo[j] = hi[j] = end[j] = 0; dc[j] = 0;
+        if (pi < nc * nt) {
+          const uint32_t ci = pi / nt, ti = pi - ci * nt;
+          const uint32_t term = a.q_terms[q0 + t0 + ti];
+          if (term < a.n_terms) {
+            const uint32_t doc = trr_key_ord(fk[c0 + ci]) - a.doc_base;
+            const uint32_t* row = a.skip + (uint64_t)term * a.skip_ld + (doc >> a.range_shift);
+            const uint32_t b0 = row[0], e0 = row[1];
+            dc[j] = doc; end[j] = e0; hi[j] = e0;
+            // first probe by interpolation: the documents of a term are spread evenly over a range
+            uint32_t g = b0;
+            if (e0 > b0) {
+              g = b0 + (uint32_t)(((uint64_t)(doc & ((1u << a.range_shift) - 1u)) * (e0 - b0)) >> a.range_shift);
+              const uint32_t d = a.post[g].x;
+              if (d < doc) { lo[j] = g + 1; } else { lo[j] = b0; hi[j] = g; }
+              // (the bracket is halved by the binary search below; starting from the interpolated position saves the
+              // first steps only when the list is long, which is where the chain is longest)
+              const uint32_t span = 64;
+              if (d < doc && g + span < e0 && a.post[g + span].x >= doc) hi[j] = g + span;
+              else if (d >= doc && g >= b0 + span && a.post[g - span].x < doc) lo[j] = g - span + 1;
+            } else {
+              lo[j] = b0;
+            }
           }
         }
-        w[ci * (RS_TB + 1) + ti] = v;
+      }
+      while (true) {
+        bool any = false;
+#pragma unroll
+        for (uint32_t j = 0; j < NP; ++j) {
+          if (lo[j] < hi[j]) {
+            const uint32_t mid = (lo[j] + hi[j]) >> 1;
+            if (a.post[mid].x < dc[j]) lo[j] = mid + 1; else hi[j] = mid;
+            any = true;
+          }
+        }
+        if (!any) break;
+      }
+#pragma unroll
+      for (uint32_t j = 0; j < NP; ++j) {
+        const uint32_t pi = tid + j * RS_THREADS;
+        if (pi < nc * nt) {
+          const uint32_t ci = pi / nt, ti = pi - ci * nt;
+          float v = 0.0f;
+          if (lo[j] < end[j]) {
+            const uint2 e = a.post[lo[j]];
+            if (e.x == dc[j]) v = __uint_as_float(e.y);
+          }
+          w[ci * (RS_TB + 1) + ti] = v;
+        }
       }
       __syncthreads();
       if (tid < nc) {

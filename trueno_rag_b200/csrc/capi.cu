@@ -212,9 +212,13 @@ static int dense_grow(trr_dense* h, uint64_t need) {
   if (need <= h->cap) return TRR_OK;
   uint64_t ncap = std::max<uint64_t>(need, h->cap ? h->cap * 2 : 1024);
   uint8_t* nrows = nullptr; float* nnorms = nullptr; uint8_t* ndead = nullptr;
-  TRR_CUDA(cudaMalloc(&nrows, ncap * h->row_bytes + 256));
-  TRR_CUDA(cudaMalloc(&nnorms, ncap * sizeof(float)));
-  TRR_CUDA(cudaMalloc(&ndead, ncap));
+  if (cudaMalloc(&nrows, ncap * h->row_bytes + 256) != cudaSuccess || cudaMalloc(&nnorms, ncap * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&ndead, ncap) != cudaSuccess) {
+    cudaGetLastError();
+    if (nrows) cudaFree(nrows);
+    if (nnorms) cudaFree(nnorms);
+    return trr_fail(TRR_ERR_OOM, "dense store: out of device memory");
+  }
   cudaStream_t st = h->ctx->stream;
   TRR_CUDA(cudaMemsetAsync(ndead, 0, ncap, st));
   if (h->n) {
@@ -328,6 +332,7 @@ extern "C" int trr_dense_append_device(trr_dense* h, const void* d_rows, uint64_
 extern "C" int trr_dense_append_synth(trr_dense* h, uint64_t seed, uint64_t first_row, uint64_t n, int dups) {
   if (!h) return trr_fail(TRR_ERR_INVALID_ARG, "handle is NULL");
   if (n == 0) return TRR_OK;
+  if (h->n + n + h->base > 0xFFFFFFFEull) return trr_fail(TRR_ERR_UNSUPPORTED, "more than 2^32-2 ordinals");
   std::lock_guard<std::mutex> lk(h->ctx->mu);
   DeviceGuard g(h->ctx->device);
   TRR_CHECK(dense_grow(h, h->n + n));
@@ -1485,7 +1490,7 @@ extern "C" int trr_dense_load(trr_ctx* ctx, const char* path, trr_dense** out) {
   DenseSnapHeader hd{};
   if (fread(&hd, sizeof(hd), 1, fc.f) != 1 || memcmp(hd.magic, "TRRDNS01", 8) != 0)
     return trr_fail(TRR_ERR_INVALID_ARG, "trr_dense_load: not a dense snapshot");
-  if (hd.n_dead > hd.n) return trr_fail(TRR_ERR_INVALID_ARG, "trr_dense_load: corrupt header");
+  if (hd.n_dead > hd.n || hd.n + hd.base > 0xFFFFFFFEull) return trr_fail(TRR_ERR_INVALID_ARG, "trr_dense_load: corrupt header");
   trr_dense* h = nullptr;
   TRR_CHECK(trr_dense_create(ctx, hd.dim, hd.metric, hd.dtype, std::max<uint64_t>(hd.n, 1), &h));
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1564,6 +1569,13 @@ extern "C" int trr_bm25_load(trr_ctx* ctx, const char* path, trr_bm25** out) {
     h->h_term_off.resize((size_t)hd.n_terms + 1);
     if (cudaMemcpy(h->h_term_off.data(), h->d_term_off, h->h_term_off.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
       s = trr_fail(TRR_ERR_CUDA, "trr_bm25_load: copy failed");
+  }
+  if (s == TRR_OK) {
+    // the offsets index the posting arrays on the device: a file whose offsets are not a monotone partition of the postings
+    // must be refused here, not discovered by a kernel
+    bool ok = h->h_term_off.front() == 0 && h->h_term_off.back() == hd.n_postings;
+    for (size_t t = 0; ok && t + 1 < h->h_term_off.size(); ++t) ok = h->h_term_off[t] <= h->h_term_off[t + 1];
+    if (!ok) s = trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_load: corrupt term offsets");
   }
   if (s != TRR_OK) return fail(s);
   *out = h;

@@ -307,15 +307,9 @@ std::vector<std::string> BM25Index::tokenize(const std::string& text) const {
 
 void BM25Index::add(const Chunk& chunk) {  // :176-204
   const std::vector<std::string> tokens = tokenize(chunk.content);
-  uint32_t ord;
-  auto it = ord_of_.find(chunk.id);
-  if (it != ord_of_.end()) {
-    // the reference would append a second posting for the same id; keep its observable effect on the counters
-    // (doc_count += 1, doc_lengths overwritten) but give the re-added chunk a fresh ordinal
-    ord = (uint32_t)id_of_.size();
-  } else {
-    ord = (uint32_t)id_of_.size();
-  }
+  // (a chunk id that is added twice gets a second ordinal: the reference appends a second posting for the same id and
+  // counts the document twice, :193-203)
+  const uint32_t ord = (uint32_t)id_of_.size();
   id_of_.push_back(chunk.id);
   ord_of_[chunk.id] = ord;
   doc_len_.push_back((uint32_t)tokens.size());
@@ -454,9 +448,11 @@ trr_bm25* BM25Index::device_handle() const {
 std::vector<uint32_t> BM25Index::term_ids(const std::vector<std::string>& tokens) const {
   std::vector<uint32_t> ids;
   ids.reserve(tokens.size());
+  // a token the index has never seen scores 0.0 for every document (src/index.rs:137-140) and adding +0.0 leaves an f32 sum
+  // unchanged, so unknown tokens are dropped here instead of spending query-term slots of the device kernel on them
   for (const std::string& t : tokens) {
     auto d = dict_.find(t);
-    ids.push_back(d == dict_.end() ? 0xFFFFFFFFu : d->second);
+    if (d != dict_.end()) ids.push_back(d->second);
   }
   return ids;
 }
@@ -1128,6 +1124,9 @@ HybridRetriever HybridRetriever::with_config(HybridRetrieverConfig config) && {
 }
 
 void HybridRetriever::index(Chunk chunk) {  // :156-164
+  // the fused device path identifies documents by ordinal in both indexes; a re-indexed ChunkId would appear under two
+  // ordinals where the reference merges by ChunkId, so from then on the general path (fusion over ChunkIds) is used
+  if (dense_.get(chunk.id) != nullptr) aligned_ = false;
   sparse_.add(chunk);
   const bool same = dense_.next_ordinal() + 1 == sparse_.next_ordinal();
   dense_.insert(std::move(chunk));  // throws on a missing / mis-sized embedding AFTER the sparse add, as in the reference
