@@ -109,4 +109,7 @@ cudaError_t trr_launch_bm25_search(const Bm25SearchArgs& a, unsigned grid, cudaS
 size_t trr_bm25_fast_smem(int bits, uint32_t range_shift, uint32_t stage_cap, uint32_t cand_cap);
 cudaError_t trr_launch_bm25_fast(const Bm25SearchArgs& a, int bits, unsigned grid, cudaStream_t st);
 cudaError_t trr_launch_bm25_rescore(const Bm25RescoreArgs& a, cudaStream_t st);
-constexpr uint32_t TRR_BM25_FAST_STAGES = 3;
+#ifndef TRR_BM25_FAST_STAGES_N
+#define TRR_BM25_FAST_STAGES_N 2  /* (two 64 KB stages: nearly every range is one pass; 5.81 vs 5.91 ms with three 48 KB stages at cfg4) */
+#endif
+constexpr uint32_t TRR_BM25_FAST_STAGES = TRR_BM25_FAST_STAGES_N;
