@@ -277,3 +277,52 @@ def test_auto_mode_picks_scan_for_single_query_and_gemm_for_batches(api, ctx):
     ix.search(bf16_round(O.synth_queries(SEED, 0, 64, d, n, True)), 10)
     assert ix.stats().mode_used == 2
     ix.close()
+
+
+# ------------------------------------------------------------------ tensor-core path: Euclidean metric and large k
+@pytest.mark.parametrize("dtype", [0, 1])
+def test_gemm_path_euclidean(api, ctx, dtype):
+    """-euclidean_distance (src/index.rs:400,452-458) through the tensor-core pass: the fast pass ranks by 2 q.d - |d|^2,
+    the survivors are re-scored with the reference's sequential sum of squared differences, and the candidate proof works
+    on squared distances.  Bit-exact ids and scores; rows of varying norms; f32 and bf16 stores; f32 (not bf16-exact) queries."""
+    n, d, B = 40000, 256, 200
+    rng = np.random.default_rng(17)
+    f = (rng.standard_normal((n, d)) * rng.uniform(0.5, 2.0, (n, 1))).astype(F32)
+    rows = bf16_round(f) if dtype == 0 else (bf16_round(f).view(np.uint32) >> 16).astype(np.uint16)
+    Q = (rng.standard_normal((B, d)) * rng.uniform(0.5, 2.0, (B, 1))).astype(F32)
+    Q[:5] = f[100:105] + 0.01 * rng.standard_normal((5, d)).astype(F32)      # near-duplicates of stored rows
+    for k in (1, 10, 50):
+        st = check(api, ctx, rows, Q, k, 1, dtype, mode=2, expect_mode=2)
+        assert st.n_guard_fallbacks <= B // 4
+
+
+def test_gemm_path_euclidean_ties_and_removed_rows(api, ctx):
+    n, d, B = 30000, 64, 64
+    rng = np.random.default_rng(18)
+    f = bf16_round(rng.standard_normal((n, d)).astype(F32))
+    f[2000:2100] = f[7]                                                         # exact distance ties
+    rows = (f.view(np.uint32) >> 16).astype(np.uint16)
+    alive = np.ones(n, bool)
+    alive[rng.integers(0, n, 500)] = False
+    Q = bf16_round(rng.standard_normal((B, d)).astype(F32))
+    Q[0] = f[7]
+    check(api, ctx, rows, Q, 20, 1, 1, mode=2, alive=alive, expect_mode=2)
+
+
+@pytest.mark.parametrize("k,B", [(200, 300), (1024, 128), (1000, 40)])
+def test_gemm_path_large_k(api, ctx, k, B):
+    """k up to 1024 on the tensor-core path (the reference's k is unbounded, src/index.rs:386-412): the re-scoring width
+    grows with k."""
+    n, d = 60000, 128
+    f, b = O.synth_corpus(SEED + 31, 0, n, d, bf16=True)
+    Q = bf16_round(O.synth_queries(SEED + 31, 0, B, d, n, corpus_bf16=True))
+    check(api, ctx, b, Q, k, 0, 1, mode=2, expect_mode=2)
+    check(api, ctx, b, Q, k, 2, 1, mode=2, expect_mode=2)
+
+
+def test_auto_mode_takes_the_tensor_path_for_euclidean_batches(api, ctx):
+    n, d, B = 50000, 96, 33
+    rng = np.random.default_rng(19)
+    f = rng.standard_normal((n, d)).astype(F32)
+    Q = rng.standard_normal((B, d)).astype(F32)
+    st = check(api, ctx, f, Q, 10, 1, 0, mode=0, expect_mode=2)                 # f32 store (bf16 shadow), AUTO

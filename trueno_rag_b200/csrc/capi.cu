@@ -586,11 +586,6 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
   bool use_gemm = false;
   if (h->mode == TRR_DENSE_GEMM) use_gemm = true;
   else if (h->mode == TRR_DENSE_AUTO) use_gemm = B >= 2 && h->n >= 16384;  // K1 re-streams the slab per query: 8 queries over 10M x 768 take 19 ms through K1, 2.6 ms through K2
-  if (h->metric == TRR_METRIC_EUCLIDEAN || k > 100) {
-    if (h->mode == TRR_DENSE_GEMM)
-      return trr_fail(TRR_ERR_UNSUPPORTED, "GEMM mode supports cosine/dot metrics with k <= 100");
-    use_gemm = false;
-  }
   // feedback of the previous GEMM search on this store (see trr_dense::cp_level)
   if (h->feedback_host && h->feedback_B) {
     const uint32_t failed = *reinterpret_cast<volatile uint32_t*>(h->feedback_host + 1);
@@ -599,14 +594,16 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
       h->feedback_host[1] = 0xFFFFFFFFu;  // consumed
     }
   }
-  uint32_t CP = (k <= 50 ? TRR_GEMM_CP : 2 * TRR_GEMM_CP) << h->cp_level;
+  // base width: k plus a margin of ranks, as a power of two (64 up to k = 50, 128 up to k = 100, ... 2048 for k = 1024)
+  uint32_t CP = std::min<uint32_t>(std::max<uint32_t>(TRR_GEMM_CP, trr_pow2_ceil(k + std::max<uint32_t>(14, k / 4))) << h->cp_level, 2048u);
   if (use_gemm) {
     // the width cannot exceed what the half-slice lists of the tensor-core pass hold (2 * slices * 32 entries)
     const uint32_t n_qb = (B + TRR_GEMM_TILE_M - 1) / TRR_GEMM_TILE_M;
     const uint64_t tiles = (h->n + TRR_GEMM_TILE_N - 1) / TRR_GEMM_TILE_N;
     const uint64_t n_sl = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->sm_count / std::max(n_qb, 1u), tiles));
-    while (CP > TRR_GEMM_CP && 2 * n_sl * TRR_GEMM_CPS_MAX < CP) CP >>= 1;
+    while (CP > TRR_GEMM_CP && CP / 2 >= k + 14 && 2 * n_sl * TRR_GEMM_CPS_MAX < CP) CP >>= 1;
     if (2 * n_sl * TRR_GEMM_CPS_MAX < CP || CP < k) {
+      // (large k with many query blocks: too few document slices per block to hold k candidates per query)
       if (h->mode == TRR_DENSE_GEMM) return trr_fail(TRR_ERR_UNSUPPORTED, "GEMM mode: batch too large for this k");
       use_gemm = false;
     }

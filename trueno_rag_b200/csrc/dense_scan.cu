@@ -540,7 +540,14 @@ topk_merge_kernel(TopkMergeArgs a) {
 //      document, none of them can reach or tie the k-th exact score if  f_min + eps < exact_k.  If the
 //      proof fails the query is flagged and re-run through the exact scan (K1).
 // =============================================================================================
-template <int IS_BF16>
+// one term of the reference's sum: dot / cosine `acc + q*x` (src/index.rs:441,461), Euclidean `acc + (q-x)^2` (:455)
+template <bool EU>
+__device__ __forceinline__ float rs_step(float acc, float q, float x) {
+  if (EU) { const float t = q - x; return acc + t * t; }
+  return acc + q * x;
+}
+
+template <int IS_BF16, bool EU>
 __global__ void __launch_bounds__(256)
 rescore_select_kernel(RescoreArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -628,10 +635,10 @@ rescore_select_kernel(RescoreArgs a) {
           for (uint32_t i = 0; i < pieces; ++i) {
             const uint4 v = rp[i];
             const float4 q0 = *reinterpret_cast<const float4*>(qq + 8 * i), q1 = *reinterpret_cast<const float4*>(qq + 8 * i + 4);
-            acc = acc + q0.x * bf16lo(v.x); acc = acc + q0.y * bf16hi(v.x);
-            acc = acc + q0.z * bf16lo(v.y); acc = acc + q0.w * bf16hi(v.y);
-            acc = acc + q1.x * bf16lo(v.z); acc = acc + q1.y * bf16hi(v.z);
-            acc = acc + q1.z * bf16lo(v.w); acc = acc + q1.w * bf16hi(v.w);
+            acc = rs_step<EU>(acc, q0.x, bf16lo(v.x)); acc = rs_step<EU>(acc, q0.y, bf16hi(v.x));
+            acc = rs_step<EU>(acc, q0.z, bf16lo(v.y)); acc = rs_step<EU>(acc, q0.w, bf16hi(v.y));
+            acc = rs_step<EU>(acc, q1.x, bf16lo(v.z)); acc = rs_step<EU>(acc, q1.y, bf16hi(v.z));
+            acc = rs_step<EU>(acc, q1.z, bf16lo(v.w)); acc = rs_step<EU>(acc, q1.w, bf16hi(v.w));
           }
         } else {
           const float* qq = qs + (c0 >> 2);
@@ -639,8 +646,8 @@ rescore_select_kernel(RescoreArgs a) {
           for (uint32_t i = 0; i < pieces; ++i) {
             const uint4 v = rp[i];
             const float4 q0 = *reinterpret_cast<const float4*>(qq + 4 * i);
-            acc = acc + q0.x * __uint_as_float(v.x); acc = acc + q0.y * __uint_as_float(v.y);
-            acc = acc + q0.z * __uint_as_float(v.z); acc = acc + q0.w * __uint_as_float(v.w);
+            acc = rs_step<EU>(acc, q0.x, __uint_as_float(v.x)); acc = rs_step<EU>(acc, q0.y, __uint_as_float(v.y));
+            acc = rs_step<EU>(acc, q0.z, __uint_as_float(v.z)); acc = rs_step<EU>(acc, q0.w, __uint_as_float(v.w));
           }
         }
         acc_staged = acc;
@@ -672,21 +679,21 @@ rescore_select_kernel(RescoreArgs a) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const float* qq = qs + j + u * 8;
-              acc = acc + qq[0] * bf16lo(v[u].x); acc = acc + qq[1] * bf16hi(v[u].x);
-              acc = acc + qq[2] * bf16lo(v[u].y); acc = acc + qq[3] * bf16hi(v[u].y);
-              acc = acc + qq[4] * bf16lo(v[u].z); acc = acc + qq[5] * bf16hi(v[u].z);
-              acc = acc + qq[6] * bf16lo(v[u].w); acc = acc + qq[7] * bf16hi(v[u].w);
+              acc = rs_step<EU>(acc, qq[0], bf16lo(v[u].x)); acc = rs_step<EU>(acc, qq[1], bf16hi(v[u].x));
+              acc = rs_step<EU>(acc, qq[2], bf16lo(v[u].y)); acc = rs_step<EU>(acc, qq[3], bf16hi(v[u].y));
+              acc = rs_step<EU>(acc, qq[4], bf16lo(v[u].z)); acc = rs_step<EU>(acc, qq[5], bf16hi(v[u].z));
+              acc = rs_step<EU>(acc, qq[6], bf16lo(v[u].w)); acc = rs_step<EU>(acc, qq[7], bf16hi(v[u].w));
             }
           }
           for (; j < a.dim; j += 8) {
             const uint4 v = __ldg(p4 + (j >> 3));
-            acc = acc + qs[j] * bf16lo(v.x);     acc = acc + qs[j + 1] * bf16hi(v.x);
-            acc = acc + qs[j + 2] * bf16lo(v.y); acc = acc + qs[j + 3] * bf16hi(v.y);
-            acc = acc + qs[j + 4] * bf16lo(v.z); acc = acc + qs[j + 5] * bf16hi(v.z);
-            acc = acc + qs[j + 6] * bf16lo(v.w); acc = acc + qs[j + 7] * bf16hi(v.w);
+            acc = rs_step<EU>(acc, qs[j], bf16lo(v.x));     acc = rs_step<EU>(acc, qs[j + 1], bf16hi(v.x));
+            acc = rs_step<EU>(acc, qs[j + 2], bf16lo(v.y)); acc = rs_step<EU>(acc, qs[j + 3], bf16hi(v.y));
+            acc = rs_step<EU>(acc, qs[j + 4], bf16lo(v.z)); acc = rs_step<EU>(acc, qs[j + 5], bf16hi(v.z));
+            acc = rs_step<EU>(acc, qs[j + 6], bf16lo(v.w)); acc = rs_step<EU>(acc, qs[j + 7], bf16hi(v.w));
           }
         }
-        for (; j < a.dim; ++j) acc = acc + qs[j] * __uint_as_float(((uint32_t)p[j]) << 16);
+        for (; j < a.dim; ++j) acc = rs_step<EU>(acc, qs[j], __uint_as_float(((uint32_t)p[j]) << 16));
       } else {
         const float* p = reinterpret_cast<const float*>(a.rows) + row * a.dim;
         uint32_t j = 0;
@@ -699,28 +706,31 @@ rescore_select_kernel(RescoreArgs a) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const float* qq = qs + j + u * 4;
-              acc = acc + qq[0] * v[u].x; acc = acc + qq[1] * v[u].y;
-              acc = acc + qq[2] * v[u].z; acc = acc + qq[3] * v[u].w;
+              acc = rs_step<EU>(acc, qq[0], v[u].x); acc = rs_step<EU>(acc, qq[1], v[u].y);
+              acc = rs_step<EU>(acc, qq[2], v[u].z); acc = rs_step<EU>(acc, qq[3], v[u].w);
             }
           }
           for (; j < a.dim; j += 4) {
             const float4 v = __ldg(p4 + (j >> 2));
-            acc = acc + qs[j] * v.x;     acc = acc + qs[j + 1] * v.y;
-            acc = acc + qs[j + 2] * v.z; acc = acc + qs[j + 3] * v.w;
+            acc = rs_step<EU>(acc, qs[j], v.x);     acc = rs_step<EU>(acc, qs[j + 1], v.y);
+            acc = rs_step<EU>(acc, qs[j + 2], v.z); acc = rs_step<EU>(acc, qs[j + 3], v.w);
           }
         }
-        for (; j < a.dim; ++j) acc = acc + qs[j] * p[j];
+        for (; j < a.dim; ++j) acc = rs_step<EU>(acc, qs[j], p[j]);
       }
       float score;
       if (a.metric == TRR_METRIC_COSINE) {
         const float dn = a.norms[row];
         score = (q_norm == 0.0f || dn == 0.0f) ? 0.0f : acc / (q_norm * dn);
+      } else if (EU) {
+        score = -sqrtf(acc);  // -euclidean_distance (src/index.rs:400,452-458)
       } else {
         score = acc;
       }
       ek = trr_make_key(score, od);
       // fast score in score units
       float fs = (a.metric == TRR_METRIC_COSINE) ? (q_norm > 0.0f ? fast / q_norm : 0.0f) : fast;
+      if (EU) fs = -sqrtf(fmaxf(q_norm * q_norm - fast, 0.0f));  // the fast pass scores 2 q.d - |d|^2 = |q|^2 - |q - d|^2
       atomicMax(reinterpret_cast<int*>(&s_gap), __float_as_int(fabsf(fs - score)));
     }
     ekeys[c] = ek;
@@ -756,7 +766,22 @@ rescore_select_kernel(RescoreArgs a) {
         if (a.metric == TRR_METRIC_COSINE) eps += (q_norm > 0.0f ? a.q_delta[b] / q_norm : 0.0f);
         else eps = (a.eps_rel * q_norm + a.q_delta[b]) * (*a.max_norm);
         const float exact_k = trr_key_score(ekeys[a.k - 1]);
-        ok = (q_norm > 0.0f || a.metric != TRR_METRIC_COSINE) && (f_excl_s + eps < exact_k);
+        if (EU) {
+          // Euclidean: the fast pass ranks by f = 2 q~.d - |d|^2 (q~ = bf16(q)), i.e. by -|q - d|^2 up to the per-query
+          // constant |q|^2.  For a document that was not re-scored f <= f_excl, hence its true squared distance is at least
+          //   D_lo = |q|^2 - f_excl - eps_D,  eps_D = 2 (eps_gemm |q~| + |q - q~|) max|d| + delta max|d|^2
+          // (tensor-core accumulation + query quantisation through Cauchy-Schwarz, and the stored f32 norm squared);
+          // the reference's f32 sum of squares is within delta of the true one, sqrt is monotone, so no such document
+          // can reach or tie the k-th exact score -sqrt(D_k) when D_lo (1 - delta) > D_k (1 + 2^-20).
+          const double delta = ((double)a.dim + 8.0) * 1.1920928955078125e-07;
+          const double mn = (double)(*a.max_norm), qn = (double)q_norm, qd = (double)a.q_delta[b];
+          const double eps_d = 2.0 * ((double)a.eps_rel * (qn + qd) + qd) * mn + delta * mn * mn;
+          const double d_lo = qn * qn * (1.0 - delta) - (double)f_excl - eps_d;
+          const double d_k = (double)exact_k * (double)exact_k;
+          ok = d_lo > 0.0 && d_lo * (1.0 - delta) > d_k * (1.0 + 9.5367431640625e-07);
+        } else {
+          ok = (q_norm > 0.0f || a.metric != TRR_METRIC_COSINE) && (f_excl_s + eps < exact_k);
+        }
       }
     }
     a.flags[b] = ok ? 0u : 1u;
@@ -868,18 +893,19 @@ cudaError_t trr_launch_topk_merge(const TopkMergeArgs& a, unsigned grid, cudaStr
   return cudaGetLastError();
 }
 
+template <int IS_BF16, bool EU>
+static cudaError_t launch_rescore_t(const RescoreArgs& a, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(rescore_select_kernel<IS_BF16, EU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  rescore_select_kernel<IS_BF16, EU><<<a.B, 256, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t trr_launch_rescore(const RescoreArgs& a, int is_bf16, cudaStream_t st) {
   if (a.B == 0) return cudaSuccess;
   size_t smem = (size_t)a.cap2 * 8 + (size_t)a.cp * 8 + (((size_t)a.dim * 4 + 15) & ~(size_t)15) + 16 +
                 (a.stage_chunk ? (size_t)a.cp * (a.stage_chunk + 16) : 0);
-  if (is_bf16) {
-    cudaError_t e = cudaFuncSetAttribute(rescore_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    rescore_select_kernel<1><<<a.B, 256, smem, st>>>(a);
-  } else {
-    cudaError_t e = cudaFuncSetAttribute(rescore_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    rescore_select_kernel<0><<<a.B, 256, smem, st>>>(a);
-  }
-  return cudaGetLastError();
+  const bool eu = a.metric == TRR_METRIC_EUCLIDEAN;
+  if (is_bf16) return eu ? launch_rescore_t<1, true>(a, smem, st) : launch_rescore_t<1, false>(a, smem, st);
+  return eu ? launch_rescore_t<0, true>(a, smem, st) : launch_rescore_t<0, false>(a, smem, st);
 }
