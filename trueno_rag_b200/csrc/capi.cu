@@ -200,6 +200,7 @@ struct trr_dense {
   // After every GEMM search the number of queries that failed the first proof lands in page-locked host memory
   // (asynchronous copy); the next search doubles the width while more than 1/64 of the batch failed.  Results are exact at
   // every width - only the time moves.
+  uint32_t* scan_done = nullptr;        // [256] arrival counters of the scan kernel's fused merge epilogue (kept zero)
   uint32_t cp_level = 0;
   uint32_t* feedback_host = nullptr;    // [2] {queries of the last search, queries that failed the first proof}
   uint32_t feedback_B = 0;
@@ -264,6 +265,7 @@ extern "C" int trr_dense_destroy(trr_dense* h) {
   if (h->dead) cudaFree(h->dead);
   if (h->stat_dev) cudaFree(h->stat_dev);
   if (h->feedback_host) cudaFreeHost(h->feedback_host);
+  if (h->scan_done) cudaFree(h->scan_done);
   h->shadow.release(); h->scale_bias.release(); h->max_norm.release(); h->qbuf.release();
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   delete h;
@@ -510,7 +512,8 @@ static int plan_scan(trr_dense* h, uint32_t k, ScanPlan* p, uint32_t n_queries =
 // d_n_sel (nullable): DEVICE count of selected queries (<= n_sel, which then only sizes the buffers and the grids)
 static int dense_scan_locked(trr_dense* h, const float* d_q, const float* d_qn, uint32_t n_sel, const uint32_t* d_sel,
                              uint32_t k, uint32_t* d_ord, float* d_score, uint32_t* d_n, uint64_t* d_keys,
-                             size_t scratch_off, const uint32_t* d_n_sel = nullptr, bool record_events = true) {
+                             size_t scratch_off, const uint32_t* d_n_sel = nullptr, bool record_events = true,
+                             bool fused = false, const float* h_q = nullptr, float h_qn = 0.0f) {
   ScanPlan p;
   TRR_CHECK(plan_scan(h, k, &p, n_sel));
   const uint64_t lists = (uint64_t)p.grid;  // one merged list per CTA
@@ -526,15 +529,24 @@ static int dense_scan_locked(trr_dense* h, const float* d_q, const float* d_qn, 
   a.ch_bytes = p.ch_bytes; a.n_chunks = p.n_chunks; a.n_slots = p.n_slots; a.k = k; a.cap = p.cap; a.base_ord = h->base;
   a.partial = partial; a.partial_n = partial_n;
   cudaStream_t st = h->ctx->stream;
+  // fused: the single-launch form (merge by the last CTA; d_qn == NULL: query norm in the kernel's prologue)
+  if (fused) {
+    if (!h->scan_done) {
+      TRR_CUDA(cudaMalloc(&h->scan_done, 256 * 4));
+      TRR_CUDA(cudaMemsetAsync(h->scan_done, 0, 256 * 4, st));
+    }
+    a.done = h->scan_done; a.out_keys = d_keys; a.out_ord = d_ord; a.out_score = d_score; a.out_n = d_n;
+  }
   if (p.tma && (h->map_scan_n != h->n || h->map_scan_base != h->rows)) {
     TRR_CHECK(trr_make_tensor_map_ex(h->map_scan, h->rows, h->n, h->dim, h->elem, 128 / h->elem, 32));
     h->map_scan_n = h->n; h->map_scan_base = h->rows;
   }
   if (record_events) TRR_CUDA(cudaEventRecord(h->ev[2], st));
-  if (p.tma) TRR_CUDA(trr_launch_scan_tma(a, h->map_scan, h->dtype == TRR_DTYPE_BF16, h->metric, p.grid, p.warps, p.nq, p.smem, st));
+  if (p.tma) TRR_CUDA(trr_launch_scan_tma(a, h->map_scan, h->dtype == TRR_DTYPE_BF16, h->metric, p.grid, p.warps, p.nq, p.smem, st, h_q, h_qn));
   else TRR_CUDA(trr_launch_scan(a, h->dtype == TRR_DTYPE_BF16, h->metric, p.bulk, p.grid, p.smem, st));
   if (record_events) TRR_CUDA(cudaEventRecord(h->ev[3], st));
   h->ctx->launches++;
+  if (fused) return TRR_OK;
   TopkMergeArgs m{};
   m.lists = partial; m.list_n = partial_n; m.n_lists = (uint32_t)lists; m.list_stride = k;
   m.n_rows = n_sel; m.n_rows_ptr = d_n_sel; m.row_map = d_sel; m.k = k; m.k2 = trr_pow2_ceil(k);
@@ -556,7 +568,8 @@ static void dense_resolve_stats(trr_dense* h) {
 }
 
 static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint32_t k, uint32_t* d_ord, float* d_score,
-                               uint32_t* d_n, bool sync_stats) {
+                               uint32_t* d_n, bool sync_stats, const float* d_qn_pre = nullptr, const float* h_q1 = nullptr,
+                               float h_qn1 = 0.0f) {
   trr_ctx* c = h->ctx;
   cudaStream_t st = c->stream;
   // very large batches are served in pieces (scratch and the query-block grid scale with B)
@@ -565,7 +578,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     for (uint32_t b0 = 0; b0 < B; b0 += kMaxBatch) {
       const uint32_t nb = std::min(kMaxBatch, B - b0);
       TRR_CHECK(dense_search_locked(h, d_q + (size_t)b0 * h->dim, nb, k, d_ord + (size_t)b0 * k, d_score + (size_t)b0 * k,
-                                    d_n + b0, sync_stats));
+                                    d_n + b0, sync_stats, d_qn_pre ? d_qn_pre + b0 : nullptr));
     }
     h->stats.n_queries = B;
     return TRR_OK;
@@ -625,9 +638,17 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     const uint64_t lists = (uint64_t)p.grid;
     TRR_CHECK(extra(c)->scratch.reserve(scratch_off + WsCarver::need({(size_t)B * lists * k * 8, (size_t)B * lists * 4})));
     d_qn = reinterpret_cast<float*>(extra(c)->scratch.p);
-    trr_launch_query_norms(d_q, h->dim, B, d_qn, st);
-    c->launches++;
-    TRR_CHECK(dense_scan_locked(h, d_q, d_qn, B, nullptr, k, d_ord, d_score, d_n, nullptr, scratch_off));
+    // few queries on the TMA kernel: ONE launch (|q| in the kernel's prologue, the merge of the per-CTA lists by the last
+    // CTA, inside the ring memory) instead of norm kernel + scan + merge kernel
+    const bool fused = p.tma && (B + p.nq - 1) / p.nq <= 256 && !TRR_KNOB("TRR_SCAN_NOFUSE");
+    const float* qn = d_qn_pre;  // norms computed by the caller (host-buffer entry point: on the host, in reference order)
+    if (!qn && !fused) {
+      trr_launch_query_norms(d_q, h->dim, B, d_qn, st);
+      c->launches++;
+      qn = d_qn;
+    }
+    TRR_CHECK(dense_scan_locked(h, d_q, qn, B, nullptr, k, d_ord, d_score, d_n, nullptr, scratch_off, nullptr, true, fused,
+                                B == 1 ? h_q1 : nullptr, h_qn1));
     h->stats.mode_used = TRR_DENSE_SCAN;
   } else {
     TRR_CHECK(dense_prepare_gemm(h));
@@ -817,6 +838,20 @@ extern "C" int trr_dense_search_device(trr_dense* h, const float* d_q, uint32_t 
   return dense_search_locked(h, d_q, B, k, d_ord, d_score, d_n, false);
 }
 
+// |q| exactly as the reference computes it (src/index.rs:442-443): sequential f32 sum of squares, then sqrt.  volatile keeps
+// the host compiler from contracting the multiply-add or re-associating the sum.
+static void host_query_norms(const float* q, uint32_t dim, uint32_t B, float* out) {
+  for (uint32_t b = 0; b < B; ++b) {
+    const float* p = q + (size_t)b * dim;
+    volatile float s = 0.0f;
+    for (uint32_t j = 0; j < dim; ++j) {
+      volatile float sq = p[j] * p[j];
+      s = s + sq;
+    }
+    out[b] = sqrtf(s);
+  }
+}
+
 extern "C" int trr_dense_search(trr_dense* h, const float* q, uint32_t B, uint32_t k, uint32_t* out_ord,
                                 float* out_score, uint32_t* out_n) {
   if (!h || (B && (!q || !out_n)) || (B && k && (!out_ord || !out_score)))
@@ -827,14 +862,56 @@ extern "C" int trr_dense_search(trr_dense* h, const float* q, uint32_t B, uint32
   trr_ctx* c = h->ctx;
   cudaStream_t st = c->stream;
   const size_t kk = std::max<uint32_t>(k, 1);
-  const size_t need = WsCarver::need({(size_t)B * h->dim * 4, (size_t)B * kk * 4, (size_t)B * kk * 4, (size_t)B * 4});
-  TRR_CHECK(extra(c)->io.reserve(need));
+  const size_t q_bytes = (size_t)B * h->dim * 4;
+  // outputs in one contiguous span (ord | score | n), so that a small search needs ONE device -> host copy
+  const size_t ord_off = 0, score_off = ((size_t)B * kk * 4 + 255) & ~size_t(255);
+  const size_t n_off = score_off + (((size_t)B * kk * 4 + 255) & ~size_t(255));
+  const size_t out_bytes = n_off + (size_t)B * 4;
+  TRR_CHECK(extra(c)->io.reserve(WsCarver::need({q_bytes + (size_t)B * 4, out_bytes})));
   WsCarver io(extra(c)->io.p);
-  float* d_q = io.take<float>((size_t)B * h->dim);
-  uint32_t* d_ord = io.take<uint32_t>((size_t)B * kk);
-  float* d_score = io.take<float>((size_t)B * kk);
-  uint32_t* d_n = io.take<uint32_t>(B);
-  TRR_CUDA(cudaMemcpyAsync(d_q, q, (size_t)B * h->dim * 4, cudaMemcpyHostToDevice, st));
+  float* d_q = io.take<float>((size_t)B * h->dim + B);  // (+ B query norms behind the queries)
+  uint8_t* d_out = io.take<uint8_t>(out_bytes);
+  uint32_t* d_ord = reinterpret_cast<uint32_t*>(d_out + ord_off);
+  float* d_score = reinterpret_cast<float*>(d_out + score_off);
+  uint32_t* d_n = reinterpret_cast<uint32_t*>(d_out + n_off);
+  // Small searches (the single-query call of VectorStore::search) go through the context's page-locked staging buffer:
+  // a copy from / to pageable memory is a synchronous driver staging of its own, three of them cost more than the merge
+  // kernel.  Large batches copy straight from the caller's buffers.
+  const bool staged = q_bytes + out_bytes <= ((size_t)256 << 10);
+  if (staged) {
+    // |q| travels with the query: the reference's sequential f32 sum of squares + sqrt (src/index.rs:442) is a fraction of
+    // a microsecond on the host, a dependent chain of `dim` steps in front of the scan on the device
+    const size_t pin_q = (q_bytes + (size_t)B * 4 + 255) & ~size_t(255);
+    TRR_CHECK(trr_ctx_reserve_pin(c, pin_q + out_bytes));
+    uint8_t* pin = static_cast<uint8_t*>(c->pin);
+    memcpy(pin, q, q_bytes);
+    host_query_norms(q, h->dim, B, reinterpret_cast<float*>(pin + q_bytes));
+    if (B == 1 && h->dim <= TRR_SCAN_PARAM_DIM && h->mode != TRR_DENSE_GEMM) {
+      // VectorStore::search is ONE query: no copy operations at all.  The query and its norm travel in the kernel's
+      // parameter space (every CTA reads them through the constant cache), and the last CTA writes the k results straight
+      // into the page-locked staging buffer, which is mapped into the device's address space (unified addressing): a
+      // kernel launch and a stream wait are all that is left around the scan (two copy operations cost ~15 us on a 240 us
+      // kernel; letting 148 CTAs read the query from host memory instead cost 24 us).
+      float* m_q = reinterpret_cast<float*>(pin);
+      TRR_CHECK(dense_search_locked(h, m_q, B, k, reinterpret_cast<uint32_t*>(pin + pin_q + ord_off),
+                                    reinterpret_cast<float*>(pin + pin_q + score_off),
+                                    reinterpret_cast<uint32_t*>(pin + pin_q + n_off), false, m_q + (size_t)B * h->dim, m_q,
+                                    m_q[(size_t)B * h->dim]));
+    } else {
+      TRR_CUDA(cudaMemcpyAsync(d_q, pin, q_bytes + (size_t)B * 4, cudaMemcpyHostToDevice, st));
+      TRR_CHECK(dense_search_locked(h, d_q, B, k, d_ord, d_score, d_n, false, d_q + (size_t)B * h->dim));
+      TRR_CUDA(cudaMemcpyAsync(pin + pin_q, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    cudaError_t se = cudaStreamSynchronize(st);
+    if (se != cudaSuccess) return trr_fail(TRR_ERR_CUDA, std::string("dense search failed: ") + cudaGetErrorString(se));
+    if (k) {
+      memcpy(out_ord, pin + pin_q + ord_off, (size_t)B * k * 4);
+      memcpy(out_score, pin + pin_q + score_off, (size_t)B * k * 4);
+    }
+    memcpy(out_n, pin + pin_q + n_off, (size_t)B * 4);
+    return TRR_OK;
+  }
+  TRR_CUDA(cudaMemcpyAsync(d_q, q, q_bytes, cudaMemcpyHostToDevice, st));
   TRR_CHECK(dense_search_locked(h, d_q, B, k, d_ord, d_score, d_n, true));
   if (k) {
     TRR_CUDA(cudaMemcpyAsync(out_ord, d_ord, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));

@@ -24,6 +24,23 @@ struct DenseScanArgs {
   uint32_t base_ord;
   uint64_t* partial;         // [n_sel][n_warps_total][k] keys
   uint32_t* partial_n;       // [n_sel][n_warps_total]
+  // TMA kernel, fused epilogue (single-call latency: VectorStore::search is one query): the last CTA to finish a query
+  // group merges the per-CTA lists and writes the results, so the search is ONE launch; q_norms may then be NULL and the
+  // kernel computes |q| itself (reference order).  Used when done != NULL.
+  uint32_t q_in_param;       // 1: the (single) query and its norm come from the ScanQueryParam kernel parameter
+  uint32_t* done;            // [ceil(n_sel / NQ)] arrival counters, zero before the launch; the kernel re-zeroes them
+  uint64_t* out_keys;        // nullable [n_sel][k]
+  uint32_t* out_ord;         // nullable [n_sel][k]
+  float* out_score;          // nullable
+  uint32_t* out_n;           // nullable [n_sel]
+};
+
+// A single query small enough for the kernel-parameter space (4 KB in all) travels with the launch: no host -> device copy
+// operation, every CTA reads it through the constant cache.  DenseScanArgs::q_in_param selects it (one query, NQ = 1).
+constexpr uint32_t TRR_SCAN_PARAM_DIM = 768;
+struct ScanQueryParam {
+  float norm;                      // |q| in reference order (computed on the host)
+  float v[TRR_SCAN_PARAM_DIM];
 };
 
 // generic merge of key lists into a canonical top-k (dense_scan.cu)
@@ -105,8 +122,10 @@ cudaError_t trr_launch_scan(const DenseScanArgs& a, int is_bf16, int metric, boo
                             cudaStream_t st);
 // K1 with a 2-D TMA ring (rows of a multiple of 16 bytes): map_rows128 = tensor map of the slab, box 32 rows x 128 bytes
 // nq = 1 or 4: queries sharing one pass over the slab
+// host_q (nullable): the single query (a.dim floats, host memory) + host_q_norm to pass as a kernel parameter (a.q_in_param)
 cudaError_t trr_launch_scan_tma(const DenseScanArgs& a, const void* map_rows128, int is_bf16, int metric, unsigned grid,
-                                unsigned n_warps, uint32_t nq, size_t smem, cudaStream_t st);
+                                unsigned n_warps, uint32_t nq, size_t smem, cudaStream_t st, const float* host_q = nullptr,
+                                float host_q_norm = 0.0f);
 size_t trr_scan_tma_smem(uint32_t dim, uint32_t cap, uint32_t n_slots, uint32_t n_warps, uint32_t nq);
 cudaError_t trr_launch_topk_merge(const TopkMergeArgs& a, unsigned grid, cudaStream_t st);
 cudaError_t trr_launch_rescore(const RescoreArgs& a, int is_bf16, cudaStream_t st);

@@ -269,7 +269,7 @@ dense_scan_bulk_kernel(DenseScanArgs a) {
 // independent strict chains, so four queries cost about one pass instead of four.
 template <int IS_BF16, int METRIC, int NQ>
 __global__ void __launch_bounds__(512, 1)
-dense_scan_tma_kernel(const __grid_constant__ CUtensorMap map, DenseScanArgs a) {
+dense_scan_tma_kernel(const __grid_constant__ CUtensorMap map, DenseScanArgs a, const __grid_constant__ ScanQueryParam qp) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t SLOT = 4096;
@@ -284,7 +284,9 @@ dense_scan_tma_kernel(const __grid_constant__ CUtensorMap map, DenseScanArgs a) 
   uint8_t* after_q = reinterpret_cast<uint8_t*>(qs) + (size_t)NQ * q_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(after_q) + (size_t)warp * S;
   uint32_t* warp_cnt = reinterpret_cast<uint32_t*>(after_q + (size_t)NWARPS * S * 8);
-  uint64_t* tk_base = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(warp_cnt) + 64);  // [NQ][NWARPS][cap]
+  float* s_qn = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(warp_cnt) + 64);      // [4] query norms (fused prologue)
+  uint32_t& s_last = *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(warp_cnt) + 96);  // fused epilogue: this CTA merges
+  uint64_t* tk_base = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(warp_cnt) + 128);  // [NQ][NWARPS][cap]
 
   if (lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map) : "memory");
@@ -311,12 +313,28 @@ dense_scan_tma_kernel(const __grid_constant__ CUtensorMap map, DenseScanArgs a) 
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       const uint32_t qi = (uint32_t)q < nq ? (a.sel ? a.sel[si + q] : si + q) : 0u;
-      for (uint32_t j = threadIdx.x; j < a.dim; j += blockDim.x)
-        qs[q * q_floats + j] = (uint32_t)q < nq ? a.q[(uint64_t)qi * a.dim + j] : 0.0f;
-      q_norm[q] = (uint32_t)q < nq ? a.q_norms[qi] : 0.0f;
+      if (a.q_in_param) {  // (one query, q == 0: it arrived with the launch)
+        for (uint32_t j = threadIdx.x; j < a.dim; j += blockDim.x) qs[q * q_floats + j] = q == 0 ? qp.v[j] : 0.0f;
+        q_norm[q] = q == 0 ? qp.norm : 0.0f;
+      } else {
+        for (uint32_t j = threadIdx.x; j < a.dim; j += blockDim.x)
+          qs[q * q_floats + j] = (uint32_t)q < nq ? a.q[(uint64_t)qi * a.dim + j] : 0.0f;
+        q_norm[q] = ((uint32_t)q < nq && a.q_norms) ? a.q_norms[qi] : 0.0f;
+      }
       tk[q].init(tk_base + ((size_t)q * NWARPS + warp) * a.cap, a.cap, a.k);
     }
     __syncthreads();
+    if (!a.q_norms && !a.q_in_param && METRIC == TRR_METRIC_COSINE) {
+      // |q| in the reference's order (src/index.rs:442): one thread per query of the group, sequential f32 sum + sqrt
+      if (lane == 0 && warp < NQ) {
+        float sq = 0.0f;
+        for (uint32_t j = 0; j < a.dim; ++j) sq = sq + qs[warp * q_floats + j] * qs[warp * q_floats + j];
+        s_qn[warp] = sqrtf(sq);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) q_norm[q] = s_qn[q];
+    }
 
     // producer state: next box to request = (group i_k, box i_c)
     uint64_t i_k = 0;
@@ -403,6 +421,59 @@ dense_scan_tma_kernel(const __grid_constant__ CUtensorMap map, DenseScanArgs a) 
         cta_merge_and_store(tk[q], tk_base + (size_t)q * NWARPS * a.cap, a.cap, NWARPS, warp, lane, warp_cnt,
                             a.partial + ((uint64_t)(si + q) * gridDim.x + blockIdx.x) * a.k,
                             a.partial_n + ((uint64_t)(si + q) * gridDim.x + blockIdx.x));
+      }
+    }
+    if (a.done) {
+      // fused epilogue: the CTA that arrives last merges the gridDim.x lists of every query of the group and writes the
+      // results - no merge kernel, no second launch
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) s_last = atomicAdd(&a.done[si / NQ], 1u) == gridDim.x - 1 ? 1u : 0u;
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        for (uint32_t q = 0; q < nq; ++q) {
+          const uint32_t out_row = a.sel ? a.sel[si + q] : si + q;
+          const uint64_t* lists = a.partial + (uint64_t)(si + q) * gridDim.x * a.k;
+          const uint32_t* list_n = a.partial_n + (uint64_t)(si + q) * gridDim.x;
+          // every warp folds its share of the per-CTA lists into its top-k buffer, then the CTA merge used above leaves
+          // the final list in this CTA's own slot of `partial` (its content has been folded already)
+          WarpTopK m;
+          m.init(tk_base + ((size_t)q * NWARPS + warp) * a.cap, a.cap, a.k);
+          // (flat walk over the gridDim.x * k slots, four independent loads per lane in flight: the lists sit in L2)
+          const uint32_t total = gridDim.x * a.k;
+          for (uint32_t eb = warp * 32; eb < total; eb += NWARPS * 32 * 4) {  // (warp-uniform bound: push is collective)
+            uint64_t key[4];
+            bool valid[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t e = eb + lane + u * NWARPS * 32;
+              valid[u] = false; key[u] = TRR_KEY_EMPTY;
+              if (e < total) {
+                const uint32_t l = e / a.k;
+                valid[u] = (e - l * a.k) < list_n[l];
+                key[u] = lists[e];
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) m.push(valid[u] ? key[u] : TRR_KEY_EMPTY, valid[u], lane);
+          }
+          m.compact(lane);
+          uint64_t* dst = a.partial + ((uint64_t)(si + q) * gridDim.x + blockIdx.x) * a.k;
+          uint32_t* dst_n = a.partial_n + ((uint64_t)(si + q) * gridDim.x + blockIdx.x);
+          cta_merge_and_store(m, tk_base + (size_t)q * NWARPS * a.cap, a.cap, NWARPS, warp, lane, warp_cnt, dst, dst_n);
+          const uint32_t n_out = *dst_n;
+          for (uint32_t i = threadIdx.x; i < a.k; i += blockDim.x) {
+            const bool ok = i < n_out;
+            const uint64_t key = ok ? dst[i] : TRR_KEY_EMPTY;
+            if (a.out_keys) a.out_keys[(uint64_t)out_row * a.k + i] = key;
+            if (a.out_ord) a.out_ord[(uint64_t)out_row * a.k + i] = ok ? trr_key_ord(key) : 0xFFFFFFFFu;
+            if (a.out_score) a.out_score[(uint64_t)out_row * a.k + i] = ok ? trr_key_score(key) : 0.0f;
+          }
+          if (threadIdx.x == 0 && a.out_n) a.out_n[out_row] = n_out;
+          __syncthreads();
+        }
+        if (threadIdx.x == 0) a.done[si / NQ] = 0;  // ready for the next launch
       }
     }
   }
@@ -852,28 +923,37 @@ cudaError_t trr_launch_scan(const DenseScanArgs& a, int is_bf16, int metric, boo
 }
 
 size_t trr_scan_tma_smem(uint32_t dim, uint32_t cap, uint32_t n_slots, uint32_t n_warps, uint32_t nq) {
-  return 1024 + (size_t)n_warps * n_slots * 4096 + (size_t)nq * ((dim * 4 + 127) & ~127u) + (size_t)n_warps * n_slots * 8 + 64 +
-         (size_t)nq * n_warps * cap * 8;
+  return 1024 + (size_t)n_warps * n_slots * 4096 + (size_t)nq * ((dim * 4 + 127) & ~127u) + (size_t)n_warps * n_slots * 8 + 128 +
+         (size_t)nq * n_warps * cap * 8;  // (+128: per-warp counts, query norms and the last-CTA flag in front of the top-k buffers)
 }
 
 template <int IS_BF16, int METRIC, int NQ>
 static cudaError_t launch_scan_tma_t(const DenseScanArgs& a, const void* map128, unsigned grid, unsigned n_warps, size_t smem,
-                                     cudaStream_t st) {
+                                     cudaStream_t st, const ScanQueryParam& qp) {
   CUtensorMap m;
   memcpy(&m, map128, 128);
   auto kern = dense_scan_tma_kernel<IS_BF16, METRIC, NQ>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, 32 * n_warps, smem, st>>>(m, a);
+  kern<<<grid, 32 * n_warps, smem, st>>>(m, a, qp);
   return cudaGetLastError();
 }
 
-cudaError_t trr_launch_scan_tma(const DenseScanArgs& a, const void* map128, int is_bf16, int metric, unsigned grid,
-                                unsigned n_warps, uint32_t nq, size_t smem, cudaStream_t st) {
+cudaError_t trr_launch_scan_tma(const DenseScanArgs& a_in, const void* map128, int is_bf16, int metric, unsigned grid,
+                                unsigned n_warps, uint32_t nq, size_t smem, cudaStream_t st, const float* host_q,
+                                float host_q_norm) {
+  DenseScanArgs a = a_in;
+  static thread_local ScanQueryParam qp;  // (3 KB: kept off the stack; unused entries are never read)
+  a.q_in_param = 0;
+  if (host_q && a.dim <= TRR_SCAN_PARAM_DIM && nq == 1 && a.n_sel == 1 && !a.n_sel_ptr && !a.sel) {
+    memcpy(qp.v, host_q, (size_t)a.dim * 4);
+    qp.norm = host_q_norm;
+    a.q_in_param = 1;
+  }
 #define TRR_SCAN_CASE(B, M)                                                                          \
   if (is_bf16 == B && metric == M)                                                                   \
-    return nq == 4 ? launch_scan_tma_t<B, M, 4>(a, map128, grid, n_warps, smem, st)                  \
-                   : launch_scan_tma_t<B, M, 1>(a, map128, grid, n_warps, smem, st)
+    return nq == 4 ? launch_scan_tma_t<B, M, 4>(a, map128, grid, n_warps, smem, st, qp)              \
+                   : launch_scan_tma_t<B, M, 1>(a, map128, grid, n_warps, smem, st, qp)
   TRR_SCAN_CASE(0, TRR_METRIC_COSINE);
   TRR_SCAN_CASE(0, TRR_METRIC_EUCLIDEAN);
   TRR_SCAN_CASE(0, TRR_METRIC_DOT);
