@@ -166,6 +166,24 @@ def step_perf_scan():
     ix.close()
 
 
+def step_perf_metrics():
+    """Batched search through the tensor-core path for each metric on the cfg4 dense shape (PROBE_DOCS x 768 bf16, B=1024,
+    k=50): the Euclidean batch against the cosine batch (within 1.3x)."""
+    n, d, B, k = int(os.environ.get("PROBE_DOCS", "10000000")), 768, 1024, 50
+    Q = O.synth_queries(SEED, 0, B, d, n, corpus_bf16=True)
+    for metric, name in ((0, "cosine"), (1, "euclidean"), (2, "dot")):
+        ctx = api.Context(0)
+        ix = api.DenseIndex(ctx, d, metric, 1, capacity=n)
+        ix.append_synth(SEED, 0, n)
+        ix.set_mode(2)
+        for it in range(4):
+            ix.search(Q, k)
+            st = ix.stats()
+        print(f"K2 {name}: {n}x{d} bf16 B={B} k={k}: call {st.ms_total:.3f} ms, tensor-core pass {st.ms_main_kernel:.3f} ms, "
+              f"re-scoring width {st.rescore_width}, exact-scan fallbacks {st.n_guard_fallbacks}", flush=True)
+        ix.close(); ctx.close()
+
+
 def step_perf_gemm():
     ctx = api.Context(0)
     n, d, B = int(os.environ.get("PROBE_DOCS", "2000000")), int(os.environ.get("PROBE_DIM", "768")), int(os.environ.get("PROBE_B", "1024"))

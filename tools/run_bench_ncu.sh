@@ -4,7 +4,7 @@
 #   launches  ncu launch list (gpu__time_duration per launch) of a short bench run
 #   gemm | bm25 | scan   ncu --set full capture of that kernel (second launch)
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --verify 0 --docs ${NCU_DOCS:-10000000}"
+CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extra --verify 0 --docs ${NCU_DOCS:-10000000}"
 case "$1" in
   bench)
     python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
@@ -15,13 +15,13 @@ case "$1" in
     echo "launch list rc=$?" ;;
   gemm)
     $CMD > gpurun_out/plain.log 2>&1 && \
-    ncu --set full --clock-control none --import-source on -k regex:dense_gemm_topk -s 1 -c 1 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu2.log 2>&1; echo "gemm prof rc=$?" ;;
-  bm25)
+    ncu --set full --clock-control none --import-source on -k regex:dense_gemm_topk -s 1 -c 1 -f -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu2.log 2>&1; echo "gemm prof rc=$?" ;;
+  bm25)  # the 16-bit fast kernel of the second step (launches alternate <16>, <32>: skip two)
     $CMD > gpurun_out/plain.log 2>&1 && \
-    ncu --set full --clock-control none --import-source on -k regex:bm25_search -s 1 -c 1 -o gpurun_out/prof_bm25 $CMD > gpurun_out/ncu3.log 2>&1; echo "bm25 prof rc=$?" ;;
+    ncu --set full --clock-control none --import-source on -k regex:bm25_fast -s 2 -c 1 -f -o gpurun_out/prof_bm25 $CMD > gpurun_out/ncu3.log 2>&1; echo "bm25 prof rc=$?" ;;
   scan)
     timeout 300 python tools/gpu_probe.py perf_scan > gpurun_out/plain_scan.log 2>&1 && \
-    ncu --set full --clock-control none --import-source on -k regex:dense_scan_tma -s 1 -c 1 -o gpurun_out/prof_scan python tools/gpu_probe.py perf_scan > gpurun_out/ncu4.log 2>&1; echo "scan prof rc=$?"
+    ncu --set full --clock-control none --import-source on -k regex:dense_scan_tma -s 1 -c 1 -f -o gpurun_out/prof_scan python tools/gpu_probe.py perf_scan > gpurun_out/ncu4.log 2>&1; echo "scan prof rc=$?"
     cat gpurun_out/plain_scan.log ;;
   *) echo "usage: $0 bench|launches|gemm|bm25|scan"; exit 2 ;;
 esac
