@@ -384,3 +384,17 @@ def test_hybrid_index_requires_embedding(api):
     r = api.HybridRetriever(api.VectorStore.with_dimension(4), api.BM25Index(), lambda t: [0.0] * 4)
     with pytest.raises(api.Error):
         r.index(api.Chunk("no embedding"))
+
+
+def test_nemotron_example_ranking(api, ctx):
+    """examples/nemotron_embeddings.rs:60-92: a handful of 4096-dimensional document embeddings ranked against one query by
+    cosine similarity (stable sort, descending) - through the exact scan kernel, bit for bit the oracle's order and scores."""
+    rng = np.random.default_rng(79)
+    docs = rng.standard_normal((6, 4096)).astype(np.float32)
+    docs[4] = docs[1]                                                    # an exact tie keeps document order
+    docs /= np.linalg.norm(docs, axis=1, keepdims=True).astype(np.float32)
+    q = (docs[2] + 0.5 * rng.standard_normal(4096)).astype(np.float32)
+    idx, sims = api.rank_by_cosine(ctx, q, docs)
+    eo, es, en = O.dense_search_batch(docs, q[None, :], 6)
+    assert int(en[0]) == 6 and np.array_equal(idx, eo[0]) and np.array_equal(sims, es[0])
+    assert idx[0] == 2 and list(idx).index(1) < list(idx).index(4)

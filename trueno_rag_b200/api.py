@@ -365,6 +365,25 @@ def hybrid_merge(ctx: Context, d_gathered: int, G: int, B: int, C_: int, strateg
     return o_ord, o_f, o_d, o_s, o_n
 
 
+def rank_by_cosine(ctx: Context, query, embeddings):
+    """The brute-force ranking of examples/nemotron_embeddings.rs:79-92 (cosine of the query against every document
+    embedding, stable sort by similarity descending) through the exact scan kernel: returns (indices, similarities) of
+    all documents, best first; equal similarities keep document order (the stable sort of the reference)."""
+    emb = np.ascontiguousarray(embeddings, dtype=np.float32)
+    if emb.ndim != 2 or emb.shape[0] == 0:
+        return np.zeros(0, np.uint32), np.zeros(0, np.float32)
+    if emb.shape[0] > 1024:
+        raise TrrError(_lib.TRR_ERR_UNSUPPORTED, "rank_by_cosine ranks at most 1024 documents per call (k <= 1024)")
+    ix = DenseIndex(ctx, emb.shape[1], COSINE, F32)
+    try:
+        ix.append(emb)
+        ix.set_mode(MODE_SCAN)
+        ords, scores, n = ix.search(np.ascontiguousarray(query, dtype=np.float32), emb.shape[0])
+        return ords[0, :int(n[0])].copy(), scores[0, :int(n[0])].copy()
+    finally:
+        ix.close()
+
+
 # ---------------------------------------------------------------------------------------------------
 # sharded search: one process per GPU, the exchange inside the call
 # ---------------------------------------------------------------------------------------------------
