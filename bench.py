@@ -354,17 +354,15 @@ def run_ours(a):
         ms = ev0.elapsed_time(ev1)
         return float(group.allreduce_u64(np.array([int(ms * 1e6)], np.uint64), op_max=True)[0]) / 1e6
 
-    # warm-up: the W steps asked for, then more until one second of device work has passed - the board's power management
-    # and the library's adaptive re-scoring width (one step of feedback delay) both need a few hundred milliseconds to settle,
-    # and W = 3 steps are 55 ms (measured: the tensor-core pass of the first timed steps ran 8 % slower without this)
-    t_w = time.perf_counter()
+    # warm-up: W steps, each followed by a wait, so that the library's adaptive re-scoring width (feedback of the previous
+    # search, read by the host at the next call) has settled before the timed region; the timed steps run back to back.
+    # (Sustained regime, for the record: after one second of back-to-back steps the board's power cap pulls the tensor-core
+    # pass from 11.9 to 12.9 ms and the step from 18.1 to 19.8 ms - profiles/r02_sustained.json.)
     n_warm = 0
-    while n_warm < a.warmup or (time.perf_counter() - t_w < 1.0 and n_warm < 200):
+    for _ in range(a.warmup):
         step_device()
+        group.sync()
         n_warm += 1
-        if n_warm % 4 == 0:
-            group.sync()
-    group.sync()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
