@@ -99,16 +99,49 @@ def zipf_cdf(n_terms: int, clip: int = 90) -> np.ndarray:
 
 # ------------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled by a host thread while the timed regions run: NVML polled every
+    ~2 ms (a step is ~18 ms, so `nvidia-smi -lms` would start too late to see it); `nvidia-smi` only if NVML is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+            0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index: int):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:
+            ids = [int(x) for x in vis.split(",") if x.strip() != ""]
+            if gpu_index < len(ids):
+                gpu_index = ids[gpu_index]
+        except ValueError:
+            pass
+        self.gpu, self.rows, self.proc, self.stop_flag, self.thread = gpu_index, [], None, False, None
+        self.sm, self.mask, self.max_mhz, self.how = [], 0, None, None
+
+    def _poll(self, nv, h):
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.how = "nvml"
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.how = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
+            self.how = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -118,6 +151,12 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+            reasons = sorted(name for bit, name in self.BITS.items() if self.mask & bit)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": reasons, "samples": len(self.sm), "source": "nvml, polled during the timed regions"}
         if self.proc:
             self.proc.terminate()
             try:
@@ -134,7 +173,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 # ------------------------------------------------------------------------------------------------- CPU legs
@@ -371,7 +410,6 @@ def run_ours(a):
     ms_dev = timed(step_device, a.steps)
     launches1 = C.c_uint64()
     L.trr_ctx_launch_count(ctx.h, C.byref(launches1))
-    clocks = sampler.stop() if rank == 0 else None
     dev_out = [t.cpu().numpy() for t in d_out]          # results of the last timed (device-resident) step
     # per-kernel device times: the library records CUDA events around its dominant kernels on the launching stream at every
     # step; what is read here (the streams are idle) are the events of the LAST TIMED step
@@ -381,6 +419,7 @@ def run_ours(a):
     for _ in range(max(1, a.warmup // 2)):
         step_e2e()
     ms_e2e = timed(step_e2e, a.steps)
+    clocks = sampler.stop() if rank == 0 else None      # (sampled over both timed regions and what lies between them)
     e2e_out = [t.numpy().copy() for t in out_pin]
     # the blocking form of the same call (what a synchronous caller gets), also the reference for the checks below
     t0 = time.perf_counter()

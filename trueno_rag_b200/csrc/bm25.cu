@@ -567,8 +567,8 @@ bm25_search_kernel(Bm25SearchArgs a) {
 // slice of every term segment on its own (a dozen postings per slice), and the f32 cells force plain read-modify-write.
 // The fast pass only SELECTS.  Every posting adds ceil(impact * scale) to an integer cell with one native shared-memory
 // atomic (ATOMS.ADD: measured 6.3 cycles per 32 random cells against 10.4 for a plain LDS/FADD/STS chain and 16.4 for
-// the CAS loop an f32 atomic compiles to; tools/ubench/smem_atom.cu), so the order inside a pass is free and all 512
-// consumer threads walk the staged postings FLAT - no sub-range ownership, no boundary searches, no per-segment shuffles.
+// the CAS loop an f32 atomic compiles to; tools/ubench/smem_atom.cu), so the order inside a pass is free and the
+// accumulate threads walk the staged postings FLAT - no sub-range ownership, no boundary searches, no per-segment shuffles.
 // ceil(impact * scale) is one FFMA with round-up onto 2^23 (the integer appears in the mantissa; F2I runs at a fraction of
 // the FMA rate).  Integer sums are exact and never below scale * (real-number sum of the impacts), which bounds the
 // reference's f32 score of every document from above:  score_f32(d) <= F(d) / scale * (1 + T * 2^-23)  (T term slots,
@@ -576,14 +576,23 @@ bm25_search_kernel(Bm25SearchArgs a) {
 // bm25_rescore_kernel recomputes their scores in the reference's order and proves that nothing that was dropped can reach
 // the k-th exact score.
 // Two cell widths (template BITS): 16-bit cells, two per word, halve the per-range scan of the accumulator - the largest
-// shared-memory cost of the pass - and leave room for 48 KB stages; their scale (65535 / sum of the query terms' largest
+// shared-memory cost of the pass - and leave room for a second accumulator (below); their scale (65535 / sum of the query terms' largest
 // impacts) makes the bound a few hundredths wide, far below the score gap between rank k and rank kf on ordinary data.
 // A query whose 16-bit proof fails is re-run with 32-bit cells (bound ~1e-5 relative), and only if that proof fails too
 // (dozens of documents within rounding distance of the k-th score, e.g. exact duplicates) by the exact kernel.  Both
 // fallbacks are device-driven: they read the number of flagged queries from device memory and leave at once when it is 0.
 //
-// Producer warp and staging are those of the exact kernel (one cp.async.bulk per term segment into a shared-memory
-// ring, here of two 64 KB stages), with one difference: a flat walk cannot mask the alignment padding of a copy by segment
+// Three warp roles: 4 PRODUCER warps (staging), 8 ACCUMULATE warps (postings -> atomics) and 16 SCAN warps (harvest +
+// re-zeroing), with a ring of two accumulators between the last two, so that range i is scanned while range i + 1
+// accumulates.  (History of the shape, cfg4 batch on one B200: one group of 16 warps doing both in turn 5.08 ms; the same
+// over two skip-table ranges per 128 KB accumulator, i.e. half the barrier intervals, 4.35 ms; two groups 4.39 ms with 8
+// loads in flight per thread, 4.26 ms with 4 / 2 - the shared-memory pipe is the limit and deep queues only delay the
+// other group; 12 + 12, 16 + 8, 4 + 20 ... warps all within 4.2 - 4.9 ms.  Also tried on this structure: FOLDING 2 or 4
+// documents into one cell, which halves the scan per document - a cell still bounds each of its documents, selection and
+// proof run on cells - but on Zipf text the sums of two mid-scoring documents crowd out the real top-k cells and 95 % of
+// the queries fail the proof.)
+// Staging is that of the exact kernel (one cp.async.bulk per term segment into a shared-memory ring, here of two ~45 KB
+// stages), with one difference: a flat walk cannot mask the alignment padding of a copy by segment
 // bounds.  Padding postings of the SAME term fall outside the document range and are dropped by the range check; the only
 // paddings that could fall inside are the last posting of the previous term / the first of the next one, i.e. when an
 // odd-aligned segment starts (ends) exactly at its term's first (last) posting.  Those segments are copied without that
@@ -602,17 +611,36 @@ constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 // take 1300 cycles per stage, from four warps 800), and a range needs one copy per query term with postings in it (~16).
 // Four producer warps run the same plan in lockstep; each issues the copies of every fourth slot, warp 0 also publishes
 // the descriptor.
-constexpr uint32_t PW = 4;
-// (28 consumer warps - the 1024-thread limit - measured no faster than 16: 5.84 vs 5.60 ms at cfg4)
-#ifndef TRR_BM25_FAST_CONSUMER_WARPS
-#define TRR_BM25_FAST_CONSUMER_WARPS 16
+#ifndef TRR_BM25_FAST_PRODUCER_WARPS
+#define TRR_BM25_FAST_PRODUCER_WARPS 4
 #endif
-constexpr uint32_t FCW = TRR_BM25_FAST_CONSUMER_WARPS;
-constexpr uint32_t FCT = FCW * 32;
-constexpr uint32_t FAST_THREADS = (FCW + PW) * 32;
-constexpr int FU = (4096 + FCT - 1) / FCT;  // loads per thread and round trip: one round covers 4096 postings / 128-bit groups
+constexpr uint32_t PW = TRR_BM25_FAST_PRODUCER_WARPS;
+// The consumer side is two groups of warps that work on different document ranges at the same time: ACCUMULATE warps
+// walk the staged postings of range i + 1 (LDS + ATOMS) while SCAN warps harvest and re-zero the accumulator of range i
+// (LDS.128 + STS.128).  With one group doing both in turn every phase was a few dependent shared-memory round trips with
+// the pipe idle in between (49 % busy); two groups keep it fed.  Hand-over through named barriers (arrive / sync pairs).
+#ifndef TRR_BM25_FAST_ACC_WARPS
+#define TRR_BM25_FAST_ACC_WARPS 8
+#endif
+#ifndef TRR_BM25_FAST_SCAN_WARPS
+#define TRR_BM25_FAST_SCAN_WARPS 16
+#endif
+constexpr uint32_t XW = TRR_BM25_FAST_ACC_WARPS, XT = XW * 32;    // accumulate warps
+constexpr uint32_t YW = TRR_BM25_FAST_SCAN_WARPS, YT = YW * 32;   // scan warps (the first warps of the CTA)
+constexpr uint32_t FAST_THREADS = (YW + XW + PW) * 32;
+#ifndef TRR_BM25_FAST_FUX
+#define TRR_BM25_FAST_FUX 4
+#endif
+#ifndef TRR_BM25_FAST_FUY
+#define TRR_BM25_FAST_FUY 2
+#endif
+constexpr int FUX = TRR_BM25_FAST_FUX;  // posting loads in flight per accumulate thread
+constexpr int FUY = TRR_BM25_FAST_FUY;  // 128-bit cell groups in flight per scan thread
+constexpr uint32_t BAR_FULL = 3, BAR_EMPTY = 5;  // named barriers of the hand-over ring (+ slot, two slots at most)
 __device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 2, %0;" ::"n"(PW * 32) : "memory"); }
-__device__ __forceinline__ void fast_bar() { asm volatile("bar.sync 1, %0;" ::"n"(FCT) : "memory"); }
+__device__ __forceinline__ void fast_bar() { asm volatile("bar.sync 1, %0;" ::"n"(YT) : "memory"); }
+__device__ __forceinline__ void ring_arrive(uint32_t id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(XT + YT) : "memory"); }
+__device__ __forceinline__ void ring_sync(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(XT + YT) : "memory"); }
 struct FastSync { __device__ __forceinline__ void operator()() const { fast_bar(); } };
 __device__ __forceinline__ bool fast_bar_or(bool pred) {
   uint32_t r;
@@ -622,7 +650,7 @@ __device__ __forceinline__ bool fast_bar_or(bool pred) {
       "barrier.red.or.pred q, 1, %2, p;\n\t"
       "selp.u32 %0, 1, 0, q;\n\t}"
       : "=r"(r)
-      : "r"((uint32_t)pred), "n"(FCT)
+      : "r"((uint32_t)pred), "n"(YT)
       : "memory");
   return r != 0;
 }
@@ -637,6 +665,9 @@ struct FastDesc {
   uint32_t pad0, pad1;
   uint2 single[64];     // [slot] first / [32 + slot] last posting of a term, when the aligned copy had to leave it out
 };
+struct FastHandoff {    // accumulate warps -> scan warps: one accumulator (or an end-of-item / quit notice)
+  uint32_t flags, range_base, item, thr0f;
+};
 
 }  // namespace
 
@@ -644,31 +675,34 @@ template <int BITS>  // width of an accumulator cell: 16 (two cells per word) or
 __global__ void __launch_bounds__(FAST_THREADS, 1)
 bm25_fast_kernel(Bm25SearchArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const uint32_t R = 1u << a.range_shift;
+  // a pass range = 2^rmul_shift consecutive ranges of the skip table (their postings are contiguous per term): fewer, larger
+  // barrier intervals per document
+  const uint32_t R = 1u << (a.range_shift + a.rmul_shift);
   const uint32_t W = BITS == 16 ? R >> 1 : R;                                             // accumulator words
-  uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                                  // R fixed-point cells
-  uint2* stage_buf = reinterpret_cast<uint2*>(acc + W);                                   // NS x stage_cap
+  const uint32_t NA = a.n_acc;                                                            // accumulators in the ring (1 or 2)
+  uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                                  // NA x R fixed-point cells
+  uint2* stage_buf = reinterpret_cast<uint2*>(acc + (size_t)NA * W);                      // NS x stage_cap
   uint64_t* cand = reinterpret_cast<uint64_t*>(stage_buf + (size_t)NS * a.stage_cap);     // cand_cap
   FastDesc* desc = reinterpret_cast<FastDesc*>(cand + a.cand_cap);                        // NS
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(desc + NS);                            // NS
   uint64_t* empty_bar = full_bar + NS;                                                    // NS
   __shared__ uint32_t s_cnt, s_overflow, s_ovf_latched, s_item;
   __shared__ uint64_t s_thr;
+  __shared__ FastHandoff s_hand[2];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) {
-    for (uint32_t s = 0; s < NS; ++s) { trr_mbar_init(&full_bar[s], 1); trr_mbar_init(&empty_bar[s], FCW); }
+    for (uint32_t s = 0; s < NS; ++s) { trr_mbar_init(&full_bar[s], 1); trr_mbar_init(&empty_bar[s], XW); }
     trr_fence_mbar_init();
     s_cnt = 0; s_overflow = 0; s_thr = TRR_KEY_EMPTY;
   }
-  if (warp < FCW) for (uint32_t i = tid; i < W; i += FCT) acc[i] = 0u;
+  if (warp < YW + XW) for (uint32_t i = tid; i < NA * W; i += XT + YT) acc[i] = 0u;
   __syncthreads();
 
-  TRI(long long w_prod = 0, w_full = 0, w_acc = 0, w_harv = 0, w_end = 0, w_b1 = 0, w_scan = 0, w_arr = 0, w_bar = 0; uint32_t n_pass = 0, n_compact = 0;)
-  TRI(const long long t_begin = clock64();)
-  if (warp >= FCW) {
+  if (warp >= YW + XW) {
     // ============================ producer warps ============================
-    const uint32_t pw = warp - FCW;
+    const uint32_t pw = warp - (YW + XW);
+    TRI(long long t_wait = 0; uint32_t t_n = 0; const long long t_begin = clock64();)
     uint32_t stage = 0, phase = 0;
     uint32_t item_thr0f = 0;
     float item_scale = 1.0f;
@@ -678,7 +712,7 @@ bm25_fast_kernel(Bm25SearchArgs a) {
                     uint32_t total_al, uint2 sf, uint2 sb) {
       TRI(const long long tw = clock64();)
       mbar_wait_or_trap<true>(&empty_bar[stage], phase ^ 1, 1, a.dbg);
-      TRI(w_prod += clock64() - tw; ++n_pass;)
+      TRI(t_wait += clock64() - tw; ++t_n;)
       if (pw == 0) {
         FastDesc& d = desc[stage];
         d.single[lane] = sf;
@@ -708,8 +742,11 @@ bm25_fast_kernel(Bm25SearchArgs a) {
       const uint32_t b = a.order[item / a.n_chunks], c = item % a.n_chunks;
       item_thr0f = a.n_chunks == 1 ? a.thr0f[b] : 0u;  // (the bootstrap counts the postings of the whole shard)
       item_scale = a.qscale[b];
-      const uint32_t r0 = (uint32_t)(((uint64_t)c * a.n_ranges) / a.n_chunks);
-      const uint32_t r1 = (uint32_t)(((uint64_t)(c + 1) * a.n_ranges) / a.n_chunks);
+      const uint32_t m = a.rmul_shift;
+      const uint32_t n_sr = (a.n_ranges + (1u << m) - 1u) >> m;  // pass ranges
+      auto sk = [&](uint32_t r) { return min(r << m, a.n_ranges); };  // pass range -> column of the skip row
+      const uint32_t r0 = (uint32_t)(((uint64_t)c * n_sr) / a.n_chunks);
+      const uint32_t r1 = (uint32_t)(((uint64_t)(c + 1) * n_sr) / a.n_chunks);
       const uint32_t q0 = a.q_off[b];
       const uint32_t T = a.q_off[b + 1] - q0;
       const uint32_t G = (T + 31) >> 5;
@@ -722,9 +759,9 @@ bm25_fast_kernel(Bm25SearchArgs a) {
         const uint32_t term = a.q_terms[q0 + lane];
         if (term < a.n_terms) {
           row1 = a.skip + (uint64_t)term * a.skip_ld;
-          c_s = row1[r0];
-          c_e = r0 < r1 ? row1[r0 + 1] : c_s;
-          c_n = r0 + 2 <= a.n_ranges ? row1[r0 + 2] : c_e;
+          c_s = row1[sk(r0)];
+          c_e = r0 < r1 ? row1[sk(r0 + 1)] : c_s;
+          c_n = r0 + 2 <= n_sr ? row1[sk(r0 + 2)] : c_e;
           ts1 = row1[0];
           te1 = row1[a.n_ranges];
           if (te1 > ts1) {
@@ -734,21 +771,21 @@ bm25_fast_kernel(Bm25SearchArgs a) {
         }
       }
       for (uint32_t r = r0; r < r1; ++r) {
-        const uint32_t range_base = r << a.range_shift;
+        const uint32_t range_base = r << (a.range_shift + m);
         bool pending_harvest = false;  // a pass of this range was emitted without the harvest flag
         for (uint32_t g = 0; g < G; ++g) {
           uint32_t s = 0, e = 0, ts = 0, te = 0;
           if (G == 1) {
             s = c_s; e = c_e; ts = ts1; te = te1;
             c_s = c_e; c_e = c_n;
-            if (row1 && r + 3 <= a.n_ranges) c_n = row1[r + 3];
+            if (row1 && r + 3 <= n_sr) c_n = row1[sk(r + 3)];
           } else {
             const uint32_t ti = g * 32 + lane;
             if (ti < T) {
               const uint32_t term = a.q_terms[q0 + ti];
               if (term < a.n_terms) {
                 const uint32_t* row = a.skip + (uint64_t)term * a.skip_ld;
-                s = row[r]; e = row[r + 1]; ts = row[0]; te = row[a.n_ranges];
+                s = row[sk(r)]; e = row[sk(r + 1)]; ts = row[0]; te = row[a.n_ranges];
               }
             }
           }
@@ -803,17 +840,81 @@ bm25_fast_kernel(Bm25SearchArgs a) {
       }
       emit(F_END_ITEM, 0, item, 0, 0, 0, 0, none2, none2);
     }
-    TRI(if (blockIdx.x == 0 && pw == 0 && lane == 0 && a.dbg && n_pass > 8) { a.dbg[9] = (uint32_t)(w_prod >> 4); a.dbg[14] = n_pass; })
+    TRI(if (blockIdx.x == 0 && pw == 0 && lane == 0 && a.triage_out && t_n > 64) {
+      a.triage_out[16] = (uint32_t)((clock64() - t_begin) >> 4); a.triage_out[17] = (uint32_t)(t_wait >> 4); a.triage_out[18] = t_n; })
+  } else if (warp >= YW) {
+    // ============================ accumulate warps ============================
+    TRI(long long t_full = 0, t_walk = 0, t_empty = 0; uint32_t t_n = 0; const long long t_begin = clock64();)
+    const uint32_t xt = tid - YT;
+    uint32_t stage = 0, phase = 0, n_msg = 0, slot = 0;
+    uint32_t* acc_cur = acc;
+    while (true) {
+      TRI(long long tc = clock64();)
+      mbar_wait_or_trap(&full_bar[stage], phase, 2, a.dbg);
+      TRI({ const long long t = clock64(); t_full += t - tc; tc = t; ++t_n; })
+      const FastDesc& d = desc[stage];
+      const uint32_t flags = d.flags, range_base = d.range_base, item = d.item, total = d.total, thr0f = d.thr0f;
+      const float scale = d.scale;
+      if (!(flags & F_QUIT)) {
+        const uint2* st = stage_buf + (size_t)stage * a.stage_cap;
+        // flat walk: posting p of the stage belongs to thread p mod XT; padding and foreign ranges fail the range check
+        const uint32_t acc_s = trr_smem_u32(acc_cur);
+        auto add1 = [&](const uint2 e) {
+          const uint32_t dd = e.x - range_base;
+          // ceil(impact * scale) in the low mantissa bits of RU(impact * scale + 2^23)  (impact * scale < 2^22)
+          uint32_t q = __float_as_uint(__fmaf_ru(__uint_as_float(e.y), scale, 8388608.0f)) & 0x7FFFFFu;
+          uint32_t addr;
+          if (BITS == 16) { addr = acc_s + ((dd >> 1) << 2); q <<= (dd & 1u) << 4; }
+          else addr = acc_s + (dd << 2);
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, %1;\n\t@p red.shared.add.u32 [%2], %3;\n\t}"
+                       ::"r"(dd), "r"(R), "r"(addr), "r"(q) : "memory");
+        };
+        // Every load of a round is issued before the first atomic.  Stage positions past `total` hold stale postings; they
+        // are read (in bounds) and replaced by a no-op.
+        const uint2 nop = make_uint2(NONE32, 0u);
+        const uint2 sg = xt < 64 ? d.single[xt] : nop;
+        for (uint32_t p = xt; p < total; p += FUX * XT) {
+          uint2 e[FUX];
+#pragma unroll
+          for (int u = 0; u < FUX; ++u) { const uint32_t pu = p + u * XT; e[u] = st[min(pu, a.stage_cap - 1)]; if (pu >= total) e[u] = nop; }
+#pragma unroll
+          for (int u = 0; u < FUX; ++u) add1(e[u]);
+        }
+        add1(sg);
+        __syncwarp();
+        if (lane == 0) trr_mbar_arrive(&empty_bar[stage]);  // stage and descriptor are free again
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+      }
+      TRI({ const long long t = clock64(); t_walk += t - tc; tc = t; })
+      if (flags & (F_HARVEST | F_END_ITEM | F_QUIT)) {
+        // hand the accumulator (or the notice) to the scan warps and take the next slot of the ring
+        if (xt == 0) s_hand[slot] = FastHandoff{flags, range_base, item, thr0f};
+        ring_arrive(BAR_FULL + slot);  // (completes when the scan warps sync on it: every add of the range has landed)
+        if (flags & F_QUIT) {
+          // leave no barrier half-arrived: consume the scan warps' releases of the slots still in flight
+          for (uint32_t j = n_msg >= NA - 1 ? n_msg - (NA - 1) : 0u; j < n_msg; ++j) ring_sync(BAR_EMPTY + j % NA);
+          break;
+        }
+        ++n_msg;
+        slot = n_msg % NA;
+        acc_cur = acc + (size_t)slot * W;
+        if (n_msg >= NA) ring_sync(BAR_EMPTY + slot);  // the scan of the range that used this slot before is done
+        TRI({ const long long t = clock64(); t_empty += t - tc; tc = t; })
+      }
+    }
+    TRI(if (blockIdx.x == 0 && xt == 0 && a.triage_out && t_n > 64) {
+      a.triage_out[0] = (uint32_t)((clock64() - t_begin) >> 4); a.triage_out[1] = (uint32_t)(t_full >> 4);
+      a.triage_out[2] = (uint32_t)(t_walk >> 4); a.triage_out[3] = (uint32_t)(t_empty >> 4); a.triage_out[4] = t_n; })
   } else {
-    // ============================ consumer warps ============================
-    uint32_t stage = 0, phase = 0;
+    // ============================ scan warps ============================
     const uint32_t compact_at = a.kf + ((a.cand_cap - a.kf) >> 1);
+    TRI(uint32_t t_ncomp = 0;)
     // block-wide (consumer warps) compaction: afterwards cand[0..s_cnt) is sorted descending and s_thr is the kf-th best
     auto compact = [&]() {
       fast_bar();
       const uint32_t cnt = min(s_cnt, a.cand_cap);
-      for (uint32_t i = cnt + tid; i < a.cand_cap; i += FCT) cand[i] = TRR_KEY_EMPTY;
-      trr_bitonic_sort_desc(cand, a.cand_cap, tid, FCT, FastSync());
+      for (uint32_t i = cnt + tid; i < a.cand_cap; i += YT) cand[i] = TRR_KEY_EMPTY;
+      trr_bitonic_sort_desc(cand, a.cand_cap, tid, YT, FastSync());
       if (tid == 0) {
         const uint32_t c2 = min(cnt, a.kf);
         s_cnt = c2;
@@ -882,21 +983,20 @@ bm25_fast_kernel(Bm25SearchArgs a) {
       };
       const uint32_t n4 = W >> 2;
       uint32_t i = tid;
-      TRI(if (a.triage & 4u) i = n4;)
-      for (; i + (FU - 1) * FCT < n4; i += FU * FCT) {  // FU 128-bit groups per round trip (see the accumulate walk)
-        uint4 v[FU];
+      for (; i + (FUY - 1) * YT < n4; i += FUY * YT) {  // FUY 128-bit groups per round trip
+        uint4 v[FUY];
 #pragma unroll
-        for (int u = 0; u < FU; ++u) v[u] = a4[i + u * FCT];
+        for (int u = 0; u < FUY; ++u) v[u] = a4[i + u * YT];
         uint32_t hits = 0;
 #pragma unroll
-        for (int u = 0; u < FU; ++u) hits |= pre4(i + u * FCT, v[u]) ? 1u << u : 0u;
+        for (int u = 0; u < FUY; ++u) hits |= pre4(i + u * YT, v[u]) ? 1u << u : 0u;
         if (hits) {
 #pragma unroll
-          for (int u = 0; u < FU; ++u)
-            if ((hits >> u) & 1u) harvest4(i + u * FCT, v[u]);
+          for (int u = 0; u < FUY; ++u)
+            if ((hits >> u) & 1u) harvest4(i + u * YT, v[u]);
         }
       }
-      for (; i < n4; i += FCT) {
+      for (; i < n4; i += YT) {
         const uint4 v = a4[i];
         if (pre4(i, v)) harvest4(i, v);
       }
@@ -906,87 +1006,51 @@ bm25_fast_kernel(Bm25SearchArgs a) {
     // candidate buffer overflowed, the cells that stayed behind are scanned again after the compaction.
     auto settle = [&](uint32_t* accx, uint32_t range_base, uint32_t thr0f, bool need) {
       while (fast_bar_or(need)) {
-        TRI(++n_compact;)
+        TRI(++t_ncomp;)
         compact();
         if (!s_ovf_latched) break;  // (stable until the next compaction, which is behind further barriers)
         need = scan(accx, range_base, thr0f);
       }
     };
-    // (Measured and dropped: two accumulators for the 16-bit cells, so that the scan of range i shares a barrier interval
-    // with the accumulation of range i + 1 - one barrier per range instead of two - ran 6.0 ms against 5.6 ms at cfg4: the
-    // time inside the barriers is not waiting for a slow warp, every warp spends it there while the shared-memory pipe
-    // drains the atomics and the zeroing stores queued by the phase, and the second accumulator costs a third of the stage.)
+    // (Round-2 history: with ONE group of warps doing accumulate and scan in turn, a second accumulator that let scan(i)
+    // share a barrier interval with accumulate(i + 1) was slower, 6.0 against 5.6 ms at cfg4 - all warps still moved through
+    // the phases together.  Walking two skip-table ranges per 128 KB accumulator (rmul_shift = 1, n_acc = 1) gave 4.35 ms.)
+    // (Measured and dropped: closing a scan behind the NEXT hand-over barrier instead of a barrier of its own - 4.50 against
+    // 4.39 ms.  The time "in the barrier" is the scan warps' own loads and zeroing stores draining through the shared-memory
+    // pipe, which they wait for wherever the next barrier instruction is.)
+    uint32_t n = 0;
+    TRI(long long t_full = 0, t_scan = 0, t_settle = 0, t_end = 0; const long long t_begin = clock64();)
     while (true) {
+      const uint32_t slot = n % NA;
       TRI(long long tc = clock64();)
-      mbar_wait_or_trap(&full_bar[stage], phase, 2, a.dbg);
-      TRI({ const long long t = clock64(); w_full += t - tc; tc = t; })
-      TRI(const long long t_pass = tc;)
-      const FastDesc& d = desc[stage];
-      const uint32_t flags = d.flags, range_base = d.range_base, item = d.item, total = d.total, thr0f = d.thr0f;
-      const float scale = d.scale;
-      if (flags & F_QUIT) break;
-      const uint2* st = stage_buf + (size_t)stage * a.stage_cap;
-      uint32_t* acc_cur = acc;
-      {
-        // flat walk: posting p of the stage belongs to thread p mod 512; padding and foreign ranges fail the range check
-        const uint32_t acc_s = trr_smem_u32(acc_cur);
-        auto add1 = [&](const uint2 e) {
-          const uint32_t dd = e.x - range_base;
-          // ceil(impact * scale) in the low mantissa bits of RU(impact * scale + 2^23)  (impact * scale < 2^22)
-          uint32_t q = __float_as_uint(__fmaf_ru(__uint_as_float(e.y), scale, 8388608.0f)) & 0x7FFFFFu;
-#ifdef TRR_TRIAGE
-          if (a.triage & 1u) { if (dd < R && q == 0x12345u) acc_cur[dd & (W - 1)] = 1u; return; }
-#endif
-          uint32_t addr;
-          if (BITS == 16) { addr = acc_s + ((dd >> 1) << 2); q <<= (dd & 1u) << 4; }
-          else addr = acc_s + (dd << 2);
-          asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, %1;\n\t@p red.shared.add.u32 [%2], %3;\n\t}"
-                       ::"r"(dd), "r"(R), "r"(addr), "r"(q) : "memory");
-        };
-        // Every load of a round is issued before the first atomic: under load a shared-memory round trip takes hundreds of
-        // cycles (the atomics of 16 warps queue in the same pipe), so the walk is bound by the number of dependent rounds.
-        // Stage positions past `total` hold stale postings; they are read (in bounds) and replaced by a no-op.
-        const uint2 nop = make_uint2(NONE32, 0u);
-        const uint2 sg = tid < 64 ? d.single[tid] : nop;
-        for (uint32_t p = tid; p < total; p += FU * FCT) {
-          uint2 e[FU];
-#pragma unroll
-          for (int u = 0; u < FU; ++u) { const uint32_t pu = p + u * FCT; e[u] = st[min(pu, a.stage_cap - 1)]; if (pu >= total) e[u] = nop; }
-#pragma unroll
-          for (int u = 0; u < FU; ++u) add1(e[u]);
-        }
-        add1(sg);
+      ring_sync(BAR_FULL + slot);  // every add of the range has landed (or a notice is posted)
+      TRI({ const long long t = clock64(); t_full += t - tc; tc = t; })
+      const FastHandoff m = s_hand[slot];
+      if (m.flags & F_QUIT) break;
+      uint32_t* accx = acc + (size_t)slot * W;
+      if (m.flags & F_HARVEST) {
+        const bool need = scan(accx, m.range_base, m.thr0f);
+        TRI({ const long long t = clock64(); t_scan += t - tc; tc = t; })
+        settle(accx, m.range_base, m.thr0f, need);
+        TRI({ const long long t = clock64(); t_settle += t - tc; tc = t; })
       }
-      __syncwarp();
-      if (lane == 0) trr_mbar_arrive(&empty_bar[stage]);  // stage and descriptor are free again
-      if (++stage == NS) { stage = 0; phase ^= 1; }
-      TRI({ const long long t = clock64(); w_acc += t - tc; tc = t; })
-      if (flags & F_HARVEST) {  // last pass of the range
-        TRI(const long long tb0 = clock64(); w_arr += tb0 - t_pass;)
-        fast_bar();  // every add of the range has landed
-        TRI({ const long long t = clock64(); w_b1 += t - tc; tc = t; w_bar += t - tb0; })
-        const bool need = scan(acc_cur, range_base, thr0f);
-        TRI({ const long long t = clock64(); w_scan += t - tc; tc = t; })
-        settle(acc_cur, range_base, thr0f, need);
-        TRI({ const long long t = clock64(); w_harv += t - tc; tc = t; })
-      }
-      if (flags & F_END_ITEM) {
+      if (m.flags & F_END_ITEM) {
         compact();
         const uint32_t n_out = s_cnt;
-        uint64_t* dst = a.fast_keys + (uint64_t)item * a.kf;  // indexed by position in `order` (x n_chunks + chunk)
-        for (uint32_t i = tid; i < a.kf; i += FCT) dst[i] = i < n_out ? cand[i] : TRR_KEY_EMPTY;
+        uint64_t* dst = a.fast_keys + (uint64_t)m.item * a.kf;  // indexed by position in `order` (x n_chunks + chunk)
+        for (uint32_t i = tid; i < a.kf; i += YT) dst[i] = i < n_out ? cand[i] : TRR_KEY_EMPTY;
         fast_bar();
         if (tid == 0) { s_cnt = 0; s_thr = TRR_KEY_EMPTY; }
         fast_bar();
-        TRI({ const long long t = clock64(); w_end += t - tc; tc = t; })
+        TRI({ const long long t = clock64(); t_end += t - tc; tc = t; })
       }
+      ring_arrive(BAR_EMPTY + slot);  // the slot (zeroed again) goes back to the accumulate warps
+      ++n;
     }
-    TRI(if (blockIdx.x == 0 && lane == 0 && a.triage_out && w_acc > 100000) { a.triage_out[warp * 2] = (uint32_t)(w_arr >> 4); a.triage_out[warp * 2 + 1] = (uint32_t)(w_bar >> 4); })
-    TRI(if (blockIdx.x == 0 && tid == 0 && a.dbg && w_acc > 100000) {
-      a.dbg[8] = (uint32_t)((clock64() - t_begin) >> 4); a.dbg[10] = (uint32_t)(w_full >> 4); a.dbg[11] = (uint32_t)(w_acc >> 4);
-      a.dbg[12] = (uint32_t)(w_harv >> 4); a.dbg[13] = (uint32_t)(w_end >> 4); a.dbg[15] = n_compact;
-      a.dbg[6] = (uint32_t)(w_b1 >> 4); a.dbg[7] = (uint32_t)(w_scan >> 4);
-    })
+    TRI(if (blockIdx.x == 0 && tid == 0 && a.triage_out && n > 64) {
+      a.triage_out[8] = (uint32_t)((clock64() - t_begin) >> 4); a.triage_out[9] = (uint32_t)(t_full >> 4);
+      a.triage_out[10] = (uint32_t)(t_scan >> 4); a.triage_out[11] = (uint32_t)(t_settle >> 4);
+      a.triage_out[12] = (uint32_t)(t_end >> 4); a.triage_out[13] = n; a.triage_out[14] = t_ncomp; })
   }
 }
 
@@ -1186,14 +1250,15 @@ cudaError_t trr_launch_bm25_search(const Bm25SearchArgs& a, unsigned grid, cudaS
 }
 
 
-size_t trr_bm25_fast_smem(int bits, uint32_t range_shift, uint32_t stage_cap, uint32_t cand_cap) {
-  return ((size_t)(bits == 16 ? 2 : 4) << range_shift) + (size_t)NS * stage_cap * 8 + (size_t)cand_cap * 8 + NS * sizeof(FastDesc) +
+size_t trr_bm25_fast_smem(int bits, uint32_t range_shift, uint32_t n_acc, uint32_t stage_cap, uint32_t cand_cap) {
+  return n_acc * ((size_t)(bits == 16 ? 2 : 4) << range_shift) + (size_t)NS * stage_cap * 8 + (size_t)cand_cap * 8 + NS * sizeof(FastDesc) +
          2 * NS * 8;
 }
 
 cudaError_t trr_launch_bm25_fast(const Bm25SearchArgs& a, int bits, unsigned grid, cudaStream_t st) {
   if (a.B == 0 || grid == 0) return cudaSuccess;
-  const size_t smem = trr_bm25_fast_smem(bits, a.range_shift, a.stage_cap, a.cand_cap);
+  if (a.n_acc < 1 || a.n_acc > 2) return cudaErrorInvalidValue;
+  const size_t smem = trr_bm25_fast_smem(bits, a.range_shift + a.rmul_shift, a.n_acc, a.stage_cap, a.cand_cap);
   auto kernel = bits == 16 ? bm25_fast_kernel<16> : bm25_fast_kernel<32>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

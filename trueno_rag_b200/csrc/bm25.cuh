@@ -66,6 +66,8 @@ struct Bm25SearchArgs {
   uint32_t* dbg;       // nullable host-mapped word: site of a barrier timeout
   // integer fast pass (bm25_fast_kernel): k = kf candidates per query by fast score
   uint32_t kf;         // candidates kept per query by the fast pass (> the k of the search)
+  uint32_t rmul_shift; // the fast pass walks 2^rmul_shift ranges of the skip table per accumulator pass
+  uint32_t n_acc;      // accumulators in the fast pass's ring (2: accumulate range i + 1 while range i is scanned)
   const float* qscale;     // [B] scale of the query's fixed-point scores for the cell width of this launch
   const uint32_t* thr0f;   // [B] initial fixed-point threshold for the cell width of this launch (0 = none)
   float* qscale16;         // plan kernel outputs: [B] scale / bootstrap threshold for 16-bit cells ...
@@ -106,10 +108,15 @@ size_t trr_bm25_search_smem(uint32_t range_shift, uint32_t stage_cap, uint32_t c
 cudaError_t trr_launch_bm25_plan(const Bm25SearchArgs& a, uint64_t* plan_keys, cudaStream_t st);
 cudaError_t trr_launch_bm25_search(const Bm25SearchArgs& a, unsigned grid, cudaStream_t st);
 // integer fast pass + exact re-scoring (the default BM25 search path)
-size_t trr_bm25_fast_smem(int bits, uint32_t range_shift, uint32_t stage_cap, uint32_t cand_cap);
+size_t trr_bm25_fast_smem(int bits, uint32_t range_shift, uint32_t n_acc, uint32_t stage_cap, uint32_t cand_cap);
 cudaError_t trr_launch_bm25_fast(const Bm25SearchArgs& a, int bits, unsigned grid, cudaStream_t st);
 cudaError_t trr_launch_bm25_rescore(const Bm25RescoreArgs& a, cudaStream_t st);
 #ifndef TRR_BM25_FAST_STAGES_N
 #define TRR_BM25_FAST_STAGES_N 2  /* (two 64 KB stages: nearly every range is one pass; 5.81 vs 5.91 ms with three 48 KB stages at cfg4) */
 #endif
 constexpr uint32_t TRR_BM25_FAST_STAGES = TRR_BM25_FAST_STAGES_N;
+// 16-bit level over 32K-document ranges: two 64 KB accumulators in a ring (default), or one 128 KB accumulator over two
+// ranges of the skip table (TRR_BM25_FAST_RMUL16 = 1)
+#ifndef TRR_BM25_FAST_RMUL16
+#define TRR_BM25_FAST_RMUL16 0
+#endif

@@ -1287,14 +1287,18 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
   a.n_ranges = h->n_ranges; a.range_shift = h->range_shift; a.doc_base = h->doc_base;
   a.q_terms = d_q_terms; a.q_off = d_q_off; a.B = B; a.k = k; a.kf = kf;
   const uint32_t cand_exact = trr_pow2_ceil(k + 512), cand_fast = trr_pow2_ceil(kf + 512);
-  uint32_t ctas_exact = a.range_shift <= 14 ? 2u : 1u, ctas16 = a.range_shift <= 15 ? 2u : 1u, ctas32 = ctas_exact;
-  if (a.range_shift == 15) ctas16 = 1;  // 64 KB of cells + three large stages: one CTA per SM
-  if (const char* e = TRR_KNOB("TRR_BM25_CTAS_PER_SM")) ctas_exact = ctas16 = ctas32 = std::min(2, std::max(1, atoi(e)));
+  uint32_t ctas_exact = a.range_shift <= 14 ? 2u : 1u, ctas16 = 1, ctas32 = 1;  // (the fast kernels fill an SM with one CTA)
+  if (const char* e = TRR_KNOB("TRR_BM25_CTAS_PER_SM")) ctas_exact = std::min(2, std::max(1, atoi(e)));
   uint32_t stage_exact = 0, stage16 = 0, stage32 = 0;
+  // accumulators of the fast pass: a ring of two wherever two fit next to the stages (16-bit cells always, 32-bit cells up
+  // to 16K documents per range), so that one range is scanned while the next accumulates
+  uint32_t rmul16 = a.range_shift == TRR_BM25_MAX_RANGE_SHIFT ? TRR_BM25_FAST_RMUL16 : 0u;
+  if (const char* e = TRR_KNOB("TRR_BM25_RMUL")) rmul16 = (uint32_t)std::min(1, std::max(0, atoi(e)));
+  const uint32_t nacc16 = rmul16 ? 1u : 2u, nacc32 = a.range_shift <= 14 ? 2u : 1u;
   TRR_CHECK(bm25_stage_cap(c, trr_bm25_search_smem(a.range_shift, 0, cand_exact) + 64, 2, &ctas_exact, &stage_exact));
   if (fast) {
-    TRR_CHECK(bm25_stage_cap(c, trr_bm25_fast_smem(16, a.range_shift, 0, cand_fast) + 64, TRR_BM25_FAST_STAGES, &ctas16, &stage16));
-    TRR_CHECK(bm25_stage_cap(c, trr_bm25_fast_smem(32, a.range_shift, 0, cand_fast) + 64, TRR_BM25_FAST_STAGES, &ctas32, &stage32));
+    TRR_CHECK(bm25_stage_cap(c, trr_bm25_fast_smem(16, a.range_shift + rmul16, nacc16, 0, cand_fast) + 128, TRR_BM25_FAST_STAGES, &ctas16, &stage16));
+    TRR_CHECK(bm25_stage_cap(c, trr_bm25_fast_smem(32, a.range_shift, nacc32, 0, cand_fast) + 128, TRR_BM25_FAST_STAGES, &ctas32, &stage32));
   }
   // few queries: split every query into chunks of document ranges so that all SMs have work
   const uint32_t slots = (uint32_t)c->sm_count * (fast ? ctas16 : ctas_exact);
@@ -1373,7 +1377,7 @@ static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint
       if (sel) x.order = const_cast<uint32_t*>(sel);
       x.n_sel_ptr = n_sel_ptr; x.queue = queue; x.n_chunks = nc;
       x.qscale = bits == 16 ? a.qscale16 : a.qscale32; x.thr0f = bits == 16 ? a.thr0f16 : a.thr0f32;
-      x.fast_keys = lists; x.stage_cap = stage_cap; x.cand_cap = cand_fast;
+      x.fast_keys = lists; x.stage_cap = stage_cap; x.cand_cap = cand_fast; x.rmul_shift = bits == 16 ? rmul16 : 0u; x.n_acc = bits == 16 ? nacc16 : nacc32;
       const unsigned grid_x = (unsigned)std::min<uint64_t>((uint64_t)B * nc, (uint64_t)c->sm_count * ctas);
       TRR_CUDA(trr_launch_bm25_fast(x, bits, grid_x, st));
       ++launches;
@@ -1466,15 +1470,10 @@ extern "C" int trr_bm25_last_stats(trr_bm25* h, trr_stats* out) {
   if (h->stats.mode_used == 2 && g_triage_out) {
     uint32_t pw[64] = {0};
     cudaMemcpy(pw, g_triage_out, 256, cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[trr] K3 fast, CTA 0, per consumer warp (x16 cycles) pass start -> range barrier / in the barrier:");
-    for (int w = 0; w < 16; ++w) fprintf(stderr, " %u/%u", pw[2 * w], pw[2 * w + 1]);
-    fprintf(stderr, "\n");
-  }
-  if (h->stats.mode_used == 2 && extra(h->ctx)->dbg_host) {
-    const uint32_t* w = extra(h->ctx)->dbg_host;
-    fprintf(stderr, "[trr] K3 fast, CTA 0 (x16 cycles): total %u; producer: %u passes, waited %u for a free stage; consumer warp 0: "
-                    "%u waiting for postings, %u accumulate, %u harvest (%u compactions; remainder after: first barrier %u, scan %u), %u end of item\n", w[8], w[14], w[9], w[10],
-            w[11], w[12], w[15], w[6], w[7], w[13]);
+    fprintf(stderr, "[trr] K3 fast, CTA 0 (x16 cycles): accumulate warp 0: total %u = wait postings %u + walk %u + wait slot %u (%u passes); "
+                    "scan warp 0: total %u = wait accumulator %u + scan %u + settle %u + end of item %u (%u hand-overs, %u compactions); "
+                    "producer: total %u, waited %u for a free stage (%u passes)\n",
+            pw[0], pw[1], pw[2], pw[3], pw[4], pw[8], pw[9], pw[10], pw[11], pw[12], pw[13], pw[14], pw[16], pw[17], pw[18]);
   }
 #endif
   if (h->stat_pending && h->stat_dev) {
