@@ -694,7 +694,17 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     // the whole search is enqueued without a host round trip; very large B x k falls back to a host-read count and chunks.
     const bool dev_fallback = (size_t)B * lists * k * 8 <= ((size_t)256 << 20) && !TRR_KNOB("TRR_GEMM_HOST_FALLBACK");
     const uint32_t fb_chunk = dev_fallback ? B : 64;  // fallback queries per scan launch
-    const size_t need = WsCarver::need({(size_t)B * 4, (size_t)B * 4, n_cand * 4, n_cand * 4, (size_t)B_pad * 4,
+    // merged thresholds (helper warps of the 2-CTA kernel): every list publishes its pub_rank-th best score
+    // (j = the smallest power of two with ceil(CP / j) lists available; s = how many lists may fall short of it)
+    uint32_t pub_rank = 0, pub_pick = 0;
+    if (pair_mode && !TRR_KNOB("TRR_GEMM_NOMERGE")) {
+      for (uint32_t j = 1; j <= std::min<uint32_t>(cps, 8u); j <<= 1) {
+        const uint32_t lists_needed = (CP + j - 1) / j;
+        if (lists_needed <= vslices) { pub_rank = j; pub_pick = std::min<uint32_t>(vslices - lists_needed + 1, 8u); break; }
+      }
+    }
+    const size_t n_pub = pub_rank ? (size_t)vslices * B_pad : 0;
+    const size_t need = WsCarver::need({(size_t)B * 4, (size_t)B * 4, n_cand * 4, n_cand * 4, (size_t)(B_pad + n_pub) * 4,
                                         (size_t)B * 4, (size_t)B * 4, (size_t)B * 4, 256, (size_t)B_pad * h->dim_pad * 2,
                                         (size_t)fb_chunk * lists * k * 8 + 512, (size_t)fb_chunk * lists * 4 + 512}) +
                         4096;
@@ -704,7 +714,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     float* d_qdelta = ws.take<float>(B);
     float* cand_score = ws.take<float>(n_cand);
     uint32_t* cand_ord = ws.take<uint32_t>(n_cand);
-    uint32_t* gthr = ws.take<uint32_t>(B_pad);
+    uint32_t* gthr = ws.take<uint32_t>(B_pad + n_pub);  // [B_pad] shared thresholds, then [vslices][B_pad] published list ranks
     uint32_t* flags = ws.take<uint32_t>(B);
     uint32_t* flagged = ws.take<uint32_t>(B);
     uint32_t* flagged2 = ws.take<uint32_t>(B);
@@ -714,7 +724,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
 
     trr_launch_query_prep(d_q, h->dim, h->dim_pad, B, B_pad, q_bf16, d_qdelta, d_qn, st);  // also ||q|| (reference order)
     c->launches += 1;
-    TRR_CUDA(cudaMemsetAsync(gthr, 0, (size_t)B_pad * 4, st));
+    TRR_CUDA(cudaMemsetAsync(gthr, 0, (size_t)(B_pad + n_pub) * 4, st));
     TRR_CUDA(cudaMemsetAsync(counters, 0, 256, st));
     alignas(64) uint8_t map_q[128];
     TRR_CHECK(trr_make_tensor_map(map_q, q_bf16, B_pad, h->dim_pad, TRR_GEMM_TILE_M));
@@ -724,6 +734,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
     ga.scale_bias = reinterpret_cast<const float2*>(h->scale_bias.p);
     ga.cand_score = cand_score; ga.cand_ord = cand_ord; ga.gthr = gthr; ga.share_thresholds = 1;
     ga.pair_mode = pair_mode; ga.cps = cps;
+    ga.pub = pub_rank ? gthr + B_pad : nullptr; ga.pub_rank = pub_rank; ga.pub_pick = pub_pick;
     ga.dbg = extra(c)->dbg_dev;
     if (const char* e = TRR_KNOB("TRR_GEMM_DEBUG")) ga.debug_mode = atoi(e);      // perf triage only; results are wrong
     if (const char* e = TRR_KNOB("TRR_GEMM_NOSHARE")) ga.share_thresholds = atoi(e) ? 0 : 1;
@@ -734,7 +745,7 @@ static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint3
 
     RescoreArgs ra{};
     ra.cand_score = cand_score; ra.cand_ord = cand_ord; ra.n_slices = vslices; ra.n_qblocks = n_qblocks;
-    ra.cps = cps; ra.cp = CP; ra.cap2 = cap2;
+    ra.cps = cps; ra.cp = CP; ra.cap2 = cap2; ra.gthr = gthr;
     ra.rows = h->rows; ra.dim = h->dim; ra.norms = h->norms; ra.base_ord = h->base; ra.n_live = n_live;
     ra.q = d_q; ra.q_norms = d_qn; ra.q_norms_out = nullptr; ra.q_delta = d_qdelta; ra.max_norm = reinterpret_cast<const float*>(h->max_norm.p);
     ra.B = B; ra.k = k; ra.metric = h->metric;

@@ -68,6 +68,7 @@ struct RescoreArgs {
   uint32_t cps;              // candidates kept per (query, slice) by the tensor-core pass
   uint32_t cp;               // candidates re-scored exactly per query (power of two, >= k)
   uint32_t cap2;             // power of two >= max(n_slices*cps, cp + 1)
+  const uint32_t* gthr;      // nullable [n_qblocks*128]: the largest threshold the tensor-core pass applied to the query (orderable)
   const void* rows;          // slab in the store dtype
   uint32_t dim;
   const float* norms;
@@ -108,6 +109,10 @@ struct GemmTopkArgs {
   uint32_t* cand_ord;
   uint32_t* gthr;            // [n_qblocks*128] shared running thresholds (orderable-encoded), zeroed by the caller
   int share_thresholds;
+  uint32_t* pub;             // nullable [2 * n_slices][n_qblocks*128]: every list's pub_rank-th best fast score (orderable; 0 = none),
+                             // zeroed by the caller; the pair kernel's helper warps turn it into merged thresholds (see there)
+  uint32_t pub_rank;         // j: 1..8; 0 = off
+  uint32_t pub_pick;         // s: 1..8, the threshold is the s-th smallest published value: (2 * n_slices - s + 1) * j >= re-scoring width
   uint32_t* dbg;             // nullable host-mapped word: site of a barrier timeout
   int pair_mode;             // 1 = 2-CTA kernel (cta_group::2); needs an even n_qblocks
   int debug_mode;            // 0 = normal; 1 = epilogue skips TMEM reads; 2 = reads but never inserts (perf triage only)

@@ -62,6 +62,7 @@ constexpr uint32_t SMEM_BAR = SMEM_SB + 2 * SB_BYTES;
 constexpr uint32_t SMEM_TOTAL = SMEM_BAR + 256;
 static_assert(SMEM_TOTAL <= 227 * 1024, "1-CTA GEMM shared memory");
 constexpr uint32_t GEMM1_THREADS = 320;  // TMA producer, MMA issuer, 8 epilogue warps
+constexpr uint32_t GEMM2_THREADS = 384;  // pair kernel: + 2 helper warps (merged thresholds)
 
 // instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), both K-major
 // (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
@@ -510,7 +511,7 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 }
 }  // namespace
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM1_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
 dense_gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d,
                             GemmTopkArgs a, float* __restrict__ dump, uint32_t dump_ld) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -522,6 +523,7 @@ dense_gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
   uint64_t* sbfull_bar = tempty_bar + 2;
   uint64_t* sbempty_bar = sbfull_bar + SB_RING;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sbempty_bar + SB_RING);
+  uint32_t* helper_flags = reinterpret_cast<uint32_t*>(smem + SMEM2_BAR + 192);  // [0] epilogue warps whose lists are initialised, [1] ... that are done
 
   const uint32_t rank = cluster_ctarank();          // 0 = leader
   const uint32_t qb = blockIdx.x % a.n_qblocks;     // n_qblocks is even; the pair owns query blocks (qb & ~1, qb | 1)
@@ -535,6 +537,7 @@ dense_gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     for (uint32_t s = 0; s < STAGES2; ++s) { trr_mbar_init(&full_bar[s], 1); trr_mbar_init(&empty_bar[s], 1); }
     for (uint32_t s = 0; s < 2; ++s) { trr_mbar_init(&tfull_bar[s], 1); trr_mbar_init(&tempty_bar[s], 16); }  // one arrival per epilogue warp of both CTAs
     for (uint32_t s = 0; s < SB_RING; ++s) { trr_mbar_init(&sbfull_bar[s], 1); trr_mbar_init(&sbempty_bar[s], 8); }
+    helper_flags[0] = 0; helper_flags[1] = 0;
     trr_fence_mbar_init();
   }
   cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / TMA / commit
@@ -610,7 +613,7 @@ dense_gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
       }
       if (timed && blockIdx.x == 0 && lane == 0) { a.dbg[10] = (uint32_t)w_full; a.dbg[11] = (uint32_t)w_tempty; }
     }
-  } else {
+  } else if (warp < 10) {
     // ===================== epilogue (both CTAs, 8 warps each; as in the 1-CTA kernel) =====================
     const uint32_t quarter = warp & 3;
     const uint32_t half = (warp - 2) >> 2;
@@ -619,6 +622,8 @@ dense_gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     uint32_t* my_lo = reinterpret_cast<uint32_t*>(smem + SMEM2_LO) + (half * BM + row) * L1STRIDE;
     const uint32_t cps = a.cps;
     for (uint32_t j = 0; j < cps; ++j) { my_ls[j] = -CUDART_INF_F; my_lo[j] = 0xFFFFFFFFu; }
+    __syncwarp();
+    if (lane == 0) atomicAdd(&helper_flags[0], 1u);  // (the helper warps read the lists once all of them are initialised)
     RowState st;
     st.list_min = -CUDART_INF_F;
     st.minpos = 0;
@@ -661,6 +666,69 @@ dense_gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     // publish this half-slice's candidates: virtual slice 2 * slice + half
     const uint64_t base = (((uint64_t)(slice * 2 + half) * a.n_qblocks + qb) * BM + row) * cps;
     for (uint32_t j = 0; j < cps; ++j) { a.cand_score[base + j] = my_ls[j]; a.cand_ord[base + j] = my_lo[j]; }
+    __syncwarp();
+    if (lane == 0) atomicAdd(&helper_flags[1], 1u);
+  } else if (a.pub != nullptr && a.pub_rank != 0) {
+    // ===================== helper warps: merged thresholds =====================
+    // A row's own list minimum is the cps-th best of what ITS slice has seen - with 2 * n_slices lists per query that is
+    // about rank cps * 2 * n_slices of the documents seen so far, while the re-scoring needs rank CP.  Half of the 32-column
+    // chunks of an epilogue warp then still have a lane above its threshold and take the insertion path.  These two warps
+    // keep publishing every list's j-th best score (j = pub_rank) and fold, per query, the pub_pick-th SMALLEST of the
+    // published values into the shared threshold: 2 * n_slices - pub_pick + 1 lists have j documents at or above it, and
+    // the host picks j and pub_pick so that this is at least CP documents.  List entries only ever grow and
+    // 32-bit shared-memory reads are single-copy atomic, so a racing read yields a value the list reached at some time:
+    // the j-th best of such a snapshot never exceeds the true one.  Exactness does not depend on it: whatever threshold was
+    // applied ends up in gthr, which the re-scoring kernel's proof treats as the bound of everything that was dropped.
+    const uint32_t h = threadIdx.x - 320;  // 0..63: rows h and h + 64
+    volatile uint32_t* hf = helper_flags;
+    while (hf[0] < 8u) __nanosleep(200);
+    const volatile float* ls = reinterpret_cast<const volatile float*>(smem + SMEM2_LS);
+    const uint32_t B_pad = a.n_qblocks * BM, nv = 2 * a.n_slices, cps = a.cps;
+    uint32_t last[2] = {0u, 0u};
+    // a sweep costs these warps ~3 us of issue slots on two of the four schedulers, and thresholds improve like 1 / (documents
+    // seen): the pause between sweeps doubles from 1 us to 64 us (polled in 1 us naps, so the kernel's end is not delayed)
+    uint32_t naps = 1;
+    while (hf[1] < 8u) {
+#pragma unroll
+      for (uint32_t rr = 0; rr < 2; ++rr) {
+        const uint32_t row = h + rr * 64;
+#pragma unroll
+        for (uint32_t half = 0; half < 2; ++half) {
+          const volatile float* l = ls + (half * BM + row) * L1STRIDE;
+          float t[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = -CUDART_INF_F;
+          for (uint32_t j = 0; j < cps; ++j) {
+            float v = l[j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float hi = fmaxf(t[i], v); v = fminf(t[i], v); t[i] = hi; }
+          }
+          float val = t[0];
+#pragma unroll
+          for (int i = 1; i < 8; ++i) val = (uint32_t)i < a.pub_rank ? t[i] : val;
+          const uint32_t enc = val > -CUDART_INF_F ? trr_f32_orderable(val) : 0u;
+          __stcg(a.pub + (uint64_t)(slice * 2 + half) * B_pad + qb * BM + row, enc);
+        }
+      }
+#pragma unroll
+      for (uint32_t rr = 0; rr < 2; ++rr) {
+        const uint32_t q = qb * BM + h + rr * 64;
+        uint32_t sm[8];  // the 8 smallest published values, ascending
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sm[i] = 0xFFFFFFFFu;
+        for (uint32_t v = 0; v < nv; ++v) {
+          uint32_t x = __ldcg(a.pub + (uint64_t)v * B_pad + q);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const uint32_t lo = min(sm[i], x); x = max(sm[i], x); sm[i] = lo; }
+        }
+        uint32_t m = sm[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) m = (uint32_t)i < a.pub_pick ? sm[i] : m;
+        if (sm[0] != 0u && m != 0xFFFFFFFFu && m > last[rr]) { atomicMax(a.gthr + q, m); last[rr] = m; }
+      }
+      for (uint32_t i = 0; i < naps && hf[1] < 8u; ++i) __nanosleep(1000);
+      naps = min(naps * 2u, 64u);
+    }
   }
 
   tc_fence_before();
@@ -800,7 +868,7 @@ cudaError_t trr_launch_gemm_topk_dump(const GemmTopkArgs& a, const void* map_q12
     cudaError_t e = cudaFuncSetAttribute(dense_gemm_topk_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)SMEM2_TOTAL);
     if (e != cudaSuccess) return e;
-    dense_gemm_topk_pair_kernel<<<grid, GEMM1_THREADS, SMEM2_TOTAL, st>>>(mq, md, a, dump, dump_ld);
+    dense_gemm_topk_pair_kernel<<<grid, GEMM2_THREADS, SMEM2_TOTAL, st>>>(mq, md, a, dump, dump_ld);
   } else {
     cudaError_t e = cudaFuncSetAttribute(dense_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)SMEM_TOTAL);

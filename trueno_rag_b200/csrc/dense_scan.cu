@@ -638,9 +638,10 @@ rescore_select_kernel(RescoreArgs a) {
   // 1. gather: slice s of query block qb = b / 128, row r = b % 128
   const uint32_t qb = b / 128, r = b % 128;
   uint32_t local_total = 0;
-  // a slice whose list is full may have dropped documents: all of them scored at most the list minimum (and the
-  // thresholds shared between slices never exceed a list minimum).  s_tmax = the largest such bound; the per-slice minimum
-  // and fill count are collected with shared-memory atomics while the candidates are gathered.
+  // a slice whose list is full may have dropped documents: all of them scored at most the list minimum or at most the
+  // largest threshold shared between the slices (a.gthr: list minima and the helper warps' merged thresholds).  s_tmax = the
+  // largest such bound; the per-slice minimum and fill count are collected with shared-memory atomics while the candidates
+  // are gathered.
   for (uint32_t s = tid; s < a.n_slices; s += blockDim.x) { s_smin[s] = 0xFFFFFFFFu; s_scnt[s] = 0; }
   __syncthreads();
   for (uint32_t i = tid; i < a.n_slices * a.cps; i += blockDim.x) {
@@ -659,6 +660,7 @@ rescore_select_kernel(RescoreArgs a) {
   __syncthreads();
   for (uint32_t s = tid; s < a.n_slices; s += blockDim.x)
     if (s_scnt[s] == a.cps) atomicMax(&s_tmax, s_smin[s]);
+  if (tid == 0 && a.gthr) atomicMax(&s_tmax, a.gthr[b]);
   __syncthreads();
   trr_bitonic_sort_desc(keys, a.cap2, tid, blockDim.x, BlockSync());
   const uint32_t n_cand = min(s_total, a.cp);
