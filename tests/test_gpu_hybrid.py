@@ -211,3 +211,43 @@ def test_hybrid_input_validation(api, ctx):
     out = api.hybrid_search(dense, None, np.ones(32, np.float32), None, None, 5, api.RRF, 60.0, 3, use_sparse=False)
     assert out[0].shape == (1, 3) and out[4][0] == 3
     dense.close()
+
+
+@pytest.mark.parametrize("exchange", [0, 1])
+def test_group_single_rank_matches_oracle(api, ctx, corpus, exchange):
+    """trr_group_* + trr_hybrid_search_sharded with a group of one rank (what a single-GPU caller of the sharded entry point
+    gets): equal to the oracle, for both exchanges, over consecutive calls (the exchange buffers alternate)."""
+    c = corpus
+    group = api.Group(ctx, 0, 1, api.group_unique_id(), exchange)
+    dense, bm = make_dense(api, ctx, c, 0, c["N"]), make_bm25(api, ctx, c, 0, c["N"])
+    assert int(group.allreduce_u64(np.array([41], np.uint64))[0]) == 41
+    for strategy, param, C_, k in ((O.RRF, 60.0, 50, 10), (O.LINEAR, 0.7, 50, 10), (O.UNION, 0.0, 10, 20)):
+        got = group.search(dense, bm, c["Q"], c["q_terms"], c["q_off"], C_, strategy, param, k)
+        assert_hybrid(got, oracle_hybrid(c, strategy, np.float32(param), C_, k))
+    group.close(); dense.close(); bm.close()
+
+
+@pytest.mark.parametrize("exchange", [0, 1])
+def test_group_two_ranks(exchange, tmp_path):
+    """Two processes, two GPUs, one shard each (skipped on a single-GPU box): tests/_group_worker.py."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    id_file = str(tmp_path / "group_id")
+    procs = [subprocess.Popen([sys.executable, os.path.join(root, "tests", "_group_worker.py"), str(r), "2", id_file,
+                               str(exchange)], cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=600)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append(out)
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"rank {r}:" in out and "OK" in out, out[-3000:]
