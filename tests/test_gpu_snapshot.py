@@ -149,3 +149,39 @@ def test_snapshot_rejects_foreign_and_truncated_files(api, ctx, tmp_path):
     open(bad, "wb").write(data[: len(data) // 2])
     with pytest.raises(api.TrrError):
         api.DenseIndex.load(ctx, bad)
+
+
+def test_bm25_snapshot_with_corrupt_indices_is_refused(api, ctx, tmp_path):
+    """A file that passes the header checks but whose skip rows / document ids would send the search kernels out of
+    bounds is refused at load time (the loaded arrays are device indices)."""
+    cdf = O.zipf_cdf(500)
+    doc_off, toks = O.synth_doc_tokens(SEED, cdf, 0, 40000)
+    oix = O.BM25(n_terms=500, doc_off=doc_off, tokens=toks)
+    term_off, post_doc, post_tf, doc_len, df = oix.csr()
+    dev = api.Bm25Device(ctx, 40000, term_off, post_doc, post_tf, doc_len, oix.avgdl, api.bm25_idf_host(40000, df))
+    good = os.path.join(tmp_path, "good.trr")
+    dev.save(good)
+    n_post = dev.n_postings
+    dev.close()
+    data = bytearray(open(good, "rb").read())
+    header = 8 + 6 * 4 + 8 + 8 + 2 * 4                      # Bm25SnapHeader (csrc/capi.cu)
+    ok = api.Bm25Device.load(ctx, good)
+    assert ok.n_postings == n_post
+    ok.close()
+    # a document id beyond the shard
+    bad_doc = bytearray(data)
+    bad_doc[header + 8 * 1000: header + 8 * 1000 + 4] = (0x7FFFFFF0).to_bytes(4, "little")
+    p1 = os.path.join(tmp_path, "bad_doc.trr")
+    open(p1, "wb").write(bad_doc)
+    with pytest.raises(api.TrrError):
+        api.Bm25Device.load(ctx, p1)
+    # a skip entry beyond the postings (second column of the row of term 3)
+    n_ranges = (40000 + 32767) // 32768
+    skip0 = header + 8 * (n_post + 2)
+    bad_skip = bytearray(data)
+    off = skip0 + 4 * (3 * (n_ranges + 1) + 1)
+    bad_skip[off: off + 4] = (0xFFFFFF00).to_bytes(4, "little")
+    p2 = os.path.join(tmp_path, "bad_skip.trr")
+    open(p2, "wb").write(bad_skip)
+    with pytest.raises(api.TrrError):
+        api.Bm25Device.load(ctx, p2)

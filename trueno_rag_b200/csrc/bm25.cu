@@ -112,6 +112,29 @@ __global__ void bm25_kill_kernel(const uint2* __restrict__ post, uint32_t* __res
   if (local) atomicAdd(n_killed, local);
 }
 
+// trr_bm25_load: a snapshot's skip rows and document ids become device indices of the search kernels (bulk-copy sources,
+// accumulator cells), so a file that passes the header checks is still verified here: every skip row is a monotone partition
+// of its term's postings, every document id is inside the shard.  *bad counts the violations.
+__global__ void bm25_check_kernel(const uint32_t* __restrict__ skip, uint32_t skip_ld, uint32_t n_terms, uint32_t n_ranges,
+                                  const uint64_t* __restrict__ term_off, const uint2* __restrict__ post, uint64_t n_postings,
+                                  uint32_t n_docs, uint32_t* __restrict__ bad) {
+  const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+  uint32_t local = 0;
+  for (uint64_t t = i0; t < n_terms; t += stride) {
+    const uint32_t* row = skip + t * skip_ld;
+    uint64_t prev = term_off[t];
+    if (row[0] != prev || row[n_ranges] != term_off[t + 1]) ++local;
+    for (uint32_t r = 1; r <= n_ranges; ++r) {
+      const uint32_t v = row[r];
+      if (v < prev || v > n_postings) { ++local; break; }
+      prev = v;
+    }
+  }
+  for (uint64_t p = i0; p < n_postings; p += stride)
+    if (post[p].x >= n_docs) ++local;
+  if (local) atomicAdd(bad, local);
+}
+
 // terms without postings: every boundary is the (empty) term's offset
 __global__ void bm25_skip_empty_kernel(Bm25BuildArgs a) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1205,6 +1228,16 @@ cudaError_t trr_launch_bm25_kill(const uint2* post, uint32_t* tf, uint64_t n_pos
   if (n_postings == 0) return cudaSuccess;
   unsigned grid = (unsigned)std::min<uint64_t>((n_postings + 255) / 256, 148u * 32u);
   bm25_kill_kernel<<<grid, 256, 0, st>>>(post, tf, n_postings, dead_bits, n_killed);
+  return cudaGetLastError();
+}
+
+cudaError_t trr_launch_bm25_check(const uint32_t* skip, uint32_t skip_ld, uint32_t n_terms, uint32_t n_ranges,
+                                  const uint64_t* term_off, const uint2* post, uint64_t n_postings, uint32_t n_docs,
+                                  uint32_t* bad, cudaStream_t st) {
+  const uint64_t work = std::max<uint64_t>(n_terms, n_postings);
+  if (work == 0) return cudaSuccess;
+  unsigned grid = (unsigned)std::min<uint64_t>((work + 255) / 256, 148u * 32u);
+  bm25_check_kernel<<<grid, 256, 0, st>>>(skip, skip_ld, n_terms, n_ranges, term_off, post, n_postings, n_docs, bad);
   return cudaGetLastError();
 }
 

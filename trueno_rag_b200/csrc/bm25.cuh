@@ -101,6 +101,9 @@ struct Bm25RescoreArgs {
 
 cudaError_t trr_launch_bm25_build(const Bm25BuildArgs& a, cudaStream_t st);
 cudaError_t trr_launch_bm25_merge(const Bm25MergeArgs& a, cudaStream_t st);
+cudaError_t trr_launch_bm25_check(const uint32_t* skip, uint32_t skip_ld, uint32_t n_terms, uint32_t n_ranges,
+                                  const uint64_t* term_off, const uint2* post, uint64_t n_postings, uint32_t n_docs,
+                                  uint32_t* bad, cudaStream_t st);
 cudaError_t trr_launch_bm25_kill(const uint2* post, uint32_t* tf, uint64_t n_postings, const uint32_t* dead_bits,
                                  uint32_t* n_killed, cudaStream_t st);
 size_t trr_bm25_search_smem(uint32_t range_shift, uint32_t stage_cap, uint32_t cand_cap);

@@ -1661,6 +1661,22 @@ extern "C" int trr_bm25_load(trr_ctx* ctx, const char* path, trr_bm25** out) {
     for (size_t t = 0; ok && t + 1 < h->h_term_off.size(); ++t) ok = h->h_term_off[t] <= h->h_term_off[t + 1];
     if (!ok) s = trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_load: corrupt term offsets");
   }
+  if (s == TRR_OK) {
+    // ... and the skip rows and document ids, which the search kernels use as indices (bm25_check_kernel)
+    uint32_t* d_bad = nullptr;
+    uint32_t bad = 1;
+    if (cudaMalloc(&d_bad, 4) != cudaSuccess || cudaMemsetAsync(d_bad, 0, 4, ctx->stream) != cudaSuccess ||
+        trr_launch_bm25_check(h->skip, h->skip_ld, h->n_terms, h->n_ranges, h->d_term_off, h->post, h->n_postings, h->n_docs,
+                              d_bad, ctx->stream) != cudaSuccess ||
+        cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      cudaGetLastError();
+      s = trr_fail(TRR_ERR_CUDA, "trr_bm25_load: validation failed to run");
+    } else if (bad) {
+      s = trr_fail(TRR_ERR_INVALID_ARG, "trr_bm25_load: corrupt skip table or document ids");
+    }
+    if (d_bad) cudaFree(d_bad);
+  }
   if (s != TRR_OK) return fail(s);
   *out = h;
   return TRR_OK;
