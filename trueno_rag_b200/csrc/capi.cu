@@ -9,10 +9,20 @@
 #include <algorithm>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler is attached
+
 #include "bm25.cuh"
 #include "common.cuh"
 #include "dense.cuh"
 #include "fusion.cuh"
+
+// NVTX range around the host side of a library step (Nsight Systems shows which entry point enqueued which kernels)
+struct TrrRange {
+  explicit TrrRange(const char* name) { nvtxRangePushA(name); }
+  ~TrrRange() { nvtxRangePop(); }
+  TrrRange(const TrrRange&) = delete;
+  TrrRange& operator=(const TrrRange&) = delete;
+};
 
 cudaError_t trr_launch_synth_rows(uint64_t seed, uint64_t first_row, uint64_t n, uint32_t dim, int dups, int to_bf16,
                                   void* out, cudaStream_t st);
@@ -514,6 +524,7 @@ static int dense_scan_locked(trr_dense* h, const float* d_q, const float* d_qn, 
                              uint32_t k, uint32_t* d_ord, float* d_score, uint32_t* d_n, uint64_t* d_keys,
                              size_t scratch_off, const uint32_t* d_n_sel = nullptr, bool record_events = true,
                              bool fused = false, const float* h_q = nullptr, float h_qn = 0.0f) {
+  TrrRange nvtx_range("trr:dense_scan");
   ScanPlan p;
   TRR_CHECK(plan_scan(h, k, &p, n_sel));
   const uint64_t lists = (uint64_t)p.grid;  // one merged list per CTA
@@ -570,6 +581,7 @@ static void dense_resolve_stats(trr_dense* h) {
 static int dense_search_locked(trr_dense* h, const float* d_q, uint32_t B, uint32_t k, uint32_t* d_ord, float* d_score,
                                uint32_t* d_n, bool sync_stats, const float* d_qn_pre = nullptr, const float* h_q1 = nullptr,
                                float h_qn1 = 0.0f) {
+  TrrRange nvtx_range("trr:dense_search");
   trr_ctx* c = h->ctx;
   cudaStream_t st = c->stream;
   // very large batches are served in pieces (scratch and the query-block grid scale with B)
@@ -1274,6 +1286,7 @@ static int bm25_stage_cap(trr_ctx* c, size_t fixed, uint32_t n_stages, uint32_t*
 
 static int bm25_search_locked(trr_bm25* h, const uint32_t* d_q_terms, const uint32_t* d_q_off, const uint32_t* h_q_off,
                               uint32_t B, uint32_t k, uint32_t* d_ord, float* d_score, uint32_t* d_n, size_t scratch_off) {
+  TrrRange nvtx_range("trr:bm25_search");
   trr_ctx* c = h->ctx;
   cudaStream_t st = c->stream;
   h->stats = trr_stats{};
@@ -1706,6 +1719,7 @@ static int fuse_locked(trr_ctx* c, const ExchangeView& v, uint64_t shard_stride,
                        int strategy, float param, uint32_t k, bool have_dense, bool have_sparse, uint32_t* d_out_ord,
                        float* d_out_fused, float* d_out_dense, float* d_out_sparse, uint32_t* d_out_n,
                        cudaStream_t st_override = nullptr) {
+  TrrRange nvtx_range("trr:fuse");
   if (strategy < 0 || strategy > 5) return trr_fail(TRR_ERR_INVALID_ARG, "bad fusion strategy");
   if (C == 0 || C > 1024) return trr_fail(TRR_ERR_UNSUPPORTED, "candidates per source must be in 1..1024");
   if ((uint64_t)G * C > 8192) return trr_fail(TRR_ERR_UNSUPPORTED, "shards x candidates > 8192");
@@ -2130,6 +2144,7 @@ static int group_step_locked(trr_group* g, trr_dense* dense, trr_bm25* bm25, con
                              const uint32_t* d_q_off, const uint32_t* h_q_off, uint32_t B, uint32_t C, int strategy,
                              float param, uint32_t k, bool use_dense, bool use_sparse, uint32_t* d_out_ord, float* d_out_fused,
                              float* d_out_dense, float* d_out_sparse, uint32_t* d_out_n) {
+  TrrRange nvtx_range("trr:sharded_step");
   trr_ctx* c = g->ctx;
   cudaStream_t st = c->stream;
   const uint32_t G = (uint32_t)g->world;
@@ -2208,6 +2223,7 @@ static int group_search_host(trr_group* g, trr_dense* dense, trr_bm25* bm25, con
                              const uint32_t* q_off, uint32_t B, uint32_t C, int strategy, float param, uint32_t k,
                              int use_dense, int use_sparse, uint32_t* out_ord, float* out_fused, float* out_dense,
                              float* out_sparse, uint32_t* out_n, bool blocking) {
+  TrrRange nvtx_range("trr:sharded_search_host");
   if (!g) return trr_fail(TRR_ERR_INVALID_ARG, "group is NULL");
   trr_ctx* c = nullptr;
   TRR_CHECK(hybrid_check(dense, bm25, q, q_off, B, C, use_dense, use_sparse, &c));
